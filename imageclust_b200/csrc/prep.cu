@@ -1,0 +1,88 @@
+// prep.cu -- K0: centring, TF32 hi/lo split and row norms of the embedding matrix.
+//
+// Feeds K1 (gram_tcgen05.cu).  The reference computes WardDistance from raw fp32
+// rows (clustering.go:136-145); the Gram identity ||x||^2+||y||^2-2<x,y> needs
+//  (1) centred data (distances are translation invariant; removes the common-mean
+//      cancellation of non-negative ResNet features),
+//  (2) x = hi + lo with hi, lo exactly representable in TF32, so that three
+//      tensor-core passes hi*hi + hi*lo + lo*hi reproduce an fp32 product to 2^-22,
+//  (3) norms of the SAME represented values (hi+lo), in double.
+// HBM-bound: reads 4ND bytes, writes 8 N_pad D_pad bytes.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ic {
+
+__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ x, int64_t n, int64_t d,
+                                                     int64_t ldx, double* __restrict__ colsum) {
+    const int64_t col = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
+    if (col >= d) return;
+    double acc = 0.0;
+    for (int64_t r = blockIdx.y; r < n; r += gridDim.y) acc += static_cast<double>(x[r * ldx + col]);
+    atomicAdd(&colsum[col], acc);
+}
+
+cudaError_t launch_colsum(const float* x, int64_t n, int64_t d, int64_t ldx, double* colsum, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(double) * d, s);
+    if (e != cudaSuccess) return e;
+    if (n == 0 || d == 0) return cudaSuccess;
+    dim3 grid(static_cast<unsigned>((d + 127) / 128), static_cast<unsigned>(n < 592 ? n : 592));
+    colsum_kernel<<<grid, 128, 0, s>>>(x, n, d, ldx, colsum);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, int64_t n, int64_t d, int64_t ldx,
+                                                    const double* __restrict__ colsum, int center,
+                                                    float* __restrict__ hi, float* __restrict__ lo,
+                                                    double* __restrict__ norms, int64_t d_pad) {
+    const int64_t row = blockIdx.x;
+    float* hrow = hi + row * d_pad;
+    float* lrow = lo + row * d_pad;
+    double acc = 0.0;
+    const double inv_n = n > 0 ? 1.0 / static_cast<double>(n) : 0.0;
+    for (int64_t k = threadIdx.x; k < d_pad; k += blockDim.x) {
+        float h = 0.0f, l = 0.0f;
+        if (row < n && k < d) {
+            float v = x[row * ldx + k];
+            if (center) v = __fsub_rn(v, static_cast<float>(colsum[k] * inv_n));
+            h = to_tf32(v);
+            l = to_tf32(__fsub_rn(v, h));
+            const double rep = static_cast<double>(h) + static_cast<double>(l);
+            acc += rep * rep;
+        }
+        hrow[k] = h;
+        lrow[k] = l;
+    }
+    // block reduce
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        norms[row] = t;
+    }
+}
+
+cudaError_t launch_split(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
+                         float* hi, float* lo, double* norms, int64_t n_pad, int64_t d_pad, cudaStream_t s) {
+    if (n_pad == 0) return cudaSuccess;
+    split_kernel<<<static_cast<unsigned>(n_pad), 256, 0, s>>>(x, n, d, ldx, colsum, center, hi, lo, norms, d_pad);
+    return cudaGetLastError();
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t count, float value) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        p[i] = value;
+}
+
+cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    fill_kernel<<<148 * 8, 256, 0, s>>>(dm, count, value);
+    return cudaGetLastError();
+}
+
+}  // namespace ic

@@ -1,0 +1,139 @@
+/*
+ * imageclust_b200.h -- C ABI of the B200-native size-constrained Ward clustering.
+ *
+ * Drop-in boundary for ONE reference path:
+ *   internal/clustering.PerformClusteringWithConstraints   clustering.go:198-284
+ *   internal/clustering.CalculateOptimalClusters           clustering.go:168-186
+ * (the reference has no FFI/plugin interface: the Go function is the boundary and
+ * its only caller is internal/workflow/workflow.go:89-94).  A cgo shim keeps the
+ * Go signatures and calls the entry points below; see INTEGRATION.md.
+ *
+ * Everything is extern "C", plain pointers and sizes.  All functions return
+ * IC_OK (0) or a negative IC_ERR_* code; ic_last_error(ctx) gives the text.
+ * There is NO CPU fallback: without a CUDA device ic_create fails.
+ *
+ * Threading: a context owns one device, one stream and its workspaces; calls on
+ * the same context must be serialised by the caller, distinct contexts may run
+ * concurrently (the reference function is re-entrant; the shim holds a mutex).
+ */
+#ifndef IMAGECLUST_B200_H
+#define IMAGECLUST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IC_OK 0
+#define IC_ERR_TOO_FEW (-1)  /* totalItems < minSize            clustering.go:169-171 */
+#define IC_ERR_UNSAT (-2)    /* ceil(N/max) > floor(N/min)      clustering.go:175-177 */
+#define IC_ERR_BAD_ARG (-3)  /* NULL / non-positive sizes / ragged input (Go would panic, :149-151) */
+#define IC_ERR_CUDA (-4)     /* CUDA runtime / driver failure */
+#define IC_ERR_OOM (-5)      /* problem does not fit this device's HBM */
+#define IC_ERR_STATE (-6)    /* staged call made out of order */
+#define IC_ERR_TIMEOUT (-7)  /* device-side watchdog tripped (internal error) */
+#define IC_ERR_INTERNAL (-9)
+
+/* ic_initial_distances modes */
+#define IC_GRAM_TCGEN05_3XTF32 0 /* K1: TMA + tcgen05 3xTF32 Gram GEMM, fp32 TMEM accumulate (product path) */
+#define IC_GRAM_EXACT_FP32 1     /* SIMT kernel with the reference's own sequential fp32 arithmetic (audit path) */
+
+typedef struct ic_ctx ic_ctx;
+
+typedef struct ic_stats {
+    int64_t n_items;       /* N */
+    int64_t dim;           /* D */
+    int32_t n_target;      /* CalculateOptimalClusters result */
+    int32_t n_merges;      /* merges performed */
+    int32_t n_final;       /* clusters alive when the loop ended */
+    int32_t n_out;         /* clusters in the output map (size >= minSize) */
+    int32_t exhausted;     /* loop ended with no admissible pair (clustering.go:222-225) */
+    int32_t n_near_ties;   /* merges whose runner-up was within near_tie_tol (relative) */
+    int32_t n_rescans;     /* row rescans done by the merge loop */
+    int32_t gram_mode;     /* IC_GRAM_* used */
+    float near_tie_tol;
+    /* device time of each phase, CUDA events on the context's stream, milliseconds */
+    float ms_h2d;          /* pinned host -> device copy of X */
+    float ms_prep;         /* K0: centring, TF32 hi/lo split, norms */
+    float ms_gram;         /* K1: initial distance matrix */
+    float ms_nn_init;      /* K2: first nearest-neighbour sweep */
+    float ms_loop;         /* K3: persistent merge loop */
+    float ms_d2h;          /* merge trace read-back */
+    float ms_host;         /* host assembly of the cluster lists (wall clock) */
+    float ms_total;        /* wall clock of the whole call */
+    int64_t kernel_launches; /* kernels this call launched */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t matrix_bytes;  /* bytes of the distance matrix resident in HBM */
+} ic_stats;
+
+/* ---- context ---------------------------------------------------------- */
+int ic_create(ic_ctx **out, int device);
+void ic_destroy(ic_ctx *ctx);
+const char *ic_last_error(const ic_ctx *ctx);
+/* pinned staging buffer for the flattened [N x D] matrix (the cgo shim copies the
+ * Go [][]float32 rows into it; Go pointers never cross the boundary) */
+void *ic_pinned_alloc(size_t bytes);
+void ic_pinned_free(void *p);
+/* knobs: "near_tie_tol" (float, default 1e-5), "center" (0/1, default 1),
+ * "gram_mode" (IC_GRAM_*), "loop_threads", "verbose" */
+int ic_set_option(ic_ctx *ctx, const char *name, double value);
+
+/* ---- CalculateOptimalClusters, clustering.go:168-186 (host, exact) ---- */
+int ic_optimal_clusters(int64_t total_items, int64_t min_size, int64_t max_size, int64_t *out);
+
+/* ---- PerformClusteringWithConstraints, clustering.go:198-284 ----------
+ * x: row-major [n x d] fp32 on the HOST (ldx = row stride in floats, >= d).
+ * cluster_offsets: capacity n+1; members: capacity n; ids are 0..n_clusters-1 in
+ * the reference's slice order, members in the reference's order (hi ++ lo,
+ * clustering.go:31); items of clusters below min_size are absent (:268-271).
+ * Returns IC_ERR_TOO_FEW / IC_ERR_UNSAT where the reference returns (nil,false). */
+int ic_cluster_with_constraints(ic_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx,
+                                int64_t min_size, int64_t max_size, int32_t *cluster_offsets,
+                                int32_t *members, int32_t *n_clusters, ic_stats *stats);
+
+/* ---- staged entry points (unit parity with the reference's functions) -- */
+/* upload X (host pointer) or adopt a device pointer (copied), then K0 prep */
+int ic_load(ic_ctx *ctx, const float *x_host, int64_t n, int64_t d, int64_t ldx);
+int ic_load_device(ic_ctx *ctx, const float *x_dev, int64_t n, int64_t d, int64_t ldx);
+/* ComputeInitialDistanceMatrix + WardDistance + DotFloat32, clustering.go:61-73,136-157 */
+int ic_initial_distances(ic_ctx *ctx, int mode, int64_t max_size);
+/* replace the resident matrix (host [n x n], row stride ld) -- test hook */
+int ic_set_matrix(ic_ctx *ctx, const float *m_host, int64_t ld);
+/* first NN sweep over the matrix (row caches used by FindClosestClusters) */
+int ic_nn_init(ic_ctx *ctx);
+/* FindClosestClusters, clustering.go:119-133, on the resident state: returns the
+ * keys (slice-order ids) of the pair and its distance; key_hi = -1 if none */
+int ic_find_closest(ic_ctx *ctx, int32_t *key_hi, int32_t *key_lo, float *dist);
+/* merge loop (clustering.go:220-246: FindClosestClusters + maxSize check +
+ * MergeClusters + UpdateDistanceMatrix); stops at n_target clusters, on
+ * exhaustion, or after max_merges (<0: no limit) */
+int ic_merge_loop(ic_ctx *ctx, int64_t min_size, int64_t max_size, int64_t max_merges);
+/* all of the above on resident data + trace read-back + host assembly */
+int ic_run_resident(ic_ctx *ctx, int64_t min_size, int64_t max_size, int32_t *cluster_offsets,
+                    int32_t *members, int32_t *n_clusters, ic_stats *stats);
+/* output assembly, clustering.go:265-280, from the merge trace */
+int ic_build_clusters(ic_ctx *ctx, int64_t min_size, int32_t *cluster_offsets, int32_t *members,
+                      int32_t *n_clusters);
+
+/* ---- inspection -------------------------------------------------------- */
+/* distance matrix by slot, host [n x n] row stride ld; dead slots hold stale values */
+int ic_read_matrix(ic_ctx *ctx, float *out_host, int64_t ld);
+/* per slot: key (-1 = retired) and size */
+int ic_read_slots(ic_ctx *ctx, int32_t *key, int32_t *size);
+/* merge trace: one entry per merge (capacity >= n): keys of the merged pair, the
+ * merge distance, the new size, and the relative gap to the runner-up candidate */
+int ic_get_merge_trace(ic_ctx *ctx, int32_t *key_hi, int32_t *key_lo, float *dist, int32_t *size,
+                       float *gap, int64_t capacity, int64_t *n_merges);
+int ic_get_stats(ic_ctx *ctx, ic_stats *stats);
+
+/* microbenchmarks used by bench.py's roofline legs: one launch of the named
+ * kernel on the resident problem, device time in ms */
+int ic_time_kernel(ic_ctx *ctx, const char *which, int repeats, float *ms_each);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGECLUST_B200_H */
