@@ -1,0 +1,805 @@
+// api.cu -- C ABI (include/imageclust_b200.h) and the host engine behind it.
+//
+// The engine owns one device, one stream and the resident problem:
+//   X [n x d] fp32  ->  K0 prep (centre, TF32 hi/lo split, norms)
+//                   ->  K1 initial Ward distances, full square [n x ld] fp32 in HBM
+//                   ->  K2 first nearest-neighbour sweep
+//                   ->  K3 persistent merge loop (one launch for all merges)
+//                   ->  merge trace back to the host -> cluster lists
+// mirroring PerformClusteringWithConstraints (clustering.go:198-284).  There is no CPU
+// path: every entry point that computes needs the device, and fails without one.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/imageclust_b200.h"
+#include "kernels.h"
+
+using namespace ic;
+
+struct ic_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    std::string err;
+    // options
+    double near_tie_tol = 1e-5;
+    int center = 1;
+    int gram_mode = IC_GRAM_TCGEN05_3XTF32;
+    int loop_threads = 0;
+    int verbose = 0;
+    // resident problem
+    int64_t n = 0, d = 0, n_pad = 0, d_pad = 0, ld = 0;
+    float* x = nullptr;  // [n x d] dense
+    float *hi = nullptr, *lo = nullptr;
+    double *colsum = nullptr, *norms = nullptr;
+    int2* tiles = nullptr;
+    int n_tiles = 0;
+    bool prepped = false;
+    float* dm = nullptr;
+    SlotKS* ks = nullptr;
+    SlotNN* nn = nullptr;
+    int32_t *tr_key_hi = nullptr, *tr_key_lo = nullptr, *tr_size = nullptr;
+    float *tr_dist = nullptr, *tr_gap = nullptr;
+    uint8_t* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int32_t* ctl = nullptr;  // separate: survives scratch zeroing
+    int loop_grid = 0, loop_thr = 0;
+    bool loaded = false, have_dm = false, have_nn = false;
+    int gram_mode_used = -1;
+    // loop state mirrored on the host
+    int64_t n_target = 0;
+    int32_t n_live = 0, n_merges = 0, exhausted = 0;
+    int32_t h_ctl[16] = {0};
+    std::vector<int32_t> h_key_hi, h_key_lo, h_size;
+    std::vector<float> h_dist, h_gap;
+    bool trace_on_host = false;
+    ic_stats stats{};
+    cudaEvent_t ev[10] = {nullptr};
+};
+
+namespace {
+
+int fail(ic_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define IC_CUDA(call)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? IC_ERR_OOM : IC_ERR_CUDA,                \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void release_problem(ic_ctx* c) {
+    dev_free(c->x);
+    dev_free(c->hi);
+    dev_free(c->lo);
+    dev_free(c->colsum);
+    dev_free(c->norms);
+    dev_free(c->tiles);
+    dev_free(c->dm);
+    dev_free(c->ks);
+    dev_free(c->nn);
+    dev_free(c->tr_key_hi);
+    dev_free(c->tr_key_lo);
+    dev_free(c->tr_size);
+    dev_free(c->tr_dist);
+    dev_free(c->tr_gap);
+    dev_free(c->scratch);
+    dev_free(c->ctl);
+    c->loaded = c->have_dm = c->have_nn = c->prepped = false;
+    c->n = c->d = 0;
+    c->trace_on_host = false;
+}
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time so that the library loads (and exports its symbols) on a
+// machine without a driver.
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_operand_map(ic_ctx* ctx, CUtensorMap* map, float* base, int64_t rows, int64_t cols) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(ctx, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * sizeof(float)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kGramBK), 128u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, IC_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(r));
+    return IC_OK;
+}
+
+// Lower-triangular tile list in square super-tiles of 2048 x 2048 outputs: the 16 + 8
+// operand panels of a super-tile (64 MB with hi+lo at D=2048) stay L2 resident while its
+// 128 tiles are computed, so every operand panel is fetched from HBM once per super-tile.
+std::vector<int2> build_tile_list(int64_t n) {
+    std::vector<int2> tiles;
+    const int rbs = static_cast<int>((n + kGramBM - 1) / kGramBM);
+    const int SR = 16, SC = 8;
+    for (int sr = 0; sr * SR < rbs; ++sr)
+        for (int sc = 0; sc <= sr; ++sc)
+            for (int rb = sr * SR; rb < (sr + 1) * SR && rb < rbs; ++rb)
+                for (int cb = sc * SC; cb < (sc + 1) * SC; ++cb) {
+                    const int64_t col0 = static_cast<int64_t>(cb) * kGramBN;
+                    const int64_t row_last = static_cast<int64_t>(rb) * kGramBM + kGramBM - 1;
+                    if (col0 >= n || col0 > row_last) continue;  // outside, or wholly above the diagonal
+                    tiles.push_back(make_int2(rb, cb));
+                }
+    return tiles;
+}
+
+int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
+    if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 &&
+        ctx->loop_thr == (ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms))) {
+        // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
+        ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = false;
+        ctx->trace_on_host = false;
+        return IC_OK;
+    }
+    release_problem(ctx);
+    ctx->n = n;
+    ctx->d = d;
+    ctx->n_pad = round_up(n, kGramBN);
+    ctx->d_pad = round_up(d, kGramBK);
+    ctx->ld = round_up(n, 32);
+    size_t free_b = 0, total_b = 0;
+    IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double need = 4.0 * n * d + 4.0 * static_cast<double>(n) * ctx->ld +
+                        (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) + 64.0 * n +
+                        (64 << 20);
+    if (need > static_cast<double>(free_b))
+        return fail(ctx, IC_ERR_OOM, "problem needs " + std::to_string(need / 1e9) + " GB, device has " +
+                                         std::to_string(free_b / 1e9) + " GB free");
+    const size_t nn1 = static_cast<size_t>(n > 0 ? n : 1);
+    IC_CUDA(cudaMalloc(&ctx->x, sizeof(float) * nn1 * static_cast<size_t>(d > 0 ? d : 1)));
+    IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * nn1 * static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
+    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->tr_key_hi, sizeof(int32_t) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->tr_key_lo, sizeof(int32_t) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->tr_size, sizeof(int32_t) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->tr_dist, sizeof(float) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16));
+    // merge-loop launch geometry and scratch
+    ctx->loop_thr = ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms);
+    if (ctx->loop_thr != 256 && ctx->loop_thr != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 256 or 512");
+    IC_CUDA(merge_loop_max_grid(ctx->loop_thr, ctx->num_sms, &ctx->loop_grid));
+    if (ctx->loop_grid <= 0) return fail(ctx, IC_ERR_CUDA, "merge loop kernel does not fit an SM");
+    if (ctx->loop_grid > ctx->loop_thr) ctx->loop_grid = ctx->loop_thr;
+    const size_t G = static_cast<size_t>(ctx->loop_grid);
+    ctx->scratch_bytes = round_up(merge_loop_part_a_bytes() * G, 256) + round_up(merge_loop_part_b_bytes() * G, 256) +
+                         round_up(merge_loop_part_r_bytes() * G * kLoopRescanSlots, 256) +
+                         round_up(sizeof(int32_t) * 2 * nn1, 256) + 256 + 256;
+    IC_CUDA(cudaMalloc(&ctx->scratch, ctx->scratch_bytes));
+    ctx->h_key_hi.clear();
+    ctx->h_key_lo.clear();
+    ctx->h_size.clear();
+    ctx->h_dist.clear();
+    ctx->h_gap.clear();
+    return IC_OK;
+}
+
+LoopState loop_state(ic_ctx* c) {
+    LoopState st{};
+    st.dm = c->dm;
+    st.ld = c->ld;
+    st.n = static_cast<int32_t>(c->n);
+    st.ks = c->ks;
+    st.nn = c->nn;
+    st.tr_key_hi = c->tr_key_hi;
+    st.tr_key_lo = c->tr_key_lo;
+    st.tr_dist = c->tr_dist;
+    st.tr_size = c->tr_size;
+    st.tr_gap = c->tr_gap;
+    const size_t G = static_cast<size_t>(c->loop_grid);
+    const size_t nn1 = static_cast<size_t>(c->n > 0 ? c->n : 1);
+    uint8_t* p = c->scratch;
+    st.part_a = p;
+    p += round_up(merge_loop_part_a_bytes() * G, 256);
+    st.part_b = p;
+    p += round_up(merge_loop_part_b_bytes() * G, 256);
+    st.part_r = p;
+    p += round_up(merge_loop_part_r_bytes() * G * kLoopRescanSlots, 256);
+    st.rlist = reinterpret_cast<int32_t*>(p);
+    p += round_up(sizeof(int32_t) * 2 * nn1, 256);
+    st.rcount = reinterpret_cast<int32_t*>(p);
+    p += 256;
+    st.barrier = reinterpret_cast<uint32_t*>(p);
+    st.ctl = c->ctl;
+    return st;
+}
+
+int do_prep(ic_ctx* ctx) {
+    if (ctx->prepped) return IC_OK;
+    const size_t pad_elems = static_cast<size_t>(ctx->n_pad) * static_cast<size_t>(ctx->d_pad);
+    if (!ctx->hi) IC_CUDA(cudaMalloc(&ctx->hi, sizeof(float) * pad_elems));
+    if (!ctx->lo) IC_CUDA(cudaMalloc(&ctx->lo, sizeof(float) * pad_elems));
+    if (!ctx->colsum) IC_CUDA(cudaMalloc(&ctx->colsum, sizeof(double) * static_cast<size_t>(ctx->d_pad)));
+    if (!ctx->norms) IC_CUDA(cudaMalloc(&ctx->norms, sizeof(double) * static_cast<size_t>(ctx->n_pad)));
+    IC_CUDA(launch_colsum(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->stream));
+    IC_CUDA(launch_split(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->center, ctx->hi, ctx->lo, ctx->norms,
+                         ctx->n_pad, ctx->d_pad, ctx->stream));
+    ctx->stats.kernel_launches += 2;
+    if (!ctx->tiles) {
+        const std::vector<int2> tiles = build_tile_list(ctx->n);
+        ctx->n_tiles = static_cast<int>(tiles.size());
+        IC_CUDA(cudaMalloc(&ctx->tiles, sizeof(int2) * (tiles.size() ? tiles.size() : 1)));
+        IC_CUDA(cudaMemcpyAsync(ctx->tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        IC_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vector goes out of scope
+    }
+    ctx->prepped = true;
+    return IC_OK;
+}
+
+int do_gram(ic_ctx* ctx, int mode) {
+    if (mode == IC_GRAM_EXACT_FP32) {
+        IC_CUDA(launch_gram_exact(ctx->x, ctx->n, ctx->d, ctx->d, ctx->dm, ctx->ld, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        return IC_OK;
+    }
+    GramPlan plan{};
+    int rc = make_operand_map(ctx, &plan.map_hi, ctx->hi, ctx->n_pad, ctx->d_pad);
+    if (rc != IC_OK) return rc;
+    rc = make_operand_map(ctx, &plan.map_lo, ctx->lo, ctx->n_pad, ctx->d_pad);
+    if (rc != IC_OK) return rc;
+    plan.tiles = ctx->tiles;
+    plan.n_tiles = ctx->n_tiles;
+    plan.k_blocks = static_cast<int>(ctx->d_pad / kGramBK);
+    IC_CUDA(launch_gram_tcgen05(plan, ctx->norms, ctx->dm, ctx->n, ctx->ld, ctx->num_sms, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    return IC_OK;
+}
+
+int init_loop_state(ic_ctx* ctx) {
+    IC_CUDA(launch_init_slots(ctx->ks, ctx->n, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    ctx->n_live = static_cast<int32_t>(ctx->n);
+    ctx->n_merges = 0;
+    ctx->exhausted = 0;
+    ctx->trace_on_host = false;
+    std::memset(ctx->h_ctl, 0, sizeof(ctx->h_ctl));
+    ctx->h_ctl[CTL_N_LIVE] = ctx->n_live;
+    IC_CUDA(cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, sizeof(ctx->h_ctl), cudaMemcpyHostToDevice, ctx->stream));
+    return IC_OK;
+}
+
+int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges) {
+    LoopState st = loop_state(ctx);
+    LoopParams p{};
+    p.n_target = static_cast<int32_t>(n_target);
+    p.max_size = static_cast<int32_t>(max_size > 0x3FFFFFFF ? 0x3FFFFFFF : max_size);
+    p.max_merges = static_cast<int32_t>(max_merges < 0 ? -1 : (max_merges > 0x7FFFFFFF ? 0x7FFFFFFF : max_merges));
+    p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
+    IC_CUDA(cudaMemsetAsync(ctx->scratch, 0, ctx->scratch_bytes, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
+    IC_CUDA(launch_merge_loop(st, p, ctx->loop_grid, ctx->loop_thr, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    IC_CUDA(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(ctx->h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->trace_on_host = false;
+    return IC_OK;
+}
+
+int sync_loop_result(ic_ctx* ctx) {
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
+    ctx->n_live = ctx->h_ctl[CTL_N_LIVE];
+    ctx->n_merges = ctx->h_ctl[CTL_N_MERGES];
+    ctx->exhausted = ctx->h_ctl[CTL_EXHAUSTED];
+    return IC_OK;
+}
+
+int fetch_trace(ic_ctx* ctx) {
+    if (ctx->trace_on_host) return IC_OK;
+    const size_t m = static_cast<size_t>(ctx->n_merges);
+    ctx->h_key_hi.resize(m);
+    ctx->h_key_lo.resize(m);
+    ctx->h_size.resize(m);
+    ctx->h_dist.resize(m);
+    ctx->h_gap.resize(m);
+    if (m) {
+        IC_CUDA(cudaMemcpyAsync(ctx->h_key_hi.data(), ctx->tr_key_hi, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaMemcpyAsync(ctx->h_key_lo.data(), ctx->tr_key_lo, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaMemcpyAsync(ctx->h_size.data(), ctx->tr_size, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaMemcpyAsync(ctx->h_dist.data(), ctx->tr_dist, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaMemcpyAsync(ctx->h_gap.data(), ctx->tr_gap, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stats.d2h_bytes += static_cast<int64_t>(20 * m + sizeof(ctx->h_ctl));
+    ctx->trace_on_host = true;
+    return IC_OK;
+}
+
+// Output assembly (clustering.go:265-280).  Slice order == key order; members of a merged
+// cluster are members(hi) ++ members(lo) (clustering.go:31,237); clusters below minSize are
+// skipped without consuming an id (:268-271).
+int assemble(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offsets, int32_t* members, int32_t* n_out) {
+    const int64_t n = ctx->n, m = ctx->n_merges;
+    std::vector<uint8_t> consumed(static_cast<size_t>(n + m), 0);
+    for (int64_t t = 0; t < m; ++t) {
+        const int32_t khi = ctx->h_key_hi[t], klo = ctx->h_key_lo[t];
+        if (khi < 0 || klo < 0 || khi >= n + t || klo >= n + t || khi <= klo || consumed[khi] || consumed[klo])
+            return fail(ctx, IC_ERR_INTERNAL, "corrupt merge trace at merge " + std::to_string(t));
+        consumed[khi] = consumed[klo] = 1;
+    }
+    std::vector<int32_t> stack;
+    int32_t cid = 0;
+    int64_t pos = 0;
+    offsets[0] = 0;
+    for (int64_t k = 0; k < n + m; ++k) {
+        if (consumed[k]) continue;
+        const int64_t size = k < n ? 1 : ctx->h_size[k - n];
+        // the reference would try to split an oversized cluster (clustering.go:249-262); no merge
+        // can create one (:228), so this is an invariant check, not a code path
+        if (max_size > 0 && size > max_size) return fail(ctx, IC_ERR_INTERNAL, "cluster exceeds maxSize");
+        if (size < min_size) continue;
+        stack.clear();
+        stack.push_back(static_cast<int32_t>(k));
+        while (!stack.empty()) {
+            const int32_t kk = stack.back();
+            stack.pop_back();
+            if (kk < n) {
+                if (pos >= n) return fail(ctx, IC_ERR_INTERNAL, "member overflow");
+                members[pos++] = kk;
+            } else {
+                stack.push_back(ctx->h_key_lo[kk - n]);
+                stack.push_back(ctx->h_key_hi[kk - n]);
+            }
+        }
+        offsets[++cid] = static_cast<int32_t>(pos);
+    }
+    *n_out = cid;
+    ctx->stats.n_out = cid;
+    return IC_OK;
+}
+
+int validate_sizes(ic_ctx* ctx, int64_t n, int64_t d, int64_t ldx) {
+    if (n < 0 || d < 0 || (n > 0 && d > 0 && ldx < d)) return fail(ctx, IC_ERR_BAD_ARG, "bad n / d / ldx");
+    if (n > 0x3FFFFFFF) return fail(ctx, IC_ERR_BAD_ARG, "too many items");
+    return IC_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+int load_common(ic_ctx* ctx, const float* x, int64_t n, int64_t d, int64_t ldx, cudaMemcpyKind kind) {
+    int rc = validate_sizes(ctx, n, d, ldx);
+    if (rc != IC_OK) return rc;
+    if (n > 0 && d > 0 && !x) return fail(ctx, IC_ERR_BAD_ARG, "x is NULL");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    rc = alloc_problem(ctx, n, d);
+    if (rc != IC_OK) return rc;
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.n_items = n;
+    ctx->stats.dim = d;
+    ctx->stats.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
+    ctx->stats.matrix_bytes = static_cast<int64_t>(sizeof(float)) * n * ctx->ld;
+    IC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (n > 0 && d > 0) {
+        if (ldx == d)
+            IC_CUDA(cudaMemcpyAsync(ctx->x, x, sizeof(float) * n * d, kind, ctx->stream));
+        else
+            IC_CUDA(cudaMemcpy2DAsync(ctx->x, sizeof(float) * d, x, sizeof(float) * ldx, sizeof(float) * d, n, kind,
+                                      ctx->stream));
+        if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += static_cast<int64_t>(sizeof(float)) * n * d;
+    }
+    IC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->loaded = true;
+    return IC_OK;
+}
+
+int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no matrix loaded");
+    if (mode != IC_GRAM_TCGEN05_3XTF32 && mode != IC_GRAM_EXACT_FP32) return fail(ctx, IC_ERR_BAD_ARG, "bad gram mode");
+    IC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (mode == IC_GRAM_TCGEN05_3XTF32) {
+        const int rc = do_prep(ctx);
+        if (rc != IC_OK) return rc;
+    }
+    IC_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (max_size >= 2) {
+        const int rc = do_gram(ctx, mode);
+        if (rc != IC_OK) return rc;
+    } else {
+        // 1 + 1 > maxSize: every pair is inadmissible from the start (clustering.go:228)
+        IC_CUDA(launch_fill(ctx->dm, ctx->n * ctx->ld, INFINITY, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    IC_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->have_dm = true;
+    ctx->have_nn = false;
+    ctx->gram_mode_used = mode;
+    ctx->stats.gram_mode = mode;
+    return IC_OK;
+}
+
+int nn_init(ic_ctx* ctx) {
+    if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
+    int rc = init_loop_state(ctx);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->have_nn = true;
+    return IC_OK;
+}
+
+void fill_stats(ic_ctx* ctx) {
+    ic_stats& s = ctx->stats;
+    s.n_target = static_cast<int32_t>(ctx->n_target);
+    s.n_merges = ctx->n_merges;
+    s.n_final = ctx->n_live;
+    s.exhausted = ctx->exhausted;
+    s.n_near_ties = ctx->h_ctl[CTL_NEAR_TIES];
+    s.n_rescans = ctx->h_ctl[CTL_RESCANS];
+}
+
+int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offsets, int32_t* members,
+                 int32_t* n_clusters, ic_stats* stats, double t_wall0) {
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no matrix loaded");
+    if (!offsets || !members || !n_clusters) return fail(ctx, IC_ERR_BAD_ARG, "NULL output");
+    int64_t n_target = 0;
+    int rc = ic_optimal_clusters(ctx->n, min_size, max_size, &n_target);
+    if (rc != IC_OK) return fail(ctx, rc, "cluster size constraints cannot be satisfied");
+    ctx->n_target = n_target;
+    ctx->prepped = false;  // K0 is part of the path: redo it on every run
+    rc = initial_distances(ctx, ctx->gram_mode, max_size);
+    if (rc != IC_OK) return rc;
+    rc = nn_init(ctx);
+    if (rc != IC_OK) return rc;
+    rc = run_loop(ctx, n_target, max_size, -1);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    rc = sync_loop_result(ctx);
+    if (rc != IC_OK) return rc;
+    rc = fetch_trace(ctx);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+    IC_CUDA(cudaEventSynchronize(ctx->ev[7]));
+    const double th0 = now_ms();
+    rc = assemble(ctx, min_size, max_size, offsets, members, n_clusters);
+    if (rc != IC_OK) return rc;
+    const double th1 = now_ms();
+    fill_stats(ctx);
+    ic_stats& s = ctx->stats;
+    s.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+    s.ms_prep = ev_ms(ctx->ev[2], ctx->ev[3]);
+    s.ms_gram = ev_ms(ctx->ev[3], ctx->ev[4]);
+    s.ms_nn_init = ev_ms(ctx->ev[4], ctx->ev[5]);
+    s.ms_loop = ev_ms(ctx->ev[5], ctx->ev[6]);
+    s.ms_d2h = ev_ms(ctx->ev[6], ctx->ev[7]);
+    s.ms_host = static_cast<float>(th1 - th0);
+    s.ms_total = static_cast<float>(th1 - t_wall0);
+    if (stats) *stats = s;
+    return IC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ic_create(ic_ctx** out, int device) {
+    if (!out) return IC_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return IC_ERR_CUDA;  // no CPU fallback
+    if (device < 0 || device >= count) return IC_ERR_BAD_ARG;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return IC_ERR_CUDA;
+    if (prop.major != 10) return IC_ERR_CUDA;  // sm_100a code only
+    if (cudaSetDevice(device) != cudaSuccess) return IC_ERR_CUDA;
+    ic_ctx* c = new ic_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return IC_ERR_CUDA;
+    }
+    for (auto& e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            ic_destroy(c);
+            return IC_ERR_CUDA;
+        }
+    *out = c;
+    return IC_OK;
+}
+
+void ic_destroy(ic_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    release_problem(ctx);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ic_last_error(const ic_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+void* ic_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void ic_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ic_set_option(ic_ctx* ctx, const char* name, double value) {
+    if (!ctx || !name) return IC_ERR_BAD_ARG;
+    const std::string k(name);
+    if (k == "near_tie_tol")
+        ctx->near_tie_tol = value;
+    else if (k == "center")
+        ctx->center = value != 0.0;
+    else if (k == "gram_mode") {
+        const int m = static_cast<int>(value);
+        if (m != IC_GRAM_TCGEN05_3XTF32 && m != IC_GRAM_EXACT_FP32) return fail(ctx, IC_ERR_BAD_ARG, "bad gram_mode");
+        ctx->gram_mode = m;
+    } else if (k == "loop_threads") {
+        const int t = static_cast<int>(value);
+        if (t != 0 && t != 256 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 256 or 512");
+        ctx->loop_threads = t;
+    } else if (k == "verbose")
+        ctx->verbose = static_cast<int>(value);
+    else
+        return fail(ctx, IC_ERR_BAD_ARG, "unknown option " + k);
+    return IC_OK;
+}
+
+// CalculateOptimalClusters, clustering.go:168-186.
+int ic_optimal_clusters(int64_t total_items, int64_t min_size, int64_t max_size, int64_t* out) {
+    if (out) *out = 0;
+    // Go divides by float64(0) here (+Inf -> implementation-defined int conversion); refuse instead
+    if (min_size < 1 || max_size < 1 || total_items < 0 || !out) return IC_ERR_BAD_ARG;
+    if (total_items < min_size) return IC_ERR_TOO_FEW;  // :169-171
+    const int64_t lo = static_cast<int64_t>(std::ceil(static_cast<double>(total_items) / static_cast<double>(max_size)));
+    const int64_t hi = static_cast<int64_t>(std::floor(static_cast<double>(total_items) / static_cast<double>(min_size)));
+    if (lo > hi) return IC_ERR_UNSAT;  // :175-177
+    *out = lo < hi ? (lo + hi) / 2 : lo;  // :180-183
+    return IC_OK;
+}
+
+int ic_load(ic_ctx* ctx, const float* x_host, int64_t n, int64_t d, int64_t ldx) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    return load_common(ctx, x_host, n, d, ldx, cudaMemcpyHostToDevice);
+}
+
+int ic_load_device(ic_ctx* ctx, const float* x_dev, int64_t n, int64_t d, int64_t ldx) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    return load_common(ctx, x_dev, n, d, ldx, cudaMemcpyDeviceToDevice);
+}
+
+int ic_initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    IC_CUDA(cudaSetDevice(ctx->device));
+    const int rc = initial_distances(ctx, mode, max_size);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.ms_prep = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->stats.ms_gram = ev_ms(ctx->ev[3], ctx->ev[4]);
+    return IC_OK;
+}
+
+int ic_set_matrix(ic_ctx* ctx, const float* m_host, int64_t ld) {
+    if (!ctx || !m_host) return IC_ERR_BAD_ARG;
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no problem loaded");
+    if (ld < ctx->n) return fail(ctx, IC_ERR_BAD_ARG, "ld < n");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->n > 0)
+        IC_CUDA(cudaMemcpy2DAsync(ctx->dm, sizeof(float) * ctx->ld, m_host, sizeof(float) * ld, sizeof(float) * ctx->n,
+                                  ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_dm = true;
+    ctx->have_nn = false;
+    return IC_OK;
+}
+
+int ic_nn_init(ic_ctx* ctx) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    IC_CUDA(cudaSetDevice(ctx->device));
+    IC_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    const int rc = nn_init(ctx);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.ms_nn_init = ev_ms(ctx->ev[4], ctx->ev[5]);
+    return IC_OK;
+}
+
+int ic_find_closest(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dist) {
+    if (!ctx || !key_hi || !key_lo || !dist) return IC_ERR_BAD_ARG;
+    if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "ic_nn_init has not run");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    int rc = run_loop(ctx, 0, 0x3FFFFFFF, 0);  // zero merges: fold the NN cache only
+    if (rc != IC_OK) return rc;
+    rc = sync_loop_result(ctx);
+    if (rc != IC_OK) return rc;
+    *key_hi = ctx->h_ctl[CTL_NEXT_HI];
+    *key_lo = ctx->h_ctl[CTL_NEXT_LO];
+    const uint32_t bits = static_cast<uint32_t>(ctx->h_ctl[CTL_NEXT_DIST]);
+    std::memcpy(dist, &bits, 4);
+    return IC_OK;
+}
+
+int ic_merge_loop(ic_ctx* ctx, int64_t min_size, int64_t max_size, int64_t max_merges) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "ic_nn_init has not run");
+    int64_t n_target = 0;
+    int rc = ic_optimal_clusters(ctx->n, min_size, max_size, &n_target);
+    if (rc != IC_OK) return fail(ctx, rc, "cluster size constraints cannot be satisfied");
+    ctx->n_target = n_target;
+    IC_CUDA(cudaSetDevice(ctx->device));
+    IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    rc = run_loop(ctx, n_target, max_size, max_merges);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    rc = sync_loop_result(ctx);
+    if (rc != IC_OK) return rc;
+    ctx->stats.ms_loop = ev_ms(ctx->ev[5], ctx->ev[6]);
+    fill_stats(ctx);
+    return IC_OK;
+}
+
+int ic_build_clusters(ic_ctx* ctx, int64_t min_size, int32_t* cluster_offsets, int32_t* members,
+                      int32_t* n_clusters) {
+    if (!ctx || !cluster_offsets || !members || !n_clusters) return IC_ERR_BAD_ARG;
+    if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "no merge state");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    const int rc = fetch_trace(ctx);
+    if (rc != IC_OK) return rc;
+    return assemble(ctx, min_size, 0, cluster_offsets, members, n_clusters);
+}
+
+int ic_run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* cluster_offsets, int32_t* members,
+                    int32_t* n_clusters, ic_stats* stats) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    IC_CUDA(cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    ctx->stats.kernel_launches = 0;
+    ctx->stats.d2h_bytes = 0;
+    return run_resident(ctx, min_size, max_size, cluster_offsets, members, n_clusters, stats, t0);
+}
+
+int ic_cluster_with_constraints(ic_ctx* ctx, const float* x, int64_t n, int64_t d, int64_t ldx, int64_t min_size,
+                                int64_t max_size, int32_t* cluster_offsets, int32_t* members, int32_t* n_clusters,
+                                ic_stats* stats) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    if (n_clusters) *n_clusters = 0;
+    const double t0 = now_ms();
+    // the reference checks the constraints before touching the data (clustering.go:203-207)
+    int64_t n_target = 0;
+    int rc = ic_optimal_clusters(n, min_size, max_size, &n_target);
+    if (rc != IC_OK) return fail(ctx, rc, "cluster size constraints cannot be satisfied");
+    rc = load_common(ctx, x, n, d, ldx, cudaMemcpyHostToDevice);
+    if (rc != IC_OK) return rc;
+    return run_resident(ctx, min_size, max_size, cluster_offsets, members, n_clusters, stats, t0);
+}
+
+int ic_read_matrix(ic_ctx* ctx, float* out_host, int64_t ld) {
+    if (!ctx || !out_host) return IC_ERR_BAD_ARG;
+    if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
+    if (ld < ctx->n) return fail(ctx, IC_ERR_BAD_ARG, "ld < n");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->n > 0)
+        IC_CUDA(cudaMemcpy2DAsync(out_host, sizeof(float) * ld, ctx->dm, sizeof(float) * ctx->ld,
+                                  sizeof(float) * ctx->n, ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IC_OK;
+}
+
+int ic_read_slots(ic_ctx* ctx, int32_t* key, int32_t* size) {
+    if (!ctx || !key || !size) return IC_ERR_BAD_ARG;
+    if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "no merge state");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int2> h(static_cast<size_t>(ctx->n));
+    if (ctx->n > 0)
+        IC_CUDA(cudaMemcpyAsync(h.data(), ctx->ks, sizeof(int2) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < ctx->n; ++i) {
+        key[i] = h[i].x;
+        size[i] = h[i].y;
+    }
+    return IC_OK;
+}
+
+int ic_get_merge_trace(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dist, int32_t* size, float* gap,
+                       int64_t capacity, int64_t* n_merges) {
+    if (!ctx || !n_merges) return IC_ERR_BAD_ARG;
+    if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "no merge state");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    const int rc = fetch_trace(ctx);
+    if (rc != IC_OK) return rc;
+    const int64_t m = ctx->n_merges;
+    *n_merges = m;
+    if (capacity < m) return fail(ctx, IC_ERR_BAD_ARG, "trace capacity too small");
+    if (key_hi) std::memcpy(key_hi, ctx->h_key_hi.data(), 4 * m);
+    if (key_lo) std::memcpy(key_lo, ctx->h_key_lo.data(), 4 * m);
+    if (dist) std::memcpy(dist, ctx->h_dist.data(), 4 * m);
+    if (size) std::memcpy(size, ctx->h_size.data(), 4 * m);
+    if (gap) std::memcpy(gap, ctx->h_gap.data(), 4 * m);
+    return IC_OK;
+}
+
+int ic_get_stats(ic_ctx* ctx, ic_stats* stats) {
+    if (!ctx || !stats) return IC_ERR_BAD_ARG;
+    fill_stats(ctx);
+    *stats = ctx->stats;
+    return IC_OK;
+}
+
+int ic_time_kernel(ic_ctx* ctx, const char* which, int repeats, float* ms_each) {
+    if (!ctx || !which || !ms_each || repeats < 1) return IC_ERR_BAD_ARG;
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no problem loaded");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    const std::string k(which);
+    if (k == "gram" || k == "split") {
+        const int rc = do_prep(ctx);
+        if (rc != IC_OK) return rc;
+    }
+    if (k == "nn_sweep" && !ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    IC_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
+    for (int r = 0; r < repeats; ++r) {
+        if (k == "gram") {
+            const int rc = do_gram(ctx, IC_GRAM_TCGEN05_3XTF32);
+            if (rc != IC_OK) return rc;
+        } else if (k == "gram_exact") {
+            const int rc = do_gram(ctx, IC_GRAM_EXACT_FP32);
+            if (rc != IC_OK) return rc;
+        } else if (k == "split") {
+            IC_CUDA(launch_split(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->center, ctx->hi, ctx->lo, ctx->norms,
+                                 ctx->n_pad, ctx->d_pad, ctx->stream));
+        } else if (k == "nn_sweep") {
+            IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->stream));
+        } else {
+            return fail(ctx, IC_ERR_BAD_ARG, "unknown kernel " + k);
+        }
+    }
+    IC_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
+    IC_CUDA(cudaEventSynchronize(ctx->ev[9]));
+    *ms_each = ev_ms(ctx->ev[8], ctx->ev[9]) / static_cast<float>(repeats);
+    if (k == "gram" || k == "gram_exact") ctx->have_dm = true;
+    if (k != "split") ctx->have_nn = false;  // the loop state no longer matches the matrix
+    return IC_OK;
+}
+
+}  // extern "C"

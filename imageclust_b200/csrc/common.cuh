@@ -39,6 +39,34 @@ IC_DEVINL float canon_dist(float v) {
     return v + 0.0f;
 }
 
+// two smallest of a set of packed candidates (m1 <= m2); kPackInf when absent
+struct Top2 {
+    uint64_t m1, m2;
+};
+IC_DEVINL void top2_insert(Top2& t, uint64_t v) {
+    if (v < t.m1) {
+        t.m2 = t.m1;
+        t.m1 = v;
+    } else if (v < t.m2) {
+        t.m2 = v;
+    }
+}
+IC_DEVINL void top2_merge(Top2& t, uint64_t o1, uint64_t o2) {
+    const uint64_t lo = umin64(t.m1, o1);
+    const uint64_t hi = t.m1 < o1 ? o1 : t.m1;
+    t.m2 = umin64(hi, umin64(t.m2, o2));
+    t.m1 = lo;
+}
+IC_DEVINL Top2 warp_top2(Top2 t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t o1 = __shfl_xor_sync(0xffffffffu, t.m1, o);
+        const uint64_t o2 = __shfl_xor_sync(0xffffffffu, t.m2, o);
+        top2_merge(t, o1, o2);
+    }
+    return t;
+}
+
 // ---- memory ------------------------------------------------------------------------------
 IC_DEVINL float4 ld_stream_f4(const float4* p) {  // read-once data: bypass L1
     float4 r;
@@ -84,7 +112,7 @@ IC_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must trap, not hang the GPU box.
 IC_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 28)) __trap();
+        if (spin > (1u << 22)) __trap();
     }
 }
 

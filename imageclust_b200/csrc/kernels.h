@@ -6,6 +6,19 @@
 
 namespace ic {
 
+// ---- resident per-slot state -------------------------------------------------------------
+// A "slot" is a row/column of the distance matrix.  Slot s holds one live cluster
+// (the reference's clusters[] entry, clustering.go:11-15) or is retired.
+//   ks[s]  = {key, size}: key is the monotone order id (item index for singletons,
+//            N + t for the cluster made by merge t) == the reference's slice order;
+//            key < 0 when the slot is retired.
+//   nn[s]  = cached nearest partner among clusters with a LOWER key:
+//            {partner key, distance bits, partner slot, partner size};
+//            y == 0xFFFFFFFF when the row has no selectable partner.
+typedef int2 SlotKS;
+typedef uint4 SlotNN;
+constexpr uint32_t kNoPartner = 0xFFFFFFFFu;
+
 // ---- K0 prep (prep.cu) -------------------------------------------------------------------
 // column sums of X [n x d] (row stride ldx) in double
 cudaError_t launch_colsum(const float* x, int64_t n, int64_t d, int64_t ldx, double* colsum, cudaStream_t s);
@@ -13,6 +26,9 @@ cudaError_t launch_colsum(const float* x, int64_t n, int64_t d, int64_t ldx, dou
 // hi/lo are [n_pad x d_pad] (zero padded), norms [n_pad].
 cudaError_t launch_split(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
                          float* hi, float* lo, double* norms, int64_t n_pad, int64_t d_pad, cudaStream_t s);
+cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s);
+// ks[s] = {s, 1}
+cudaError_t launch_init_slots(SlotKS* ks, int64_t n, cudaStream_t s);
 
 // ---- K1 Gram / initial Ward distances ----------------------------------------------------
 constexpr int kGramBM = 128;  // tile rows   (UMMA M)
@@ -32,48 +48,48 @@ size_t gram_tcgen05_smem_bytes();
 // audit kernel: the reference's own arithmetic (sequential fp32, clustering.go:136-157), bit exact
 cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx, float* dm, int64_t ld,
                               cudaStream_t s);
-cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s);
 
 // ---- K2 nearest-neighbour sweep ----------------------------------------------------------
-// nn_pack[s] = min over partners u with key[u] < key[s] (alive) of (dm[s][u], key[u]);
-// nn_slot[s] = slot of that partner (-1 if none).  identity_keys: key[s] == s (first sweep).
-cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, const int32_t* key, const int32_t* slot_of_key,
-                            int identity_keys, unsigned long long* nn_pack, int32_t* nn_slot, cudaStream_t s);
+// First sweep (keys are the slot indices): nn[s] = min over columns u < s of (dm[s][u], u).
+cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, SlotNN* nn, cudaStream_t s);
 
 // ---- K3 persistent merge loop ------------------------------------------------------------
+constexpr int kLoopRescanSlots = 8;  // rows rescanned cooperatively per merge (more: block-per-row path)
 struct LoopState {
     float* dm;
     int64_t ld;
-    int32_t n;                    // slots
-    int32_t* key;                 // [n] -1 = retired
-    int32_t* size;                // [n]
-    int32_t* slot_of_key;         // [2n]
-    unsigned long long* nn_pack;  // [n]
-    int32_t* nn_slot;             // [n]
-    // trace, capacity n
+    int32_t n;    // slots (== items)
+    SlotKS* ks;   // [n]
+    SlotNN* nn;   // [n]
+    // merge trace, capacity n
     int32_t* tr_key_hi;
     int32_t* tr_key_lo;
     float* tr_dist;
     int32_t* tr_size;
     float* tr_gap;
-    // scratch
-    unsigned long long* partials;  // [2][grid][4]
-    int32_t* rlist;                // [3][n]
-    int32_t* rcount;               // [3]
-    uint32_t* barrier;             // [1]
-    int32_t* ctl;                  // [16]: see merge_loop.cu
+    // scratch (zeroed by the host before every launch)
+    void* part_a;       // [grid] 48-byte records
+    void* part_b;       // [grid] 32-byte records
+    void* part_r;       // [kLoopRescanSlots][grid] 16-byte records
+    int32_t* rlist;     // [2][n]
+    int32_t* rcount;    // [2]
+    uint32_t* barrier;  // [1]
+    int32_t* ctl;       // [16], see CTL_*
 };
 struct LoopParams {
-    int32_t n_target;
-    int32_t max_size;
-    int32_t max_merges;  // <0: unlimited
+    int32_t n_target;    // CalculateOptimalClusters result (clustering.go:220)
+    int32_t max_size;    // clustering.go:228
+    int32_t max_merges;  // stop after this many merges in this launch (<0: unlimited)
     float near_tie_tol;
 };
-int merge_loop_max_grid(int threads);
-cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int grid, int threads, cudaStream_t s);
-
-// ctl[] indices
+// ctl[] indices.  N_LIVE and N_MERGES are read at launch (resume) and written at exit.
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,
-       CTL_DONE = 6 };
+       CTL_DONE = 6, CTL_BIG_RESCANS = 7, CTL_NEXT_HI = 8, CTL_NEXT_LO = 9, CTL_NEXT_DIST = 10 };
+int merge_loop_threads(int64_t n, int num_sms);
+cudaError_t merge_loop_max_grid(int threads, int num_sms, int* grid);
+cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int grid, int threads, cudaStream_t s);
+size_t merge_loop_part_a_bytes();
+size_t merge_loop_part_b_bytes();
+size_t merge_loop_part_r_bytes();
 
 }  // namespace ic

@@ -85,4 +85,15 @@ cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+__global__ void init_slots_kernel(SlotKS* __restrict__ ks, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) ks[i] = make_int2(static_cast<int32_t>(i), 1);  // NewCluster, clustering.go:18-26
+}
+
+cudaError_t launch_init_slots(SlotKS* ks, int64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    init_slots_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(ks, n);
+    return cudaGetLastError();
+}
+
 }  // namespace ic

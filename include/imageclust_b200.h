@@ -25,6 +25,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 #define IC_OK 0
 #define IC_ERR_TOO_FEW (-1)  /* totalItems < minSize            clustering.go:169-171 */
@@ -133,6 +136,9 @@ int ic_get_stats(ic_ctx *ctx, ic_stats *stats);
  * kernel on the resident problem, device time in ms */
 int ic_time_kernel(ic_ctx *ctx, const char *which, int repeats, float *ms_each);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif
