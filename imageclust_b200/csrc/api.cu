@@ -31,6 +31,7 @@ struct ic_ctx {
     int gram_mode = IC_GRAM_TCGEN05_3XTF32;
     int loop_threads = 0;
     int verbose = 0;
+    int gram_terms = 23;  // debug: which of the 3xTF32 products to issue
     // resident problem
     int64_t n = 0, d = 0, n_pad = 0, d_pad = 0, ld = 0;
     float* x = nullptr;  // [n x d] dense
@@ -280,7 +281,7 @@ int do_gram(ic_ctx* ctx, int mode) {
     plan.tiles = ctx->tiles;
     plan.n_tiles = ctx->n_tiles;
     plan.k_blocks = static_cast<int>(ctx->d_pad / kGramBK);
-    IC_CUDA(launch_gram_tcgen05(plan, ctx->norms, ctx->dm, ctx->n, ctx->ld, ctx->num_sms, ctx->stream));
+    IC_CUDA(launch_gram_tcgen05(plan, ctx->norms, ctx->dm, ctx->n, ctx->ld, ctx->num_sms, ctx->stream, ctx->gram_terms));
     ctx->stats.kernel_launches += 1;
     return IC_OK;
 }
@@ -579,6 +580,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         const int t = static_cast<int>(value);
         if (t != 0 && t != 256 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 256 or 512");
         ctx->loop_threads = t;
+    } else if (k == "gram_terms") {
+        ctx->gram_terms = static_cast<int>(value);
     } else if (k == "verbose")
         ctx->verbose = static_cast<int>(value);
     else

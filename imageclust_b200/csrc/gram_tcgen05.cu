@@ -5,19 +5,25 @@
 // |a||b|/(|a|+|b|) is exactly 1/2:
 //      d(i,j) = 0.5*||x_i - x_j||^2 = 0.5*(||x_i||^2 + ||x_j||^2) - <x_i, x_j>.
 // The contraction <x_i, x_j> runs on the 5th-gen tensor cores:
-//   * operands: the TF32 hi/lo split written by K0 (prep.cu), K-major, fetched
-//     by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a shared-memory ring;
-//   * 3xTF32: lo*hi + hi*lo + hi*hi, issued as tcgen05.mma kind::tf32 by one
-//     thread, accumulated in fp32 in TMEM (two 128x256 accumulators, so the
-//     epilogue of tile t overlaps the MMAs of tile t+1);
-//   * epilogue warps: tcgen05.ld -> norms/half/clamp in double -> fp32, coalesced
-//     stores of BOTH triangles (direct rows through a shared-memory transpose,
-//     mirrored rows straight from registers: lane = row makes them contiguous).
+//   * operands: the split x = s1 + rt written by K0 (prep.cu): s1 a short
+//     fixed-point slice, rt the TF32 residual; both K-major fp32 containers,
+//     fetched by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a shared-memory ring;
+//   * four tcgen05.mma kind::tf32 per k-step, issued by one thread, into TWO fp32
+//     TMEM accumulators: s1*s1 alone (every partial sum is exactly representable, so
+//     the tensor core's truncating accumulation loses nothing) and
+//     rt*s1 + s1*rt + rt*rt (small: its truncation error is ~1e-9 of the result).
+//     A plain 3xTF32 split into ONE accumulator measured 2.6e-4 relative error on the
+//     distances at D=2048 (experiments/gram_error.py): the accumulator truncates ~1 ulp
+//     of its magnitude per MMA, which the Gram identity's cancellation amplifies;
+//   * epilogue warps: tcgen05.ld of both accumulators -> sum, norms, half, clamp in
+//     double -> fp32, coalesced stores of BOTH triangles (direct rows through a
+//     shared-memory transpose, mirrored rows straight from registers: lane = row
+//     makes them contiguous).
 // Only tiles that touch the lower triangle are computed.  Persistent kernel, one
 // CTA per SM, static tile list in an L2-friendly order (built on the host).
 //
 // Roofline: tensor pipe.  Algorithmic flops = 2*D per unordered pair;
-// the 3-pass split issues 3x that on the pipe.
+// the 4-product split issues 4x that on the pipe.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -45,8 +51,8 @@ struct __align__(8) SmemTail {
     float stage[4][kStageTile];
     uint64_t full[kStages];
     uint64_t empty[kStages];
-    uint64_t tfull[2];
-    uint64_t tempty[2];
+    uint64_t tfull[1];
+    uint64_t tempty[1];
     uint32_t tmem_slot;
 };
 }  // namespace
@@ -56,7 +62,7 @@ size_t gram_tcgen05_smem_bytes() { return 1024 + static_cast<size_t>(kStages) * 
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const int2* __restrict__ tiles, int n_tiles, int k_blocks, const double* __restrict__ norms,
-                    float* __restrict__ dm, int64_t n, int64_t ld) {
+                    float* __restrict__ dm, int64_t n, int64_t ld, int terms) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     SmemTail* tail = reinterpret_cast<SmemTail*>(smem + static_cast<size_t>(kStages) * kStageBytes);
@@ -73,10 +79,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             mbar_init(&tail->full[s], 1);
             mbar_init(&tail->empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tail->tfull[a], 1);
-            mbar_init(&tail->tempty[a], 4);  // one arrive per epilogue warp
-        }
+        mbar_init(&tail->tfull[0], 1);
+        mbar_init(&tail->tempty[0], 4);  // one arrive per epilogue warp
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -119,12 +123,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
             uint32_t acc_phase = 0;
+            const uint32_t d_exact = tmem_base;        // s1*s1
+            const uint32_t d_small = tmem_base + BN;   // rt*s1 + s1*rt + rt*rt
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                mbar_wait(&tail->tempty[acc], acc_phase ^ 1u);
+                mbar_wait(&tail->tempty[0], acc_phase ^ 1u);  // epilogue drained both accumulators
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&tail->full[stage], phase);
                     tc_fence_after();
@@ -139,9 +143,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         const uint64_t a_lo = umma_desc_k_sw128(sa_lo + off);
                         const uint64_t b_hi = umma_desc_k_sw128(sb_hi + off);
                         const uint64_t b_lo = umma_desc_k_sw128(sb_lo + off);
-                        umma_tf32(d_tmem, a_lo, b_hi, kIdesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
-                        umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1u);
-                        umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1u);
+                        const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+                        uint32_t accum = first;
+                        if (terms & 1) { umma_tf32(d_small, a_lo, b_hi, kIdesc, accum); accum = 1u; }
+                        if (terms & 2) { umma_tf32(d_small, a_hi, b_lo, kIdesc, accum); accum = 1u; }
+                        if (terms & 16) { umma_tf32(d_small, a_lo, b_lo, kIdesc, accum); accum = 1u; }
+                        if (terms & 4) umma_tf32(d_exact, a_hi, b_hi, kIdesc, first);
                     }
                     umma_commit(&tail->empty[stage]);  // frees the smem stage when these MMAs retire
                     if (++stage == kStages) {
@@ -149,11 +156,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         phase ^= 1u;
                     }
                 }
-                umma_commit(&tail->tfull[acc]);  // accumulator complete
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1u;
-                }
+                umma_commit(&tail->tfull[0]);  // both accumulators complete
+                acc_phase ^= 1u;
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -161,7 +165,6 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         const int ew = warp - kEpiWarp0;      // TMEM lane quadrant of this warp
         const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
         float* stg = tail->stage[ew];
-        int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int2 tile = tiles[t];
@@ -171,24 +174,27 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             tail->norm_b[et] = norms[col0 + et];
             tail->norm_b[et + 128] = norms[col0 + et + 128];
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(&tail->tfull[acc], acc_phase);
+            mbar_wait(&tail->tfull[0], acc_phase);
             tc_fence_after();
             const int64_t gi = row0 + ew * 32 + lane;  // this thread's matrix row
             const double ni = tail->norm_a[ew * 32 + lane];
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc) * BN;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr0 + c * 32, r);
+                uint32_t r[32], r2[32];
+                tmem_ld_32x32(taddr0 + c * 32, r);        // exact part
+                tmem_ld_32x32(taddr0 + BN + c * 32, r2);  // small part
                 tmem_ld_wait();
                 const int64_t gj0 = col0 + c * 32;
                 if (gj0 > row0 + BM - 1) continue;  // chunk entirely above the diagonal (warp uniform)
                 float v[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
-                    const double tq = 0.5 * (ni + tail->norm_b[c * 32 + q]) - static_cast<double>(__uint_as_float(r[q]));
+                    const double g = static_cast<double>(__uint_as_float(r[q])) + static_cast<double>(__uint_as_float(r2[q]));
+                    const double tq = 0.5 * (ni + tail->norm_b[c * 32 + q]) - g;
                     float f = static_cast<float>(tq);
                     v[q] = (tq < 0.0) ? 0.0f : f;  // clamp the cancellation residue; NaN stays NaN
+                    if (terms & 8) v[q] = static_cast<float>(g);  // debug: the raw Gram value
                 }
                 // mirrored entries dm[j][i]: for a fixed column j the 32 lanes hold consecutive i
 #pragma unroll
@@ -211,11 +217,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tail->tempty[acc]);
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1u;
-            }
+            if (lane == 0) mbar_arrive(&tail->tempty[0]);
+            acc_phase ^= 1u;
         }
     }
 
@@ -225,7 +228,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 }
 
 cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float* dm, int64_t n, int64_t ld,
-                                int num_sms, cudaStream_t s) {
+                                int num_sms, cudaStream_t s, int terms) {
     if (plan.n_tiles == 0) return cudaSuccess;
     const size_t smem = gram_tcgen05_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -233,7 +236,7 @@ cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float
     if (e != cudaSuccess) return e;
     const int grid = plan.n_tiles < num_sms ? plan.n_tiles : num_sms;
     gram_tcgen05_kernel<<<grid, kThreads, smem, s>>>(plan.map_hi, plan.map_lo, plan.tiles, plan.n_tiles,
-                                                     plan.k_blocks, norms, dm, n, ld);
+                                                     plan.k_blocks, norms, dm, n, ld, terms);
     return cudaGetLastError();
 }
 

@@ -43,7 +43,7 @@ struct GramPlan {
 };
 // dm[i][j] = dm[j][i] = max(0.5*(norm_i + norm_j) - <x_i, x_j>, 0), diag 0; full square, row stride ld
 cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float* dm, int64_t n, int64_t ld,
-                                int num_sms, cudaStream_t s);
+                                int num_sms, cudaStream_t s, int terms = 23);
 size_t gram_tcgen05_smem_bytes();
 // audit kernel: the reference's own arithmetic (sequential fp32, clustering.go:136-157), bit exact
 cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx, float* dm, int64_t ld,

@@ -4,9 +4,10 @@
 // rows (clustering.go:136-145); the Gram identity ||x||^2+||y||^2-2<x,y> needs
 //  (1) centred data (distances are translation invariant; removes the common-mean
 //      cancellation of non-negative ResNet features),
-//  (2) x = hi + lo with hi, lo exactly representable in TF32, so that three
-//      tensor-core passes hi*hi + hi*lo + lo*hi reproduce an fp32 product to 2^-22,
-//  (3) norms of the SAME represented values (hi+lo), in double.
+//  (2) x = s1 + rt with s1 a short fixed-point slice (exact tensor-core accumulation of
+//      s1*s1) and rt the TF32-rounded residual; s1*s1 + s1*rt + rt*s1 + rt*rt reproduces
+//      the fp32 Gram value to ~1e-8 relative (see split_kernel),
+//  (3) norms of the SAME represented values (s1+rt), in double.
 // HBM-bound: reads 4ND bytes, writes 8 N_pad D_pad bytes.
 #include "common.cuh"
 #include "kernels.h"
@@ -31,22 +32,52 @@ cudaError_t launch_colsum(const float* x, int64_t n, int64_t d, int64_t ldx, dou
     return cudaGetLastError();
 }
 
+// One block per row.  x_c = x - mean is split as  x_c = s1 + rt (+ dropped remainder):
+//   s1 = q_i * rint(x_c / q_i),  q_i = 2^(e_i - bits),  |x_c| < 2^e_i   (fixed point, per-row scale)
+//   rt = tf32(x_c - s1)          (x_c - s1 is exact in fp32; |rt| <= q_i / 2)
+// With bits = floor(log2(2^24 / d_pad) / 2) every partial sum of s1_i * s1_j over k is an
+// integer multiple of q_i q_j below 2^24, so the tensor core's fp32 accumulation of the
+// leading product is EXACT (measured: experiments/gram_error.py); the three small products
+// go to a second accumulator whose truncation error is ~1e-9 of the Gram value.
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, int64_t n, int64_t d, int64_t ldx,
-                                                    const double* __restrict__ colsum, int center,
+                                                    const double* __restrict__ colsum, int center, int bits,
                                                     float* __restrict__ hi, float* __restrict__ lo,
                                                     double* __restrict__ norms, int64_t d_pad) {
     const int64_t row = blockIdx.x;
     float* hrow = hi + row * d_pad;
     float* lrow = lo + row * d_pad;
-    double acc = 0.0;
     const double inv_n = n > 0 ? 1.0 / static_cast<double>(n) : 0.0;
+    __shared__ float redf[8];
+    __shared__ double red[8];
+    // pass 1: row maximum of |x_c|
+    float amax = 0.0f;
+    if (row < n)
+        for (int64_t k = threadIdx.x; k < d; k += blockDim.x) {
+            float v = x[row * ldx + k];
+            if (center) v = __fsub_rn(v, static_cast<float>(colsum[k] * inv_n));
+            const float a = fabsf(v);
+            if (a > amax && a <= 3.0e38f) amax = a;  // NaN / Inf never set the scale
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = redf[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) amax = fmaxf(amax, redf[w]);
+    if (amax < 1e-30f) amax = 0.0f;  // degenerate row: everything goes to the residual
+    int e = 0;
+    frexpf(amax, &e);                        // amax = f * 2^e, f in [0.5, 1)  ->  |x_c| < 2^e
+    const float q = ldexpf(1.0f, e - bits);  // quantum of the fixed-point slice
+    const float inv_q = ldexpf(1.0f, bits - e);
+    double acc = 0.0;
     for (int64_t k = threadIdx.x; k < d_pad; k += blockDim.x) {
         float h = 0.0f, l = 0.0f;
         if (row < n && k < d) {
             float v = x[row * ldx + k];
             if (center) v = __fsub_rn(v, static_cast<float>(colsum[k] * inv_n));
-            h = to_tf32(v);
-            l = to_tf32(__fsub_rn(v, h));
+            if (amax > 0.0f && fabsf(v) <= 3.0e38f) h = __fmul_rn(rintf(__fmul_rn(v, inv_q)), q);
+            l = to_tf32(__fsub_rn(v, h));  // NaN / Inf inputs stay in the residual and poison the row, as in the reference
             const double rep = static_cast<double>(h) + static_cast<double>(l);
             acc += rep * rep;
         }
@@ -54,7 +85,6 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
         lrow[k] = l;
     }
     // block reduce
-    __shared__ double red[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -66,10 +96,17 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
     }
 }
 
+int split_slice_bits(int64_t d_pad) {
+    int bits = 1;
+    while (bits < 10 && (static_cast<int64_t>(d_pad) << (2 * (bits + 1))) <= (int64_t(1) << 24)) ++bits;
+    return bits;
+}
+
 cudaError_t launch_split(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
                          float* hi, float* lo, double* norms, int64_t n_pad, int64_t d_pad, cudaStream_t s) {
     if (n_pad == 0) return cudaSuccess;
-    split_kernel<<<static_cast<unsigned>(n_pad), 256, 0, s>>>(x, n, d, ldx, colsum, center, hi, lo, norms, d_pad);
+    split_kernel<<<static_cast<unsigned>(n_pad), 256, 0, s>>>(x, n, d, ldx, colsum, center, split_slice_bits(d_pad), hi,
+                                                              lo, norms, d_pad);
     return cudaGetLastError();
 }
 

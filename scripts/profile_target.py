@@ -1,0 +1,21 @@
+"""Tiny profiling target: ONE resident clustering pass (every kernel of the path once).
+usage: python scripts/profile_target.py [config] [n-override] [passes]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from imageclust_b200 import clustering, synth
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "B"
+n, d, mn, mx = synth.CONFIGS[cfg]
+if len(sys.argv) > 2 and int(sys.argv[2]) > 0:
+    n = int(sys.argv[2])
+passes = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+x = synth.gaussian_mixture(n, d, mn, mx, seed=20240 + ord(cfg) - ord("A"))
+with clustering.Engine(0) as eng:
+    eng.load(x)
+    for _ in range(passes):
+        r = eng.run_resident(mn, mx)
+    s = r.stats
+    print(f"config {cfg} N={n} D={d}: merges={s['n_merges']} out={s['n_out']} prep {s['ms_prep']:.3f} gram {s['ms_gram']:.3f} "
+          f"nn {s['ms_nn_init']:.3f} loop {s['ms_loop']:.3f} ms  rescans={s['n_rescans']} near_ties={s['n_near_ties']}")
