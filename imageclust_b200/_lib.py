@@ -32,7 +32,7 @@ SYMBOLS = [
     "ic_optimal_clusters", "ic_cluster_with_constraints", "ic_load", "ic_load_device",
     "ic_initial_distances", "ic_set_matrix", "ic_nn_init", "ic_find_closest", "ic_merge_loop",
     "ic_run_resident", "ic_build_clusters", "ic_read_matrix", "ic_read_slots", "ic_get_merge_trace",
-    "ic_get_stats", "ic_time_kernel",
+    "ic_get_stats", "ic_get_loop_profile", "ic_time_kernel",
 ]
 
 
@@ -93,6 +93,7 @@ def load():
         "ic_read_slots": (i32, [vp, i32p, i32p]),
         "ic_get_merge_trace": (i32, [vp, i32p, i32p, fp, i32p, fp, i64, i64p]),
         "ic_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "ic_get_loop_profile": (i32, [vp, i64p]),
         "ic_time_kernel": (i32, [vp, C.c_char_p, i32, fp]),
     }
     assert sorted(sig) == sorted(SYMBOLS)

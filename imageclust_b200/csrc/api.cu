@@ -31,7 +31,9 @@ struct ic_ctx {
     int gram_mode = IC_GRAM_TCGEN05_3XTF32;
     int loop_threads = 0;
     int verbose = 0;
-    int gram_terms = 23;  // debug: which of the 3xTF32 products to issue
+    int gram_terms = 23;
+    int profile_loop = 0;     // debug: per-phase cycle counters of the merge loop
+    long long h_prof[16] = {0};  // debug: which of the 3xTF32 products to issue
     // resident problem
     int64_t n = 0, d = 0, n_pad = 0, d_pad = 0, ld = 0;
     float* x = nullptr;  // [n x d] dense
@@ -197,14 +199,13 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16));
     // merge-loop launch geometry and scratch
     ctx->loop_thr = ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms);
-    if (ctx->loop_thr != 256 && ctx->loop_thr != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 256 or 512");
-    IC_CUDA(merge_loop_max_grid(ctx->loop_thr, ctx->num_sms, &ctx->loop_grid));
-    if (ctx->loop_grid <= 0) return fail(ctx, IC_ERR_CUDA, "merge loop kernel does not fit an SM");
-    if (ctx->loop_grid > ctx->loop_thr) ctx->loop_grid = ctx->loop_thr;
+    if (ctx->loop_thr != 384 && ctx->loop_thr != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 384 or 512");
+    IC_CUDA(merge_loop_max_grid(ctx->loop_thr, ctx->num_sms, n, &ctx->loop_grid));
+    if (ctx->loop_grid <= 0) return fail(ctx, IC_ERR_OOM, "merge loop slice does not fit an SM's shared memory");
     const size_t G = static_cast<size_t>(ctx->loop_grid);
     ctx->scratch_bytes = round_up(merge_loop_part_a_bytes() * G, 256) + round_up(merge_loop_part_b_bytes() * G, 256) +
                          round_up(merge_loop_part_r_bytes() * G * kLoopRescanSlots, 256) +
-                         round_up(sizeof(int32_t) * 2 * nn1, 256) + 256 + 256;
+                         round_up(sizeof(int4) * 2 * nn1, 256) + 256 + 256 + 256;
     IC_CUDA(cudaMalloc(&ctx->scratch, ctx->scratch_bytes));
     ctx->h_key_hi.clear();
     ctx->h_key_lo.clear();
@@ -236,10 +237,12 @@ LoopState loop_state(ic_ctx* c) {
     st.part_r = p;
     p += round_up(merge_loop_part_r_bytes() * G * kLoopRescanSlots, 256);
     st.rlist = reinterpret_cast<int32_t*>(p);
-    p += round_up(sizeof(int32_t) * 2 * nn1, 256);
+    p += round_up(sizeof(int4) * 2 * nn1, 256);
     st.rcount = reinterpret_cast<int32_t*>(p);
     p += 256;
     st.barrier = reinterpret_cast<uint32_t*>(p);
+    p += 256;
+    st.prof = c->profile_loop ? reinterpret_cast<long long*>(p) : nullptr;
     st.ctl = c->ctl;
     return st;
 }
@@ -311,6 +314,8 @@ int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges
     IC_CUDA(launch_merge_loop(st, p, ctx->loop_grid, ctx->loop_thr, ctx->stream));
     ctx->stats.kernel_launches += 1;
     IC_CUDA(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(ctx->h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    if (st.prof)
+        IC_CUDA(cudaMemcpyAsync(ctx->h_prof, st.prof, sizeof(ctx->h_prof), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->trace_on_host = false;
     return IC_OK;
 }
@@ -578,8 +583,10 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         ctx->gram_mode = m;
     } else if (k == "loop_threads") {
         const int t = static_cast<int>(value);
-        if (t != 0 && t != 256 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 256 or 512");
+        if (t != 0 && t != 384 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 384 or 512");
         ctx->loop_threads = t;
+    } else if (k == "profile_loop") {
+        ctx->profile_loop = value != 0.0;
     } else if (k == "gram_terms") {
         ctx->gram_terms = static_cast<int>(value);
     } else if (k == "verbose")
@@ -759,6 +766,14 @@ int ic_get_merge_trace(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dis
     if (dist) std::memcpy(dist, ctx->h_dist.data(), 4 * m);
     if (size) std::memcpy(size, ctx->h_size.data(), 4 * m);
     if (gap) std::memcpy(gap, ctx->h_gap.data(), 4 * m);
+    return IC_OK;
+}
+
+int ic_get_loop_profile(ic_ctx* ctx, int64_t* out16) {
+    if (!ctx || !out16) return IC_ERR_BAD_ARG;
+    for (int i = 0; i < 16; ++i) out16[i] = ctx->h_prof[i];
+    out16[6] = ctx->h_ctl[CTL_BIG_RESCANS];
+    out16[7] = ctx->h_ctl[CTL_RESCANS];
     return IC_OK;
 }
 

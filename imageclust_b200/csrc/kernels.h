@@ -71,10 +71,11 @@ struct LoopState {
     void* part_a;       // [grid] 48-byte records
     void* part_b;       // [grid] 32-byte records
     void* part_r;       // [kLoopRescanSlots][grid] 16-byte records
-    int32_t* rlist;     // [2][n]
+    int32_t* rlist;     // [2][n] int4 entries {slot, key, size, 0}
     int32_t* rcount;    // [2]
     uint32_t* barrier;  // [1]
     int32_t* ctl;       // [16], see CTL_*
+    long long* prof;    // [16] or NULL: SM cycles block 0 spent per phase (A, barrier 1, fold, update, barrier 2), merges
 };
 struct LoopParams {
     int32_t n_target;    // CalculateOptimalClusters result (clustering.go:220)
@@ -86,7 +87,8 @@ struct LoopParams {
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,
        CTL_DONE = 6, CTL_BIG_RESCANS = 7, CTL_NEXT_HI = 8, CTL_NEXT_LO = 9, CTL_NEXT_DIST = 10 };
 int merge_loop_threads(int64_t n, int num_sms);
-cudaError_t merge_loop_max_grid(int threads, int num_sms, int* grid);
+cudaError_t merge_loop_max_grid(int threads, int num_sms, int64_t n, int* grid);
+size_t merge_loop_smem_bytes(int64_t n, int grid);
 cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int grid, int threads, cudaStream_t s);
 size_t merge_loop_part_a_bytes();
 size_t merge_loop_part_b_bytes();

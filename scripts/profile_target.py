@@ -13,9 +13,14 @@ if len(sys.argv) > 2 and int(sys.argv[2]) > 0:
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 x = synth.gaussian_mixture(n, d, mn, mx, seed=20240 + ord(cfg) - ord("A"))
 with clustering.Engine(0) as eng:
+    eng.set_option("profile_loop", 1)
     eng.load(x)
     for _ in range(passes):
         r = eng.run_resident(mn, mx)
     s = r.stats
     print(f"config {cfg} N={n} D={d}: merges={s['n_merges']} out={s['n_out']} prep {s['ms_prep']:.3f} gram {s['ms_gram']:.3f} "
           f"nn {s['ms_nn_init']:.3f} loop {s['ms_loop']:.3f} ms  rescans={s['n_rescans']} near_ties={s['n_near_ties']}")
+    p = eng.loop_profile()
+    m = max(p["merges"], 1)
+    print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "big_rescans", "rescans"))
+          + f" | big_rescans={p['big_rescans']} rescans={p['rescans']}")
