@@ -32,6 +32,8 @@ struct ic_ctx {
     int loop_threads = 0;
     int verbose = 0;
     int gram_terms = 23;
+    int loop_blocks = 0;      // 0 = auto
+    int loop_blocks_alloc = -1;
     int profile_loop = 0;     // debug: per-phase cycle counters of the merge loop
     long long h_prof[16] = {0};  // debug: which of the 3xTF32 products to issue
     // resident problem
@@ -44,6 +46,7 @@ struct ic_ctx {
     bool prepped = false;
     float* dm = nullptr;
     SlotKS* ks = nullptr;
+    int32_t* gkey = nullptr;
     SlotNN* nn = nullptr;
     int32_t *tr_key_hi = nullptr, *tr_key_lo = nullptr, *tr_size = nullptr;
     float *tr_dist = nullptr, *tr_gap = nullptr;
@@ -94,6 +97,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->tiles);
     dev_free(c->dm);
     dev_free(c->ks);
+    dev_free(c->gkey);
     dev_free(c->nn);
     dev_free(c->tr_key_hi);
     dev_free(c->tr_key_lo);
@@ -166,7 +170,8 @@ std::vector<int2> build_tile_list(int64_t n) {
 
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 &&
-        ctx->loop_thr == (ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms))) {
+        ctx->loop_thr == (ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms)) &&
+        ctx->loop_blocks == ctx->loop_blocks_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
         ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = false;
         ctx->trace_on_host = false;
@@ -190,6 +195,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->x, sizeof(float) * nn1 * static_cast<size_t>(d > 0 ? d : 1)));
     IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * nn1 * static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
     IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->gkey, sizeof(int32_t) * (nn1 + 4)));
     IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1));
     IC_CUDA(cudaMalloc(&ctx->tr_key_hi, sizeof(int32_t) * nn1));
     IC_CUDA(cudaMalloc(&ctx->tr_key_lo, sizeof(int32_t) * nn1));
@@ -199,13 +205,18 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16));
     // merge-loop launch geometry and scratch
     ctx->loop_thr = ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms);
-    if (ctx->loop_thr != 384 && ctx->loop_thr != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 384 or 512");
+    if (ctx->loop_thr != 256 && ctx->loop_thr != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 256 or 512");
     IC_CUDA(merge_loop_max_grid(ctx->loop_thr, ctx->num_sms, n, &ctx->loop_grid));
     if (ctx->loop_grid <= 0) return fail(ctx, IC_ERR_OOM, "merge loop slice does not fit an SM's shared memory");
+    // the exchange costs grow with the number of blocks: small problems use fewer
+    {
+        int64_t want = ctx->loop_blocks > 0 ? ctx->loop_blocks : (n + 127) / 128;
+        if (want < 1) want = 1;
+        if (want < ctx->loop_grid) ctx->loop_grid = static_cast<int>(want);
+        ctx->loop_blocks_alloc = ctx->loop_blocks;
+    }
     const size_t G = static_cast<size_t>(ctx->loop_grid);
-    ctx->scratch_bytes = round_up(merge_loop_part_a_bytes() * G, 256) + round_up(merge_loop_part_b_bytes() * G, 256) +
-                         round_up(merge_loop_part_r_bytes() * G * kLoopRescanSlots, 256) +
-                         round_up(sizeof(int4) * 2 * nn1, 256) + 256 + 256 + 256;
+    ctx->scratch_bytes = round_up(2 * merge_loop_record_bytes() * G * G, 256) + 256;
     IC_CUDA(cudaMalloc(&ctx->scratch, ctx->scratch_bytes));
     ctx->h_key_hi.clear();
     ctx->h_key_lo.clear();
@@ -228,21 +239,11 @@ LoopState loop_state(ic_ctx* c) {
     st.tr_size = c->tr_size;
     st.tr_gap = c->tr_gap;
     const size_t G = static_cast<size_t>(c->loop_grid);
-    const size_t nn1 = static_cast<size_t>(c->n > 0 ? c->n : 1);
     uint8_t* p = c->scratch;
-    st.part_a = p;
-    p += round_up(merge_loop_part_a_bytes() * G, 256);
-    st.part_b = p;
-    p += round_up(merge_loop_part_b_bytes() * G, 256);
-    st.part_r = p;
-    p += round_up(merge_loop_part_r_bytes() * G * kLoopRescanSlots, 256);
-    st.rlist = reinterpret_cast<int32_t*>(p);
-    p += round_up(sizeof(int4) * 2 * nn1, 256);
-    st.rcount = reinterpret_cast<int32_t*>(p);
-    p += 256;
-    st.barrier = reinterpret_cast<uint32_t*>(p);
-    p += 256;
+    st.records = p;
+    p += round_up(2 * merge_loop_record_bytes() * G * G, 256);
     st.prof = c->profile_loop ? reinterpret_cast<long long*>(p) : nullptr;
+    st.gkey = c->gkey;
     st.ctl = c->ctl;
     return st;
 }
@@ -290,7 +291,7 @@ int do_gram(ic_ctx* ctx, int mode) {
 }
 
 int init_loop_state(ic_ctx* ctx) {
-    IC_CUDA(launch_init_slots(ctx->ks, ctx->n, ctx->stream));
+    IC_CUDA(launch_init_slots(ctx->ks, ctx->gkey, ctx->n, ctx->stream));
     ctx->stats.kernel_launches += 1;
     ctx->n_live = static_cast<int32_t>(ctx->n);
     ctx->n_merges = 0;
@@ -583,8 +584,10 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         ctx->gram_mode = m;
     } else if (k == "loop_threads") {
         const int t = static_cast<int>(value);
-        if (t != 0 && t != 384 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 384 or 512");
+        if (t != 0 && t != 256 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 256 or 512");
         ctx->loop_threads = t;
+    } else if (k == "loop_blocks") {
+        ctx->loop_blocks = static_cast<int>(value);
     } else if (k == "profile_loop") {
         ctx->profile_loop = value != 0.0;
     } else if (k == "gram_terms") {

@@ -27,8 +27,8 @@ cudaError_t launch_colsum(const float* x, int64_t n, int64_t d, int64_t ldx, dou
 cudaError_t launch_split(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
                          float* hi, float* lo, double* norms, int64_t n_pad, int64_t d_pad, cudaStream_t s);
 cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s);
-// ks[s] = {s, 1}
-cudaError_t launch_init_slots(SlotKS* ks, int64_t n, cudaStream_t s);
+// ks[s] = {s, 1}, gkey[s] = s (padding up to a multiple of 4: -1)
+cudaError_t launch_init_slots(SlotKS* ks, int32_t* gkey, int64_t n, cudaStream_t s);
 
 // ---- K1 Gram / initial Ward distances ----------------------------------------------------
 constexpr int kGramBM = 128;  // tile rows   (UMMA M)
@@ -54,13 +54,13 @@ cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx,
 cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, SlotNN* nn, cudaStream_t s);
 
 // ---- K3 persistent merge loop ------------------------------------------------------------
-constexpr int kLoopRescanSlots = 8;  // rows rescanned cooperatively per merge (more: block-per-row path)
 struct LoopState {
     float* dm;
     int64_t ld;
-    int32_t n;    // slots (== items)
-    SlotKS* ks;   // [n]
-    SlotNN* nn;   // [n]
+    int32_t n;       // slots (== items)
+    SlotKS* ks;      // [n]
+    int32_t* gkey;   // [round_up(n, 4)] keys only (what a whole-row rescan streams); padding = -1
+    SlotNN* nn;      // [n]
     // merge trace, capacity n
     int32_t* tr_key_hi;
     int32_t* tr_key_lo;
@@ -68,14 +68,9 @@ struct LoopState {
     int32_t* tr_size;
     float* tr_gap;
     // scratch (zeroed by the host before every launch)
-    void* part_a;       // [grid] 48-byte records
-    void* part_b;       // [grid] 32-byte records
-    void* part_r;       // [kLoopRescanSlots][grid] 16-byte records
-    int32_t* rlist;     // [2][n] int4 entries {slot, key, size, 0}
-    int32_t* rcount;    // [2]
-    uint32_t* barrier;  // [1]
-    int32_t* ctl;       // [16], see CTL_*
-    long long* prof;    // [16] or NULL: SM cycles block 0 spent per phase (A, barrier 1, fold, update, barrier 2), merges
+    void* records;   // [2][grid] 128-byte exchange records
+    int32_t* ctl;    // [16], see CTL_*
+    long long* prof; // [16] or NULL: SM cycles block 0 spent per phase
 };
 struct LoopParams {
     int32_t n_target;    // CalculateOptimalClusters result (clustering.go:220)
@@ -89,9 +84,7 @@ enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_N
 int merge_loop_threads(int64_t n, int num_sms);
 cudaError_t merge_loop_max_grid(int threads, int num_sms, int64_t n, int* grid);
 size_t merge_loop_smem_bytes(int64_t n, int grid);
+size_t merge_loop_record_bytes();
 cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int grid, int threads, cudaStream_t s);
-size_t merge_loop_part_a_bytes();
-size_t merge_loop_part_b_bytes();
-size_t merge_loop_part_r_bytes();
 
 }  // namespace ic

@@ -122,14 +122,16 @@ cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-__global__ void init_slots_kernel(SlotKS* __restrict__ ks, int64_t n) {
+__global__ void init_slots_kernel(SlotKS* __restrict__ ks, int32_t* __restrict__ gkey, int64_t n, int64_t n4) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) ks[i] = make_int2(static_cast<int32_t>(i), 1);  // NewCluster, clustering.go:18-26
+    if (i < n4) gkey[i] = i < n ? static_cast<int32_t>(i) : -1;
 }
 
-cudaError_t launch_init_slots(SlotKS* ks, int64_t n, cudaStream_t s) {
+cudaError_t launch_init_slots(SlotKS* ks, int32_t* gkey, int64_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    init_slots_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(ks, n);
+    const int64_t n4 = (n + 3) / 4 * 4;
+    init_slots_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(ks, gkey, n, n4);
     return cudaGetLastError();
 }
 

@@ -81,7 +81,7 @@ const char *ic_last_error(const ic_ctx *ctx);
 void *ic_pinned_alloc(size_t bytes);
 void ic_pinned_free(void *p);
 /* knobs: "near_tie_tol" (float, default 1e-5), "center" (0/1, default 1),
- * "gram_mode" (IC_GRAM_*), "loop_threads" (0 = auto, 384, 512), "profile_loop", "verbose" */
+ * "gram_mode" (IC_GRAM_*), "loop_threads" (0 = auto, 256, 512), "profile_loop", "verbose" */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 
 /* ---- CalculateOptimalClusters, clustering.go:168-186 (host, exact) ---- */
@@ -132,8 +132,7 @@ int ic_get_merge_trace(ic_ctx *ctx, int32_t *key_hi, int32_t *key_lo, float *dis
                        float *gap, int64_t capacity, int64_t *n_merges);
 int ic_get_stats(ic_ctx *ctx, ic_stats *stats);
 /* debug (option "profile_loop" = 1): SM cycles block 0 spent in each phase of the merge loop
- * {phase A, barrier 1, fold, update, barrier 2, merges, whole-row rescan rounds, rescans,
- *  A: list load, A: slice scan, A: block reduce, B: record fold, B: update loop, 0, 0, 0} of the last launch */
+ * {publish, exchange poll + fold, decision + update, rescans, tail, merges, 0, rescans, 0...} of the last launch */
 int ic_get_loop_profile(ic_ctx *ctx, int64_t *out16);
 
 /* microbenchmarks used by bench.py's roofline legs: one launch of the named

@@ -185,7 +185,7 @@ def test_many_rows_lose_their_partner(eng, oracle):
         assert same_clusters(res.clusters, lit.clusters)
 
 
-@pytest.mark.parametrize("n,d,mn,mx,threads", [(3000, 64, 4, 12, 384), (3000, 64, 4, 12, 512), (5000, 32, 6, 8, 0),
+@pytest.mark.parametrize("n,d,mn,mx,threads", [(3000, 64, 4, 12, 0), (3000, 64, 4, 12, 512), (5000, 32, 6, 8, 0),
                                                (2500, 100, 1, 2500, 0)])
 def test_loop_replays_bit_exact_from_device_matrix(eng, oracle, n, d, mn, mx, threads):
     """Tensor-core initial matrix -> device loop; the oracle replays the SAME matrix."""
