@@ -252,8 +252,8 @@ class Engine:
         """Cycles block 0 spent per phase of the last merge-loop launch (option profile_loop=1)."""
         out = (C.c_int64 * 16)()
         self._check(self._L.ic_get_loop_profile(self._h, out))
-        return dict(zip(("publish", "exchange", "update", "rescan", "tail", "merges", "big_rescans", "rescans"),
-                        list(out)))
+        return dict(zip(("publish", "exchange", "update", "rescan", "tail", "merges", "big_rescans", "rescans",
+                         "rescan_cycles_all_blocks"), list(out)))
 
     def time_kernel(self, which: str, repeats: int = 1) -> float:
         ms = C.c_float(0)

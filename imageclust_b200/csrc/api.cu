@@ -48,6 +48,7 @@ struct ic_ctx {
     SlotKS* ks = nullptr;
     int32_t* gkey = nullptr;
     SlotNN* nn = nullptr;
+    int32_t* nn_more = nullptr;
     int32_t *tr_key_hi = nullptr, *tr_key_lo = nullptr, *tr_size = nullptr;
     float *tr_dist = nullptr, *tr_gap = nullptr;
     uint8_t* scratch = nullptr;
@@ -99,6 +100,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->ks);
     dev_free(c->gkey);
     dev_free(c->nn);
+    dev_free(c->nn_more);
     dev_free(c->tr_key_hi);
     dev_free(c->tr_key_lo);
     dev_free(c->tr_size);
@@ -196,7 +198,8 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * nn1 * static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
     IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * nn1));
     IC_CUDA(cudaMalloc(&ctx->gkey, sizeof(int32_t) * (nn1 + 4)));
-    IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1));
+    IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1 * kNNK));
+    IC_CUDA(cudaMalloc(&ctx->nn_more, sizeof(int32_t) * nn1));
     IC_CUDA(cudaMalloc(&ctx->tr_key_hi, sizeof(int32_t) * nn1));
     IC_CUDA(cudaMalloc(&ctx->tr_key_lo, sizeof(int32_t) * nn1));
     IC_CUDA(cudaMalloc(&ctx->tr_size, sizeof(int32_t) * nn1));
@@ -233,6 +236,7 @@ LoopState loop_state(ic_ctx* c) {
     st.n = static_cast<int32_t>(c->n);
     st.ks = c->ks;
     st.nn = c->nn;
+    st.nn_more = c->nn_more;
     st.tr_key_hi = c->tr_key_hi;
     st.tr_key_lo = c->tr_key_lo;
     st.tr_dist = c->tr_dist;
@@ -461,7 +465,7 @@ int nn_init(ic_ctx* ctx) {
     if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
     int rc = init_loop_state(ctx);
     if (rc != IC_OK) return rc;
-    IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->stream));
+    IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
     ctx->stats.kernel_launches += 1;
     IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->have_nn = true;
@@ -810,7 +814,7 @@ int ic_time_kernel(ic_ctx* ctx, const char* which, int repeats, float* ms_each) 
             IC_CUDA(launch_split(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->center, ctx->hi, ctx->lo, ctx->norms,
                                  ctx->n_pad, ctx->d_pad, ctx->stream));
         } else if (k == "nn_sweep") {
-            IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->stream));
+            IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
         } else {
             return fail(ctx, IC_ERR_BAD_ARG, "unknown kernel " + k);
         }

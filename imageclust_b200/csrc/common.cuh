@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernels.h"
+
 #ifndef IC_DEVINL
 #define IC_DEVINL __device__ __forceinline__
 #endif
@@ -65,6 +67,90 @@ IC_DEVINL Top2 warp_top2(Top2 t) {
         top2_merge(t, o1, o2);
     }
     return t;
+}
+
+// ---- per-row partner lists ----------------------------------------------------------------
+// d(r,u) between two unchanged clusters never changes and a new cluster is never a partner of an
+// existing row (it carries the highest key), so a row's sorted partner list is static: partners
+// only die.  Each row therefore caches its kNNK smallest partners; a whole-row rescan is needed
+// only when all of them have died.
+struct Cand2 {  // two smallest packed candidates seen by one thread, and how many it saw
+    uint64_t c1, c2;
+    int32_t s1, s2;
+    int32_t cnt;
+};
+IC_DEVINL void cand2_init(Cand2& c) {
+    c.c1 = c.c2 = kPackInf;
+    c.s1 = c.s2 = -1;
+    c.cnt = 0;
+}
+IC_DEVINL void cand2_insert(Cand2& c, uint64_t p, int32_t slot) {
+    ++c.cnt;
+    if (p < c.c2) {
+        if (p < c.c1) {
+            c.c2 = c.c1;
+            c.s2 = c.s1;
+            c.c1 = p;
+            c.s1 = slot;
+        } else {
+            c.c2 = p;
+            c.s2 = slot;
+        }
+    }
+}
+
+struct TopKScratch {
+    uint64_t red[32];
+    int32_t cnt[32];
+    uint64_t pack[kNNK];
+    int32_t slot[kNNK];
+    int32_t stop;
+};
+
+// Block-wide selection of the (up to) kNNK smallest candidates from every thread's two smallest.
+// EXACT: the list is cut right after an entry that was a thread's second smallest while that
+// thread saw more than two candidates (its unseen third could be smaller than what follows).
+// Returns the number of entries m (sc.pack / sc.slot[0..m) valid for all threads after return)
+// and sets `more` when eligible candidates exist beyond the list.
+template <int kT>
+IC_DEVINL int block_select_topk(const Cand2& c, TopKScratch& sc, bool& more) {
+    constexpr int kW = kT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int taken = 0, m = 0, total = 0;
+    for (int r = 0; r < kNNK; ++r) {
+        const uint64_t cand = taken == 0 ? c.c1 : (taken == 1 ? c.c2 : kPackInf);
+        const uint64_t wm = warp_min_u64(cand);
+        int wc = c.cnt;
+        if (r == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wc += __shfl_xor_sync(0xffffffffu, wc, o);
+        }
+        if (lane == 0) {
+            sc.red[warp] = wm;
+            if (r == 0) sc.cnt[warp] = wc;
+        }
+        __syncthreads();
+        uint64_t bm = sc.red[0];
+#pragma unroll
+        for (int w = 1; w < kW; ++w) bm = umin64(bm, sc.red[w]);
+        if (r == 0) {
+#pragma unroll
+            for (int w = 0; w < kW; ++w) total += sc.cnt[w];
+        }
+        if (bm == kPackInf) break;  // uniform
+        if (cand == bm) {           // packs are unique: exactly one thread
+            sc.pack[r] = bm;
+            sc.slot[r] = taken == 0 ? c.s1 : c.s2;
+            ++taken;
+            sc.stop = (taken == 2 && c.cnt > 2) ? 1 : 0;
+        }
+        __syncthreads();
+        m = r + 1;
+        if (sc.stop) break;  // uniform
+    }
+    more = total > m;
+    __syncthreads();
+    return m;
 }
 
 // ---- memory ------------------------------------------------------------------------------

@@ -12,11 +12,13 @@ namespace ic {
 //   ks[s]  = {key, size}: key is the monotone order id (item index for singletons,
 //            N + t for the cluster made by merge t) == the reference's slice order;
 //            key < 0 when the slot is retired.
-//   nn[s]  = cached nearest partner among clusters with a LOWER key:
+//   nn[s*kNNK + j] = j-th smallest cached partner among clusters with a LOWER key:
 //            {partner key, distance bits, partner slot, partner size};
-//            y == 0xFFFFFFFF when the row has no selectable partner.
+//            y == 0xFFFFFFFF for an empty entry.  nn_more[s] != 0: selectable partners
+//            may exist beyond the list (rescan the row when the list runs dry).
 typedef int2 SlotKS;
 typedef uint4 SlotNN;
+constexpr int kNNK = 4;  // cached partners per row
 constexpr uint32_t kNoPartner = 0xFFFFFFFFu;
 
 // ---- K0 prep (prep.cu) -------------------------------------------------------------------
@@ -50,8 +52,8 @@ cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx,
                               cudaStream_t s);
 
 // ---- K2 nearest-neighbour sweep ----------------------------------------------------------
-// First sweep (keys are the slot indices): nn[s] = min over columns u < s of (dm[s][u], u).
-cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, SlotNN* nn, cudaStream_t s);
+// First sweep (keys are the slot indices): nn[s][*] = the kNNK smallest (dm[s][u], u) over columns u < s.
+cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, SlotNN* nn, int32_t* nn_more, cudaStream_t s);
 
 // ---- K3 persistent merge loop ------------------------------------------------------------
 struct LoopState {
@@ -60,7 +62,8 @@ struct LoopState {
     int32_t n;       // slots (== items)
     SlotKS* ks;      // [n]
     int32_t* gkey;   // [round_up(n, 4)] keys only (what a whole-row rescan streams); padding = -1
-    SlotNN* nn;      // [n]
+    SlotNN* nn;      // [n][kNNK]
+    int32_t* nn_more; // [n]
     // merge trace, capacity n
     int32_t* tr_key_hi;
     int32_t* tr_key_lo;

@@ -28,9 +28,10 @@
 //     acquire fence after the poll);
 //   * every block folds the same records, so all blocks take the same decision without
 //     a broadcast, then update their slice of row/column b;
-//   * a row whose cached partner died is rescanned by its OWNER block alone (whole row,
-//     many 16-byte loads in flight) right after the update -- the row only depends on
-//     entries its owner wrote itself or that were published at least one exchange ago.
+//   * every row caches its kNNK smallest partners (common.cuh); only when ALL of them have died
+//     is the row rescanned, by its OWNER block alone (whole row, many 16-byte loads in flight)
+//     right after the update -- the row only depends on entries its owner wrote itself or that
+//     were published at least one exchange ago.
 // HBM roofline: algorithmic bytes = 12*n per merge; reported as merges/s too.
 #include "common.cuh"
 #include "kernels.h"
@@ -94,7 +95,7 @@ bool merge_loop_uses_replica(int64_t n) { return n <= kReplicaMaxSlots; }
 size_t merge_loop_smem_bytes(int64_t n, int grid) {
     const int64_t chunk = (n + grid - 1) / grid;
     const int64_t c = chunk > 0 ? chunk : 1;
-    size_t bytes = static_cast<size_t>(c) * (sizeof(uint4) + sizeof(int2) + sizeof(int32_t));
+    size_t bytes = static_cast<size_t>(c) * (kNNK * sizeof(uint4) + sizeof(int2) + 2 * sizeof(int32_t));
     bytes = (bytes + 15) & ~size_t(15);
     if (merge_loop_uses_replica(n)) bytes += static_cast<size_t>((n + 3) / 4 * 4) * sizeof(int32_t);
     return bytes;
@@ -118,35 +119,38 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
     const int32_t cnt = hi - lo;
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const size_t c1 = static_cast<size_t>(chunk > 0 ? chunk : 1);
-    uint4* const s_nn = reinterpret_cast<uint4*>(dyn_smem);
-    int2* const s_ks = reinterpret_cast<int2*>(dyn_smem + c1 * sizeof(uint4));
-    int32_t* const s_resc = reinterpret_cast<int32_t*>(dyn_smem + c1 * (sizeof(uint4) + sizeof(int2)));
+    uint4* const s_nn = reinterpret_cast<uint4*>(dyn_smem);                                  // [chunk][kNNK]
+    int2* const s_ks = reinterpret_cast<int2*>(dyn_smem + c1 * kNNK * sizeof(uint4));        // [chunk]
+    int32_t* const s_more = reinterpret_cast<int32_t*>(dyn_smem + c1 * (kNNK * sizeof(uint4) + sizeof(int2)));
+    int32_t* const s_resc = s_more + c1;
     const int32_t n4 = (n + 3) & ~3;
     int32_t* const s_key = reinterpret_cast<int32_t*>(
-        dyn_smem + ((c1 * (sizeof(uint4) + sizeof(int2) + sizeof(int32_t)) + 15) & ~size_t(15)));  // [n4] if kReplica
+        dyn_smem + ((c1 * (kNNK * sizeof(uint4) + sizeof(int2) + 2 * sizeof(int32_t)) + 15) & ~size_t(15)));  // [n4] if kReplica
     for (int32_t i = tid; i < cnt; i += kT) {
         s_ks[i] = __ldcg(st.ks + lo + i);
-        s_nn[i] = __ldcg(st.nn + lo + i);
+        s_more[i] = __ldcg(st.nn_more + lo + i);
     }
+    for (int32_t i = tid; i < cnt * kNNK; i += kT) s_nn[i] = __ldcg(st.nn + static_cast<int64_t>(lo) * kNNK + i);
     if (kReplica)
         for (int32_t u = tid; u < n4; u += kT) s_key[u] = __ldcg(st.gkey + u);
     const int npw = (G + 31) / 32;  // warps that poll one part of the records (one record per lane)
 
-    __shared__ uint64_t s_m1[kW], s_m2[kW], s_up[kW], s_ur[kW], s_rs[kW];
+    __shared__ uint64_t s_m1[kW], s_m2[kW], s_up[kW], s_ur[kW];
     __shared__ Decision s_dec;
     __shared__ NewRow s_new;
     __shared__ Decision s_pdec[kW];
     __shared__ NewRow s_pnew[kW];
     __shared__ uint4 s_pub[kChunks];
     __shared__ int32_t s_rcount;
-    __shared__ uint64_t s_rwin_pack[8];
-    __shared__ int32_t s_rwin_slot[8];
+    __shared__ int32_t s_bwin[2];
+    __shared__ TopKScratch s_topk;
 
     int32_t n_live = st.ctl[CTL_N_LIVE];
     int32_t t = st.ctl[CTL_N_MERGES];  // merges done so far == index of the next merge
     int32_t launched = 0;
     int32_t exhausted = 0;
     int32_t my_rescans = 0;
+    long long my_rescan_cycles = 0;
     // pending merge (bookkeeping applied after the next exchange)
     bool pending = false;
     int32_t pa = -1, pb = -1, p_snew = 0, p_keyhi = 0, p_keylo = 0;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                 if (pending && (s == pa || s == pb)) continue;  // a is retired; b's candidate travels in the B-part
                 const int2 k = s_ks[i];
                 if (k.x < 0) continue;
-                const uint4 q = s_nn[i];
+                const uint4 q = s_nn[i * kNNK];      // head of the row's partner list
                 if (q.y >= kMaxFloatBits) continue;  // nothing selectable in this row
                 const uint64_t cand = (static_cast<uint64_t>(q.y) << 32) | static_cast<uint32_t>(k.x);
                 if (cand < top.m1) {
@@ -341,10 +345,12 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                                                         static_cast<uint32_t>(s_new.slot), static_cast<uint32_t>(s_new.size))
                                            : nn_none();
                     s_ks[pb - lo] = make_int2(new_key, p_snew);
-                    s_nn[pb - lo] = nb;
+                    s_nn[(pb - lo) * kNNK] = nb;  // only the head of the new row is known: the rest is "more"
+#pragma unroll
+                    for (int j = 1; j < kNNK; ++j) s_nn[(pb - lo) * kNNK + j] = nn_none();
+                    s_more[pb - lo] = b_sel ? 1 : 0;
                     st.ks[pb] = make_int2(new_key, p_snew);
                     st.gkey[pb] = new_key;
-                    st.nn[pb] = nb;
                     // trace entry of merge t-1 with the exact runner-up distance
                     const uint32_t second = min(p_second, s_new.runner);
                     const float sd = __uint_as_float(second);
@@ -406,7 +412,6 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                 const float* own = dm + static_cast<int64_t>(k) * ld;
                 const float dka = __ldcg(kk.x < key_a ? row_a + k : own + a);
                 const float dkb = __ldcg(kk.x < key_b ? row_b + k : own + b);
-                const uint4 q = s_nn[i];
                 float v;
                 if (kk.y + snew > prm.max_size)
                     v = __uint_as_float(kInfBits);  // inadmissible for good: sizes only grow (:228)
@@ -420,8 +425,27 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     usize = kk.y;
                 }
                 urun = min(urun, min(__float_as_uint(dka), __float_as_uint(dkb)));
-                if (q.y != kNoPartner && (static_cast<int32_t>(q.z) == a || static_cast<int32_t>(q.z) == b))
-                    s_resc[atomicAdd(&s_rcount, 1)] = i;  // its cached partner died: rescan
+                // drop a and b from the row's partner list; rescan only when the list runs dry
+                {
+                    uint4 e[kNNK];
+                    int kept = 0;
+                    bool changed = false;
+#pragma unroll
+                    for (int j = 0; j < kNNK; ++j) {
+                        const uint4 q = s_nn[i * kNNK + j];
+                        if (q.y == kNoPartner) continue;
+                        if (static_cast<int32_t>(q.z) == a || static_cast<int32_t>(q.z) == b) {
+                            changed = true;
+                            continue;
+                        }
+                        e[kept++] = q;
+                    }
+                    if (changed) {
+#pragma unroll
+                        for (int j = 0; j < kNNK; ++j) s_nn[i * kNNK + j] = j < kept ? e[j] : nn_none();
+                        if (kept == 0 && s_more[i]) s_resc[atomicAdd(&s_rcount, 1)] = i;
+                    }
+                }
             }
         }
         {
@@ -446,8 +470,8 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
             pub_brun = static_cast<uint32_t>(br);
             // slot / size of the block's best entry: broadcast through shared memory
             if (bu != kPackInf && ubest == bu) {
-                s_rwin_slot[0] = uslot;
-                s_rwin_slot[1] = usize;
+                s_bwin[0] = uslot;
+                s_bwin[1] = usize;
             }
         }
         const int32_t R = s_rcount;
@@ -456,98 +480,76 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
             s_key[b] = -1;
         }
         __syncthreads();
-        pub_bslot = pub_bpack != kPackInf ? s_rwin_slot[0] : -1;
-        pub_bsize = pub_bpack != kPackInf ? s_rwin_slot[1] : 0;
+        pub_bslot = pub_bpack != kPackInf ? s_bwin[0] : -1;
+        pub_bsize = pub_bpack != kPackInf ? s_bwin[1] : 0;
 
-        // ====== owner rescans: whole rows of the own slice whose cached partner died ======
-        for (int32_t r0 = 0; r0 < R; r0 += 8) {
-            const int32_t rn = min(8, R - r0);
-            for (int32_t ri = 0; ri < rn; ++ri) {
-                const int32_t i = s_resc[r0 + ri];
-                const int32_t r = lo + i;
-                const int32_t kr = s_ks[i].x;
-                const float* row = dm + static_cast<int64_t>(r) * ld;
-                uint32_t bbits = 0xFFFFFFFFu, bkey = 0xFFFFFFFFu;  // best (dist bits, partner key) of this thread
-                int32_t bslot = -1;
-                constexpr int kU = kReplica ? 12 : 6;  // 16-byte row loads in flight per thread
-                const uint32_t ukr = static_cast<uint32_t>(kr);
-                for (int32_t base = 0; base < n4; base += kT * 4 * kU) {
-                    float4 v[kU];
-                    int4 kq[kReplica ? 1 : kU];
+        // ====== owner rescans: whole rows of the own slice whose cached partners have all died ======
+        const long long tr0 = (st.prof != nullptr && tid == 0 && R > 0) ? clock64() : 0;
+        for (int32_t ri = 0; ri < R; ++ri) {
+            const int32_t i = s_resc[ri];
+            const int32_t r = lo + i;
+            const int32_t kr = s_ks[i].x;
+            const float* row = dm + static_cast<int64_t>(r) * ld;
+            Cand2 c;
+            cand2_init(c);
+            constexpr int kU = kReplica ? 12 : 6;  // 16-byte row loads in flight per thread
+            const uint32_t ukr = static_cast<uint32_t>(kr);
+            for (int32_t base = 0; base < n4; base += kT * 4 * kU) {
+                float4 v[kU];
+                int4 kq[kReplica ? 1 : kU];
 #pragma unroll
-                    for (int j = 0; j < kU; ++j) {
-                        const int32_t u0 = base + (j * kT + tid) * 4;
-                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (!kReplica) kq[j] = make_int4(-1, -1, -1, -1);
-                        if (u0 < n4) {
-                            v[j] = __ldcg(reinterpret_cast<const float4*>(row + u0));
-                            if (!kReplica) kq[j] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < kU; ++j) {
-                        if (base + j * kT * 4 >= n4) break;  // block-uniform: nothing of this slab is inside the row
-                        const int32_t u0 = base + (j * kT + tid) * 4;
-                        int4 kj = make_int4(-1, -1, -1, -1);
-                        if (kReplica) {
-                            if (u0 < n4) kj = *reinterpret_cast<const int4*>(s_key + u0);
-                        } else {
-                            kj = kq[j];
-                        }
-                        const uint32_t ks4[4] = {static_cast<uint32_t>(kj.x), static_cast<uint32_t>(kj.y),
-                                                 static_cast<uint32_t>(kj.z), static_cast<uint32_t>(kj.w)};
-                        const uint32_t vs4[4] = {__float_as_uint(v[j].x), __float_as_uint(v[j].y),
-                                                 __float_as_uint(v[j].z), __float_as_uint(v[j].w)};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int32_t u = u0 + e;
-                            const uint32_t ku = ks4[e];  // retired slots hold -1 == 0xFFFFFFFF: never below kr
-                            bool ok = ku < ukr;
-                            // without the replica the four slots in flux are excluded by index: a and prev_a
-                            // are retired, b and prev_b carry the two highest keys
-                            if (!kReplica) ok = ok && u != a && u != b && u != prev_a && u != prev_b;
-                            if (ok && (vs4[e] < bbits || (vs4[e] == bbits && ku < bkey))) {
-                                bbits = vs4[e];
-                                bkey = ku;
-                                bslot = u;
-                            }
-                        }
+                for (int j = 0; j < kU; ++j) {
+                    const int32_t u0 = base + (j * kT + tid) * 4;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!kReplica) kq[j] = make_int4(-1, -1, -1, -1);
+                    if (u0 < n4) {
+                        v[j] = __ldcg(reinterpret_cast<const float4*>(row + u0));
+                        if (!kReplica) kq[j] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
                     }
                 }
-                const uint64_t best = bslot >= 0 ? ((static_cast<uint64_t>(bbits) << 32) | bkey) : kPackInf;
-                const uint64_t wm = warp_min_u64(best);
-                if (lane == 0) s_rs[warp] = wm;
-                __syncthreads();
-                uint64_t bm = s_rs[0];
 #pragma unroll
-                for (int w = 1; w < kW; ++w) bm = umin64(bm, s_rs[w]);
-                if (!pack_selectable(bm)) {
-                    if (tid == 0) {
-                        s_rwin_pack[ri] = kPackInf;
-                        s_rwin_slot[ri] = -1;
+                for (int j = 0; j < kU; ++j) {
+                    if (base + j * kT * 4 >= n4) break;  // block-uniform: nothing of this slab is inside the row
+                    const int32_t u0 = base + (j * kT + tid) * 4;
+                    int4 kj = make_int4(-1, -1, -1, -1);
+                    if (kReplica) {
+                        if (u0 < n4) kj = *reinterpret_cast<const int4*>(s_key + u0);
+                    } else {
+                        kj = kq[j];
                     }
-                } else if (best == bm) {  // partner keys are unique: exactly one thread
-                    s_rwin_pack[ri] = bm;
-                    s_rwin_slot[ri] = bslot;
+                    const uint32_t ks4[4] = {static_cast<uint32_t>(kj.x), static_cast<uint32_t>(kj.y),
+                                             static_cast<uint32_t>(kj.z), static_cast<uint32_t>(kj.w)};
+                    const uint32_t vs4[4] = {__float_as_uint(v[j].x), __float_as_uint(v[j].y), __float_as_uint(v[j].z),
+                                             __float_as_uint(v[j].w)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int32_t u = u0 + e;
+                        const uint32_t ku = ks4[e];  // retired slots hold -1 == 0xFFFFFFFF: never below kr
+                        bool ok = ku < ukr && vs4[e] < kMaxFloatBits;
+                        // without the replica the four slots in flux are excluded by index: a and prev_a
+                        // are retired, b and prev_b carry the two highest keys
+                        if (!kReplica) ok = ok && u != a && u != b && u != prev_a && u != prev_b;
+                        if (ok) cand2_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ku, u);
+                    }
                 }
-                __syncthreads();
             }
-            // sizes of the winners: one round trip for the whole batch
-            if (tid < rn) {
-                const int32_t i = s_resc[r0 + tid];
-                const uint64_t p = s_rwin_pack[tid];
+            bool more = false;
+            const int m = block_select_topk<kT>(c, s_topk, more);
+            if (tid < kNNK) {  // sizes of the listed partners: one round trip
                 uint4 nr = nn_none();
-                if (p != kPackInf) {
-                    const int32_t ws = s_rwin_slot[tid];
+                if (tid < m) {
+                    const uint64_t p = s_topk.pack[tid];
+                    const int32_t ws = s_topk.slot[tid];
                     const int32_t wsz = __ldcg(st.ks + ws).y;
                     nr = make_uint4(pack_key(p), static_cast<uint32_t>(p >> 32), static_cast<uint32_t>(ws),
                                     static_cast<uint32_t>(wsz));
                 }
-                s_nn[i] = nr;
-                st.nn[lo + i] = nr;
+                s_nn[i * kNNK + tid] = nr;
+                if (tid == 0) s_more[i] = more ? 1 : 0;
             }
             __syncthreads();
         }
+        if (st.prof != nullptr && tid == 0 && R > 0) my_rescan_cycles += clock64() - tr0;
         if (tid == 0) {
             my_rescans += R;
             s_rcount = 0;
@@ -583,7 +585,13 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
         st.prof[4] = c_fold;
         st.prof[5] = launched;
     }
+    // the partner lists live in shared memory during the loop: write the slice back for resume / read-back
+    __syncthreads();
+    for (int32_t i = tid; i < cnt * kNNK; i += kT) st.nn[static_cast<int64_t>(lo) * kNNK + i] = s_nn[i];
+    for (int32_t i = tid; i < cnt; i += kT) st.nn_more[lo + i] = s_more[i];
     if (tid == 0 && my_rescans > 0) atomicAdd(st.ctl + CTL_RESCANS, my_rescans);
+    if (st.prof != nullptr && tid == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(st.prof + 8), static_cast<unsigned long long>(my_rescan_cycles));
     if (blk == 0 && tid == 0) {
         st.ctl[CTL_N_LIVE] = n_live;
         st.ctl[CTL_N_MERGES] = t;
