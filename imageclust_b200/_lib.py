@@ -33,7 +33,9 @@ SYMBOLS = [
     "ic_initial_distances", "ic_set_matrix", "ic_nn_init", "ic_find_closest", "ic_merge_loop",
     "ic_run_resident", "ic_build_clusters", "ic_read_matrix", "ic_read_slots", "ic_get_merge_trace",
     "ic_get_stats", "ic_get_loop_profile", "ic_time_kernel",
+    "ic_shard_init", "ic_shard_export", "ic_shard_connect", "ic_shard_rows",
 ]
+SHARD_HANDLE_BYTES = 192
 
 
 class Stats(C.Structure):
@@ -95,6 +97,10 @@ def load():
         "ic_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "ic_get_loop_profile": (i32, [vp, i64p]),
         "ic_time_kernel": (i32, [vp, C.c_char_p, i32, fp]),
+        "ic_shard_init": (i32, [vp, i32, i32]),
+        "ic_shard_export": (i32, [vp, vp]),
+        "ic_shard_connect": (i32, [vp, vp]),
+        "ic_shard_rows": (i32, [vp, i64p, i64p]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():

@@ -252,8 +252,32 @@ class Engine:
         """Cycles block 0 spent per phase of the last merge-loop launch (option profile_loop=1)."""
         out = (C.c_int64 * 16)()
         self._check(self._L.ic_get_loop_profile(self._h, out))
-        return dict(zip(("publish", "exchange", "update", "rescan", "tail", "merges", "big_rescans", "rescans",
-                         "rescan_cycles_all_blocks"), list(out)))
+        return dict(zip(("publish", "exchange", "update", "scan", "fold", "merges", "iterations", "rescans",
+                         "reserved", "bubbles"), list(out)))
+
+    # -- row-block sharding over several GPUs: one process (and Engine) per GPU ------------------
+    def shard_init(self, rank: int, world: int):
+        """Declare this engine rank ``rank`` of ``world`` row-block shards (before :meth:`load`)."""
+        self._check(self._L.ic_shard_init(self._h, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def shard_export(self) -> bytes:
+        """CUDA-IPC handles of this rank's row block and mailbox (after :meth:`load`)."""
+        buf = C.create_string_buffer(_lib.SHARD_HANDLE_BYTES)
+        self._check(self._L.ic_shard_export(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def shard_connect(self, blobs):
+        """Peer-map the other ranks' row blocks; ``blobs`` = every rank's export, in rank order."""
+        raw = b"".join(blobs)
+        assert len(raw) == self.world * _lib.SHARD_HANDLE_BYTES
+        buf = C.create_string_buffer(raw, len(raw))
+        self._check(self._L.ic_shard_connect(self._h, C.cast(buf, C.c_void_p)))
+
+    def shard_rows(self):
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.ic_shard_rows(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def time_kernel(self, which: str, repeats: int = 1) -> float:
         ms = C.c_float(0)

@@ -8,6 +8,7 @@
 //                   ->  merge trace back to the host -> cluster lists
 // mirroring PerformClusteringWithConstraints (clustering.go:198-284).  There is no CPU
 // path: every entry point that computes needs the device, and fails without one.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -29,13 +30,29 @@ struct ic_ctx {
     double near_tie_tol = 1e-5;
     int center = 1;
     int gram_mode = IC_GRAM_TCGEN05_3XTF32;
-    int loop_threads = 0;
     int verbose = 0;
-    int gram_terms = 23;
-    int loop_blocks = 0;      // 0 = auto
+    int gram_terms = 23;      // debug: which products of the split K1 issues
+    int loop_blocks = 0;      // merge-loop blocks per rank, 0 = auto
     int loop_blocks_alloc = -1;
     int profile_loop = 0;     // debug: per-phase cycle counters of the merge loop
-    long long h_prof[16] = {0};  // debug: which of the 3xTF32 products to issue
+    long long h_prof[16] = {0};
+    // row-block sharding.  vranks > 1: P virtual shards emulated on this one GPU by one
+    // cooperative launch (same kernel code path as the multi-GPU build; test hook).
+    int vranks = 1;
+    int vranks_alloc = -1;
+    int no_replica = 0, no_replica_alloc = -1;  // test hook: stream the keys from L2 even when the replica would fit
+    bool loop_replica = false;
+    uint32_t loop_gen = 0;    // generation of the last merge-loop launch (mailbox tags)
+    int64_t loop_launches = 0;
+    int64_t loop_n_target = 0, loop_max_size = 0, loop_max_merges = -1;
+    int32_t loop_merges_at_start = 0;
+    // real shards: one process / GPU / rank (ic_shard_*)
+    int shard_rank = 0, shard_world = 1;
+    int shard_rank_alloc = -1, shard_world_alloc = -1;
+    bool peers_open = false;
+    void* peer_dm[kMaxRanks] = {nullptr};   // every rank's row block (own + cudaIpc mapped)
+    void* peer_box[kMaxRanks] = {nullptr};  // every rank's inter-rank mailbox
+    uint64_t barrier_seq = 0;
     // resident problem
     int64_t n = 0, d = 0, n_pad = 0, d_pad = 0, ld = 0;
     float* x = nullptr;  // [n x d] dense
@@ -51,10 +68,10 @@ struct ic_ctx {
     int32_t* nn_more = nullptr;
     int32_t *tr_key_hi = nullptr, *tr_key_lo = nullptr, *tr_size = nullptr;
     float *tr_dist = nullptr, *tr_gap = nullptr;
-    uint8_t* scratch = nullptr;
-    size_t scratch_bytes = 0;
-    int32_t* ctl = nullptr;  // separate: survives scratch zeroing
-    int loop_grid = 0, loop_thr = 0;
+    uint8_t *records = nullptr, *partials = nullptr, *rankbox = nullptr;  // mailboxes, zeroed once at allocation
+    long long* prof = nullptr;
+    int32_t* ctl = nullptr;
+    int loop_grid = 0;  // blocks per rank
     bool loaded = false, have_dm = false, have_nn = false;
     int gram_mode_used = -1;
     // loop state mirrored on the host
@@ -89,7 +106,19 @@ void dev_free(T*& p) {
     p = nullptr;
 }
 
+void close_peers(ic_ctx* c) {
+    for (int q = 0; q < kMaxRanks; ++q) {
+        if (c->peers_open && q != c->shard_rank_alloc) {
+            if (c->peer_dm[q]) cudaIpcCloseMemHandle(c->peer_dm[q]);
+            if (c->peer_box[q]) cudaIpcCloseMemHandle(c->peer_box[q]);
+        }
+        c->peer_dm[q] = c->peer_box[q] = nullptr;
+    }
+    c->peers_open = false;
+}
+
 void release_problem(ic_ctx* c) {
+    close_peers(c);
     dev_free(c->x);
     dev_free(c->hi);
     dev_free(c->lo);
@@ -106,7 +135,10 @@ void release_problem(ic_ctx* c) {
     dev_free(c->tr_size);
     dev_free(c->tr_dist);
     dev_free(c->tr_gap);
-    dev_free(c->scratch);
+    dev_free(c->records);
+    dev_free(c->partials);
+    dev_free(c->rankbox);
+    dev_free(c->prof);
     dev_free(c->ctl);
     c->loaded = c->have_dm = c->have_nn = c->prepped = false;
     c->n = c->d = 0;
@@ -154,7 +186,7 @@ int make_operand_map(ic_ctx* ctx, CUtensorMap* map, float* base, int64_t rows, i
 // Lower-triangular tile list in square super-tiles of 2048 x 2048 outputs: the 16 + 8
 // operand panels of a super-tile (64 MB with hi+lo at D=2048) stay L2 resident while its
 // 128 tiles are computed, so every operand panel is fetched from HBM once per super-tile.
-std::vector<int2> build_tile_list(int64_t n) {
+std::vector<int2> build_tile_list(int64_t n, int64_t row_begin, int64_t row_end) {
     std::vector<int2> tiles;
     const int rbs = static_cast<int>((n + kGramBM - 1) / kGramBM);
     const int SR = 16, SC = 8;
@@ -165,15 +197,28 @@ std::vector<int2> build_tile_list(int64_t n) {
                     const int64_t col0 = static_cast<int64_t>(cb) * kGramBN;
                     const int64_t row_last = static_cast<int64_t>(rb) * kGramBM + kGramBM - 1;
                     if (col0 >= n || col0 > row_last) continue;  // outside, or wholly above the diagonal
+                    // a rank computes the tiles of its own rows (lower triangle: unequal shares, K1 is ~3 % of the path)
+                    if (row_last < row_begin || static_cast<int64_t>(rb) * kGramBM >= row_end) continue;
                     tiles.push_back(make_int2(rb, cb));
                 }
     return tiles;
 }
 
+// sharding geometry of the resident problem
+int n_ranks(const ic_ctx* c) { return c->shard_world > 1 ? c->shard_world : c->vranks; }
+int n_local(const ic_ctx* c) { return c->shard_world > 1 ? 1 : c->vranks; }
+int rank0(const ic_ctx* c) { return c->shard_world > 1 ? c->shard_rank : 0; }
+int64_t rows_per_rank(const ic_ctx* c) { return (c->n + n_ranks(c) - 1) / n_ranks(c); }
+// rows of the distance matrix resident on this device: [row_begin, row_end)
+int64_t row_begin(const ic_ctx* c) { return c->shard_world > 1 ? std::min(c->n, c->shard_rank * rows_per_rank(c)) : 0; }
+int64_t row_end(const ic_ctx* c) {
+    return c->shard_world > 1 ? std::min(c->n, row_begin(c) + rows_per_rank(c)) : c->n;
+}
+
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
-    if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 &&
-        ctx->loop_thr == (ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms)) &&
-        ctx->loop_blocks == ctx->loop_blocks_alloc) {
+    if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 && ctx->loop_blocks == ctx->loop_blocks_alloc &&
+        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && ctx->shard_world == ctx->shard_world_alloc &&
+        ctx->shard_rank == ctx->shard_rank_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
         ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = false;
         ctx->trace_on_host = false;
@@ -185,42 +230,56 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     ctx->n_pad = round_up(n, kGramBN);
     ctx->d_pad = round_up(d, kGramBK);
     ctx->ld = round_up(n, 32);
+    ctx->vranks_alloc = ctx->vranks;
+    ctx->no_replica_alloc = ctx->no_replica;
+    ctx->loop_replica = merge_loop_replica_fits(n) && !ctx->no_replica;
+    ctx->shard_world_alloc = ctx->shard_world;
+    ctx->shard_rank_alloc = ctx->shard_rank;
+    ctx->loop_blocks_alloc = ctx->loop_blocks;
+    const int P = n_ranks(ctx), NL = n_local(ctx);
+    if (P > kMaxRanks) return fail(ctx, IC_ERR_BAD_ARG, "at most 8 ranks");
+    // a sharded context holds only its own row block (all columns)
+    const int64_t rows = ctx->shard_world > 1 ? rows_per_rank(ctx) : n;
     size_t free_b = 0, total_b = 0;
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const double need = 4.0 * n * d + 4.0 * static_cast<double>(n) * ctx->ld +
-                        (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) + 64.0 * n +
-                        (64 << 20);
+    const double need = 4.0 * n * d + 4.0 * static_cast<double>(rows) * ctx->ld +
+                        (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) + 160.0 * n +
+                        (96 << 20);
     if (need > static_cast<double>(free_b))
         return fail(ctx, IC_ERR_OOM, "problem needs " + std::to_string(need / 1e9) + " GB, device has " +
                                          std::to_string(free_b / 1e9) + " GB free");
     const size_t nn1 = static_cast<size_t>(n > 0 ? n : 1);
+    const size_t n4 = (nn1 + 3) / 4 * 4;
     IC_CUDA(cudaMalloc(&ctx->x, sizeof(float) * nn1 * static_cast<size_t>(d > 0 ? d : 1)));
-    IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * nn1 * static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
-    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->gkey, sizeof(int32_t) * (nn1 + 4)));
+    IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * static_cast<size_t>(rows > 0 ? rows : 1) *
+                                     static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
+    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->gkey, sizeof(int32_t) * n4 * NL));
     IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1 * kNNK));
     IC_CUDA(cudaMalloc(&ctx->nn_more, sizeof(int32_t) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->tr_key_hi, sizeof(int32_t) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->tr_key_lo, sizeof(int32_t) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->tr_size, sizeof(int32_t) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->tr_dist, sizeof(float) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1));
-    IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16));
-    // merge-loop launch geometry and scratch
-    ctx->loop_thr = ctx->loop_threads > 0 ? ctx->loop_threads : merge_loop_threads(n, ctx->num_sms);
-    if (ctx->loop_thr != 256 && ctx->loop_thr != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 256 or 512");
-    IC_CUDA(merge_loop_max_grid(ctx->loop_thr, ctx->num_sms, n, &ctx->loop_grid));
+    IC_CUDA(cudaMalloc(&ctx->tr_key_hi, sizeof(int32_t) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->tr_key_lo, sizeof(int32_t) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->tr_size, sizeof(int32_t) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->tr_dist, sizeof(float) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16 * NL));
+    IC_CUDA(cudaMalloc(&ctx->prof, sizeof(long long) * 16));
+    // merge-loop launch geometry and mailboxes (zeroed once: tags carry the launch generation)
+    IC_CUDA(merge_loop_grid(ctx->num_sms, n, P, NL, ctx->loop_blocks, ctx->loop_replica, &ctx->loop_grid));
     if (ctx->loop_grid <= 0) return fail(ctx, IC_ERR_OOM, "merge loop slice does not fit an SM's shared memory");
-    // the exchange costs grow with the number of blocks: small problems use fewer
-    {
-        int64_t want = ctx->loop_blocks > 0 ? ctx->loop_blocks : (n + 127) / 128;
-        if (want < 1) want = 1;
-        if (want < ctx->loop_grid) ctx->loop_grid = static_cast<int>(want);
-        ctx->loop_blocks_alloc = ctx->loop_blocks;
-    }
-    const size_t G = static_cast<size_t>(ctx->loop_grid);
-    ctx->scratch_bytes = round_up(2 * merge_loop_record_bytes() * G * G, 256) + 256;
-    IC_CUDA(cudaMalloc(&ctx->scratch, ctx->scratch_bytes));
+    const size_t rb = merge_loop_records_bytes(ctx->loop_grid), pb = merge_loop_partials_bytes(ctx->loop_grid),
+                 xb = merge_loop_rankbox_bytes();
+    IC_CUDA(cudaMalloc(&ctx->records, rb * NL));
+    IC_CUDA(cudaMalloc(&ctx->partials, pb * NL));
+    IC_CUDA(cudaMalloc(&ctx->rankbox, xb * NL));
+    IC_CUDA(cudaMemsetAsync(ctx->records, 0, rb * NL, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->partials, 0, pb * NL, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 16, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->loop_gen = 0;
+    ctx->loop_launches = 0;
+    ctx->barrier_seq = 0;
     ctx->h_key_hi.clear();
     ctx->h_key_lo.clear();
     ctx->h_size.clear();
@@ -229,12 +288,29 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     return IC_OK;
 }
 
-LoopState loop_state(ic_ctx* c) {
+int loop_state(ic_ctx* c, LoopState* out) {
     LoopState st{};
-    st.dm = c->dm;
-    st.ld = c->ld;
+    const int P = n_ranks(c), NL = n_local(c);
     st.n = static_cast<int32_t>(c->n);
+    st.n_ranks = P;
+    st.rank0 = rank0(c);
+    st.n_local = NL;
+    st.rows_per_rank = static_cast<int32_t>(rows_per_rank(c));
+    st.ld = c->ld;
+    if (c->shard_world > 1) {
+        if (!c->peers_open) return fail(c, IC_ERR_STATE, "sharded context: ic_shard_connect has not run");
+        for (int q = 0; q < P; ++q) {
+            st.dm_rank[q] = static_cast<float*>(c->peer_dm[q]);
+            st.rankbox[q] = c->peer_box[q];
+        }
+    } else {
+        for (int q = 0; q < P; ++q) {
+            st.dm_rank[q] = c->dm + static_cast<int64_t>(q) * st.rows_per_rank * c->ld;
+            st.rankbox[q] = c->rankbox + static_cast<size_t>(q) * merge_loop_rankbox_bytes();
+        }
+    }
     st.ks = c->ks;
+    st.gkey = c->gkey;
     st.nn = c->nn;
     st.nn_more = c->nn_more;
     st.tr_key_hi = c->tr_key_hi;
@@ -242,14 +318,14 @@ LoopState loop_state(ic_ctx* c) {
     st.tr_dist = c->tr_dist;
     st.tr_size = c->tr_size;
     st.tr_gap = c->tr_gap;
-    const size_t G = static_cast<size_t>(c->loop_grid);
-    uint8_t* p = c->scratch;
-    st.records = p;
-    p += round_up(2 * merge_loop_record_bytes() * G * G, 256);
-    st.prof = c->profile_loop ? reinterpret_cast<long long*>(p) : nullptr;
-    st.gkey = c->gkey;
+    st.records = c->records;
+    st.records_stride = static_cast<int64_t>(merge_loop_records_bytes(c->loop_grid));
+    st.partials = c->partials;
+    st.partials_stride = static_cast<int64_t>(merge_loop_partials_bytes(c->loop_grid));
     st.ctl = c->ctl;
-    return st;
+    st.prof = c->profile_loop ? c->prof : nullptr;
+    *out = st;
+    return IC_OK;
 }
 
 int do_prep(ic_ctx* ctx) {
@@ -264,7 +340,7 @@ int do_prep(ic_ctx* ctx) {
                          ctx->n_pad, ctx->d_pad, ctx->stream));
     ctx->stats.kernel_launches += 2;
     if (!ctx->tiles) {
-        const std::vector<int2> tiles = build_tile_list(ctx->n);
+        const std::vector<int2> tiles = build_tile_list(ctx->n, row_begin(ctx), row_end(ctx));
         ctx->n_tiles = static_cast<int>(tiles.size());
         IC_CUDA(cudaMalloc(&ctx->tiles, sizeof(int2) * (tiles.size() ? tiles.size() : 1)));
         IC_CUDA(cudaMemcpyAsync(ctx->tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice,
@@ -277,7 +353,7 @@ int do_prep(ic_ctx* ctx) {
 
 int do_gram(ic_ctx* ctx, int mode) {
     if (mode == IC_GRAM_EXACT_FP32) {
-        IC_CUDA(launch_gram_exact(ctx->x, ctx->n, ctx->d, ctx->d, ctx->dm, ctx->ld, ctx->stream));
+        IC_CUDA(launch_gram_exact(ctx->x, ctx->n, ctx->d, ctx->d, ctx->dm, ctx->ld, row_begin(ctx), row_end(ctx), ctx->stream));
         ctx->stats.kernel_launches += 1;
         return IC_OK;
     }
@@ -289,12 +365,15 @@ int do_gram(ic_ctx* ctx, int mode) {
     plan.tiles = ctx->tiles;
     plan.n_tiles = ctx->n_tiles;
     plan.k_blocks = static_cast<int>(ctx->d_pad / kGramBK);
-    IC_CUDA(launch_gram_tcgen05(plan, ctx->norms, ctx->dm, ctx->n, ctx->ld, ctx->num_sms, ctx->stream, ctx->gram_terms));
+    IC_CUDA(launch_gram_tcgen05(plan, ctx->norms, ctx->dm, ctx->n, ctx->ld, row_begin(ctx), row_end(ctx), ctx->num_sms,
+                                ctx->stream, ctx->gram_terms));
     ctx->stats.kernel_launches += 1;
     return IC_OK;
 }
 
 int init_loop_state(ic_ctx* ctx) {
+    const int NL = n_local(ctx);
+    const size_t n = static_cast<size_t>(ctx->n), n4 = (n + 3) / 4 * 4;
     IC_CUDA(launch_init_slots(ctx->ks, ctx->gkey, ctx->n, ctx->stream));
     ctx->stats.kernel_launches += 1;
     ctx->n_live = static_cast<int32_t>(ctx->n);
@@ -303,20 +382,47 @@ int init_loop_state(ic_ctx* ctx) {
     ctx->trace_on_host = false;
     std::memset(ctx->h_ctl, 0, sizeof(ctx->h_ctl));
     ctx->h_ctl[CTL_N_LIVE] = ctx->n_live;
-    IC_CUDA(cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, sizeof(ctx->h_ctl), cudaMemcpyHostToDevice, ctx->stream));
+    for (int v = 0; v < NL; ++v) {
+        if (v > 0 && n > 0) {  // every (virtual) rank keeps its own replica of the slot table
+            IC_CUDA(cudaMemcpyAsync(ctx->ks + v * n, ctx->ks, sizeof(SlotKS) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+            IC_CUDA(cudaMemcpyAsync(ctx->gkey + v * n4, ctx->gkey, sizeof(int32_t) * n4, cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
+        }
+        IC_CUDA(cudaMemcpyAsync(ctx->ctl + 16 * v, ctx->h_ctl, sizeof(ctx->h_ctl), cudaMemcpyHostToDevice, ctx->stream));
+    }
     return IC_OK;
 }
 
-int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges) {
-    LoopState st = loop_state(ctx);
+// One launch of the persistent loop (enqueued; sync_loop_result waits and relaunches if the kernel ran out of
+// mailbox epochs, which takes ~1e6 iterations).
+int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges) {
+    LoopState st{};
+    int rc = loop_state(ctx, &st);
+    if (rc != IC_OK) return rc;
     LoopParams p{};
     p.n_target = static_cast<int32_t>(n_target);
     p.max_size = static_cast<int32_t>(max_size > 0x3FFFFFFF ? 0x3FFFFFFF : max_size);
     p.max_merges = static_cast<int32_t>(max_merges < 0 ? -1 : (max_merges > 0x7FFFFFFF ? 0x7FFFFFFF : max_merges));
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
-    IC_CUDA(cudaMemsetAsync(ctx->scratch, 0, ctx->scratch_bytes, ctx->stream));
-    IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
-    IC_CUDA(launch_merge_loop(st, p, ctx->loop_grid, ctx->loop_thr, ctx->stream));
+    ctx->loop_gen = ctx->loop_gen % 4095u + 1u;
+    st.gen = ctx->loop_gen;
+    if (ctx->loop_gen == 1u && ctx->loop_launches > 0) {  // generation wrapped: forget every old tag
+        const int NL = n_local(ctx);
+        IC_CUDA(cudaMemsetAsync(ctx->records, 0, merge_loop_records_bytes(ctx->loop_grid) * NL, ctx->stream));
+        IC_CUDA(cudaMemsetAsync(ctx->partials, 0, merge_loop_partials_bytes(ctx->loop_grid) * NL, ctx->stream));
+        IC_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(ctx->rankbox) + 256, 0, merge_loop_rankbox_bytes() * NL - 256,
+                                ctx->stream));
+    }
+    for (int v = 0; v < n_local(ctx); ++v)
+        IC_CUDA(cudaMemsetAsync(ctx->ctl + 16 * v + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
+    if (ctx->shard_world > 1) {
+        // all ranks have left their previous launch (and cleared what they had to) before anyone talks
+        ++ctx->barrier_seq;
+        IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    IC_CUDA(launch_merge_loop(st, p, ctx->loop_grid, ctx->loop_replica, ctx->stream));
+    ++ctx->loop_launches;
     ctx->stats.kernel_launches += 1;
     IC_CUDA(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(ctx->h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
     if (st.prof)
@@ -325,13 +431,29 @@ int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges
     return IC_OK;
 }
 
+int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges) {
+    ctx->loop_n_target = n_target;
+    ctx->loop_max_size = max_size;
+    ctx->loop_max_merges = max_merges;
+    ctx->loop_merges_at_start = ctx->n_merges;
+    return enqueue_loop(ctx, n_target, max_size, max_merges);
+}
+
 int sync_loop_result(ic_ctx* ctx) {
-    IC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
-    ctx->n_live = ctx->h_ctl[CTL_N_LIVE];
-    ctx->n_merges = ctx->h_ctl[CTL_N_MERGES];
-    ctx->exhausted = ctx->h_ctl[CTL_EXHAUSTED];
-    return IC_OK;
+    for (;;) {
+        IC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
+        if (ctx->h_ctl[CTL_ERROR] != 0)
+            return fail(ctx, IC_ERR_INTERNAL, "merge loop protocol error " + std::to_string(ctx->h_ctl[CTL_ERROR]));
+        ctx->n_live = ctx->h_ctl[CTL_N_LIVE];
+        ctx->n_merges = ctx->h_ctl[CTL_N_MERGES];
+        ctx->exhausted = ctx->h_ctl[CTL_EXHAUSTED];
+        if (ctx->h_ctl[CTL_STOP] != STOP_EPOCHS) return IC_OK;
+        int64_t left = ctx->loop_max_merges;
+        if (left >= 0) left -= ctx->n_merges - ctx->loop_merges_at_start;
+        const int rc = enqueue_loop(ctx, ctx->loop_n_target, ctx->loop_max_size, left < 0 ? -1 : left);
+        if (rc != IC_OK) return rc;
+    }
 }
 
 int fetch_trace(ic_ctx* ctx) {
@@ -450,7 +572,7 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
         if (rc != IC_OK) return rc;
     } else {
         // 1 + 1 > maxSize: every pair is inadmissible from the start (clustering.go:228)
-        IC_CUDA(launch_fill(ctx->dm, ctx->n * ctx->ld, INFINITY, ctx->stream));
+        IC_CUDA(launch_fill(ctx->dm, (row_end(ctx) - row_begin(ctx)) * ctx->ld, INFINITY, ctx->stream));
         ctx->stats.kernel_launches += 1;
     }
     IC_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -465,7 +587,7 @@ int nn_init(ic_ctx* ctx) {
     if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
     int rc = init_loop_state(ctx);
     if (rc != IC_OK) return rc;
-    IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
+    IC_CUDA(launch_nn_sweep(ctx->dm, row_begin(ctx), row_end(ctx), ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
     ctx->stats.kernel_launches += 1;
     IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->have_nn = true;
@@ -587,9 +709,15 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         if (m != IC_GRAM_TCGEN05_3XTF32 && m != IC_GRAM_EXACT_FP32) return fail(ctx, IC_ERR_BAD_ARG, "bad gram_mode");
         ctx->gram_mode = m;
     } else if (k == "loop_threads") {
-        const int t = static_cast<int>(value);
-        if (t != 0 && t != 256 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0, 256 or 512");
-        ctx->loop_threads = t;
+        const int t = static_cast<int>(value);  // kept for compatibility: the loop kernel has 512 threads
+        if (t != 0 && t != 512) return fail(ctx, IC_ERR_BAD_ARG, "loop_threads must be 0 or 512");
+    } else if (k == "virtual_ranks") {
+        const int r = static_cast<int>(value);
+        if (r < 1 || r > kMaxRanks) return fail(ctx, IC_ERR_BAD_ARG, "virtual_ranks must be 1..8");
+        if (ctx->shard_world > 1) return fail(ctx, IC_ERR_STATE, "virtual_ranks on a sharded context");
+        ctx->vranks = r;
+    } else if (k == "no_replica") {
+        ctx->no_replica = value != 0.0;
     } else if (k == "loop_blocks") {
         ctx->loop_blocks = static_cast<int>(value);
     } else if (k == "profile_loop") {
@@ -642,9 +770,10 @@ int ic_set_matrix(ic_ctx* ctx, const float* m_host, int64_t ld) {
     if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no problem loaded");
     if (ld < ctx->n) return fail(ctx, IC_ERR_BAD_ARG, "ld < n");
     IC_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->n > 0)
-        IC_CUDA(cudaMemcpy2DAsync(ctx->dm, sizeof(float) * ctx->ld, m_host, sizeof(float) * ld, sizeof(float) * ctx->n,
-                                  ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t r0 = row_begin(ctx), r1 = row_end(ctx);  // a sharded context keeps its own row block
+    if (r1 > r0)
+        IC_CUDA(cudaMemcpy2DAsync(ctx->dm, sizeof(float) * ctx->ld, m_host + r0 * ld, sizeof(float) * ld,
+                                  sizeof(float) * ctx->n, r1 - r0, cudaMemcpyHostToDevice, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_dm = true;
     ctx->have_nn = false;
@@ -731,14 +860,88 @@ int ic_cluster_with_constraints(ic_ctx* ctx, const float* x, int64_t n, int64_t 
     return run_resident(ctx, min_size, max_size, cluster_offsets, members, n_clusters, stats, t0);
 }
 
+
+// ---- row-block sharding across GPUs: one process per GPU --------------------------------
+namespace {
+struct ShardHandle {  // what ic_shard_export writes (IC_SHARD_HANDLE_BYTES)
+    uint32_t magic;
+    int32_t rank, world;
+    int32_t pad;
+    int64_t n, ld, rows;
+    cudaIpcMemHandle_t dm, box;
+};
+static_assert(sizeof(ShardHandle) <= IC_SHARD_HANDLE_BYTES, "handle blob too small");
+constexpr uint32_t kShardMagic = 0x49435348u;
+}  // namespace
+
+int ic_shard_init(ic_ctx* ctx, int rank, int world) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(ctx, IC_ERR_BAD_ARG, "bad rank / world");
+    if (ctx->vranks > 1 && world > 1) return fail(ctx, IC_ERR_STATE, "virtual_ranks is set");
+    ctx->shard_rank = rank;
+    ctx->shard_world = world;
+    return IC_OK;
+}
+
+int ic_shard_export(ic_ctx* ctx, void* handle) {
+    if (!ctx || !handle) return IC_ERR_BAD_ARG;
+    if (ctx->shard_world <= 1) return fail(ctx, IC_ERR_STATE, "not a sharded context");
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no problem loaded");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    ShardHandle h{};
+    h.magic = kShardMagic;
+    h.rank = ctx->shard_rank;
+    h.world = ctx->shard_world;
+    h.n = ctx->n;
+    h.ld = ctx->ld;
+    h.rows = rows_per_rank(ctx);
+    IC_CUDA(cudaIpcGetMemHandle(&h.dm, ctx->dm));
+    IC_CUDA(cudaIpcGetMemHandle(&h.box, ctx->rankbox));
+    std::memset(handle, 0, IC_SHARD_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof(h));
+    return IC_OK;
+}
+
+int ic_shard_connect(ic_ctx* ctx, const void* handles) {
+    if (!ctx || !handles) return IC_ERR_BAD_ARG;
+    if (ctx->shard_world <= 1) return fail(ctx, IC_ERR_STATE, "not a sharded context");
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no problem loaded");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->peers_open) return IC_OK;  // same allocations as before (alloc_problem keeps them across loads)
+    for (int q = 0; q < ctx->shard_world; ++q) {
+        ShardHandle h{};
+        std::memcpy(&h, static_cast<const uint8_t*>(handles) + static_cast<size_t>(q) * IC_SHARD_HANDLE_BYTES, sizeof(h));
+        if (h.magic != kShardMagic || h.rank != q || h.world != ctx->shard_world || h.n != ctx->n || h.ld != ctx->ld ||
+            h.rows != rows_per_rank(ctx))
+            return fail(ctx, IC_ERR_BAD_ARG, "shard handle of rank " + std::to_string(q) + " does not match this problem");
+        if (q == ctx->shard_rank) {
+            ctx->peer_dm[q] = ctx->dm;
+            ctx->peer_box[q] = ctx->rankbox;
+        } else {
+            IC_CUDA(cudaIpcOpenMemHandle(&ctx->peer_dm[q], h.dm, cudaIpcMemLazyEnablePeerAccess));
+            IC_CUDA(cudaIpcOpenMemHandle(&ctx->peer_box[q], h.box, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    ctx->peers_open = true;
+    return IC_OK;
+}
+
+int ic_shard_rows(ic_ctx* ctx, int64_t* row_begin_out, int64_t* row_end_out) {
+    if (!ctx || !row_begin_out || !row_end_out) return IC_ERR_BAD_ARG;
+    *row_begin_out = row_begin(ctx);
+    *row_end_out = row_end(ctx);
+    return IC_OK;
+}
+
 int ic_read_matrix(ic_ctx* ctx, float* out_host, int64_t ld) {
     if (!ctx || !out_host) return IC_ERR_BAD_ARG;
     if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
     if (ld < ctx->n) return fail(ctx, IC_ERR_BAD_ARG, "ld < n");
     IC_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->n > 0)
-        IC_CUDA(cudaMemcpy2DAsync(out_host, sizeof(float) * ld, ctx->dm, sizeof(float) * ctx->ld,
-                                  sizeof(float) * ctx->n, ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    const int64_t r0 = row_begin(ctx), r1 = row_end(ctx);  // a sharded context fills its own rows only
+    if (r1 > r0)
+        IC_CUDA(cudaMemcpy2DAsync(out_host + r0 * ld, sizeof(float) * ld, ctx->dm, sizeof(float) * ctx->ld,
+                                  sizeof(float) * ctx->n, r1 - r0, cudaMemcpyDeviceToHost, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     return IC_OK;
 }
@@ -779,7 +982,7 @@ int ic_get_merge_trace(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dis
 int ic_get_loop_profile(ic_ctx* ctx, int64_t* out16) {
     if (!ctx || !out16) return IC_ERR_BAD_ARG;
     for (int i = 0; i < 16; ++i) out16[i] = ctx->h_prof[i];
-    out16[6] = ctx->h_ctl[CTL_BIG_RESCANS];
+    out16[9] = ctx->h_ctl[CTL_BUBBLES];
     out16[7] = ctx->h_ctl[CTL_RESCANS];
     return IC_OK;
 }
@@ -814,7 +1017,7 @@ int ic_time_kernel(ic_ctx* ctx, const char* which, int repeats, float* ms_each) 
             IC_CUDA(launch_split(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->center, ctx->hi, ctx->lo, ctx->norms,
                                  ctx->n_pad, ctx->d_pad, ctx->stream));
         } else if (k == "nn_sweep") {
-            IC_CUDA(launch_nn_sweep(ctx->dm, ctx->n, ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
+            IC_CUDA(launch_nn_sweep(ctx->dm, row_begin(ctx), row_end(ctx), ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
         } else {
             return fail(ctx, IC_ERR_BAD_ARG, "unknown kernel " + k);
         }

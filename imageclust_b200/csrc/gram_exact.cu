@@ -19,9 +19,14 @@ constexpr int KT = 16;   // k tile
 }
 
 __global__ void __launch_bounds__(256) gram_exact_kernel(const float* __restrict__ x, int64_t n, int64_t d,
-                                                         int64_t ldx, float* __restrict__ dm, int64_t ld) {
+                                                         int64_t ldx, float* __restrict__ dm, int64_t ld,
+                                                         int64_t row_begin, int64_t row_end) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;  // lower triangle of tiles only
+    // dm holds the rows [row_begin, row_end) (a rank's row block, or the whole matrix)
+    if (static_cast<int64_t>(bi) * T >= row_end ||
+        (static_cast<int64_t>(bi) * T + T <= row_begin && static_cast<int64_t>(bj) * T + T <= row_begin))
+        return;
     __shared__ float sa[T][KT + 1];
     __shared__ float sb[T][KT + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -67,20 +72,20 @@ __global__ void __launch_bounds__(256) gram_exact_kernel(const float* __restrict
             if (gi >= n || gj >= n) continue;
             if (gj < gi) {
                 const float v = __fmul_rn(w, acc[r][c]);
-                dm[gi * ld + gj] = v;
-                dm[gj * ld + gi] = v;
+                if (gi >= row_begin && gi < row_end) dm[(gi - row_begin) * ld + gj] = v;
+                if (gj >= row_begin && gj < row_end) dm[(gj - row_begin) * ld + gi] = v;  // mirrored entry, if resident
             } else if (gj == gi) {
-                dm[gi * ld + gi] = 0.0f;
+                if (gi >= row_begin && gi < row_end) dm[(gi - row_begin) * ld + gi] = 0.0f;
             }
         }
 }
 
 cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx, float* dm, int64_t ld,
-                              cudaStream_t s) {
+                              int64_t row_begin, int64_t row_end, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const unsigned nb = static_cast<unsigned>((n + T - 1) / T);
     dim3 grid(nb, nb);
-    gram_exact_kernel<<<grid, 256, 0, s>>>(x, n, d, ldx, dm, ld);
+    gram_exact_kernel<<<grid, 256, 0, s>>>(x, n, d, ldx, dm, ld, row_begin, row_end);
     return cudaGetLastError();
 }
 

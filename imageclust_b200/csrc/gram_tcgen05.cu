@@ -62,7 +62,7 @@ size_t gram_tcgen05_smem_bytes() { return 1024 + static_cast<size_t>(kStages) * 
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const int2* __restrict__ tiles, int n_tiles, int k_blocks, const double* __restrict__ norms,
-                    float* __restrict__ dm, int64_t n, int64_t ld, int terms) {
+                    float* __restrict__ dm, int64_t n, int64_t ld, int64_t row_begin, int64_t row_end, int terms) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     SmemTail* tail = reinterpret_cast<SmemTail*>(smem + static_cast<size_t>(kStages) * kStageBytes);
@@ -200,7 +200,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const int64_t gj = gj0 + q;
-                    if (gj < gi && gi < n) __stcs(dm + gj * ld + gi, v[q]);
+                    if (gj < gi && gi < n && gj >= row_begin && gj < row_end) __stcs(dm + (gj - row_begin) * ld + gi, v[q]);
                 }
                 // direct entries dm[i][j]: transpose through shared memory so lanes hold consecutive j
 #pragma unroll
@@ -211,7 +211,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                 for (int rr = 0; rr < 32; ++rr) {
                     const int64_t gr = row0 + ew * 32 + rr;
                     const float val = stg[rr * 33 + lane];
-                    if (gr < n && gj <= gr) __stcs(dm + gr * ld + gj, gj == gr ? 0.0f : val);
+                    if (gr < row_end && gr >= row_begin && gj <= gr)
+                        __stcs(dm + (gr - row_begin) * ld + gj, gj == gr ? 0.0f : val);
                 }
                 __syncwarp();
             }
@@ -228,7 +229,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 }
 
 cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float* dm, int64_t n, int64_t ld,
-                                int num_sms, cudaStream_t s, int terms) {
+                                int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s, int terms) {
     if (plan.n_tiles == 0) return cudaSuccess;
     const size_t smem = gram_tcgen05_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -236,7 +237,7 @@ cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float
     if (e != cudaSuccess) return e;
     const int grid = plan.n_tiles < num_sms ? plan.n_tiles : num_sms;
     gram_tcgen05_kernel<<<grid, kThreads, smem, s>>>(plan.map_hi, plan.map_lo, plan.tiles, plan.n_tiles,
-                                                     plan.k_blocks, norms, dm, n, ld, terms);
+                                                     plan.k_blocks, norms, dm, n, ld, row_begin, row_end, terms);
     return cudaGetLastError();
 }
 

@@ -43,37 +43,59 @@ struct GramPlan {
     int n_tiles;
     int k_blocks;        // d_pad / 32
 };
-// dm[i][j] = dm[j][i] = max(0.5*(norm_i + norm_j) - <x_i, x_j>, 0), diag 0; full square, row stride ld
+// dm[i][j] = dm[j][i] = max(0.5*(norm_i + norm_j) - <x_i, x_j>, 0), diag 0; full square, row stride ld.
+// dm holds the rows [row_begin, row_end) only (a rank's row block; 0..n on one GPU): entries of other rows
+// are not stored (the merge loop never reads the initial upper triangle).
 cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float* dm, int64_t n, int64_t ld,
-                                int num_sms, cudaStream_t s, int terms = 23);
+                                int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s, int terms = 23);
 size_t gram_tcgen05_smem_bytes();
 // audit kernel: the reference's own arithmetic (sequential fp32, clustering.go:136-157), bit exact
 cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx, float* dm, int64_t ld,
-                              cudaStream_t s);
+                              int64_t row_begin, int64_t row_end, cudaStream_t s);
 
 // ---- K2 nearest-neighbour sweep ----------------------------------------------------------
-// First sweep (keys are the slot indices): nn[s][*] = the kNNK smallest (dm[s][u], u) over columns u < s.
-cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, SlotNN* nn, int32_t* nn_more, cudaStream_t s);
+// First sweep (keys are the slot indices): nn[s][*] = the kNNK smallest (dm[s][u], u) over columns u < s,
+// for the resident rows s in [row_begin, row_end).
+cudaError_t launch_nn_sweep(const float* dm, int64_t row_begin, int64_t row_end, int64_t ld, SlotNN* nn,
+                            int32_t* nn_more, cudaStream_t s);
 
 // ---- K3 persistent merge loop ------------------------------------------------------------
+// The distance matrix is row-block sharded over P "ranks" (SURVEY 8e): rank q owns slots
+// [q*C, (q+1)*C), C = ceil(n / P), i.e. the rows of those slots with ALL their columns.
+//   * one GPU:            P = 1.
+//   * several GPUs:       one process / GPU / rank; every rank launches the kernel with n_local = 1
+//                         and reaches its peers' rows and rank mailboxes through peer-mapped pointers.
+//   * virtual shards:     P ranks emulated by ONE cooperative launch on one GPU (n_local = P): same code
+//                         path, used to test the sharded protocol on a single device.
+constexpr int kMaxRanks = 8;
+constexpr int kReqPerBlock = 2;  // row rescans a block may request per iteration
 struct LoopState {
-    float* dm;
+    int32_t n;              // slots (== items)
+    int32_t n_ranks;        // P
+    int32_t rank0;          // first rank this launch runs (multi-GPU: my rank; otherwise 0)
+    int32_t n_local;        // ranks this launch runs (1, or P for virtual shards)
+    int32_t rows_per_rank;  // C
+    uint32_t gen;           // launch generation: part of every mailbox tag (mailboxes are never re-zeroed)
     int64_t ld;
-    int32_t n;       // slots (== items)
-    SlotKS* ks;      // [n]
-    int32_t* gkey;   // [round_up(n, 4)] keys only (what a whole-row rescan streams); padding = -1
-    SlotNN* nn;      // [n][kNNK]
-    int32_t* nn_more; // [n]
-    // merge trace, capacity n
+    float* dm_rank[kMaxRanks];   // first row of rank q's row block [C x ld]
+    void* rankbox[kMaxRanks];    // rank q's inter-rank mailbox: [2][P] 128-byte records
+    // per local rank v (v = rank - rank0): base + v * stride
+    SlotKS* ks;        // [n_local][n]   replica of every slot's {key, size}, maintained by block 0 of the rank
+    int32_t* gkey;     // [n_local][n4]  keys only (what a row scan streams); padding = -1
+    SlotNN* nn;        // [n][kNNK]      slot indexed: only the owner of a slot touches its entries
+    int32_t* nn_more;  // [n]            bit 0: partners beyond the list; bit 1: list ran dry (entry 0 = lower bound)
+    // merge trace, [n_local][n] each (every rank records the same trace)
     int32_t* tr_key_hi;
     int32_t* tr_key_lo;
     float* tr_dist;
     int32_t* tr_size;
     float* tr_gap;
-    // scratch (zeroed by the host before every launch)
-    void* records;   // [2][grid] 128-byte exchange records
-    int32_t* ctl;    // [16], see CTL_*
-    long long* prof; // [16] or NULL: SM cycles block 0 spent per phase
+    void* records;     // [n_local] x { [reader G][2][writer G] 128-byte records }
+    int64_t records_stride;
+    void* partials;    // [n_local] x { [owner G][2][kReqPerBlock][sender G] 128-byte records }
+    int64_t partials_stride;
+    int32_t* ctl;      // [n_local][16], see CTL_*
+    long long* prof;   // [16] or NULL: SM cycles block 0 of local rank 0 spent per phase
 };
 struct LoopParams {
     int32_t n_target;    // CalculateOptimalClusters result (clustering.go:220)
@@ -83,11 +105,22 @@ struct LoopParams {
 };
 // ctl[] indices.  N_LIVE and N_MERGES are read at launch (resume) and written at exit.
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,
-       CTL_DONE = 6, CTL_BIG_RESCANS = 7, CTL_NEXT_HI = 8, CTL_NEXT_LO = 9, CTL_NEXT_DIST = 10 };
-int merge_loop_threads(int64_t n, int num_sms);
-cudaError_t merge_loop_max_grid(int threads, int num_sms, int64_t n, int* grid);
-size_t merge_loop_smem_bytes(int64_t n, int grid);
-size_t merge_loop_record_bytes();
-cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int grid, int threads, cudaStream_t s);
+       CTL_DONE = 6, CTL_BUBBLES = 7, CTL_NEXT_HI = 8, CTL_NEXT_LO = 9, CTL_NEXT_DIST = 10, CTL_STOP = 11 };
+// CTL_STOP values
+enum { STOP_TARGET = 1, STOP_EXHAUSTED = 2, STOP_MAX_MERGES = 3, STOP_EPOCHS = 4, STOP_ERROR = 5 };
+constexpr int kLoopThreads = 512;
+// blocks per rank for a problem of n slots over n_ranks ranks, n_local of them in this launch
+// `replica`: every block keeps the keys of ALL slots in shared memory (needs merge_loop_replica_fits(n))
+bool merge_loop_replica_fits(int64_t n);
+cudaError_t merge_loop_grid(int num_sms, int64_t n, int n_ranks, int n_local, int want_blocks, bool replica,
+                            int* blocks_per_rank);
+size_t merge_loop_smem_bytes(int64_t n, int n_ranks, int blocks_per_rank, bool replica);
+size_t merge_loop_records_bytes(int blocks_per_rank);   // per rank
+size_t merge_loop_partials_bytes(int blocks_per_rank);  // per rank
+size_t merge_loop_rankbox_bytes();                      // per rank (barrier flags + [2][kMaxRanks] records)
+cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int blocks_per_rank, bool replica,
+                              cudaStream_t s);
+// device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
+cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);
 
 }  // namespace ic

@@ -1,7 +1,7 @@
-// merge_loop.cu -- K3: the whole agglomeration loop as ONE persistent cooperative kernel.
+// merge_loop.cu -- K3: the whole agglomeration loop as ONE persistent kernel per GPU.
 //
 // Replaces the body of the reference's merge loop (clustering.go:220-246):
-//   FindClosestClusters (:119-133)  -> reduction over the per-row NN cache, u64 order
+//   FindClosestClusters (:119-133)  -> reduction over the per-row partner lists, u64 order
 //                                      (dist bits, row key) == the reference's (d, i, j)
 //   maxSize check (:228-234)        -> eager admissibility: an entry whose size sum
 //                                      exceeds maxSize is stored as +inf when written,
@@ -10,28 +10,30 @@
 //   MergeClusters (:29-47)          -> slot b keeps the merged cluster (key N+t, the
 //                                      highest so far == appended last, :241), slot a
 //                                      (the larger position) is retired
-//   UpdateDistanceMatrix (:76-96)   -> Lance-Williams recurrence from rows a and b
-//                                      (two coalesced row reads + one row write + the
-//                                      mirrored column write), in double, stored fp32
+//   UpdateDistanceMatrix (:76-96)   -> Lance-Williams recurrence from rows a and b, in
+//                                      double, stored fp32, one coalesced row write
 //   RemoveRowsAndColumns (:100-116) -> nothing moves; retired slots are skipped
 //
 // The loop is a chain of ~N dependent steps with a few hundred KB of traffic each, so it
 // is bound by synchronisation latency, not bandwidth.  Design for that:
-//   * every block owns a contiguous slice of slots and keeps that slice's {key, size}
-//     and NN cache in SHARED MEMORY for the whole loop; only the owner writes them
-//     (global copies are written through for read-back and resume);
-//   * ONE all-to-all exchange per merge and no separate barrier: at the end of an
-//     iteration each block publishes one 128-byte record (its slice's best cached
-//     candidate + its part of the freshly written row's minimum) whose 16-byte chunks
-//     carry the epoch as a tag; at the start of the next iteration two warps poll all
-//     records directly and fold them with shuffles (release fence before the publish,
-//     acquire fence after the poll);
-//   * every block folds the same records, so all blocks take the same decision without
-//     a broadcast, then update their slice of row/column b;
-//   * every row caches its kNNK smallest partners (common.cuh); only when ALL of them have died
-//     is the row rescanned, by its OWNER block alone (whole row, many 16-byte loads in flight)
-//     right after the update -- the row only depends on entries its owner wrote itself or that
-//     were published at least one exchange ago.
+//   * the matrix is row-block sharded over P ranks (kernels.h); inside a rank every block
+//     owns a contiguous slice of slots and keeps that slice's {key, size} and partner
+//     lists in SHARED MEMORY for the whole loop;
+//   * ONE all-to-all exchange per iteration and no separate barrier: each block pushes a
+//     128-byte record (best candidate of its slice + its part of the freshly written row's
+//     minimum + its rescan requests) into a private mailbox line of every block of its
+//     rank; 16-byte chunks carry (launch generation, epoch) as a tag, readers poll their own
+//     lines (one record per lane) and fold with shuffles.  With P > 1 the rank's block 0
+//     then pushes the rank's fold into every rank's mailbox (peer-mapped memory over
+//     NVLink) and all blocks fold those P records: same decision everywhere, no broadcast;
+//   * a row whose cached partners have all died is NOT rescanned by its owner alone (one SM
+//     streams a 100k-column row in ~26 us): the row stays in the reduction with a LOWER
+//     BOUND (the distance of its last listed partner; the list is sorted and static), its
+//     owner publishes a request, and every block of the rank scans its own column window of
+//     that row in the same iteration and mails its partial top-k to the owner.  If a bound
+//     wins the global reduction nothing is merged in that iteration (a "bubble"): a merge
+//     is only taken when the minimum is an exact candidate below every bound, so the merge
+//     sequence is exactly the sequential one.
 // HBM roofline: algorithmic bytes = 12*n per merge; reported as merges/s too.
 #include "common.cuh"
 #include "kernels.h"
@@ -41,15 +43,27 @@ namespace ic {
 namespace {
 
 constexpr uint32_t kSpinLimit = 1u << 24;
-constexpr int kRecWords = 32;  // 128 bytes per block record: one cache line per writer
+constexpr int kRecU4 = 8;  // 128 bytes per record: one cache line per (reader, writer) pair
+constexpr int kT = kLoopThreads;
+constexpr int kW = kT / 32;
+constexpr int kMaxBlocks = 160;  // blocks per rank: one record per lane of 5 polling warps, x3 parts
+constexpr int kMaxReqTotal = kMaxBlocks * kReqPerBlock;
+constexpr uint32_t kMoreBit = 1u, kDryBit = 2u, kReqBit = 4u;
+constexpr int kRankboxFlagBytes = 256;
 
-// record chunks (uint4 each, .w = epoch tag)
-//   c0 {row key, dist bits, runner-up dist bits, tag}      slice's best cached candidate
+// block record chunks (uint4 each, .w = tag)
+//   c0 {row key, dist bits, runner-up dist bits, tag}      slice's best candidate (exact or bound)
 //   c1 {row slot a, partner slot b, size a, tag}
-//   c2 {size b, partner key, 0, tag}
+//   c2 {size b, partner key, 1 if the candidate is only a lower bound, tag}
 //   c3 {key of k, dist bits, slot k, tag}                   best entry of the new row in this slice
 //   c4 {size k, runner bits, 0, tag}
-constexpr int kChunks = 5;
+//   c5 {request 0 row, request 0 key, request 1 row, tag}   rows of this slice to rescan (-1: none)
+//   c6 {request 1 key, 0, 0, tag}
+constexpr int kChunks = 7;
+
+// partial record (one per request and scanning block): c0..c3 {partner key, dist bits, slot, tag},
+// c4 {size 0, size 1, size 2, tag}, c5 {size 3, more, count, tag}
+
 
 IC_DEVINL uint4 ld_volatile_u4(const uint4* p) {
     uint4 v;
@@ -59,7 +73,14 @@ IC_DEVINL uint4 ld_volatile_u4(const uint4* p) {
 IC_DEVINL void st_volatile_u4(uint4* p, uint4 v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-IC_DEVINL void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// fences: gpu scope on one device; system scope as soon as peers' memory is involved
+template <bool kSys>
+IC_DEVINL void fence_acq_rel() {
+    if (kSys)
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 
 // Lance-Williams update of Ward's distance (clustering.go:141-144 is the closed form it
 // equals): exact integer weights, double arithmetic, one rounding to fp32.  The CPU
@@ -73,67 +94,156 @@ IC_DEVINL float lance_williams(int sa, int sb, int sk, float dka, float dkb, flo
 }
 
 IC_DEVINL uint4 nn_none() { return make_uint4(kNoPartner, kNoPartner, kNoPartner, 0u); }
+// a dry row's placeholder: no partner, only the lower bound of whatever a rescan will find
+IC_DEVINL uint4 nn_bound(uint32_t dist_bits) { return make_uint4(kNoPartner, dist_bits, kNoPartner, 0u); }
 
 struct Decision {  // what every block derives from the exchange
     uint64_t m1, m2;   // best / second best (dist bits << 32 | row key)
     int32_t a, b, sa, sb;
     uint32_t pkey;
+    uint32_t stale;    // the best candidate is a lower bound, not a pair
 };
 struct NewRow {  // fold of the B-parts: best entry of the previous merge's new row
     uint64_t pack;
     int32_t slot, size;
     uint32_t runner;
 };
+struct PartList {  // a sorted partner list under construction
+    uint64_t pk[kNNK];
+    int32_t sl[kNNK], sz[kNNK];
+    int32_t m, more;
+};
+
+template <typename T>
+IC_DEVINL T sel4(const T (&v)[kNNK], int i) {
+    return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
+}
+
+// Warp-wide selection of the (up to) kNNK smallest candidates from every lane's two smallest.
+// EXACT: the list is cut right after an entry that was a lane's second smallest while that lane
+// saw more than two candidates (its unseen third could be smaller than what follows).
+IC_DEVINL int warp_select_topk(const Cand2& c, uint64_t (&pk)[kNNK], int32_t (&sl)[kNNK], bool& more) {
+    int total = c.cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    int taken = 0, m = 0;
+#pragma unroll
+    for (int r = 0; r < kNNK; ++r) {
+        pk[r] = kPackInf;
+        sl[r] = -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kNNK; ++r) {
+        const uint64_t cand = taken == 0 ? c.c1 : (taken == 1 ? c.c2 : kPackInf);
+        const uint64_t wm = warp_min_u64(cand);
+        if (wm == kPackInf) break;  // warp uniform
+        const bool win = cand == wm;  // packs are unique: exactly one lane
+        const int src = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+        const int32_t myslot = taken == 0 ? c.s1 : c.s2;
+        pk[r] = wm;
+        sl[r] = __shfl_sync(0xffffffffu, myslot, src);
+        if (win) ++taken;
+        m = r + 1;
+        if (__ballot_sync(0xffffffffu, win && taken == 2 && c.cnt > 2)) break;
+    }
+    more = total > m;
+    return m;
+}
+
+// Warp-wide merge of one sorted list per lane (m entries, `more`: unlisted entries >= the last one
+// exist).  Same exactness rule: cut right after a list's last entry if that list has more.
+IC_DEVINL void warp_merge_lists(const PartList& in, PartList& out) {
+    int ptr = 0;
+    out.m = 0;
+#pragma unroll
+    for (int r = 0; r < kNNK; ++r) {
+        out.pk[r] = kPackInf;
+        out.sl[r] = -1;
+        out.sz[r] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < kNNK; ++r) {
+        const uint64_t head = ptr < in.m ? sel4(in.pk, ptr) : kPackInf;
+        const uint64_t wm = warp_min_u64(head);
+        if (wm == kPackInf) break;
+        const bool win = head == wm;
+        const int src = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+        out.pk[r] = wm;
+        out.sl[r] = __shfl_sync(0xffffffffu, sel4(in.sl, ptr), src);
+        out.sz[r] = __shfl_sync(0xffffffffu, sel4(in.sz, ptr), src);
+        if (win) ++ptr;
+        out.m = r + 1;
+        if (__ballot_sync(0xffffffffu, win && ptr == in.m && in.more != 0)) break;
+    }
+    out.more = __any_sync(0xffffffffu, ptr < in.m || in.more != 0) ? 1 : 0;
+}
 
 }  // namespace
 
-size_t merge_loop_record_bytes() { return kRecWords * sizeof(uint32_t); }
-// Keys of ALL slots replicated in every block's shared memory when they fit: a whole-row
-// rescan then streams only the row itself.
+size_t merge_loop_records_bytes(int G) { return static_cast<size_t>(G) * 2 * G * kRecU4 * sizeof(uint4); }
+size_t merge_loop_partials_bytes(int G) {
+    return static_cast<size_t>(G) * 2 * kReqPerBlock * G * kRecU4 * sizeof(uint4);
+}
+size_t merge_loop_rankbox_bytes() { return kRankboxFlagBytes + 2 * kMaxRanks * kRecU4 * sizeof(uint4); }
+
+// Keys of ALL slots replicated in every block's shared memory when they fit: a row scan then
+// streams only the row itself.
 constexpr int64_t kReplicaMaxSlots = 36 * 1024;
-bool merge_loop_uses_replica(int64_t n) { return n <= kReplicaMaxSlots; }
-size_t merge_loop_smem_bytes(int64_t n, int grid) {
-    const int64_t chunk = (n + grid - 1) / grid;
-    const int64_t c = chunk > 0 ? chunk : 1;
-    size_t bytes = static_cast<size_t>(c) * (kNNK * sizeof(uint4) + sizeof(int2) + 2 * sizeof(int32_t));
+bool merge_loop_replica_fits(int64_t n) { return n <= kReplicaMaxSlots; }
+static int64_t slice_slots(int64_t n, int n_ranks, int G) {
+    const int64_t C = (n + n_ranks - 1) / n_ranks;
+    const int64_t c = (C + G - 1) / G;
+    return c > 0 ? c : 1;
+}
+size_t merge_loop_smem_bytes(int64_t n, int n_ranks, int G, bool replica) {
+    const int64_t c = slice_slots(n, n_ranks, G);
+    // partner lists, {key,size}, state bits, dry queue (2 entries per slot)
+    size_t bytes = static_cast<size_t>(c) * (kNNK * sizeof(uint4) + sizeof(int2) + 3 * sizeof(int32_t));
     bytes = (bytes + 15) & ~size_t(15);
-    if (merge_loop_uses_replica(n)) bytes += static_cast<size_t>((n + 3) / 4 * 4) * sizeof(int32_t);
+    if (replica) bytes += static_cast<size_t>((n + 3) / 4 * 4) * sizeof(int32_t);
     return bytes;
 }
 
-template <int kT, bool kReplica>
-__global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopParams prm) {
-    constexpr int kW = kT / 32;
+template <bool kReplica, bool kMulti>
+__global__ void __launch_bounds__(kT, 1)
+merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ LoopParams prm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int blk = blockIdx.x, G = gridDim.x;
-    const int32_t n = st.n;
+    const int G = static_cast<int>(gridDim.x) / st.n_local;  // blocks per rank
+    const int v = static_cast<int>(blockIdx.x) / G;           // local rank of this block
+    const int blk = static_cast<int>(blockIdx.x) - v * G;
+    const int P = st.n_ranks, rank = st.rank0 + v;
+    const int32_t n = st.n, C = st.rows_per_rank;
     const int64_t ld = st.ld;
-    float* const dm = st.dm;
+    const int32_t n4 = (n + 3) & ~3;
+
+    // this rank's views
+    SlotKS* const g_ks = st.ks + static_cast<size_t>(v) * n;
+    int32_t* const g_key = st.gkey + static_cast<size_t>(v) * n4;
+    int32_t* const ctl = st.ctl + v * 16;
     // mailboxes: every writer pushes its record into a private line of every reader, so a polled
     // line has exactly one reader and one writer (148 blocks polling shared lines was 3x slower)
-    uint4* const records = static_cast<uint4*>(st.records);  // [reader G][2][writer G][8]
+    uint4* const records = reinterpret_cast<uint4*>(static_cast<uint8_t*>(st.records) + v * st.records_stride);
+    uint4* const partials = reinterpret_cast<uint4*>(static_cast<uint8_t*>(st.partials) + v * st.partials_stride);
+    float* const dm_own = st.dm_rank[rank];
 
-    // slot slice owned by this block; its state lives in shared memory
-    const int32_t chunk = (n + G - 1) / G;
-    const int32_t lo = min(n, blk * chunk), hi = min(n, lo + chunk);
+    // slot slice owned by this block (rows of this rank); its state lives in shared memory
+    const int32_t r_lo = min(n, rank * C), r_hi = min(n, r_lo + C);
+    const int32_t chunk = (C + G - 1) / G;
+    const int32_t lo = min(r_hi, r_lo + blk * chunk), hi = min(r_hi, lo + chunk);
     const int32_t cnt = hi - lo;
+    // column window this block scans when a row of its rank is rescanned
+    const int32_t W = (((n4 + G - 1) / G) + 3) & ~3;
+    const int32_t w0 = min(n4, blk * W), w1 = min(n4, w0 + W);
+
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const size_t c1 = static_cast<size_t>(chunk > 0 ? chunk : 1);
     uint4* const s_nn = reinterpret_cast<uint4*>(dyn_smem);                                  // [chunk][kNNK]
     int2* const s_ks = reinterpret_cast<int2*>(dyn_smem + c1 * kNNK * sizeof(uint4));        // [chunk]
-    int32_t* const s_more = reinterpret_cast<int32_t*>(dyn_smem + c1 * (kNNK * sizeof(uint4) + sizeof(int2)));
-    int32_t* const s_resc = s_more + c1;
-    const int32_t n4 = (n + 3) & ~3;
+    uint32_t* const s_more = reinterpret_cast<uint32_t*>(dyn_smem + c1 * (kNNK * sizeof(uint4) + sizeof(int2)));
+    int32_t* const s_dryq = reinterpret_cast<int32_t*>(s_more + c1);                         // ring, [2 * chunk]
+    const int32_t qcap = static_cast<int32_t>(2 * c1);
     int32_t* const s_key = reinterpret_cast<int32_t*>(
-        dyn_smem + ((c1 * (kNNK * sizeof(uint4) + sizeof(int2) + 2 * sizeof(int32_t)) + 15) & ~size_t(15)));  // [n4] if kReplica
-    for (int32_t i = tid; i < cnt; i += kT) {
-        s_ks[i] = __ldcg(st.ks + lo + i);
-        s_more[i] = __ldcg(st.nn_more + lo + i);
-    }
-    for (int32_t i = tid; i < cnt * kNNK; i += kT) s_nn[i] = __ldcg(st.nn + static_cast<int64_t>(lo) * kNNK + i);
-    if (kReplica)
-        for (int32_t u = tid; u < n4; u += kT) s_key[u] = __ldcg(st.gkey + u);
-    const int npw = (G + 31) / 32;  // warps that poll one part of the records (one record per lane)
+        dyn_smem + ((c1 * (kNNK * sizeof(uint4) + sizeof(int2) + 3 * sizeof(int32_t)) + 15) & ~size_t(15)));  // [n4] if kReplica
 
     __shared__ uint64_t s_m1[kW], s_m2[kW], s_up[kW], s_ur[kW];
     __shared__ Decision s_dec;
@@ -141,45 +251,69 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
     __shared__ Decision s_pdec[kW];
     __shared__ NewRow s_pnew[kW];
     __shared__ uint4 s_pub[kChunks];
-    __shared__ int32_t s_rcount;
     __shared__ int32_t s_bwin[2];
-    __shared__ TopKScratch s_topk;
+    __shared__ int32_t s_qhead, s_qtail;        // dry-row queue of this slice
+    __shared__ int32_t s_nmine, s_req_i[kReqPerBlock];  // requests this block published in this iteration
+    __shared__ int32_t s_nreq;                  // requests of the whole rank in this iteration
+    __shared__ int4 s_rlist[kMaxReqTotal];      // {row, row key, owner block, request index}
+    __shared__ PartList s_wl[kW];
+    __shared__ int32_t s_err;
 
-    int32_t n_live = st.ctl[CTL_N_LIVE];
-    int32_t t = st.ctl[CTL_N_MERGES];  // merges done so far == index of the next merge
+    if (tid == 0) {
+        s_qhead = 0;
+        s_qtail = 0;
+        s_nmine = 0;
+        s_nreq = 0;
+        s_err = 0;
+    }
+    for (int32_t i = tid; i < cnt; i += kT) {
+        s_ks[i] = __ldcg(g_ks + lo + i);
+        s_more[i] = static_cast<uint32_t>(__ldcg(st.nn_more + lo + i)) & (kMoreBit | kDryBit);
+    }
+    for (int32_t i = tid; i < cnt * kNNK; i += kT) s_nn[i] = __ldcg(st.nn + static_cast<int64_t>(lo) * kNNK + i);
+    if (kReplica)
+        for (int32_t u = tid; u < n4; u += kT) s_key[u] = __ldcg(g_key + u);
+    __syncthreads();
+    for (int32_t i = tid; i < cnt; i += kT)  // rows that were dry when the previous launch stopped
+        if (s_more[i] & kDryBit) s_dryq[atomicAdd(&s_qtail, 1) % qcap] = i;
+    const int npw = (G + 31) / 32;  // warps that poll one part of the records (one record per lane)
+
+    int32_t n_live = ctl[CTL_N_LIVE];
+    int32_t t = ctl[CTL_N_MERGES];  // merges done so far == index of the next merge
     int32_t launched = 0;
-    int32_t exhausted = 0;
-    int32_t my_rescans = 0;
-    long long my_rescan_cycles = 0;
+    int32_t stop_reason = 0;
+    int32_t my_rescans = 0, n_bubbles = 0, bubbles_in_a_row = 0;
     // pending merge (bookkeeping applied after the next exchange)
     bool pending = false;
     int32_t pa = -1, pb = -1, p_snew = 0, p_keyhi = 0, p_keylo = 0;
     float p_dist = 0.0f;
-    uint32_t p_second = kInfBits;  // runner-up among the cached candidates when the pending merge was picked
+    uint32_t p_second = kInfBits;  // runner-up among the candidates when the pending merge was picked
     // this block's part of the freshly written row (B-part of the record it publishes)
     uint64_t pub_bpack = kPackInf;
     int32_t pub_bslot = -1, pub_bsize = 0;
     uint32_t pub_brun = kInfBits;
-    if (tid == 0) s_rcount = 0;
     __syncthreads();
 
-    const bool timed = st.prof != nullptr && blk == 0 && tid == 0;
-    long long c_poll = 0, c_fold = 0, c_upd = 0, c_resc = 0, c_pub = 0;
-    uint32_t epoch = 0;  // iteration index; records read in iteration i carry tag i+1
+    const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long c_pub = 0, c_exch = 0, c_scan = 0, c_upd = 0, c_fold = 0;
+    uint32_t epoch = 0;  // iteration index; records of iteration i carry tag (gen, i+1)
+    const uint32_t tagbase = st.gen << 20;
 
     for (;;) {
-        // ====== publish: slice argmin over the shared NN cache -> record of this epoch ======
+        const uint32_t tag = tagbase | (epoch + 1u);
+        const uint32_t par = epoch & 1u;
+        // ====== publish: slice argmin over the partner lists -> record of this epoch ======
         const long long t0 = timed ? clock64() : 0;
         {
             Top2 top = {kPackInf, kPackInf};
             int32_t w_a = -1, w_b = -1, w_sa = 0, w_sb = 0;
-            uint32_t w_pkey = 0;
+            uint32_t w_pkey = 0, w_stale = 0;
             for (int32_t i = tid; i < cnt; i += kT) {
                 const int32_t s = lo + i;
                 if (pending && (s == pa || s == pb)) continue;  // a is retired; b's candidate travels in the B-part
                 const int2 k = s_ks[i];
                 if (k.x < 0) continue;
-                const uint4 q = s_nn[i * kNNK];      // head of the row's partner list
+                const uint4 q = s_nn[i * kNNK];      // head of the row's partner list, or its lower bound
                 if (q.y >= kMaxFloatBits) continue;  // nothing selectable in this row
                 const uint64_t cand = (static_cast<uint64_t>(q.y) << 32) | static_cast<uint32_t>(k.x);
                 if (cand < top.m1) {
@@ -188,8 +322,27 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     w_sa = k.y;
                     w_sb = static_cast<int32_t>(q.w);
                     w_pkey = q.x;
+                    w_stale = q.z == kNoPartner ? 1u : 0u;
                 }
                 top2_insert(top, cand);
+            }
+            if (tid == 0) {  // rescan requests: oldest dry rows of the slice first
+                int32_t nreq = 0;
+                while (nreq < kReqPerBlock && s_qhead != s_qtail) {
+                    const int32_t i = s_dryq[s_qhead % qcap];
+                    ++s_qhead;
+                    const int32_t s = lo + i;
+                    if (pending && (s == pa || s == pb)) continue;  // the row is gone / is being rebuilt
+                    if (s_ks[i].x < 0 || (s_more[i] & (kDryBit | kReqBit)) != kDryBit) continue;
+                    s_more[i] |= kReqBit;
+                    s_req_i[nreq++] = i;
+                }
+                s_nmine = nreq;
+                const int32_t i0 = nreq > 0 ? s_req_i[0] : -1, i1 = nreq > 1 ? s_req_i[1] : -1;
+                s_pub[5] = make_uint4(static_cast<uint32_t>(i0 >= 0 ? lo + i0 : -1),
+                                      static_cast<uint32_t>(i0 >= 0 ? s_ks[i0].x : -1),
+                                      static_cast<uint32_t>(i1 >= 0 ? lo + i1 : -1), tag);
+                s_pub[6] = make_uint4(static_cast<uint32_t>(i1 >= 0 ? s_ks[i1].x : -1), 0u, 0u, tag);
             }
             const Top2 wt = warp_top2(top);
             if (lane == 0) {
@@ -200,21 +353,20 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
             Top2 bt = {s_m1[0], s_m2[0]};
 #pragma unroll
             for (int w = 1; w < kW; ++w) top2_merge(bt, s_m1[w], s_m2[w]);
-            const uint32_t tag = epoch + 1u;
             const bool none = bt.m1 == kPackInf;
             if (none ? tid == 0 : top.m1 == bt.m1) {  // row keys are unique: exactly one thread
                 s_pub[0] = make_uint4(static_cast<uint32_t>(bt.m1), static_cast<uint32_t>(bt.m1 >> 32),
                                       static_cast<uint32_t>(bt.m2 >> 32), tag);
                 s_pub[1] = make_uint4(static_cast<uint32_t>(w_a), static_cast<uint32_t>(w_b), static_cast<uint32_t>(w_sa), tag);
-                s_pub[2] = make_uint4(static_cast<uint32_t>(w_sb), w_pkey, 0u, tag);
+                s_pub[2] = make_uint4(static_cast<uint32_t>(w_sb), w_pkey, w_stale, tag);
                 s_pub[3] = make_uint4(static_cast<uint32_t>(pub_bpack), static_cast<uint32_t>(pub_bpack >> 32),
                                       static_cast<uint32_t>(pub_bslot), tag);
                 s_pub[4] = make_uint4(static_cast<uint32_t>(pub_bsize), pub_brun, 0u, tag);
             }
             __syncthreads();
             if (tid < G) {  // push to reader `tid`
-                uint4* rec = records + ((static_cast<size_t>(tid) * 2 + (epoch & 1u)) * G + blk) * (kRecWords / 4);
-                fence_acq_rel_gpu();  // release: the block's stores (ordered by the bar.sync above) before the record
+                uint4* rec = records + ((static_cast<size_t>(tid) * 2 + par) * G + blk) * kRecU4;
+                fence_acq_rel<kMulti>();  // release: the block's stores (ordered by the bar.sync above) before the record
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) st_volatile_u4(rec + c, s_pub[c]);
             }
@@ -223,14 +375,13 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
 
         // ====== exchange: poll every block's record (one record per lane) and fold with shuffles ======
         {
-            const uint32_t tag = epoch + 1u;
-            const uint4* base = records + (static_cast<size_t>(blk) * 2 + (epoch & 1u)) * G * (kRecWords / 4);
+            const uint4* base = records + (static_cast<size_t>(blk) * 2 + par) * G * kRecU4;
             if (warp < npw) {  // A-parts: two smallest candidates + the winner's payload
                 const int g = warp * 32 + lane;
                 Top2 ft = {kPackInf, kPackInf};
                 uint4 r1 = make_uint4(0, 0, 0, 0), r2 = make_uint4(0, 0, 0, 0);
                 if (g < G) {
-                    const uint4* rec = base + static_cast<size_t>(g) * (kRecWords / 4);
+                    const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
                     uint4 r0;
                     uint32_t spins = 0;
                     for (;;) {
@@ -242,7 +393,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     }
                     ft.m1 = (static_cast<uint64_t>(r0.y) << 32) | r0.x;
                     ft.m2 = (static_cast<uint64_t>(r0.z) << 32) | 0xFFFFFFFFull;  // only its distance matters
-                    fence_acq_rel_gpu();  // acquire: everything published before that record
+                    fence_acq_rel<kMulti>();  // acquire: everything published before that record
                 }
                 const uint64_t mine = ft.m1;
                 ft = warp_top2(ft);
@@ -251,6 +402,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     if (lane == 0) {
                         s_pdec[warp].m1 = kPackInf;
                         s_pdec[warp].m2 = kPackInf;
+                        s_pdec[warp].stale = 0u;
                     }
                 } else if (lane == __ffs(who) - 1) {
                     Decision d;
@@ -261,6 +413,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     d.sa = static_cast<int32_t>(r1.z);
                     d.sb = static_cast<int32_t>(r2.x);
                     d.pkey = r2.y;
+                    d.stale = r2.z;
                     s_pdec[warp] = d;
                 }
             } else if (warp < 2 * npw) {  // B-parts: the pending merge's new row: best entry + exact runner-up distance
@@ -269,7 +422,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                 uint32_t run = 0xFFFFFFFFu;
                 int32_t bslot = -1, bsize = 0;
                 if (g < G) {
-                    const uint4* rec = base + static_cast<size_t>(g) * (kRecWords / 4);
+                    const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
                     uint4 r3, r4;
                     uint32_t spins = 0;
                     for (;;) {
@@ -282,7 +435,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     bslot = static_cast<int32_t>(r3.z);
                     bsize = static_cast<int32_t>(r4.x);
                     run = r4.y;
-                    fence_acq_rel_gpu();
+                    fence_acq_rel<kMulti>();
                 }
                 const uint64_t wm = warp_min_u64(best);
 #pragma unroll
@@ -295,6 +448,23 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     nr.size = bsize;
                     nr.runner = run;
                     s_pnew[warp - npw] = nr;
+                }
+            } else if (warp < 3 * npw) {  // rescan requests of the rank
+                const int g = (warp - 2 * npw) * 32 + lane;
+                if (g < G) {
+                    const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
+                    uint4 r5, r6;
+                    uint32_t spins = 0;
+                    for (;;) {
+                        r5 = ld_volatile_u4(rec + 5);
+                        r6 = ld_volatile_u4(rec + 6);
+                        if (r5.w == tag && r6.w == tag) break;
+                        if (++spins > kSpinLimit) __trap();
+                    }
+                    if (static_cast<int32_t>(r5.x) >= 0)
+                        s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.x), static_cast<int32_t>(r5.y), g, 0);
+                    if (static_cast<int32_t>(r5.z) >= 0)
+                        s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.z), static_cast<int32_t>(r6.x), g, 1);
                 }
             }
             __syncthreads();
@@ -319,11 +489,92 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                 }
                 s_new = nr;
             }
+            if (kMulti) {
+                // ---- second level: the rank's fold goes to every rank, all blocks fold the P rank records ----
+                __syncthreads();
+                if (blk == 0 && tid < P) {
+                    const Decision d = s_dec;
+                    const NewRow nr = s_new;
+                    uint4* rec = static_cast<uint4*>(static_cast<void*>(static_cast<uint8_t*>(st.rankbox[tid]) + kRankboxFlagBytes)) +
+                                 (static_cast<size_t>(par) * kMaxRanks + rank) * kRecU4;
+                    fence_acq_rel<true>();  // cumulative: what this rank's blocks published travels before the record
+                    st_volatile_u4(rec + 0, make_uint4(static_cast<uint32_t>(d.m1), static_cast<uint32_t>(d.m1 >> 32),
+                                                       static_cast<uint32_t>(d.m2 >> 32), tag));
+                    st_volatile_u4(rec + 1, make_uint4(static_cast<uint32_t>(d.a), static_cast<uint32_t>(d.b),
+                                                       static_cast<uint32_t>(d.sa), tag));
+                    st_volatile_u4(rec + 2, make_uint4(static_cast<uint32_t>(d.sb), d.pkey, d.stale, tag));
+                    st_volatile_u4(rec + 3, make_uint4(static_cast<uint32_t>(nr.pack), static_cast<uint32_t>(nr.pack >> 32),
+                                                       static_cast<uint32_t>(nr.slot), tag));
+                    st_volatile_u4(rec + 4, make_uint4(static_cast<uint32_t>(nr.size), nr.runner, 0u, tag));
+                }
+                __syncthreads();  // s_dec / s_new were read by the pushing threads
+                if (warp == 0) {
+                    const uint4* rbase = static_cast<const uint4*>(static_cast<const void*>(
+                                             static_cast<const uint8_t*>(st.rankbox[rank]) + kRankboxFlagBytes)) +
+                                         static_cast<size_t>(par) * kMaxRanks * kRecU4;
+                    Top2 ft = {kPackInf, kPackInf};
+                    uint4 r1 = make_uint4(0, 0, 0, 0), r2 = r1, r3 = r1, r4 = r1;
+                    uint64_t best = kPackInf;
+                    uint32_t run = 0xFFFFFFFFu;
+                    if (lane < P) {
+                        const uint4* rec = rbase + static_cast<size_t>(lane) * kRecU4;
+                        uint4 r0;
+                        uint32_t spins = 0;
+                        for (;;) {
+                            r0 = ld_volatile_u4(rec + 0);
+                            r1 = ld_volatile_u4(rec + 1);
+                            r2 = ld_volatile_u4(rec + 2);
+                            r3 = ld_volatile_u4(rec + 3);
+                            r4 = ld_volatile_u4(rec + 4);
+                            if (r0.w == tag && r1.w == tag && r2.w == tag && r3.w == tag && r4.w == tag) break;
+                            if (++spins > kSpinLimit) __trap();
+                        }
+                        ft.m1 = (static_cast<uint64_t>(r0.y) << 32) | r0.x;
+                        ft.m2 = (static_cast<uint64_t>(r0.z) << 32) | 0xFFFFFFFFull;
+                        best = (static_cast<uint64_t>(r3.y) << 32) | r3.x;
+                        run = r4.y;
+                        fence_acq_rel<true>();
+                    }
+                    const uint64_t mine = ft.m1;
+                    ft = warp_top2(ft);
+                    const unsigned who = __ballot_sync(0xffffffffu, mine == ft.m1 && mine != kPackInf);
+                    if (who == 0u) {
+                        if (lane == 0) {
+                            s_dec.m1 = kPackInf;
+                            s_dec.m2 = kPackInf;
+                            s_dec.stale = 0u;
+                        }
+                    } else if (lane == __ffs(who) - 1) {
+                        Decision d;
+                        d.m1 = ft.m1;
+                        d.m2 = ft.m2;
+                        d.a = static_cast<int32_t>(r1.x);
+                        d.b = static_cast<int32_t>(r1.y);
+                        d.sa = static_cast<int32_t>(r1.z);
+                        d.sb = static_cast<int32_t>(r2.x);
+                        d.pkey = r2.y;
+                        d.stale = r2.z;
+                        s_dec = d;
+                    }
+                    const uint64_t wm = warp_min_u64(best);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) run = min(run, __shfl_xor_sync(0xffffffffu, run, o));
+                    const unsigned whob = __ballot_sync(0xffffffffu, best == wm && lane < P);
+                    if (lane == __ffs(whob) - 1) {
+                        NewRow nr;
+                        nr.pack = wm;
+                        nr.slot = static_cast<int32_t>(r3.z);
+                        nr.size = static_cast<int32_t>(r4.x);
+                        nr.runner = run;
+                        s_new = nr;
+                    }
+                }
+            }
         }
         __syncthreads();
         const long long t2 = timed ? clock64() : 0;
 
-        // ====== decision (identical in every block) ======
+        // ====== decision (identical in every block of every rank) ======
         Top2 gt = {s_dec.m1, s_dec.m2};
         const uint64_t g_bp = pending ? s_new.pack : kPackInf;
         bool from_new = false;
@@ -337,8 +588,7 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
             if (tid == 0) {  // bookkeeping of merge t-1 for the slots this block owns
                 if (pa >= lo && pa < hi) {
                     s_ks[pa - lo] = make_int2(-1, 0);
-                    st.ks[pa] = make_int2(-1, 0);
-                    st.gkey[pa] = -1;
+                    s_more[pa - lo] = 0u;
                 }
                 if (pb >= lo && pb < hi) {
                     const uint4 nb = b_sel ? make_uint4(pack_key(g_bp), static_cast<uint32_t>(g_bp >> 32),
@@ -348,20 +598,25 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                     s_nn[(pb - lo) * kNNK] = nb;  // only the head of the new row is known: the rest is "more"
 #pragma unroll
                     for (int j = 1; j < kNNK; ++j) s_nn[(pb - lo) * kNNK + j] = nn_none();
-                    s_more[pb - lo] = b_sel ? 1 : 0;
-                    st.ks[pb] = make_int2(new_key, p_snew);
-                    st.gkey[pb] = new_key;
-                    // trace entry of merge t-1 with the exact runner-up distance
-                    const uint32_t second = min(p_second, s_new.runner);
-                    const float sd = __uint_as_float(second);
-                    const float gap = (sd - p_dist) / fmaxf(p_dist, 1e-30f);
-                    st.tr_key_hi[t - 1] = p_keyhi;
-                    st.tr_key_lo[t - 1] = p_keylo;
-                    st.tr_dist[t - 1] = p_dist;
-                    st.tr_size[t - 1] = p_snew;
-                    st.tr_gap[t - 1] = gap;
-                    if (gap < prm.near_tie_tol) atomicAdd(st.ctl + CTL_NEAR_TIES, 1);
+                    s_more[pb - lo] = b_sel ? kMoreBit : 0u;
                 }
+            }
+            if (blk == 0 && tid == 64) {  // the rank's replica of all slots + the merge trace
+                g_ks[pa] = make_int2(-1, 0);
+                g_key[pa] = -1;
+                g_ks[pb] = make_int2(new_key, p_snew);
+                g_key[pb] = new_key;
+                // trace entry of merge t-1 with the runner-up distance
+                const uint32_t second = min(p_second, s_new.runner);
+                const float sd = __uint_as_float(second);
+                const float gap = (sd - p_dist) / fmaxf(p_dist, 1e-30f);
+                const size_t to = static_cast<size_t>(v) * n + (t - 1);
+                st.tr_key_hi[to] = p_keyhi;
+                st.tr_key_lo[to] = p_keylo;
+                st.tr_dist[to] = p_dist;
+                st.tr_size[to] = p_snew;
+                st.tr_gap[to] = gap;
+                if (gap < prm.near_tie_tol) atomicAdd(ctl + CTL_NEAR_TIES, 1);
             }
             if (b_sel) {
                 const uint64_t cand = (g_bp & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(new_key);
@@ -372,78 +627,167 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
         const int32_t prev_a = pending ? pa : -1, prev_b = pending ? pb : -1;
         pending = false;
 
-        // termination (clustering.go:220 loop condition, :222-225 exhaustion)
+        // termination (clustering.go:220 loop condition, :222-225 exhaustion); a lower bound at the top of
+        // the reduction is resolved (bubble) before it may be reported or before max_merges stops the launch
         const bool selectable = pack_selectable(gt.m1);
-        const bool stop = (n_live <= prm.n_target) || !selectable || (prm.max_merges >= 0 && launched >= prm.max_merges);
-        if (stop) {
-            if (n_live > prm.n_target && !selectable) exhausted = 1;
+        const bool bubble = selectable && !from_new && s_dec.stale != 0u;
+        if (n_live <= prm.n_target)
+            stop_reason = STOP_TARGET;
+        else if (!selectable)
+            stop_reason = STOP_EXHAUSTED;
+        else if (!bubble && prm.max_merges >= 0 && launched >= prm.max_merges)
+            stop_reason = STOP_MAX_MERGES;
+        else if (epoch + 8u >= (1u << 20))
+            stop_reason = STOP_EPOCHS;
+        else if (bubbles_in_a_row > chunk + 64)
+            stop_reason = STOP_ERROR;  // cannot happen: every bubble serves kReqPerBlock dry rows per block
+        if (stop_reason != 0) {
             if (blk == 0 && tid == 0) {  // what FindClosestClusters would return next
-                st.ctl[CTL_NEXT_HI] = selectable ? static_cast<int32_t>(pack_key(gt.m1)) : -1;
-                st.ctl[CTL_NEXT_LO] = selectable ? static_cast<int32_t>(from_new ? pack_key(g_bp) : s_dec.pkey) : -1;
-                st.ctl[CTL_NEXT_DIST] = selectable ? static_cast<int32_t>(gt.m1 >> 32) : static_cast<int32_t>(kInfBits);
+                const bool exact = selectable && !bubble;
+                ctl[CTL_NEXT_HI] = exact ? static_cast<int32_t>(pack_key(gt.m1)) : -1;
+                ctl[CTL_NEXT_LO] = exact ? static_cast<int32_t>(from_new ? pack_key(g_bp) : s_dec.pkey) : -1;
+                ctl[CTL_NEXT_DIST] = exact ? static_cast<int32_t>(gt.m1 >> 32) : static_cast<int32_t>(kInfBits);
             }
             break;
         }
 
         // the merge.  a = row slot (higher key), b = partner slot (lower key)
-        const int32_t a = from_new ? prev_b : s_dec.a;
-        const int32_t b = from_new ? s_new.slot : s_dec.b;
+        const bool merged = !bubble;
+        const int32_t a = !merged ? -1 : (from_new ? prev_b : s_dec.a);
+        const int32_t b = !merged ? -1 : (from_new ? s_new.slot : s_dec.b);
         const int32_t sa = from_new ? p_snew : s_dec.sa;
         const int32_t sb = from_new ? s_new.size : s_dec.sb;
         const uint32_t key_lo = from_new ? pack_key(g_bp) : s_dec.pkey;
         const float dab = __uint_as_float(static_cast<uint32_t>(gt.m1 >> 32));
         const int32_t snew = sa + sb;
-        __syncthreads();  // the owner's shared-memory stores above are visible; s_dec / s_new were read
+        const int32_t nreq_all = s_nreq, nmine = s_nmine;
+        __syncthreads();  // the owner's shared-memory stores above are visible; s_dec / s_new / s_nreq were read
 
-        // ====== update pass over the own slice: Lance-Williams row / column b ======
+        // ====== cooperative row scans: this block's column window of every requested row of the rank ======
+        for (int32_t j = warp; j < nreq_all; j += kW) {
+            const int4 rq = s_rlist[j];
+            const int32_t r = rq.x;
+            if (r == a || r == b) continue;  // merged away in this very iteration: its owner drops the request
+            const uint32_t ukr = static_cast<uint32_t>(rq.y);
+            const float* rowp = dm_own + static_cast<int64_t>(r - r_lo) * ld;
+            Cand2 c;
+            cand2_init(c);
+            constexpr int kU = 4;  // 16-byte row loads in flight per lane
+            for (int32_t base = w0; base < w1; base += 128 * kU) {
+                float4 vv[kU];
+                int4 kq[kU];
+#pragma unroll
+                for (int q = 0; q < kU; ++q) {
+                    const int32_t u0 = base + (q * 32 + lane) * 4;
+                    vv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    kq[q] = make_int4(-1, -1, -1, -1);
+                    if (u0 < w1) {
+                        vv[q] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
+                        kq[q] = kReplica ? *reinterpret_cast<const int4*>(s_key + u0)
+                                         : __ldcg(reinterpret_cast<const int4*>(g_key + u0));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kU; ++q) {
+                    const int32_t u0 = base + (q * 32 + lane) * 4;
+                    const uint32_t ks4[4] = {static_cast<uint32_t>(kq[q].x), static_cast<uint32_t>(kq[q].y),
+                                             static_cast<uint32_t>(kq[q].z), static_cast<uint32_t>(kq[q].w)};
+                    const uint32_t vs4[4] = {__float_as_uint(vv[q].x), __float_as_uint(vv[q].y), __float_as_uint(vv[q].z),
+                                             __float_as_uint(vv[q].w)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int32_t u = u0 + e;
+                        const uint32_t ku = ks4[e];  // retired slots hold -1 == 0xFFFFFFFF: never below the row's key
+                        // the four slots in flux are excluded by index: a and prev_a are retired, b and
+                        // prev_b carry the two highest keys (their replica entries may lag one exchange)
+                        const bool ok = ku < ukr && vs4[e] < kMaxFloatBits && u != a && u != b && u != prev_a && u != prev_b;
+                        if (ok) cand2_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ku, u);
+                    }
+                }
+            }
+            uint64_t pk[kNNK];
+            int32_t sl[kNNK];
+            bool more = false;
+            const int m = warp_select_topk(c, pk, sl, more);
+            // lanes 0..3 carry one entry each (with the partner's size), lanes 4..5 the size chunks
+            const uint64_t myp = sel4(pk, lane & 3);
+            const int32_t mys = sel4(sl, lane & 3);
+            int32_t mysz = 0;
+            if (lane < m) mysz = __ldcg(g_ks + mys).y;
+            const int32_t z0 = __shfl_sync(0xffffffffu, mysz, 0), z1 = __shfl_sync(0xffffffffu, mysz, 1);
+            const int32_t z2 = __shfl_sync(0xffffffffu, mysz, 2), z3 = __shfl_sync(0xffffffffu, mysz, 3);
+            uint4* prec = partials + (((static_cast<size_t>(rq.z) * 2 + par) * kReqPerBlock + rq.w) * G + blk) * kRecU4;
+            if (lane < kNNK)
+                st_volatile_u4(prec + lane, lane < m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                                  static_cast<uint32_t>(mys), tag)
+                                                     : make_uint4(kNoPartner, kNoPartner, kNoPartner, tag));
+            else if (lane == 4)
+                st_volatile_u4(prec + 4, make_uint4(static_cast<uint32_t>(z0), static_cast<uint32_t>(z1),
+                                                    static_cast<uint32_t>(z2), tag));
+            else if (lane == 5)
+                st_volatile_u4(prec + 5, make_uint4(static_cast<uint32_t>(z3), more ? 1u : 0u, static_cast<uint32_t>(m), tag));
+        }
+        const long long t3 = timed ? clock64() : 0;
+
+        // ====== update pass over the own slice: Lance-Williams row b ======
         uint64_t ubest = kPackInf;
         int32_t uslot = -1, usize = 0;
         uint32_t urun = kInfBits;
-        {
+        if (merged) {
             // a pair is stored in the row of its higher-key cluster (the new cluster always has the
-            // highest key, so its distances are one coalesced row write and nothing is mirrored)
-            const float* row_a = dm + static_cast<int64_t>(a) * ld;
-            float* row_b = dm + static_cast<int64_t>(b) * ld;
+            // highest key, so its distances are one coalesced row write and nothing is mirrored);
+            // rows a and b may live on another rank: peer-mapped loads / stores
+            const int32_t qa = a / C, qb = b / C;
+            const float* row_a = st.dm_rank[qa] + static_cast<int64_t>(a - qa * C) * ld;
+            float* row_b = st.dm_rank[qb] + static_cast<int64_t>(b - qb * C) * ld;
             const int32_t key_a = static_cast<int32_t>(pack_key(gt.m1)), key_b = static_cast<int32_t>(key_lo);
             for (int32_t i = tid; i < cnt; i += kT) {
                 const int32_t k = lo + i;
                 const int2 kk = s_ks[i];
                 if (k == a || k == b || kk.x < 0) continue;
-                const float* own = dm + static_cast<int64_t>(k) * ld;
+                const float* own = dm_own + static_cast<int64_t>(k - r_lo) * ld;
                 const float dka = __ldcg(kk.x < key_a ? row_a + k : own + a);
                 const float dkb = __ldcg(kk.x < key_b ? row_b + k : own + b);
-                float v;
+                float val;
                 if (kk.y + snew > prm.max_size)
-                    v = __uint_as_float(kInfBits);  // inadmissible for good: sizes only grow (:228)
+                    val = __uint_as_float(kInfBits);  // inadmissible for good: sizes only grow (:228)
                 else
-                    v = lance_williams(sa, sb, kk.y, dka, dkb, dab);
-                __stcg(row_b + k, v);
-                const uint64_t c = pack_cand(v, static_cast<uint32_t>(kk.x));
-                if (c < ubest) {
-                    ubest = c;
+                    val = lance_williams(sa, sb, kk.y, dka, dkb, dab);
+                __stcg(row_b + k, val);
+                const uint64_t cd = pack_cand(val, static_cast<uint32_t>(kk.x));
+                if (cd < ubest) {
+                    ubest = cd;
                     uslot = k;
                     usize = kk.y;
                 }
                 urun = min(urun, min(__float_as_uint(dka), __float_as_uint(dkb)));
-                // drop a and b from the row's partner list; rescan only when the list runs dry
+                // drop a and b from the row's partner list; when the list runs dry the row keeps the
+                // distance of its last listed partner as a lower bound and queues for a rescan
                 {
                     uint4 e[kNNK];
                     int kept = 0;
                     bool changed = false;
+                    uint32_t last_removed = 0u;
 #pragma unroll
                     for (int j = 0; j < kNNK; ++j) {
                         const uint4 q = s_nn[i * kNNK + j];
-                        if (q.y == kNoPartner) continue;
+                        if (q.z == kNoPartner) continue;  // empty entry or a bound
                         if (static_cast<int32_t>(q.z) == a || static_cast<int32_t>(q.z) == b) {
                             changed = true;
+                            last_removed = q.y;
                             continue;
                         }
                         e[kept++] = q;
                     }
                     if (changed) {
+                        const bool dry = kept == 0 && (s_more[i] & kMoreBit) != 0u;
 #pragma unroll
                         for (int j = 0; j < kNNK; ++j) s_nn[i * kNNK + j] = j < kept ? e[j] : nn_none();
-                        if (kept == 0 && s_more[i]) s_resc[atomicAdd(&s_rcount, 1)] = i;
+                        if (dry) {
+                            s_nn[i * kNNK] = nn_bound(last_removed);
+                            s_more[i] = kMoreBit | kDryBit;
+                            s_dryq[atomicAdd(&s_qtail, 1) % qcap] = i;
+                        }
                     }
                 }
             }
@@ -457,7 +801,6 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
             }
         }
         __syncthreads();
-        const long long t3 = timed ? clock64() : 0;
         {
             uint64_t bu = s_up[0], br = s_ur[0];
 #pragma unroll
@@ -474,178 +817,241 @@ __global__ void __launch_bounds__(kT, 1) merge_loop_kernel(LoopState st, LoopPar
                 s_bwin[1] = usize;
             }
         }
-        const int32_t R = s_rcount;
-        if (kReplica && tid == 1) {  // a is retired, b is about to carry the highest key: never partners again
+        if (kReplica && merged && tid == 1) {  // a is retired, b is about to carry the highest key: never partners again
             s_key[a] = -1;
             s_key[b] = -1;
         }
+        if (tid == 0 && s_qtail - s_qhead > qcap) s_err = 1;  // dry queue overflow (cannot happen)
         __syncthreads();
         pub_bslot = pub_bpack != kPackInf ? s_bwin[0] : -1;
         pub_bsize = pub_bpack != kPackInf ? s_bwin[1] : 0;
+        const long long t4 = timed ? clock64() : 0;
 
-        // ====== owner rescans: whole rows of the own slice whose cached partners have all died ======
-        const long long tr0 = (st.prof != nullptr && tid == 0 && R > 0) ? clock64() : 0;
-        for (int32_t ri = 0; ri < R; ++ri) {
-            const int32_t i = s_resc[ri];
-            const int32_t r = lo + i;
-            const int32_t kr = s_ks[i].x;
-            const float* row = dm + static_cast<int64_t>(r) * ld;
-            Cand2 c;
-            cand2_init(c);
-            constexpr int kU = kReplica ? 12 : 6;  // 16-byte row loads in flight per thread
-            const uint32_t ukr = static_cast<uint32_t>(kr);
-            for (int32_t base = 0; base < n4; base += kT * 4 * kU) {
-                float4 v[kU];
-                int4 kq[kReplica ? 1 : kU];
+        // ====== owner: fold the partial lists of the rows this block asked for ======
+        for (int32_t q = 0; q < nmine; ++q) {
+            const int32_t i = s_req_i[q];
+            const int32_t s = lo + i;
+            if (s == a || s == b) continue;  // block uniform; the slot's state is rebuilt by the next decision
+            if (warp < npw) {
+                const int g = warp * 32 + lane;
+                PartList in;
+                in.m = 0;
+                in.more = 0;
 #pragma unroll
-                for (int j = 0; j < kU; ++j) {
-                    const int32_t u0 = base + (j * kT + tid) * 4;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!kReplica) kq[j] = make_int4(-1, -1, -1, -1);
-                    if (u0 < n4) {
-                        v[j] = __ldcg(reinterpret_cast<const float4*>(row + u0));
-                        if (!kReplica) kq[j] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
-                    }
+                for (int j = 0; j < kNNK; ++j) {
+                    in.pk[j] = kPackInf;
+                    in.sl[j] = -1;
+                    in.sz[j] = 0;
                 }
-#pragma unroll
-                for (int j = 0; j < kU; ++j) {
-                    if (base + j * kT * 4 >= n4) break;  // block-uniform: nothing of this slab is inside the row
-                    const int32_t u0 = base + (j * kT + tid) * 4;
-                    int4 kj = make_int4(-1, -1, -1, -1);
-                    if (kReplica) {
-                        if (u0 < n4) kj = *reinterpret_cast<const int4*>(s_key + u0);
-                    } else {
-                        kj = kq[j];
+                if (g < G) {
+                    const uint4* prec = partials + (((static_cast<size_t>(blk) * 2 + par) * kReqPerBlock + q) * G + g) * kRecU4;
+                    uint4 e0, e1, e2, e3, z0, z1;
+                    uint32_t spins = 0;
+                    for (;;) {
+                        e0 = ld_volatile_u4(prec + 0);
+                        e1 = ld_volatile_u4(prec + 1);
+                        e2 = ld_volatile_u4(prec + 2);
+                        e3 = ld_volatile_u4(prec + 3);
+                        z0 = ld_volatile_u4(prec + 4);
+                        z1 = ld_volatile_u4(prec + 5);
+                        if (e0.w == tag && e1.w == tag && e2.w == tag && e3.w == tag && z0.w == tag && z1.w == tag) break;
+                        if (++spins > kSpinLimit) __trap();
                     }
-                    const uint32_t ks4[4] = {static_cast<uint32_t>(kj.x), static_cast<uint32_t>(kj.y),
-                                             static_cast<uint32_t>(kj.z), static_cast<uint32_t>(kj.w)};
-                    const uint32_t vs4[4] = {__float_as_uint(v[j].x), __float_as_uint(v[j].y), __float_as_uint(v[j].z),
-                                             __float_as_uint(v[j].w)};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int32_t u = u0 + e;
-                        const uint32_t ku = ks4[e];  // retired slots hold -1 == 0xFFFFFFFF: never below kr
-                        bool ok = ku < ukr && vs4[e] < kMaxFloatBits;
-                        // without the replica the four slots in flux are excluded by index: a and prev_a
-                        // are retired, b and prev_b carry the two highest keys
-                        if (!kReplica) ok = ok && u != a && u != b && u != prev_a && u != prev_b;
-                        if (ok) cand2_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ku, u);
-                    }
+                    in.m = static_cast<int32_t>(z1.z);
+                    in.more = static_cast<int32_t>(z1.y);
+                    in.pk[0] = (static_cast<uint64_t>(e0.y) << 32) | e0.x;
+                    in.pk[1] = (static_cast<uint64_t>(e1.y) << 32) | e1.x;
+                    in.pk[2] = (static_cast<uint64_t>(e2.y) << 32) | e2.x;
+                    in.pk[3] = (static_cast<uint64_t>(e3.y) << 32) | e3.x;
+                    in.sl[0] = static_cast<int32_t>(e0.z);
+                    in.sl[1] = static_cast<int32_t>(e1.z);
+                    in.sl[2] = static_cast<int32_t>(e2.z);
+                    in.sl[3] = static_cast<int32_t>(e3.z);
+                    in.sz[0] = static_cast<int32_t>(z0.x);
+                    in.sz[1] = static_cast<int32_t>(z0.y);
+                    in.sz[2] = static_cast<int32_t>(z0.z);
+                    in.sz[3] = static_cast<int32_t>(z1.x);
                 }
+                PartList out;
+                warp_merge_lists(in, out);
+                if (lane == 0) s_wl[warp] = out;
             }
-            bool more = false;
-            const int m = block_select_topk<kT>(c, s_topk, more);
-            if (tid < kNNK) {  // sizes of the listed partners: one round trip
-                uint4 nr = nn_none();
-                if (tid < m) {
-                    const uint64_t p = s_topk.pack[tid];
-                    const int32_t ws = s_topk.slot[tid];
-                    const int32_t wsz = __ldcg(st.ks + ws).y;
-                    nr = make_uint4(pack_key(p), static_cast<uint32_t>(p >> 32), static_cast<uint32_t>(ws),
-                                    static_cast<uint32_t>(wsz));
+            __syncthreads();
+            if (tid == 0) {  // merge the per-warp lists with the same cut rule
+                int ptr[kW];
+                for (int w = 0; w < npw; ++w) ptr[w] = 0;
+                int m = 0;
+                bool cut = false;
+                for (int r = 0; r < kNNK && !cut; ++r) {
+                    int bw = -1;
+                    uint64_t bp = kPackInf;
+                    for (int w = 0; w < npw; ++w)
+                        if (ptr[w] < s_wl[w].m && s_wl[w].pk[ptr[w]] < bp) {
+                            bp = s_wl[w].pk[ptr[w]];
+                            bw = w;
+                        }
+                    if (bw < 0) break;
+                    const int p = ptr[bw]++;
+                    s_nn[i * kNNK + r] = make_uint4(pack_key(bp), static_cast<uint32_t>(bp >> 32),
+                                                    static_cast<uint32_t>(s_wl[bw].sl[p]), static_cast<uint32_t>(s_wl[bw].sz[p]));
+                    m = r + 1;
+                    cut = ptr[bw] == s_wl[bw].m && s_wl[bw].more != 0;
                 }
-                s_nn[i * kNNK + tid] = nr;
-                if (tid == 0) s_more[i] = more ? 1 : 0;
+                bool more = false;
+                for (int w = 0; w < npw; ++w) more = more || ptr[w] < s_wl[w].m || s_wl[w].more != 0;
+                for (int r = m; r < kNNK; ++r) s_nn[i * kNNK + r] = nn_none();
+                s_more[i] = more ? kMoreBit : 0u;  // fresh again (an empty list without `more`: no partner left)
+                ++my_rescans;
             }
             __syncthreads();
         }
-        if (st.prof != nullptr && tid == 0 && R > 0) my_rescan_cycles += clock64() - tr0;
         if (tid == 0) {
-            my_rescans += R;
-            s_rcount = 0;
+            s_nreq = 0;
+            s_nmine = 0;
         }
-        const long long t4 = timed ? clock64() : 0;
+        const long long t5 = timed ? clock64() : 0;
 
         // remember the merge; its bookkeeping is applied after the next exchange
-        pending = true;
-        pa = a;
-        pb = b;
-        p_snew = snew;
-        p_keyhi = static_cast<int32_t>(pack_key(gt.m1));
-        p_keylo = static_cast<int32_t>(key_lo);
-        p_dist = dab;
-        p_second = static_cast<uint32_t>(gt.m2 >> 32);
-        ++t;
-        ++launched;
-        --n_live;
+        if (merged) {
+            pending = true;
+            pa = a;
+            pb = b;
+            p_snew = snew;
+            p_keyhi = static_cast<int32_t>(pack_key(gt.m1));
+            p_keylo = static_cast<int32_t>(key_lo);
+            p_dist = dab;
+            p_second = static_cast<uint32_t>(gt.m2 >> 32);
+            ++t;
+            ++launched;
+            --n_live;
+            bubbles_in_a_row = 0;
+        } else {
+            pub_bpack = kPackInf;
+            pub_bslot = -1;
+            pub_bsize = 0;
+            pub_brun = kInfBits;
+            ++n_bubbles;
+            ++bubbles_in_a_row;
+        }
         ++epoch;
         if (timed) {
             c_pub += t1 - t0;
-            c_poll += t2 - t1;
-            c_upd += t3 - t2;
-            c_resc += t4 - t3;
-            c_fold += clock64() - t4;
+            c_exch += t2 - t1;
+            c_scan += t3 - t2;
+            c_upd += t4 - t3;
+            c_fold += t5 - t4;
         }
     }
     if (timed) {
         st.prof[0] = c_pub;
-        st.prof[1] = c_poll;
+        st.prof[1] = c_exch;
         st.prof[2] = c_upd;
-        st.prof[3] = c_resc;
+        st.prof[3] = c_scan;
         st.prof[4] = c_fold;
         st.prof[5] = launched;
+        st.prof[6] = epoch;
     }
     // the partner lists live in shared memory during the loop: write the slice back for resume / read-back
     __syncthreads();
     for (int32_t i = tid; i < cnt * kNNK; i += kT) st.nn[static_cast<int64_t>(lo) * kNNK + i] = s_nn[i];
-    for (int32_t i = tid; i < cnt; i += kT) st.nn_more[lo + i] = s_more[i];
-    if (tid == 0 && my_rescans > 0) atomicAdd(st.ctl + CTL_RESCANS, my_rescans);
-    if (st.prof != nullptr && tid == 0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(st.prof + 8), static_cast<unsigned long long>(my_rescan_cycles));
+    for (int32_t i = tid; i < cnt; i += kT) st.nn_more[lo + i] = static_cast<int32_t>(s_more[i] & (kMoreBit | kDryBit));
+    if (tid == 0 && my_rescans > 0) atomicAdd(ctl + CTL_RESCANS, my_rescans);
+    if (tid == 0 && s_err) atomicExch(ctl + CTL_ERROR, 1);
     if (blk == 0 && tid == 0) {
-        st.ctl[CTL_N_LIVE] = n_live;
-        st.ctl[CTL_N_MERGES] = t;
-        st.ctl[CTL_EXHAUSTED] = exhausted;
-        st.ctl[CTL_DONE] = 1;
+        ctl[CTL_N_LIVE] = n_live;
+        ctl[CTL_N_MERGES] = t;
+        ctl[CTL_EXHAUSTED] = stop_reason == STOP_EXHAUSTED ? 1 : 0;
+        ctl[CTL_BUBBLES] = ctl[CTL_BUBBLES] + n_bubbles;
+        ctl[CTL_STOP] = stop_reason;
+        if (stop_reason == STOP_ERROR) ctl[CTL_ERROR] = 2;
+        __threadfence();
+        ctl[CTL_DONE] = 1;
     }
 }
 
-int merge_loop_threads(int64_t n, int num_sms) {
-    (void)n;
-    (void)num_sms;
-    return 512;
+// ---- rank barrier: the P single-GPU processes line up before they start talking -------------------------
+__global__ void rank_barrier_kernel(void* b0, void* b1, void* b2, void* b3, void* b4, void* b5, void* b6, void* b7,
+                                    int n_ranks, int rank, unsigned long long seq) {
+    void* boxes[kMaxRanks] = {b0, b1, b2, b3, b4, b5, b6, b7};
+    const int q = threadIdx.x;
+    if (q >= n_ranks) return;
+    unsigned long long* theirs = static_cast<unsigned long long*>(boxes[q]) + rank;  // my flag in rank q's box
+    const unsigned long long* mine = static_cast<const unsigned long long*>(boxes[rank]) + q;
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(seq) : "memory");
+    unsigned long long seen = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= seq) break;
+        if (spins > (1u << 26)) __trap();  // a missing peer must not hang the GPU box
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
+cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s) {
+    void* b[kMaxRanks];
+    for (int i = 0; i < kMaxRanks; ++i) b[i] = i < n_ranks ? rankbox[i] : nullptr;
+    rank_barrier_kernel<<<1, 32, 0, s>>>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], n_ranks, rank,
+                                         static_cast<unsigned long long>(seq));
+    return cudaGetLastError();
 }
 
 namespace {
-template <int kT, bool kReplica>
+template <bool kReplica, bool kMulti>
 cudaError_t prepare(size_t smem, int* per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(merge_loop_kernel<kT, kReplica>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(merge_loop_kernel<kReplica, kMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, merge_loop_kernel<kT, kReplica>, kT, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, merge_loop_kernel<kReplica, kMulti>, kT, smem);
 }
-template <int kT, bool kReplica>
+template <bool kReplica, bool kMulti>
 cudaError_t launch(void** args, int grid, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(merge_loop_kernel<kT, kReplica>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(merge_loop_kernel<kReplica, kMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // cooperative launch: guarantees that all blocks are resident at once (they wait on one another)
-    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(merge_loop_kernel<kT, kReplica>), dim3(grid), dim3(kT),
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(merge_loop_kernel<kReplica, kMulti>), dim3(grid), dim3(kT),
                                        args, smem, s);
 }
 }  // namespace
 
-cudaError_t merge_loop_max_grid(int threads, int num_sms, int64_t n, int* grid) {
-    int per_sm = 0;
-    const size_t smem = merge_loop_smem_bytes(n, num_sms);
-    const bool rep = merge_loop_uses_replica(n);
-    cudaError_t e = threads == 256 ? (rep ? prepare<256, true>(smem, &per_sm) : prepare<256, false>(smem, &per_sm))
-                                   : (rep ? prepare<512, true>(smem, &per_sm) : prepare<512, false>(smem, &per_sm));
-    if (e != cudaSuccess) return e;
-    *grid = per_sm > 0 ? num_sms : 0;  // one CTA per SM
-    if (2 * ((*grid + 31) / 32) > threads / 32 || *grid > threads) *grid = 0;  // one lane per record, one thread per reader
+cudaError_t merge_loop_grid(int num_sms, int64_t n, int n_ranks, int n_local, int want_blocks, bool rep,
+                            int* blocks_per_rank) {
+    *blocks_per_rank = 0;
+    if (n_ranks < 1 || n_ranks > kMaxRanks || n_local < 1 || n_local > n_ranks) return cudaErrorInvalidValue;
+    const int64_t C = (n + n_ranks - 1) / n_ranks;
+    // the exchange costs grow with the number of blocks: small problems use fewer
+    int64_t G = want_blocks > 0 ? want_blocks : (C + 127) / 128;
+    const int64_t cap = num_sms / n_local;  // one CTA per SM, all resident
+    if (G > cap) G = cap;
+    if (G > kMaxBlocks) G = kMaxBlocks;
+    if (G < 1) G = 1;
+    for (;;) {  // the slice state must fit one SM's shared memory
+        int per_sm = 0;
+        const size_t smem = merge_loop_smem_bytes(n, n_ranks, static_cast<int>(G), rep);
+        const bool multi = n_ranks > 1;
+        cudaError_t e = rep ? (multi ? prepare<true, true>(smem, &per_sm) : prepare<true, false>(smem, &per_sm))
+                            : (multi ? prepare<false, true>(smem, &per_sm) : prepare<false, false>(smem, &per_sm));
+        if (e == cudaSuccess && per_sm > 0) break;
+        if (e != cudaSuccess && e != cudaErrorInvalidValue) return e;
+        (void)cudaGetLastError();
+        if (G >= cap || G >= kMaxBlocks) return cudaSuccess;  // does not fit: *blocks_per_rank stays 0
+        G = G * 2 < cap ? G * 2 : cap;
+    }
+    *blocks_per_rank = static_cast<int>(G);
     return cudaSuccess;
 }
 
-cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int grid, int threads, cudaStream_t s) {
-    if (grid <= 0) return cudaErrorInvalidConfiguration;
+cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int blocks_per_rank, bool rep, cudaStream_t s) {
+    if (blocks_per_rank <= 0 || blocks_per_rank > kMaxBlocks) return cudaErrorInvalidConfiguration;
     LoopState st_copy = st;
     LoopParams p_copy = p;
     void* args[] = {&st_copy, &p_copy};
-    const size_t smem = merge_loop_smem_bytes(st.n, grid);
-    const bool rep = merge_loop_uses_replica(st.n);
-    if (threads == 256) return rep ? launch<256, true>(args, grid, smem, s) : launch<256, false>(args, grid, smem, s);
-    return rep ? launch<512, true>(args, grid, smem, s) : launch<512, false>(args, grid, smem, s);
+    const size_t smem = merge_loop_smem_bytes(st.n, st.n_ranks, blocks_per_rank, rep);
+    const bool multi = st.n_ranks > 1;
+    const int grid = blocks_per_rank * st.n_local;
+    if (rep) return multi ? launch<true, true>(args, grid, smem, s) : launch<true, false>(args, grid, smem, s);
+    return multi ? launch<false, true>(args, grid, smem, s) : launch<false, false>(args, grid, smem, s);
 }
 
 }  // namespace ic

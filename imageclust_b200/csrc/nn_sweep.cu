@@ -26,11 +26,13 @@ IC_DEVINL void consider(Cand2& c, float v, uint32_t col) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(kSweepThreads) nn_sweep_kernel(const float* __restrict__ dm, int64_t n, int64_t ld,
-                                                                 SlotNN* __restrict__ nn, int32_t* __restrict__ nn_more) {
-    // long rows first: the triangle's big rows start while the short ones fill the tail
-    const int64_t s = n - 1 - static_cast<int64_t>(blockIdx.x);
-    const float* row = dm + s * ld;
+__global__ void __launch_bounds__(kSweepThreads) nn_sweep_kernel(const float* __restrict__ dm, int64_t row_begin,
+                                                                 int64_t row_end, int64_t ld, SlotNN* __restrict__ nn,
+                                                                 int32_t* __restrict__ nn_more) {
+    // dm holds the rows [row_begin, row_end).  Long rows first: the triangle's big rows start while the
+    // short ones fill the tail
+    const int64_t s = row_end - 1 - static_cast<int64_t>(blockIdx.x);
+    const float* row = dm + (s - row_begin) * ld;
     Cand2 c;
     cand2_init(c);
     const int64_t limit = s;  // partners are exactly the columns u < s
@@ -76,9 +78,11 @@ __global__ void __launch_bounds__(kSweepThreads) nn_sweep_kernel(const float* __
     if (threadIdx.x == 0) nn_more[s] = more ? 1 : 0;
 }
 
-cudaError_t launch_nn_sweep(const float* dm, int64_t n, int64_t ld, SlotNN* nn, int32_t* nn_more, cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    nn_sweep_kernel<<<static_cast<unsigned>(n), kSweepThreads, 0, s>>>(dm, n, ld, nn, nn_more);
+cudaError_t launch_nn_sweep(const float* dm, int64_t row_begin, int64_t row_end, int64_t ld, SlotNN* nn,
+                            int32_t* nn_more, cudaStream_t s) {
+    if (row_end <= row_begin) return cudaSuccess;
+    nn_sweep_kernel<<<static_cast<unsigned>(row_end - row_begin), kSweepThreads, 0, s>>>(dm, row_begin, row_end, ld, nn,
+                                                                                        nn_more);
     return cudaGetLastError();
 }
 

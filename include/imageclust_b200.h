@@ -81,7 +81,9 @@ const char *ic_last_error(const ic_ctx *ctx);
 void *ic_pinned_alloc(size_t bytes);
 void ic_pinned_free(void *p);
 /* knobs: "near_tie_tol" (float, default 1e-5), "center" (0/1, default 1),
- * "gram_mode" (IC_GRAM_*), "loop_threads" (0 = auto, 256, 512), "profile_loop", "verbose" */
+ * "gram_mode" (IC_GRAM_*), "loop_blocks" (merge-loop blocks per rank, 0 = auto),
+ * "virtual_ranks" (1..8: row-block shards emulated on ONE GPU by one cooperative launch --
+ * the same kernel path as the multi-GPU build, for tests), "profile_loop", "verbose" */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 
 /* ---- CalculateOptimalClusters, clustering.go:168-186 (host, exact) ---- */
@@ -121,6 +123,26 @@ int ic_run_resident(ic_ctx *ctx, int64_t min_size, int64_t max_size, int32_t *cl
 int ic_build_clusters(ic_ctx *ctx, int64_t min_size, int32_t *cluster_offsets, int32_t *members,
                       int32_t *n_clusters);
 
+/* ---- row-block sharding of ONE clustering across the GPUs of a box ----------
+ * (BASELINE north_star: "the distance matrix is row-block sharded across the 8 GPUs";
+ * the reference has no counterpart: its [][]float32 matrix lives in one process,
+ * clustering.go:61-73.)  One process per GPU; rank r keeps the rows of the slots
+ * [r*C, (r+1)*C), C = ceil(n / world), with all their columns.  Every rank makes the
+ * same calls with the same X, min/max; every rank gets the complete result.
+ *   ic_shard_init(ctx, rank, world)            before ic_load
+ *   ic_load(ctx, x, ...)                        the whole X on every rank (replicated, <= 2 GB)
+ *   ic_shard_export(ctx, blob)                  CUDA-IPC handles of my row block + rank mailbox
+ *   <host all-gathers the world blobs, rank order>   (torch.distributed / MPI / Go net: plumbing)
+ *   ic_shard_connect(ctx, blobs)                peer-maps the other ranks' row blocks over NVLink
+ *   ic_run_resident(...) / ic_merge_loop(...)   as on one GPU; the ranks' persistent kernels exchange
+ *                                               one 128-byte record per merge through peer memory
+ * ic_read_matrix / ic_set_matrix touch only the rows [row_begin,row_end) of ic_shard_rows. */
+#define IC_SHARD_HANDLE_BYTES 192
+int ic_shard_init(ic_ctx *ctx, int rank, int world);
+int ic_shard_export(ic_ctx *ctx, void *handle);
+int ic_shard_connect(ic_ctx *ctx, const void *handles);
+int ic_shard_rows(ic_ctx *ctx, int64_t *row_begin, int64_t *row_end);
+
 /* ---- inspection -------------------------------------------------------- */
 /* distance matrix by slot, host [n x n] row stride ld; dead slots hold stale values */
 int ic_read_matrix(ic_ctx *ctx, float *out_host, int64_t ld);
@@ -132,7 +154,8 @@ int ic_get_merge_trace(ic_ctx *ctx, int32_t *key_hi, int32_t *key_lo, float *dis
                        float *gap, int64_t capacity, int64_t *n_merges);
 int ic_get_stats(ic_ctx *ctx, ic_stats *stats);
 /* debug (option "profile_loop" = 1): SM cycles block 0 spent in each phase of the merge loop
- * {publish, exchange poll + fold, decision + update, rescans, tail, merges, 0, rescans, 0...} of the last launch */
+ * {publish, exchange poll + fold, decision + update, row scans, partial folds, merges, iterations, rescans,
+ *  0, bubbles ...} of the last launch */
 int ic_get_loop_profile(ic_ctx *ctx, int64_t *out16);
 
 /* microbenchmarks used by bench.py's roofline legs: one launch of the named

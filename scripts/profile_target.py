@@ -24,5 +24,5 @@ with clustering.Engine(0) as eng:
           f"nn {s['ms_nn_init']:.3f} loop {s['ms_loop']:.3f} ms  rescans={s['n_rescans']} near_ties={s['n_near_ties']}")
     p = eng.loop_profile()
     m = max(p["merges"], 1)
-    print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "big_rescans", "rescans", "rescan_cycles_all_blocks"))
-          + f" | rescans={p['rescans']} avg cycles per rescan={p['rescan_cycles_all_blocks'] / max(p['rescans'], 1):.0f}")
+    print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
+          + f" | iterations={p["iterations"]} rescans={p["rescans"]} bubbles={p["bubbles"]}")

@@ -259,3 +259,89 @@ def test_members_follow_the_reference_order(eng, oracle):
         eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
     for a, b in zip(res.clusters, golden_clusters(g)):
         assert a.tolist() == b.tolist()
+
+
+# ---- row-block sharding on ONE GPU: P virtual ranks in one cooperative launch -------------
+# The same kernel path as the multi-GPU build (two-level exchange, per-rank replicas of the slot
+# table, peer row pointers); only the peers' memory happens to be on the same device.
+
+@pytest.fixture
+def knobs(eng):
+    """Set merge-loop options for one test and restore the defaults afterwards."""
+    def set_(**kw):
+        for k, v in kw.items():
+            eng.set_option(k, v)
+    yield set_
+    for k in ("virtual_ranks", "loop_blocks", "no_replica"):
+        eng.set_option(k, 1 if k == "virtual_ranks" else 0)
+
+
+@pytest.mark.parametrize("name", SMALL_GOLDENS)
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+def test_virtual_shards_goldens_bit_exact(eng, oracle, knobs, name, ranks):
+    g = load_golden(name)
+    mn, mx = int(g["min_size"]), int(g["max_size"])
+    o = oracle.fast_cluster(g["x"], mn, mx, flags=LW_EAGER, init_matrix=g["init_matrix"])
+    knobs(virtual_ranks=ranks)
+    eng.load(g["x"])
+    eng.set_matrix(g["init_matrix"])
+    eng.nn_init()
+    eng.merge_loop(mn, mx)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(eng.build_clusters(mn), o.clusters)
+
+
+@pytest.mark.parametrize("n,d,mn,mx,ranks,blocks,no_replica", [
+    (3000, 64, 4, 12, 2, 0, 0), (3000, 64, 4, 12, 4, 8, 0), (3001, 64, 4, 12, 8, 3, 1), (5000, 32, 6, 8, 3, 16, 0),
+    (2500, 100, 1, 2500, 2, 5, 1), (3000, 64, 4, 12, 1, 7, 1), (4000, 24, 2, 6, 1, 148, 0)])
+def test_sharded_loop_replays_bit_exact(eng, oracle, knobs, n, d, mn, mx, ranks, blocks, no_replica):
+    """Tensor-core initial matrix -> sharded device loop (virtual ranks, forced block counts, keys streamed
+    from L2 instead of the shared-memory replica); the oracle replays the SAME matrix."""
+    x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=n + d)
+    knobs(virtual_ranks=ranks, loop_blocks=blocks, no_replica=no_replica)
+    eng.load(x)
+    eng.initial_distances(_lib.GRAM_TCGEN05_3XTF32, mx)
+    m0 = eng.read_matrix()
+    eng.nn_init()
+    eng.merge_loop(mn, mx)
+    o = oracle.fast_cluster(x, mn, mx, flags=LW_EAGER, init_matrix=m0)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(eng.build_clusters(mn), o.clusters)
+    key, size = eng.read_slots()
+    assert int((key >= 0).sum()) == o.n_final and int(size[key >= 0].sum()) == n
+
+
+def test_sharded_duplicates_many_dry_rows(eng, oracle, knobs):
+    """Dozens of rows lose all their cached partners at once (exact duplicates): their rescans are served
+    a few per iteration while lower bounds hold the merge back (bubbles), on 4 virtual ranks."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((400, 8)).astype(np.float32)
+    x[50:120] = x[7]
+    x[200:230] = x[9]
+    o = oracle.fast_cluster(x, 1, 6, flags=LW_EAGER)
+    knobs(virtual_ranks=4, loop_blocks=2)
+    eng.set_option("gram_mode", _lib.GRAM_EXACT_FP32)
+    try:
+        res = eng.cluster(x, 1, 6)
+    finally:
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(res.clusters, o.clusters)
+
+
+def test_sharded_staged_resume(eng, oracle, knobs):
+    x = synth.gaussian_mixture(700, 48, 3, 10, seed=34)
+    o = oracle.fast_cluster(x, 3, 10, flags=LW_EAGER)
+    knobs(virtual_ranks=2, loop_blocks=3)
+    eng.load(x)
+    eng.initial_distances(_lib.GRAM_EXACT_FP32, 10)
+    eng.nn_init()
+    for step in (1, 7, 100, 0, 13):
+        eng.merge_loop(3, 10, step)
+        hi, lo, d = eng.find_closest()
+        t = eng.stats()["n_merges"]
+        if t < o.n_merges:
+            assert (hi, lo) == (int(o.key_hi[t]), int(o.key_lo[t])) and np.float32(d) == o.dist[t]
+    eng.merge_loop(3, 10)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(eng.build_clusters(3), o.clusters)
