@@ -15,9 +15,12 @@ roofline the dominant kernel (the persistent merge loop, HBM-bound by design,
          latency-bound in practice) + the other kernels under "kernels"
 cpu_baseline  the CPU oracle (C restatement of the Go reference) on a bounded sample
 
-With --gpus N > 1 (torchrun) every rank clusters its own matrix of the same shape
-(weak scaling over independent clustering jobs; the row-block sharded path for one
-matrix across GPUs is not built yet -- see DESIGN.md section 7).
+With --gpus N > 1 (torchrun) the SAME clustering is row-block sharded over the N GPUs
+(BASELINE config "N=100,000 x 2048 on 1 x B200 vs 8 x B200 row-block sharded"): rank r keeps
+the rows of its slot block, the ranks' persistent kernels exchange one record per merge
+through peer-mapped memory over NVLink (imageclust_b200/sharding.py).
+Total work is fixed => "scaling": "strong".  --replicas runs N independent clusterings
+instead (one per GPU, "weak").
 """
 from __future__ import annotations
 
@@ -110,7 +113,8 @@ def workload(args):
 
 
 def make_matrix(args, n, d, mn, mx, rank, out):
-    seed = 20240 + ord(args.config) - ord("A") + 1000 * rank
+    # sharded run: every rank holds the same matrix; replicas: one matrix per rank
+    seed = 20240 + ord(args.config) - ord("A") + (1000 * rank if args.replicas else 0)
     if args.config == "E":
         out[:] = synth.combined_features(n, 2048, d - 2048, mn, mx, seed=seed)
     else:
@@ -191,6 +195,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=1500, help="sample size of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gram-mode", type=int, default=0)
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent clusterings instead of one sharded one")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,14 +216,21 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from imageclust_b200 import clustering
+    from imageclust_b200 import clustering, sharding
 
     n, d, mn, mx = workload(args)
     peaks = load_peaks()
     eng = clustering.Engine(local_rank)
     eng.set_option("gram_mode", args.gram_mode)
+    sharded = world > 1 and not args.replicas
     x_host = eng.pinned_empty((n, d))
     make_matrix(args, n, d, mn, mx, rank, x_host)
+    if sharded:
+        # one clustering over all ranks: the wrapper exchanges the CUDA-IPC handles once, everything
+        # else (load / run_resident / cluster) is the same call on every rank
+        runner = sharding.ShardedEngine(eng, rank, world)
+    else:
+        runner = eng
 
     def barrier():
         torch.cuda.synchronize()
@@ -234,17 +246,17 @@ def main():
         return float(t.item())
 
     # ---- resident leg: X in HBM before the timed region --------------------------------
-    eng.load(x_host)
+    runner.load(x_host)
     stats = []
     for _ in range(args.warmup):
-        eng.run_resident(mn, mx)
+        runner.run_resident(mn, mx)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = eng.run_resident(mn, mx)
+        r = runner.run_resident(mn, mx)
         stats.append(r.stats)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
@@ -253,12 +265,12 @@ def main():
 
     # ---- e2e leg: host buffers through the reference-facing call ---------------------------
     for _ in range(1):
-        eng.cluster(x_host, mn, mx)
+        runner.cluster(x_host, mn, mx)
     barrier()
     t0 = time.perf_counter()
     e2e_stats = []
     for _ in range(args.steps):
-        r = eng.cluster(x_host, mn, mx)
+        r = runner.cluster(x_host, mn, mx)
         e2e_stats.append(r.stats)
     barrier()
     e2e_dt = max_over_ranks(time.perf_counter() - t0)
@@ -266,7 +278,7 @@ def main():
 
     # ---- kernel microbenchmarks for the roofline legs (rank 0) ----------------------------
     kern = {}
-    if rank == 0:
+    if rank == 0 and not sharded:
         eng.load(x_host)
         if args.gram_mode == 0:
             kern["gram_ms"] = eng.time_kernel("gram", 3)
@@ -300,13 +312,16 @@ def main():
         dominant = max(("ms_loop", "ms_gram", "ms_nn_init", "ms_prep"), key=lambda k: phases[k])
         line = {
             "metric": METRIC, "value": sec_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": False, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.gram_mode else "tf32x3+f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": False,
+            "scaling": "strong" if sharded else "weak",
+            "vs_baseline": None, "dtype": "f32" if args.gram_mode else "tf32+f32", "data": "synthetic",
             "config": {"workload": f"config {args.config}: N={n} x {d} Gaussian-mixture fp32 embeddings, "
                                    f"minSize={mn}, maxSize={mx} -> {stats[-1]['n_target']} clusters, {merges} merges",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent clustering jobs (one per GPU)",
+                       "parallelism": "1 GPU" if world == 1 else (
+                           f"one clustering row-block sharded over {world} GPUs (peer-mapped rows + per-merge record "
+                           f"exchange over NVLink)" if sharded else f"{world} independent clustering jobs (one per GPU)"),
                        "l2": "inputs larger than L2 (X %.0f MB, distance matrix %.1f GB)" % (4e-6 * n * d, stats[-1]["matrix_bytes"] / 1e9),
-                       "gram": "tcgen05 3xTF32" if args.gram_mode == 0 else "exact fp32 SIMT"},
+                       "gram": "tcgen05 kind::tf32, exact fixed-point slice + residual (4 products)" if args.gram_mode == 0 else "exact fp32 SIMT"},
             "merges_per_s": merges / (ms_loop * 1e-3) if ms_loop > 0 else None,
             "dist_matrix_gbs": 4.0 * pairs / (ms_gram * 1e-3) / 1e9 if ms_gram > 0 else None,
             "phases_ms": phases,
@@ -320,14 +335,16 @@ def main():
             "roofline": {"kernel": "merge_loop_kernel (K3, persistent)", "bound": "hbm", "achieved": loop_gbs,
                          "peak": hbm, "unit": "GB/s", "frac": loop_gbs / hbm, "traffic": None,
                          "peak_source": peaks["source"] + " copy bandwidth",
-                         "note": "algorithmic bytes 12*n per merge; the loop is bound by 2 grid barriers per merge "
-                                 "(merges_per_s), not by bandwidth", "dominant_phase": dominant},
-            "kernels": {
+                         "note": "algorithmic bytes 12*n per merge; the loop is a chain of dependent merges bound by one "
+                                 "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth",
+                         "dominant_phase": dominant},
+            "kernels": None if sharded else {
                 "gram_tcgen05" if args.gram_mode == 0 else "gram_exact": {
                     "bound": "tensor", "achieved": gram_tf, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": gram_tf / tf32_peak, "ms": kern.get("gram_ms"),
-                    "note": "algorithmic flops 2*D per unordered pair; the 3xTF32 split issues 3x that on the pipe; "
-                            "peak = measured sustained bf16 / 2 (TF32 dense)"},
+                    "note": "algorithmic flops 2*D per unordered pair; the exact-slice split issues 4 tcgen05.mma "
+                            "kind::tf32 per k-step (4x the algorithmic flops on the pipe); peak = measured sustained "
+                            "bf16 / 2 (TF32 dense)"},
                 "nn_sweep": {"bound": "hbm", "achieved": sweep_gbs, "peak": hbm, "unit": "GB/s", "frac": sweep_gbs / hbm,
                              "ms": kern.get("nn_sweep_ms"), "note": "algorithmic bytes 4 per pair (lower triangle read once)"},
             },

@@ -253,7 +253,8 @@ class Engine:
         out = (C.c_int64 * 16)()
         self._check(self._L.ic_get_loop_profile(self._h, out))
         return dict(zip(("publish", "exchange", "update", "scan", "fold", "merges", "iterations", "rescans",
-                         "reserved", "bubbles"), list(out)))
+                         "reserved", "bubbles", "pub_argmin", "pub_reduce", "pub_fence", "pub_stores", "exch_poll",
+                         "exch_spare"), list(out)))
 
     # -- row-block sharding over several GPUs: one process (and Engine) per GPU ------------------
     def shard_init(self, rank: int, world: int):

@@ -296,6 +296,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
 
     const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long c_pub = 0, c_exch = 0, c_scan = 0, c_upd = 0, c_fold = 0;
+    long long c_sub[6] = {0, 0, 0, 0, 0, 0};  // publish: argmin, reduce, fence, stores; exchange: poll, fold
     uint32_t epoch = 0;  // iteration index; records of iteration i carry tag (gen, i+1)
     const uint32_t tagbase = st.gen << 20;
 
@@ -344,6 +345,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                                       static_cast<uint32_t>(i1 >= 0 ? lo + i1 : -1), tag);
                 s_pub[6] = make_uint4(static_cast<uint32_t>(i1 >= 0 ? s_ks[i1].x : -1), 0u, 0u, tag);
             }
+            const long long ta = timed ? clock64() : 0;
             const Top2 wt = warp_top2(top);
             if (lane == 0) {
                 s_m1[warp] = wt.m1;
@@ -364,11 +366,20 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                 s_pub[4] = make_uint4(static_cast<uint32_t>(pub_bsize), pub_brun, 0u, tag);
             }
             __syncthreads();
+            const long long tb = timed ? clock64() : 0;
+            long long tc = 0;
             if (tid < G) {  // push to reader `tid`
                 uint4* rec = records + ((static_cast<size_t>(tid) * 2 + par) * G + blk) * kRecU4;
                 fence_acq_rel<kMulti>();  // release: the block's stores (ordered by the bar.sync above) before the record
+                tc = timed ? clock64() : 0;
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) st_volatile_u4(rec + c, s_pub[c]);
+            }
+            if (timed) {
+                c_sub[0] += ta - t0;
+                c_sub[1] += tb - ta;
+                c_sub[2] += tc - tb;
+                c_sub[3] += clock64() - tc;
             }
         }
         const long long t1 = timed ? clock64() : 0;
@@ -393,6 +404,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     }
                     ft.m1 = (static_cast<uint64_t>(r0.y) << 32) | r0.x;
                     ft.m2 = (static_cast<uint64_t>(r0.z) << 32) | 0xFFFFFFFFull;  // only its distance matters
+                    if (timed) c_sub[4] += clock64() - t1;
                     fence_acq_rel<kMulti>();  // acquire: everything published before that record
                 }
                 const uint64_t mine = ft.m1;
@@ -950,6 +962,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         st.prof[4] = c_fold;
         st.prof[5] = launched;
         st.prof[6] = epoch;
+        for (int i = 0; i < 6; ++i) st.prof[10 + i] = c_sub[i];
     }
     // the partner lists live in shared memory during the loop: write the slice back for resume / read-back
     __syncthreads();

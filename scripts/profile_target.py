@@ -22,6 +22,9 @@ with clustering.Engine(0) as eng:
     s = r.stats
     print(f"config {cfg} N={n} D={d}: merges={s['n_merges']} out={s['n_out']} prep {s['ms_prep']:.3f} gram {s['ms_gram']:.3f} "
           f"nn {s['ms_nn_init']:.3f} loop {s['ms_loop']:.3f} ms  rescans={s['n_rescans']} near_ties={s['n_near_ties']}")
+    import hashlib
+    tr = eng.merge_trace()
+    print("trace_sha=" + hashlib.sha256(tr.key_hi.tobytes() + tr.key_lo.tobytes() + tr.dist.tobytes()).hexdigest()[:12])
     p = eng.loop_profile()
     m = max(p["merges"], 1)
     print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
