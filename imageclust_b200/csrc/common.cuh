@@ -28,10 +28,14 @@ IC_DEVINL bool pack_selectable(uint64_t p) { return static_cast<uint32_t>(p >> 3
 
 IC_DEVINL uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
+// warp-wide minimum of a u64 with two redux.sync.min.u32: high words first, then the low words of the
+// lanes that hold the minimal high word (a shuffle butterfly costs 10 shuffles and 5 dependent steps)
 IC_DEVINL uint64_t warp_min_u64(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = umin64(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const uint32_t hi = static_cast<uint32_t>(v >> 32);
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t lo = hi == mh ? static_cast<uint32_t>(v) : 0xFFFFFFFFu;
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, lo);
+    return (static_cast<uint64_t>(mh) << 32) | ml;
 }
 
 // canonical non-negative distance: NaN -> +inf (never selectable, like the reference's
@@ -59,14 +63,13 @@ IC_DEVINL void top2_merge(Top2& t, uint64_t o1, uint64_t o2) {
     t.m2 = umin64(hi, umin64(t.m2, o2));
     t.m1 = lo;
 }
+// warp-wide two smallest of every lane's two smallest (m1 values are unique unless kPackInf): the runner-up is
+// the winner lane's second or another lane's first
 IC_DEVINL Top2 warp_top2(Top2 t) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint64_t o1 = __shfl_xor_sync(0xffffffffu, t.m1, o);
-        const uint64_t o2 = __shfl_xor_sync(0xffffffffu, t.m2, o);
-        top2_merge(t, o1, o2);
-    }
-    return t;
+    Top2 r;
+    r.m1 = warp_min_u64(t.m1);
+    r.m2 = warp_min_u64(t.m1 == r.m1 ? t.m2 : t.m1);
+    return r;
 }
 
 // ---- per-row partner lists ----------------------------------------------------------------

@@ -35,6 +35,8 @@
 //     is only taken when the minimum is an exact candidate below every bound, so the merge
 //     sequence is exactly the sequential one.
 // HBM roofline: algorithmic bytes = 12*n per merge; reported as merges/s too.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -56,13 +58,13 @@ constexpr int kRankboxFlagBytes = 256;
 //   c1 {row slot a, partner slot b, size a, tag}
 //   c2 {size b, partner key, 1 if the candidate is only a lower bound, tag}
 //   c3 {key of k, dist bits, slot k, tag}                   best entry of the new row in this slice
-//   c4 {size k, runner bits, 0, tag}
-//   c5 {request 0 row, request 0 key, request 1 row, tag}   rows of this slice to rescan (-1: none)
-//   c6 {request 1 key, 0, 0, tag}
+//   c4 {size k, runner bits, number of requests, tag}
+//   c5 {request 0 row, request 0 key, request 1 row, tag}   rows of this slice to rescan (-1: none);
+//   c6 {request 1 key, 0, 0, tag}                           c5, c6 are only written when there are requests
 constexpr int kChunks = 7;
 
 // partial record (one per request and scanning block): c0..c3 {partner key, dist bits, slot, tag},
-// c4 {size 0, size 1, size 2, tag}, c5 {size 3, more, count, tag}
+// c4 {count, more, 0, tag}; the owner looks the partners' sizes up when it folds the lists
 
 
 IC_DEVINL uint4 ld_volatile_u4(const uint4* p) {
@@ -117,6 +119,64 @@ struct PartList {  // a sorted partner list under construction
 template <typename T>
 IC_DEVINL T sel4(const T (&v)[kNNK], int i) {
     return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
+}
+
+// Per-lane state of a row scan: the two smallest candidates and whether the lane may have passed over others.
+// Elements are pre-filtered on their distance bits alone (one compare); only the rare survivor pays for the key /
+// liveness tests, so `extra` is conservative: a passed-over element counts as a possible candidate.  That only
+// ever shortens the exact list (see the cut rule below) -- it never admits a wrong entry.
+struct ScanCand {
+    uint64_t c1, c2;
+    int32_t s1, s2;
+    bool extra;
+};
+IC_DEVINL void scan_init(ScanCand& c) {
+    c.c1 = c.c2 = kPackInf;
+    c.s1 = c.s2 = -1;
+    c.extra = false;
+}
+IC_DEVINL void scan_insert(ScanCand& c, uint64_t p, int32_t slot) {
+    if (p < c.c2) {
+        if (c.c2 != kPackInf) c.extra = true;  // the old second is passed over
+        if (p < c.c1) {
+            c.c2 = c.c1;
+            c.s2 = c.s1;
+            c.c1 = p;
+            c.s1 = slot;
+        } else {
+            c.c2 = p;
+            c.s2 = slot;
+        }
+    } else {
+        c.extra = true;
+    }
+}
+// Warp-wide selection of the (up to) kNNK smallest candidates from every lane's two smallest.  EXACT: the list
+// is cut right after an entry that was a lane's second smallest while that lane may have passed over others.
+IC_DEVINL int warp_select_scan(const ScanCand& c, uint64_t (&pk)[kNNK], int32_t (&sl)[kNNK], bool& more) {
+    int taken = 0, m = 0;
+#pragma unroll
+    for (int r = 0; r < kNNK; ++r) {
+        pk[r] = kPackInf;
+        sl[r] = -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kNNK; ++r) {
+        const uint64_t cand = taken == 0 ? c.c1 : (taken == 1 ? c.c2 : kPackInf);
+        const uint64_t wm = warp_min_u64(cand);
+        if (wm == kPackInf) break;  // warp uniform
+        const bool win = cand == wm;  // packs are unique: exactly one lane
+        const int src = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+        const int32_t myslot = taken == 0 ? c.s1 : c.s2;
+        pk[r] = wm;
+        sl[r] = __shfl_sync(0xffffffffu, myslot, src);
+        if (win) ++taken;
+        m = r + 1;
+        if (__ballot_sync(0xffffffffu, win && taken == 2 && c.extra)) break;
+    }
+    const int held = (c.c1 != kPackInf ? 1 : 0) + (c.c2 != kPackInf ? 1 : 0);
+    more = __any_sync(0xffffffffu, taken < held || c.extra);
+    return m;
 }
 
 // Warp-wide selection of the (up to) kNNK smallest candidates from every lane's two smallest.
@@ -251,18 +311,21 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     __shared__ Decision s_pdec[kW];
     __shared__ NewRow s_pnew[kW];
     __shared__ uint4 s_pub[kChunks];
-    __shared__ int32_t s_bwin[2];
+    __shared__ uint4 s_wpay[kW];   // per warp: payload of its best candidate {a, b, size a << 1 | bound, size b}
+    __shared__ uint32_t s_wkey[kW];  //           and the partner's key
+    __shared__ int2 s_uwin[kW];    // per warp: {slot, size} of its best entry of the new row
     __shared__ int32_t s_qhead, s_qtail;        // dry-row queue of this slice
-    __shared__ int32_t s_nmine, s_req_i[kReqPerBlock];  // requests this block published in this iteration
+    __shared__ int32_t s_nmine[2], s_req_i[2][kReqPerBlock];  // requests this block published, by epoch parity
     __shared__ int32_t s_nreq;                  // requests of the whole rank in this iteration
     __shared__ int4 s_rlist[kMaxReqTotal];      // {row, row key, owner block, request index}
     __shared__ PartList s_wl[kW];
     __shared__ int32_t s_err;
+    __shared__ int32_t s_uwork;  // next unprocessed slot of the update pass
 
     if (tid == 0) {
         s_qhead = 0;
         s_qtail = 0;
-        s_nmine = 0;
+        s_nmine[0] = s_nmine[1] = 0;
         s_nreq = 0;
         s_err = 0;
     }
@@ -288,10 +351,10 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     int32_t pa = -1, pb = -1, p_snew = 0, p_keyhi = 0, p_keylo = 0;
     float p_dist = 0.0f;
     uint32_t p_second = kInfBits;  // runner-up among the candidates when the pending merge was picked
-    // this block's part of the freshly written row (B-part of the record it publishes)
-    uint64_t pub_bpack = kPackInf;
-    int32_t pub_bslot = -1, pub_bsize = 0;
-    uint32_t pub_brun = kInfBits;
+    if (tid < kW) {  // this block's part of the freshly written row (B-part of the record): none yet
+        s_up[tid] = kPackInf;
+        s_ur[tid] = kInfBits;
+    }
     __syncthreads();
 
     const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
@@ -336,10 +399,10 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     if (pending && (s == pa || s == pb)) continue;  // the row is gone / is being rebuilt
                     if (s_ks[i].x < 0 || (s_more[i] & (kDryBit | kReqBit)) != kDryBit) continue;
                     s_more[i] |= kReqBit;
-                    s_req_i[nreq++] = i;
+                    s_req_i[par][nreq++] = i;
                 }
-                s_nmine = nreq;
-                const int32_t i0 = nreq > 0 ? s_req_i[0] : -1, i1 = nreq > 1 ? s_req_i[1] : -1;
+                s_nmine[par] = nreq;
+                const int32_t i0 = nreq > 0 ? s_req_i[par][0] : -1, i1 = nreq > 1 ? s_req_i[par][1] : -1;
                 s_pub[5] = make_uint4(static_cast<uint32_t>(i0 >= 0 ? lo + i0 : -1),
                                       static_cast<uint32_t>(i0 >= 0 ? s_ks[i0].x : -1),
                                       static_cast<uint32_t>(i1 >= 0 ? lo + i1 : -1), tag);
@@ -347,33 +410,50 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             }
             const long long ta = timed ? clock64() : 0;
             const Top2 wt = warp_top2(top);
+            if (top.m1 == wt.m1 && wt.m1 != kPackInf)  // row keys are unique: exactly one lane of the warp
+                s_wpay[warp] = make_uint4(static_cast<uint32_t>(w_a), static_cast<uint32_t>(w_b),
+                                          (static_cast<uint32_t>(w_sa) << 1) | w_stale, static_cast<uint32_t>(w_sb));
+            if (top.m1 == wt.m1 && wt.m1 != kPackInf) s_wkey[warp] = w_pkey;
             if (lane == 0) {
                 s_m1[warp] = wt.m1;
                 s_m2[warp] = wt.m2;
             }
             __syncthreads();  // also: every global store of this iteration was issued before this point
-            Top2 bt = {s_m1[0], s_m2[0]};
-#pragma unroll
-            for (int w = 1; w < kW; ++w) top2_merge(bt, s_m1[w], s_m2[w]);
-            const bool none = bt.m1 == kPackInf;
-            if (none ? tid == 0 : top.m1 == bt.m1) {  // row keys are unique: exactly one thread
-                s_pub[0] = make_uint4(static_cast<uint32_t>(bt.m1), static_cast<uint32_t>(bt.m1 >> 32),
-                                      static_cast<uint32_t>(bt.m2 >> 32), tag);
-                s_pub[1] = make_uint4(static_cast<uint32_t>(w_a), static_cast<uint32_t>(w_b), static_cast<uint32_t>(w_sa), tag);
-                s_pub[2] = make_uint4(static_cast<uint32_t>(w_sb), w_pkey, w_stale, tag);
-                s_pub[3] = make_uint4(static_cast<uint32_t>(pub_bpack), static_cast<uint32_t>(pub_bpack >> 32),
-                                      static_cast<uint32_t>(pub_bslot), tag);
-                s_pub[4] = make_uint4(static_cast<uint32_t>(pub_bsize), pub_brun, 0u, tag);
+            if (warp == 0) {  // final fold of the kW warp results (A-part) and of the update pass's B-part
+                Top2 bt = {lane < kW ? s_m1[lane] : kPackInf, lane < kW ? s_m2[lane] : kPackInf};
+                const uint64_t mine = bt.m1;
+                bt = warp_top2(bt);
+                const int wwin = __ffs(__ballot_sync(0xffffffffu, mine == bt.m1 && mine != kPackInf)) - 1;
+                const uint64_t ub = lane < kW ? s_up[lane] : kPackInf;
+                const uint64_t bu = warp_min_u64(ub);
+                const uint64_t br = warp_min_u64(lane < kW ? s_ur[lane] : static_cast<uint64_t>(kInfBits));
+                const int uwin = __ffs(__ballot_sync(0xffffffffu, ub == bu && bu != kPackInf)) - 1;
+                if (lane == 0) {
+                    const uint4 pay = wwin >= 0 ? s_wpay[wwin] : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+                    const uint32_t pkey = wwin >= 0 ? s_wkey[wwin] : 0u;
+                    const int2 uw = uwin >= 0 ? s_uwin[uwin] : make_int2(-1, 0);
+                    s_pub[0] = make_uint4(static_cast<uint32_t>(bt.m1), static_cast<uint32_t>(bt.m1 >> 32),
+                                          static_cast<uint32_t>(bt.m2 >> 32), tag);
+                    s_pub[1] = make_uint4(pay.x, pay.y, pay.z >> 1, tag);
+                    s_pub[2] = make_uint4(pay.w, pkey, pay.z & 1u, tag);
+                    s_pub[3] = make_uint4(static_cast<uint32_t>(bu), static_cast<uint32_t>(bu >> 32),
+                                          static_cast<uint32_t>(uw.x), tag);
+                    s_pub[4] = make_uint4(static_cast<uint32_t>(uw.y), static_cast<uint32_t>(br),
+                                          static_cast<uint32_t>(s_nmine[par]), tag);
+                }
             }
+            // release: ONE thread fences (every store of the block was ordered before it by the bar.sync above,
+            // the pushes below are ordered after it by the next bar.sync -- the grid-barrier idiom); a fence per
+            // pushing warp serialises and cost 3x more
+            if (tid == kT - 1) fence_acq_rel<kMulti>();
             __syncthreads();
             const long long tb = timed ? clock64() : 0;
             long long tc = 0;
             if (tid < G) {  // push to reader `tid`
                 uint4* rec = records + ((static_cast<size_t>(tid) * 2 + par) * G + blk) * kRecU4;
-                fence_acq_rel<kMulti>();  // release: the block's stores (ordered by the bar.sync above) before the record
                 tc = timed ? clock64() : 0;
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) st_volatile_u4(rec + c, s_pub[c]);
+                const int nch = s_nmine[par] > 0 ? kChunks : kChunks - 2;  // the request chunks travel only when used
+                for (int c = 0; c < nch; ++c) st_volatile_u4(rec + c, s_pub[c]);
             }
             if (timed) {
                 c_sub[0] += ta - t0;
@@ -382,6 +462,91 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                 c_sub[3] += clock64() - tc;
             }
         }
+        // ====== owner: fold the partial lists of the rows this block asked for in the PREVIOUS iteration ======
+        // (their scans had a whole iteration to arrive; the rows stayed in the reduction with their bounds, and
+        //  this work overlaps the flight time of the records just pushed)
+        const long long tf0 = timed ? clock64() : 0;
+        const uint32_t ptag = tagbase | epoch, ppar = par ^ 1u;  // tag / parity of iteration epoch-1
+        const int32_t nprev = epoch > 0 ? s_nmine[ppar] : 0;
+        for (int32_t q = 0; q < nprev; ++q) {
+            const int32_t i = s_req_i[ppar][q];
+            const int32_t s = lo + i;
+            // merged away by the merge decided in that iteration (still pending here): the scanners skipped it
+            // and the slot's state is rebuilt by the next decision
+            if (pending && (s == pa || s == pb)) continue;  // block uniform
+            if (warp < npw) {
+                const int g = warp * 32 + lane;
+                PartList in;
+                in.m = 0;
+                in.more = 0;
+#pragma unroll
+                for (int j = 0; j < kNNK; ++j) {
+                    in.pk[j] = kPackInf;
+                    in.sl[j] = -1;
+                    in.sz[j] = 0;
+                }
+                if (g < G) {
+                    const uint4* prec = partials + (((static_cast<size_t>(blk) * 2 + ppar) * kReqPerBlock + q) * G + g) * kRecU4;
+                    uint4 e0, e1, e2, e3, z0;
+                    uint32_t spins = 0;
+                    for (;;) {
+                        e0 = ld_volatile_u4(prec + 0);
+                        e1 = ld_volatile_u4(prec + 1);
+                        e2 = ld_volatile_u4(prec + 2);
+                        e3 = ld_volatile_u4(prec + 3);
+                        z0 = ld_volatile_u4(prec + 4);
+                        if (e0.w == ptag && e1.w == ptag && e2.w == ptag && e3.w == ptag && z0.w == ptag) break;
+                        if (++spins > kSpinLimit) __trap();
+                    }
+                    in.m = static_cast<int32_t>(z0.x);
+                    in.more = static_cast<int32_t>(z0.y);
+                    in.pk[0] = (static_cast<uint64_t>(e0.y) << 32) | e0.x;
+                    in.pk[1] = (static_cast<uint64_t>(e1.y) << 32) | e1.x;
+                    in.pk[2] = (static_cast<uint64_t>(e2.y) << 32) | e2.x;
+                    in.pk[3] = (static_cast<uint64_t>(e3.y) << 32) | e3.x;
+                    in.sl[0] = static_cast<int32_t>(e0.z);
+                    in.sl[1] = static_cast<int32_t>(e1.z);
+                    in.sl[2] = static_cast<int32_t>(e2.z);
+                    in.sl[3] = static_cast<int32_t>(e3.z);
+                }
+                PartList out;
+                warp_merge_lists(in, out);
+                if (lane == 0) s_wl[warp] = out;
+            }
+            __syncthreads();
+            if (tid == 0) {  // merge the per-warp lists with the same cut rule
+                int ptr[kW];
+                for (int w = 0; w < npw; ++w) ptr[w] = 0;
+                int m = 0;
+                bool cut = false;
+                for (int r = 0; r < kNNK && !cut; ++r) {
+                    int bw = -1;
+                    uint64_t bp = kPackInf;
+                    for (int w = 0; w < npw; ++w)
+                        if (ptr[w] < s_wl[w].m && s_wl[w].pk[ptr[w]] < bp) {
+                            bp = s_wl[w].pk[ptr[w]];
+                            bw = w;
+                        }
+                    if (bw < 0) break;
+                    const int p = ptr[bw]++;
+                    s_nn[i * kNNK + r] = make_uint4(pack_key(bp), static_cast<uint32_t>(bp >> 32),
+                                                    static_cast<uint32_t>(s_wl[bw].sl[p]), static_cast<uint32_t>(s_wl[bw].sz[p]));
+                    m = r + 1;
+                    cut = ptr[bw] == s_wl[bw].m && s_wl[bw].more != 0;
+                }
+                bool more = false;
+                for (int w = 0; w < npw; ++w) more = more || ptr[w] < s_wl[w].m || s_wl[w].more != 0;
+                for (int r = m; r < kNNK; ++r) s_nn[i * kNNK + r] = nn_none();
+                s_more[i] = more ? kMoreBit : 0u;  // fresh again (an empty list without `more`: no partner left)
+                ++my_rescans;
+            }
+            __syncthreads();
+            if (tid < kNNK) {  // sizes of the listed partners (none of them is in flux): one L2 round trip, off the critical path
+                const uint4 q4 = s_nn[i * kNNK + tid];
+                if (q4.z != kNoPartner) s_nn[i * kNNK + tid].w = static_cast<uint32_t>(__ldcg(g_ks + q4.z).y);
+            }
+        }
+        const long long tfold = timed ? clock64() - tf0 : 0;
         const long long t1 = timed ? clock64() : 0;
 
         // ====== exchange: poll every block's record (one record per lane) and fold with shuffles ======
@@ -405,7 +570,6 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     ft.m1 = (static_cast<uint64_t>(r0.y) << 32) | r0.x;
                     ft.m2 = (static_cast<uint64_t>(r0.z) << 32) | 0xFFFFFFFFull;  // only its distance matters
                     if (timed) c_sub[4] += clock64() - t1;
-                    fence_acq_rel<kMulti>();  // acquire: everything published before that record
                 }
                 const uint64_t mine = ft.m1;
                 ft = warp_top2(ft);
@@ -447,7 +611,6 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     bslot = static_cast<int32_t>(r3.z);
                     bsize = static_cast<int32_t>(r4.x);
                     run = r4.y;
-                    fence_acq_rel<kMulti>();
                 }
                 const uint64_t wm = warp_min_u64(best);
 #pragma unroll
@@ -465,13 +628,20 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                 const int g = (warp - 2 * npw) * 32 + lane;
                 if (g < G) {
                     const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
-                    uint4 r5, r6;
+                    uint4 r4, r5 = make_uint4(0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u), r6 = make_uint4(0u, 0u, 0u, 0u);
                     uint32_t spins = 0;
                     for (;;) {
-                        r5 = ld_volatile_u4(rec + 5);
-                        r6 = ld_volatile_u4(rec + 6);
-                        if (r5.w == tag && r6.w == tag) break;
+                        r4 = ld_volatile_u4(rec + 4);
+                        if (r4.w == tag) break;
                         if (++spins > kSpinLimit) __trap();
+                    }
+                    if (r4.z != 0u) {
+                        for (;;) {
+                            r5 = ld_volatile_u4(rec + 5);
+                            r6 = ld_volatile_u4(rec + 6);
+                            if (r5.w == tag && r6.w == tag) break;
+                            if (++spins > kSpinLimit) __trap();
+                        }
                     }
                     if (static_cast<int32_t>(r5.x) >= 0)
                         s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.x), static_cast<int32_t>(r5.y), g, 0);
@@ -480,6 +650,9 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                 }
             }
             __syncthreads();
+            // acquire: one thread fences after ALL polls of the block completed (ordered by the bar.sync above); the
+            // data reads of this iteration come after the bar.sync below
+            if (tid == kT - 1) fence_acq_rel<kMulti>();
             if (tid == 0) {  // combine the per-warp folds
                 Decision d = s_pdec[0];
                 Top2 ft = {d.m1, d.m2};
@@ -672,73 +845,132 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         const uint32_t key_lo = from_new ? pack_key(g_bp) : s_dec.pkey;
         const float dab = __uint_as_float(static_cast<uint32_t>(gt.m1 >> 32));
         const int32_t snew = sa + sb;
-        const int32_t nreq_all = s_nreq, nmine = s_nmine;
+        const int32_t nreq_all = s_nreq;
+        const int32_t qt0 = s_qtail;  // dry queue before this iteration's update pass
+        if (tid == 0) s_uwork = 0;
         __syncthreads();  // the owner's shared-memory stores above are visible; s_dec / s_new / s_nreq were read
 
+        // Lance-Williams inputs of this thread's first slot: issued now so that their DRAM round trip overlaps
+        // the row scans below
+        const int32_t qa = merged ? a / C : 0, qb = merged ? b / C : 0;
+        const float* row_a = merged ? st.dm_rank[qa] + static_cast<int64_t>(a - qa * C) * ld : nullptr;
+        float* row_b = merged ? st.dm_rank[qb] + static_cast<int64_t>(b - qb * C) * ld : nullptr;
+        const int32_t key_a = static_cast<int32_t>(pack_key(gt.m1)), key_b = static_cast<int32_t>(key_lo);
+        // warps [0, ns) scan the requested rows while the others update: the two passes are independent.  Up to
+        // kW/2 scanning warps share the first kW/2 requests evenly (a request's window is split over wpr warps)
+        constexpr int kScanWarps = kW / 2;
+        const int nreq0 = min(nreq_all, kScanWarps);
+        // (splitting one request's window over several warps + a second merge step measured slower than one warp
+        //  per request on B200 at every size tried: the selection rounds dominate, not the loads)
+        constexpr bool kSplitScans = false;
+        int wpr = 1;
+        while (kSplitScans && nreq0 > 0 && wpr * 2 * nreq0 <= kScanWarps) wpr *= 2;
+        const int ns = nreq0 * wpr;
+
         // ====== cooperative row scans: this block's column window of every requested row of the rank ======
-        for (int32_t j = warp; j < nreq_all; j += kW) {
+        // scan_part: one warp scans part `sub` of `parts` of the window for request j -> its sorted partial list
+        auto scan_part = [&](int32_t j, int sub, int parts) {
             const int4 rq = s_rlist[j];
             const int32_t r = rq.x;
-            if (r == a || r == b) continue;  // merged away in this very iteration: its owner drops the request
-            const uint32_t ukr = static_cast<uint32_t>(rq.y);
-            const float* rowp = dm_own + static_cast<int64_t>(r - r_lo) * ld;
-            Cand2 c;
-            cand2_init(c);
-            constexpr int kU = 4;  // 16-byte row loads in flight per lane
-            for (int32_t base = w0; base < w1; base += 128 * kU) {
-                float4 vv[kU];
-                int4 kq[kU];
+            PartList out;
+            out.m = 0;
+            out.more = 0;
 #pragma unroll
-                for (int q = 0; q < kU; ++q) {
-                    const int32_t u0 = base + (q * 32 + lane) * 4;
-                    vv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    kq[q] = make_int4(-1, -1, -1, -1);
-                    if (u0 < w1) {
-                        vv[q] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
-                        kq[q] = kReplica ? *reinterpret_cast<const int4*>(s_key + u0)
-                                         : __ldcg(reinterpret_cast<const int4*>(g_key + u0));
+            for (int q = 0; q < kNNK; ++q) {
+                out.pk[q] = kPackInf;
+                out.sl[q] = -1;
+                out.sz[q] = 0;
+            }
+            if (r != a && r != b) {  // else: merged away in this very iteration, its owner drops the request
+                const uint32_t ukr = static_cast<uint32_t>(rq.y);
+                const float* rowp = dm_own + static_cast<int64_t>(r - r_lo) * ld;
+                const int32_t part = ((((w1 - w0) >> 2) + parts - 1) / parts) << 2;
+                const int32_t sw0 = min(w1, w0 + sub * part), sw1 = min(w1, sw0 + part);
+                ScanCand c;
+                scan_init(c);
+                constexpr int kU = 4;  // 16-byte row loads in flight per lane
+                for (int32_t base = sw0; base < sw1; base += 128 * kU) {
+                    float4 vv[kU];
+                    int4 kq[kU];
+#pragma unroll
+                    for (int q = 0; q < kU; ++q) {
+                        const int32_t u0 = base + (q * 32 + lane) * 4;
+                        vv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        kq[q] = make_int4(-1, -1, -1, -1);
+                        if (u0 < sw1) {
+                            vv[q] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
+                            kq[q] = kReplica ? *reinterpret_cast<const int4*>(s_key + u0)
+                                             : __ldcg(reinterpret_cast<const int4*>(g_key + u0));
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < kU; ++q) {
+                        const int32_t u0 = base + (q * 32 + lane) * 4;
+                        const uint32_t ks4[4] = {static_cast<uint32_t>(kq[q].x), static_cast<uint32_t>(kq[q].y),
+                                                 static_cast<uint32_t>(kq[q].z), static_cast<uint32_t>(kq[q].w)};
+                        const uint32_t vs4[4] = {__float_as_uint(vv[q].x), __float_as_uint(vv[q].y),
+                                                 __float_as_uint(vv[q].z), __float_as_uint(vv[q].w)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            // one compare per element; survivors (a handful per lane) take the full test
+                            if (vs4[e] <= static_cast<uint32_t>(c.c2 >> 32)) {
+                                const int32_t u = u0 + e;
+                                const uint32_t ku = ks4[e];  // retired slots hold -1 == 0xFFFFFFFF: never below the row's key
+                                // the four slots in flux are excluded by index: a and prev_a are retired, b and
+                                // prev_b carry the two highest keys (their replica entries may lag one exchange)
+                                if (ku < ukr && vs4[e] < kMaxFloatBits && u != a && u != b && u != prev_a && u != prev_b)
+                                    scan_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ku, u);
+                            } else {
+                                c.extra = true;
+                            }
+                        }
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < kU; ++q) {
-                    const int32_t u0 = base + (q * 32 + lane) * 4;
-                    const uint32_t ks4[4] = {static_cast<uint32_t>(kq[q].x), static_cast<uint32_t>(kq[q].y),
-                                             static_cast<uint32_t>(kq[q].z), static_cast<uint32_t>(kq[q].w)};
-                    const uint32_t vs4[4] = {__float_as_uint(vv[q].x), __float_as_uint(vv[q].y), __float_as_uint(vv[q].z),
-                                             __float_as_uint(vv[q].w)};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int32_t u = u0 + e;
-                        const uint32_t ku = ks4[e];  // retired slots hold -1 == 0xFFFFFFFF: never below the row's key
-                        // the four slots in flux are excluded by index: a and prev_a are retired, b and
-                        // prev_b carry the two highest keys (their replica entries may lag one exchange)
-                        const bool ok = ku < ukr && vs4[e] < kMaxFloatBits && u != a && u != b && u != prev_a && u != prev_b;
-                        if (ok) cand2_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ku, u);
-                    }
+                bool more = false;
+                out.m = warp_select_scan(c, out.pk, out.sl, more);
+                out.more = more ? 1 : 0;
+            }
+            if (parts > 1) {  // merged with the other parts after the block barrier (push_partial)
+                if (lane == 0) s_wl[warp] = out;
+            } else if (r != a && r != b) {  // the whole window: mail the list to the row's owner right away
+                uint4* prec = partials + (((static_cast<size_t>(rq.z) * 2 + par) * kReqPerBlock + rq.w) * G + blk) * kRecU4;
+                if (lane < kNNK) {
+                    const uint64_t myp = sel4(out.pk, lane);
+                    st_volatile_u4(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                                          static_cast<uint32_t>(sel4(out.sl, lane)), tag)
+                                                             : make_uint4(kNoPartner, kNoPartner, kNoPartner, tag));
+                } else if (lane == kNNK) {
+                    st_volatile_u4(prec + kNNK, make_uint4(static_cast<uint32_t>(out.m), static_cast<uint32_t>(out.more), 0u, tag));
                 }
             }
-            uint64_t pk[kNNK];
-            int32_t sl[kNNK];
-            bool more = false;
-            const int m = warp_select_topk(c, pk, sl, more);
-            // lanes 0..3 carry one entry each (with the partner's size), lanes 4..5 the size chunks
-            const uint64_t myp = sel4(pk, lane & 3);
-            const int32_t mys = sel4(sl, lane & 3);
-            int32_t mysz = 0;
-            if (lane < m) mysz = __ldcg(g_ks + mys).y;
-            const int32_t z0 = __shfl_sync(0xffffffffu, mysz, 0), z1 = __shfl_sync(0xffffffffu, mysz, 1);
-            const int32_t z2 = __shfl_sync(0xffffffffu, mysz, 2), z3 = __shfl_sync(0xffffffffu, mysz, 3);
+        };
+        // push_partial: warp-merge the `parts` lists s_wl[first..] of request j and mail them to the row's owner
+        auto push_partial = [&](int32_t j, int first, int parts) {
+            const int4 rq = s_rlist[j];
+            if (rq.x == a || rq.x == b) return;
+            PartList in;
+            in.m = 0;
+            in.more = 0;
+#pragma unroll
+            for (int q = 0; q < kNNK; ++q) {
+                in.pk[q] = kPackInf;
+                in.sl[q] = -1;
+                in.sz[q] = 0;
+            }
+            if (lane < parts) in = s_wl[first + lane];
+            PartList out;
+            warp_merge_lists(in, out);
             uint4* prec = partials + (((static_cast<size_t>(rq.z) * 2 + par) * kReqPerBlock + rq.w) * G + blk) * kRecU4;
-            if (lane < kNNK)
-                st_volatile_u4(prec + lane, lane < m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
-                                                                  static_cast<uint32_t>(mys), tag)
-                                                     : make_uint4(kNoPartner, kNoPartner, kNoPartner, tag));
-            else if (lane == 4)
-                st_volatile_u4(prec + 4, make_uint4(static_cast<uint32_t>(z0), static_cast<uint32_t>(z1),
-                                                    static_cast<uint32_t>(z2), tag));
-            else if (lane == 5)
-                st_volatile_u4(prec + 5, make_uint4(static_cast<uint32_t>(z3), more ? 1u : 0u, static_cast<uint32_t>(m), tag));
-        }
+            if (lane < kNNK) {
+                const uint64_t myp = sel4(out.pk, lane);
+                st_volatile_u4(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                                      static_cast<uint32_t>(sel4(out.sl, lane)), tag)
+                                                         : make_uint4(kNoPartner, kNoPartner, kNoPartner, tag));
+            } else if (lane == kNNK) {
+                st_volatile_u4(prec + kNNK, make_uint4(static_cast<uint32_t>(out.m), static_cast<uint32_t>(out.more), 0u, tag));
+            }
+        };
+        if (warp < ns) scan_part(warp / wpr, warp % wpr, wpr);
         const long long t3 = timed ? clock64() : 0;
 
         // ====== update pass over the own slice: Lance-Williams row b ======
@@ -748,18 +980,10 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         if (merged) {
             // a pair is stored in the row of its higher-key cluster (the new cluster always has the
             // highest key, so its distances are one coalesced row write and nothing is mirrored);
-            // rows a and b may live on another rank: peer-mapped loads / stores
-            const int32_t qa = a / C, qb = b / C;
-            const float* row_a = st.dm_rank[qa] + static_cast<int64_t>(a - qa * C) * ld;
-            float* row_b = st.dm_rank[qb] + static_cast<int64_t>(b - qb * C) * ld;
-            const int32_t key_a = static_cast<int32_t>(pack_key(gt.m1)), key_b = static_cast<int32_t>(key_lo);
-            for (int32_t i = tid; i < cnt; i += kT) {
+            // rows a and b may live on another rank: peer-mapped loads / stores.
+            // Work units of 64 slots are handed out dynamically: the warps that scanned rows above join late.
+            auto update_slot = [&](int32_t i, int2 kk, float dka, float dkb) {
                 const int32_t k = lo + i;
-                const int2 kk = s_ks[i];
-                if (k == a || k == b || kk.x < 0) continue;
-                const float* own = dm_own + static_cast<int64_t>(k - r_lo) * ld;
-                const float dka = __ldcg(kk.x < key_a ? row_a + k : own + a);
-                const float dkb = __ldcg(kk.x < key_b ? row_b + k : own + b);
                 float val;
                 if (kk.y + snew > prm.max_size)
                     val = __uint_as_float(kInfBits);  // inadmissible for good: sizes only grow (:228)
@@ -802,31 +1026,47 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                         }
                     }
                 }
+            };
+            for (;;) {
+                int32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_uwork, 64);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= cnt) break;
+                const int32_t i0 = base + lane, i1 = base + 32 + lane;
+                int2 kk0 = make_int2(-1, 0), kk1 = make_int2(-1, 0);
+                float da0 = 0.f, db0 = 0.f, da1 = 0.f, db1 = 0.f;
+                bool ok0 = false, ok1 = false;
+                if (i0 < cnt) {
+                    kk0 = s_ks[i0];
+                    const int32_t k = lo + i0;
+                    ok0 = k != a && k != b && kk0.x >= 0;
+                    if (ok0) {
+                        const float* own = dm_own + static_cast<int64_t>(k - r_lo) * ld;
+                        da0 = __ldcg(kk0.x < key_a ? row_a + k : own + a);
+                        db0 = __ldcg(kk0.x < key_b ? row_b + k : own + b);
+                    }
+                }
+                if (i1 < cnt) {
+                    kk1 = s_ks[i1];
+                    const int32_t k = lo + i1;
+                    ok1 = k != a && k != b && kk1.x >= 0;
+                    if (ok1) {
+                        const float* own = dm_own + static_cast<int64_t>(k - r_lo) * ld;
+                        da1 = __ldcg(kk1.x < key_a ? row_a + k : own + a);
+                        db1 = __ldcg(kk1.x < key_b ? row_b + k : own + b);
+                    }
+                }
+                if (ok0) update_slot(i0, kk0, da0, db0);
+                if (ok1) update_slot(i1, kk1, da1, db1);
             }
         }
-        {
+        {  // per-warp part of the new row's minimum; the block's fold happens in the next publish
             const uint64_t wu = warp_min_u64(ubest);
             const uint64_t wr = warp_min_u64(static_cast<uint64_t>(urun));
+            if (ubest == wu && wu != kPackInf) s_uwin[warp] = make_int2(uslot, usize);
             if (lane == 0) {
                 s_up[warp] = wu;
                 s_ur[warp] = wr;
-            }
-        }
-        __syncthreads();
-        {
-            uint64_t bu = s_up[0], br = s_ur[0];
-#pragma unroll
-            for (int w = 1; w < kW; ++w) {
-                bu = umin64(bu, s_up[w]);
-                br = umin64(br, s_ur[w]);
-            }
-            // every thread keeps the block's B-part; the publishing thread may be any of them
-            pub_bpack = bu;
-            pub_brun = static_cast<uint32_t>(br);
-            // slot / size of the block's best entry: broadcast through shared memory
-            if (bu != kPackInf && ubest == bu) {
-                s_bwin[0] = uslot;
-                s_bwin[1] = usize;
             }
         }
         if (kReplica && merged && tid == 1) {  // a is retired, b is about to carry the highest key: never partners again
@@ -835,93 +1075,24 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         }
         if (tid == 0 && s_qtail - s_qhead > qcap) s_err = 1;  // dry queue overflow (cannot happen)
         __syncthreads();
-        pub_bslot = pub_bpack != kPackInf ? s_bwin[0] : -1;
-        pub_bsize = pub_bpack != kPackInf ? s_bwin[1] : 0;
+        if (wpr > 1 && warp < nreq0) push_partial(warp, warp * wpr, wpr);
+        // rare: more requests than scanning warps
+        for (int32_t j = kScanWarps + warp; j < nreq_all; j += kW) scan_part(j, 0, 1);
         const long long t4 = timed ? clock64() : 0;
 
-        // ====== owner: fold the partial lists of the rows this block asked for ======
-        for (int32_t q = 0; q < nmine; ++q) {
-            const int32_t i = s_req_i[q];
-            const int32_t s = lo + i;
-            if (s == a || s == b) continue;  // block uniform; the slot's state is rebuilt by the next decision
-            if (warp < npw) {
-                const int g = warp * 32 + lane;
-                PartList in;
-                in.m = 0;
-                in.more = 0;
-#pragma unroll
-                for (int j = 0; j < kNNK; ++j) {
-                    in.pk[j] = kPackInf;
-                    in.sl[j] = -1;
-                    in.sz[j] = 0;
-                }
-                if (g < G) {
-                    const uint4* prec = partials + (((static_cast<size_t>(blk) * 2 + par) * kReqPerBlock + q) * G + g) * kRecU4;
-                    uint4 e0, e1, e2, e3, z0, z1;
-                    uint32_t spins = 0;
-                    for (;;) {
-                        e0 = ld_volatile_u4(prec + 0);
-                        e1 = ld_volatile_u4(prec + 1);
-                        e2 = ld_volatile_u4(prec + 2);
-                        e3 = ld_volatile_u4(prec + 3);
-                        z0 = ld_volatile_u4(prec + 4);
-                        z1 = ld_volatile_u4(prec + 5);
-                        if (e0.w == tag && e1.w == tag && e2.w == tag && e3.w == tag && z0.w == tag && z1.w == tag) break;
-                        if (++spins > kSpinLimit) __trap();
-                    }
-                    in.m = static_cast<int32_t>(z1.z);
-                    in.more = static_cast<int32_t>(z1.y);
-                    in.pk[0] = (static_cast<uint64_t>(e0.y) << 32) | e0.x;
-                    in.pk[1] = (static_cast<uint64_t>(e1.y) << 32) | e1.x;
-                    in.pk[2] = (static_cast<uint64_t>(e2.y) << 32) | e2.x;
-                    in.pk[3] = (static_cast<uint64_t>(e3.y) << 32) | e3.x;
-                    in.sl[0] = static_cast<int32_t>(e0.z);
-                    in.sl[1] = static_cast<int32_t>(e1.z);
-                    in.sl[2] = static_cast<int32_t>(e2.z);
-                    in.sl[3] = static_cast<int32_t>(e3.z);
-                    in.sz[0] = static_cast<int32_t>(z0.x);
-                    in.sz[1] = static_cast<int32_t>(z0.y);
-                    in.sz[2] = static_cast<int32_t>(z0.z);
-                    in.sz[3] = static_cast<int32_t>(z1.x);
-                }
-                PartList out;
-                warp_merge_lists(in, out);
-                if (lane == 0) s_wl[warp] = out;
+        // rows that ran dry in this update pass will be scanned one or two iterations from now: pull them into L2
+        // (a cold 100k-column row costs every scanning warp two DRAM round trips otherwise)
+        {
+            const int32_t qt1 = s_qtail;
+            for (int32_t qi = qt0; qi != qt1; ++qi) {
+                const float* rowp = dm_own + static_cast<int64_t>(lo + s_dryq[qi % qcap] - r_lo) * ld;
+                for (int32_t off = tid * 32; off < n; off += kT * 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + off));
             }
-            __syncthreads();
-            if (tid == 0) {  // merge the per-warp lists with the same cut rule
-                int ptr[kW];
-                for (int w = 0; w < npw; ++w) ptr[w] = 0;
-                int m = 0;
-                bool cut = false;
-                for (int r = 0; r < kNNK && !cut; ++r) {
-                    int bw = -1;
-                    uint64_t bp = kPackInf;
-                    for (int w = 0; w < npw; ++w)
-                        if (ptr[w] < s_wl[w].m && s_wl[w].pk[ptr[w]] < bp) {
-                            bp = s_wl[w].pk[ptr[w]];
-                            bw = w;
-                        }
-                    if (bw < 0) break;
-                    const int p = ptr[bw]++;
-                    s_nn[i * kNNK + r] = make_uint4(pack_key(bp), static_cast<uint32_t>(bp >> 32),
-                                                    static_cast<uint32_t>(s_wl[bw].sl[p]), static_cast<uint32_t>(s_wl[bw].sz[p]));
-                    m = r + 1;
-                    cut = ptr[bw] == s_wl[bw].m && s_wl[bw].more != 0;
-                }
-                bool more = false;
-                for (int w = 0; w < npw; ++w) more = more || ptr[w] < s_wl[w].m || s_wl[w].more != 0;
-                for (int r = m; r < kNNK; ++r) s_nn[i * kNNK + r] = nn_none();
-                s_more[i] = more ? kMoreBit : 0u;  // fresh again (an empty list without `more`: no partner left)
-                ++my_rescans;
-            }
-            __syncthreads();
         }
         if (tid == 0) {
             s_nreq = 0;
-            s_nmine = 0;
         }
-        const long long t5 = timed ? clock64() : 0;
 
         // remember the merge; its bookkeeping is applied after the next exchange
         if (merged) {
@@ -938,20 +1109,16 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             --n_live;
             bubbles_in_a_row = 0;
         } else {
-            pub_bpack = kPackInf;
-            pub_bslot = -1;
-            pub_bsize = 0;
-            pub_brun = kInfBits;
             ++n_bubbles;
             ++bubbles_in_a_row;
         }
         ++epoch;
         if (timed) {
-            c_pub += t1 - t0;
+            c_pub += t1 - t0 - tfold;
+            c_fold += tfold;
             c_exch += t2 - t1;
             c_scan += t3 - t2;
             c_upd += t4 - t3;
-            c_fold += t5 - t4;
         }
     }
     if (timed) {
@@ -1034,7 +1201,14 @@ cudaError_t merge_loop_grid(int num_sms, int64_t n, int n_ranks, int n_local, in
     if (n_ranks < 1 || n_ranks > kMaxRanks || n_local < 1 || n_local > n_ranks) return cudaErrorInvalidValue;
     const int64_t C = (n + n_ranks - 1) / n_ranks;
     // the exchange costs grow with the number of blocks: small problems use fewer
-    int64_t G = want_blocks > 0 ? want_blocks : (C + 127) / 128;
+    // (measured on B200: 48 blocks at n = 20k, 111 at n = 100k; more blocks make the all-to-all dearer than the
+    // per-block work they save)
+    int64_t G = want_blocks;
+    if (G <= 0) {
+        G = (C + 399) / 400;
+        if (G < 8) G = std::min<int64_t>(8, (C + 63) / 64);
+        if (G > 111) G = 111;
+    }
     const int64_t cap = num_sms / n_local;  // one CTA per SM, all resident
     if (G > cap) G = cap;
     if (G > kMaxBlocks) G = kMaxBlocks;
