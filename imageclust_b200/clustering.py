@@ -254,7 +254,7 @@ class Engine:
         self._check(self._L.ic_get_loop_profile(self._h, out))
         return dict(zip(("publish", "exchange", "update", "scan", "fold", "merges", "iterations", "rescans",
                          "reserved", "bubbles", "pub_argmin", "pub_reduce", "pub_fence", "pub_stores", "exch_poll",
-                         "exch_spare"), list(out)))
+                         "exch_rank"), list(out)))
 
     # -- row-block sharding over several GPUs: one process (and Engine) per GPU ------------------
     def shard_init(self, rank: int, world: int):

@@ -652,7 +652,9 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             __syncthreads();
             // acquire: one thread fences after ALL polls of the block completed (ordered by the bar.sync above); the
             // data reads of this iteration come after the bar.sync below
-            if (tid == kT - 1) fence_acq_rel<kMulti>();
+            // (with P > 1 only the rank's leader needs it here -- it re-releases what it acquired; everybody
+            //  acquires at system scope after the rank records below)
+            if (tid == kT - 1 && (!kMulti || blk == 0)) fence_acq_rel<kMulti>();
             if (tid == 0) {  // combine the per-warp folds
                 Decision d = s_pdec[0];
                 Top2 ft = {d.m1, d.m2};
@@ -676,13 +678,15 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             }
             if (kMulti) {
                 // ---- second level: the rank's fold goes to every rank, all blocks fold the P rank records ----
+                const long long tr0 = timed ? clock64() : 0;
                 __syncthreads();
                 if (blk == 0 && tid < P) {
                     const Decision d = s_dec;
                     const NewRow nr = s_new;
                     uint4* rec = static_cast<uint4*>(static_cast<void*>(static_cast<uint8_t*>(st.rankbox[tid]) + kRankboxFlagBytes)) +
                                  (static_cast<size_t>(par) * kMaxRanks + rank) * kRecU4;
-                    fence_acq_rel<true>();  // cumulative: what this rank's blocks published travels before the record
+                    // release: thread kT-1 fenced (acq_rel.sys) after ALL local polls, the bar.sync above orders these
+                    // stores after it -- what this rank's blocks published travels before the rank record
                     st_volatile_u4(rec + 0, make_uint4(static_cast<uint32_t>(d.m1), static_cast<uint32_t>(d.m1 >> 32),
                                                        static_cast<uint32_t>(d.m2 >> 32), tag));
                     st_volatile_u4(rec + 1, make_uint4(static_cast<uint32_t>(d.a), static_cast<uint32_t>(d.b),
@@ -754,6 +758,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                         s_new = nr;
                     }
                 }
+                if (timed) c_sub[5] += clock64() - tr0;
             }
         }
         __syncthreads();

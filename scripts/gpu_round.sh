@@ -19,6 +19,6 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/summary.txt
 timeout 1200 python bench.py --config "$CFG" --steps "$STEPS" --warmup 3 > gpurun_out/bench_$CFG.json 2> gpurun_out/bench_$CFG.err
 echo "bench $CFG exit $?" >> gpurun_out/summary.txt
-tail -3 gpurun_out/pytest_g1.log gpurun_out/pytest_g2.log gpurun_out/smoke.log
+tail -n 3 gpurun_out/pytest_g1.log gpurun_out/pytest_g2.log gpurun_out/smoke.log
 cat gpurun_out/summary.txt
 head -c 3000 gpurun_out/bench_$CFG.json

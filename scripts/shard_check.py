@@ -81,7 +81,7 @@ if big:
                 print(f"config {cfg} W={world}: {dt:.3f} s  merges={s['n_merges']} out={s['n_out']} ranks_agree={len(set(digests)) == 1} "
                       f"prep {s['ms_prep']:.2f} gram {s['ms_gram']:.2f} nn {s['ms_nn_init']:.2f} loop {s['ms_loop']:.2f} ms "
                       f"rescans={s['n_rescans']} trace_sha={digest[:12]} | cycles/merge "
-                      + " ".join(f"{k}={v / mg:.0f}" for k, v in p.items() if k in ("publish", "exchange", "update", "scan", "fold"))
+                      + " ".join(f"{k}={v / mg:.0f}" for k, v in p.items() if k in ("publish", "exchange", "update", "scan", "fold", "pub_fence", "pub_stores", "exch_poll", "exch_rank"))
                       + f" bubbles={p['bubbles']}", flush=True)
                 ok = ok and len(set(digests)) == 1
 

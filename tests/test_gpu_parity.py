@@ -345,3 +345,66 @@ def test_sharded_staged_resume(eng, oracle, knobs):
     eng.merge_loop(3, 10)
     _same_trace(eng.merge_trace(), o)
     assert same_clusters(eng.build_clusters(3), o.clusters)
+
+
+# ---- BASELINE.json's full sizes --------------------------------------------------------------------
+
+def _trace_digest(tr):
+    import hashlib
+    return hashlib.sha256(tr.key_hi.tobytes() + tr.key_lo.tobytes() + tr.dist.tobytes() + tr.size.tobytes()).hexdigest()
+
+
+def test_config_b_full_size_bit_exact_vs_oracle(eng, oracle):
+    """BASELINE config 2 (N=20,000 x 2048, 10/50) at full size: the oracle (Lance-Williams mode, all host
+    cores) replays the device's own tensor-core initial matrix; 18,800 merges must agree bit for bit, and
+    the initial distances must be within 1e-5 of the reference arithmetic on a sampled block."""
+    n, d, mn, mx = synth.CONFIGS["B"]
+    x = synth.gaussian_mixture(n, d, mn, mx, seed=20241)
+    eng.load(x)
+    eng.initial_distances(_lib.GRAM_TCGEN05_3XTF32, mx)
+    m0 = eng.read_matrix()
+    rows = np.arange(0, n, 97)[:200]
+    ref = oracle.initial_matrix(np.ascontiguousarray(x[rows]))
+    sub = m0[np.ix_(rows, rows)]
+    off = ~np.eye(len(rows), dtype=bool)
+    assert float(np.max(np.abs(sub[off] - ref[off]) / ref[off])) <= RTOL
+    eng.nn_init()
+    eng.merge_loop(mn, mx)
+    tr = eng.merge_trace()
+    o = oracle.fast_cluster(x, mn, mx, flags=LW_EAGER, init_matrix=m0)
+    _same_trace(tr, o)
+    cl = eng.build_clusters(mn)
+    assert same_clusters(cl, o.clusters)
+    assert all(mn <= len(c) <= mx for c in cl)
+
+
+def test_config_c_full_size_properties_and_sharded_identity(eng, knobs):
+    """BASELINE config 3 (N=100,000 x 2048, 20/200) at full size, where no CPU oracle finishes: size-independent
+    properties of the result, and the row-block sharded loop (4 virtual ranks) must reproduce the single-rank
+    merge trace bit for bit (97,250 merges)."""
+    n, d, mn, mx = synth.CONFIGS["C"]
+    x = synth.gaussian_mixture(n, d, mn, mx, seed=20242)
+    res = eng.cluster(x, mn, mx)
+    tr = eng.merge_trace()
+    st = res.stats
+    assert st["n_target"] == 2750 and st["n_merges"] == n - 2750 and not st["exhausted"]
+    sizes = np.array([len(c) for c in res.clusters])
+    assert sizes.min() >= mn and sizes.max() <= mx
+    flat = np.concatenate(res.clusters)
+    assert len(np.unique(flat)) == len(flat) and flat.min() >= 0 and flat.max() < n  # every item at most once
+    # the trace is a valid dendrogram prefix: keys in range, each consumed once, sizes add up
+    consumed = np.zeros(n + len(tr.key_hi), bool)
+    size_of = np.concatenate([np.ones(n, np.int64), tr.size.astype(np.int64)])
+    for t in range(len(tr.key_hi)):
+        hi, lo = int(tr.key_hi[t]), int(tr.key_lo[t])
+        assert lo < hi < n + t and not consumed[hi] and not consumed[lo]
+        consumed[hi] = consumed[lo] = True
+        assert size_of[n + t] == size_of[hi] + size_of[lo] <= mx
+    # Ward heights never decrease by more than rounding (reducibility; exact in real arithmetic)
+    dist = tr.dist.astype(np.float64)
+    assert np.all(dist[1:] >= dist[:-1] * (1 - 1e-5))
+    want = _trace_digest(tr)
+    knobs(virtual_ranks=4)
+    eng.load(x)
+    eng.run_resident(mn, mx)
+    assert _trace_digest(eng.merge_trace()) == want
