@@ -652,9 +652,11 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             __syncthreads();
             // acquire: one thread fences after ALL polls of the block completed (ordered by the bar.sync above); the
             // data reads of this iteration come after the bar.sync below
-            // (with P > 1 only the rank's leader needs it here -- it re-releases what it acquired; everybody
-            //  acquires at system scope after the rank records below)
-            if (tid == kT - 1 && (!kMulti || blk == 0)) fence_acq_rel<kMulti>();
+            // With P > 1 nobody fences here: every block of the rank completed a system-scope release fence before
+            // it wrote its local record, so what the leader forwards is already performed system-wide, and
+            // everybody acquires at system scope after the rank records below (a third fence.sys in the chain cost
+            // ~3 us per merge).
+            if (tid == kT - 1 && !kMulti) fence_acq_rel<false>();
             if (tid == 0) {  // combine the per-warp folds
                 Decision d = s_pdec[0];
                 Top2 ft = {d.m1, d.m2};
@@ -685,8 +687,8 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     const NewRow nr = s_new;
                     uint4* rec = static_cast<uint4*>(static_cast<void*>(static_cast<uint8_t*>(st.rankbox[tid]) + kRankboxFlagBytes)) +
                                  (static_cast<size_t>(par) * kMaxRanks + rank) * kRecU4;
-                    // release: thread kT-1 fenced (acq_rel.sys) after ALL local polls, the bar.sync above orders these
-                    // stores after it -- what this rank's blocks published travels before the rank record
+                    // what this rank's blocks published was system-visible before their local records were written
+                    // (fence.sys in every block's publish), i.e. before the leader could see them
                     st_volatile_u4(rec + 0, make_uint4(static_cast<uint32_t>(d.m1), static_cast<uint32_t>(d.m1 >> 32),
                                                        static_cast<uint32_t>(d.m2 >> 32), tag));
                     st_volatile_u4(rec + 1, make_uint4(static_cast<uint32_t>(d.a), static_cast<uint32_t>(d.b),
