@@ -197,8 +197,11 @@ std::vector<int2> build_tile_list(int64_t n, int64_t row_begin, int64_t row_end)
                     const int64_t col0 = static_cast<int64_t>(cb) * kGramBN;
                     const int64_t row_last = static_cast<int64_t>(rb) * kGramBM + kGramBM - 1;
                     if (col0 >= n || col0 > row_last) continue;  // outside, or wholly above the diagonal
-                    // a rank computes the tiles of its own rows (lower triangle: unequal shares, K1 is ~3 % of the path)
-                    if (row_last < row_begin || static_cast<int64_t>(rb) * kGramBM >= row_end) continue;
+                    // a rank keeps its rows at full width and symmetric: it needs the tiles whose rows (direct entries)
+                    // or whose columns (mirrored entries) touch its row block
+                    const bool rows_in = !(row_last < row_begin || static_cast<int64_t>(rb) * kGramBM >= row_end);
+                    const bool cols_in = !(col0 + kGramBN <= row_begin || col0 >= row_end);
+                    if (!rows_in && !cols_in) continue;
                     tiles.push_back(make_int2(rb, cb));
                 }
     return tiles;

@@ -24,9 +24,9 @@ __global__ void __launch_bounds__(256) gram_exact_kernel(const float* __restrict
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;  // lower triangle of tiles only
     // dm holds the rows [row_begin, row_end) (a rank's row block, or the whole matrix)
-    if (static_cast<int64_t>(bi) * T >= row_end ||
-        (static_cast<int64_t>(bi) * T + T <= row_begin && static_cast<int64_t>(bj) * T + T <= row_begin))
-        return;
+    // (a tile is needed if its rows OR its columns -- the mirrored entries -- touch the resident rows)
+    const int64_t r0 = static_cast<int64_t>(bi) * T, c0 = static_cast<int64_t>(bj) * T;
+    if ((r0 >= row_end || r0 + T <= row_begin) && (c0 >= row_end || c0 + T <= row_begin)) return;
     __shared__ float sa[T][KT + 1];
     __shared__ float sb[T][KT + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;

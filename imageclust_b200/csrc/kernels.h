@@ -44,8 +44,8 @@ struct GramPlan {
     int k_blocks;        // d_pad / 32
 };
 // dm[i][j] = dm[j][i] = max(0.5*(norm_i + norm_j) - <x_i, x_j>, 0), diag 0; full square, row stride ld.
-// dm holds the rows [row_begin, row_end) only (a rank's row block; 0..n on one GPU): entries of other rows
-// are not stored (the merge loop never reads the initial upper triangle).
+// dm holds the rows [row_begin, row_end) only (a rank's row block; 0..n on one GPU), symmetric and at full
+// width: the plan's tile list covers every tile whose rows or columns touch them.
 cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float* dm, int64_t n, int64_t ld,
                                 int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s, int terms = 23);
 size_t gram_tcgen05_smem_bytes();

@@ -51,6 +51,7 @@ constexpr int kW = kT / 32;
 constexpr int kMaxBlocks = 160;  // blocks per rank: one record per lane of 5 polling warps, x3 parts
 constexpr int kMaxReqTotal = kMaxBlocks * kReqPerBlock;
 constexpr uint32_t kMoreBit = 1u, kDryBit = 2u, kReqBit = 4u;
+constexpr int kMaxSplit = 2;  // parts a block's scan window may be split into
 constexpr int kRankboxFlagBytes = 256;
 
 // block record chunks (uint4 each, .w = tag)
@@ -242,7 +243,7 @@ IC_DEVINL void warp_merge_lists(const PartList& in, PartList& out) {
 
 size_t merge_loop_records_bytes(int G) { return static_cast<size_t>(G) * 2 * G * kRecU4 * sizeof(uint4); }
 size_t merge_loop_partials_bytes(int G) {
-    return static_cast<size_t>(G) * 2 * kReqPerBlock * G * kRecU4 * sizeof(uint4);
+    return static_cast<size_t>(G) * 2 * kReqPerBlock * G * kMaxSplit * kRecU4 * sizeof(uint4);
 }
 size_t merge_loop_rankbox_bytes() { return kRankboxFlagBytes + 2 * kMaxRanks * kRecU4 * sizeof(uint4); }
 
@@ -294,6 +295,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     // column window this block scans when a row of its rank is rescanned
     const int32_t W = (((n4 + G - 1) / G) + 3) & ~3;
     const int32_t w0 = min(n4, blk * W), w1 = min(n4, w0 + W);
+    const int split = W > 512 ? kMaxSplit : 1;  // warps per (request, block): one batch of 4 x 16-byte loads per lane
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const size_t c1 = static_cast<size_t>(chunk > 0 ? chunk : 1);
@@ -456,9 +458,11 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                 for (int c = 0; c < nch; ++c) st_volatile_u4(rec + c, s_pub[c]);
             }
             if (timed) {
+#ifndef IC_SCAN_PROF
                 c_sub[0] += ta - t0;
                 c_sub[1] += tb - ta;
                 c_sub[2] += tc - tb;
+#endif
                 c_sub[3] += clock64() - tc;
             }
         }
@@ -474,7 +478,9 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             // merged away by the merge decided in that iteration (still pending here): the scanners skipped it
             // and the slot's state is rebuilt by the next decision
             if (pending && (s == pa || s == pb)) continue;  // block uniform
-            if (warp < npw) {
+            const int nsend = G * split;            // partial lists per request
+            const int npf = (nsend + 31) / 32;      // warps that poll them
+            if (warp < npf) {
                 const int g = warp * 32 + lane;
                 PartList in;
                 in.m = 0;
@@ -485,8 +491,8 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     in.sl[j] = -1;
                     in.sz[j] = 0;
                 }
-                if (g < G) {
-                    const uint4* prec = partials + (((static_cast<size_t>(blk) * 2 + ppar) * kReqPerBlock + q) * G + g) * kRecU4;
+                if (g < nsend) {
+                    const uint4* prec = partials + (((static_cast<size_t>(blk) * 2 + ppar) * kReqPerBlock + q) * (G * kMaxSplit) + g) * kRecU4;
                     uint4 e0, e1, e2, e3, z0;
                     uint32_t spins = 0;
                     for (;;) {
@@ -516,13 +522,13 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             __syncthreads();
             if (tid == 0) {  // merge the per-warp lists with the same cut rule
                 int ptr[kW];
-                for (int w = 0; w < npw; ++w) ptr[w] = 0;
+                for (int w = 0; w < npf; ++w) ptr[w] = 0;
                 int m = 0;
                 bool cut = false;
                 for (int r = 0; r < kNNK && !cut; ++r) {
                     int bw = -1;
                     uint64_t bp = kPackInf;
-                    for (int w = 0; w < npw; ++w)
+                    for (int w = 0; w < npf; ++w)
                         if (ptr[w] < s_wl[w].m && s_wl[w].pk[ptr[w]] < bp) {
                             bp = s_wl[w].pk[ptr[w]];
                             bw = w;
@@ -535,7 +541,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     cut = ptr[bw] == s_wl[bw].m && s_wl[bw].more != 0;
                 }
                 bool more = false;
-                for (int w = 0; w < npw; ++w) more = more || ptr[w] < s_wl[w].m || s_wl[w].more != 0;
+                for (int w = 0; w < npf; ++w) more = more || ptr[w] < s_wl[w].m || s_wl[w].more != 0;
                 for (int r = m; r < kNNK; ++r) s_nn[i * kNNK + r] = nn_none();
                 s_more[i] = more ? kMoreBit : 0u;  // fresh again (an empty list without `more`: no partner left)
                 ++my_rescans;
@@ -862,21 +868,20 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         const int32_t qa = merged ? a / C : 0, qb = merged ? b / C : 0;
         const float* row_a = merged ? st.dm_rank[qa] + static_cast<int64_t>(a - qa * C) * ld : nullptr;
         float* row_b = merged ? st.dm_rank[qb] + static_cast<int64_t>(b - qb * C) * ld : nullptr;
-        const int32_t key_a = static_cast<int32_t>(pack_key(gt.m1)), key_b = static_cast<int32_t>(key_lo);
-        // warps [0, ns) scan the requested rows while the others update: the two passes are independent.  Up to
-        // kW/2 scanning warps share the first kW/2 requests evenly (a request's window is split over wpr warps)
+        // warps [0, ns) scan the requested rows while the others update: the two passes are independent.  A wide
+        // window is split over kSplit warps, each mailing its own partial list (the owner folds G * split lists one
+        // iteration later, off the critical path), so that a scanning warp needs one batch of loads, not two.
         constexpr int kScanWarps = kW / 2;
-        const int nreq0 = min(nreq_all, kScanWarps);
-        // (splitting one request's window over several warps + a second merge step measured slower than one warp
-        //  per request on B200 at every size tried: the selection rounds dominate, not the loads)
-        constexpr bool kSplitScans = false;
-        int wpr = 1;
-        while (kSplitScans && nreq0 > 0 && wpr * 2 * nreq0 <= kScanWarps) wpr *= 2;
-        const int ns = nreq0 * wpr;
+        const int nparts = nreq_all * split;                 // (request, part) pairs of this iteration
+        const int ns = min(nparts, kScanWarps);
 
         // ====== cooperative row scans: this block's column window of every requested row of the rank ======
         // scan_part: one warp scans part `sub` of `parts` of the window for request j -> its sorted partial list
         auto scan_part = [&](int32_t j, int sub, int parts) {
+#ifdef IC_SCAN_PROF
+            const long long ts0 = timed ? clock64() : 0;
+            if (timed) c_sub[0] += ts0 - t2;  // decision + barrier
+#endif
             const int4 rq = s_rlist[j];
             const int32_t r = rq.x;
             PartList out;
@@ -933,14 +938,20 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                         }
                     }
                 }
+#ifdef IC_SCAN_PROF
+                const long long ts1 = timed ? clock64() : 0;
+                if (timed) c_sub[1] += ts1 - ts0;  // loads + filtering
+#endif
                 bool more = false;
                 out.m = warp_select_scan(c, out.pk, out.sl, more);
+#ifdef IC_SCAN_PROF
+                if (timed) c_sub[2] += clock64() - ts1;  // selection
+#endif
                 out.more = more ? 1 : 0;
             }
-            if (parts > 1) {  // merged with the other parts after the block barrier (push_partial)
-                if (lane == 0) s_wl[warp] = out;
-            } else if (r != a && r != b) {  // the whole window: mail the list to the row's owner right away
-                uint4* prec = partials + (((static_cast<size_t>(rq.z) * 2 + par) * kReqPerBlock + rq.w) * G + blk) * kRecU4;
+            if (r != a && r != b) {  // mail the list of this part to the row's owner
+                uint4* prec = partials + (((static_cast<size_t>(rq.z) * 2 + par) * kReqPerBlock + rq.w) * (G * kMaxSplit) +
+                                          blk * parts + sub) * kRecU4;
                 if (lane < kNNK) {
                     const uint64_t myp = sel4(out.pk, lane);
                     st_volatile_u4(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
@@ -951,33 +962,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                 }
             }
         };
-        // push_partial: warp-merge the `parts` lists s_wl[first..] of request j and mail them to the row's owner
-        auto push_partial = [&](int32_t j, int first, int parts) {
-            const int4 rq = s_rlist[j];
-            if (rq.x == a || rq.x == b) return;
-            PartList in;
-            in.m = 0;
-            in.more = 0;
-#pragma unroll
-            for (int q = 0; q < kNNK; ++q) {
-                in.pk[q] = kPackInf;
-                in.sl[q] = -1;
-                in.sz[q] = 0;
-            }
-            if (lane < parts) in = s_wl[first + lane];
-            PartList out;
-            warp_merge_lists(in, out);
-            uint4* prec = partials + (((static_cast<size_t>(rq.z) * 2 + par) * kReqPerBlock + rq.w) * G + blk) * kRecU4;
-            if (lane < kNNK) {
-                const uint64_t myp = sel4(out.pk, lane);
-                st_volatile_u4(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
-                                                                      static_cast<uint32_t>(sel4(out.sl, lane)), tag)
-                                                         : make_uint4(kNoPartner, kNoPartner, kNoPartner, tag));
-            } else if (lane == kNNK) {
-                st_volatile_u4(prec + kNNK, make_uint4(static_cast<uint32_t>(out.m), static_cast<uint32_t>(out.more), 0u, tag));
-            }
-        };
-        if (warp < ns) scan_part(warp / wpr, warp % wpr, wpr);
+        for (int32_t jj = warp; warp < ns && jj < nparts; jj += ns) scan_part(jj / split, jj % split, split);
         const long long t3 = timed ? clock64() : 0;
 
         // ====== update pass over the own slice: Lance-Williams row b ======
@@ -985,9 +970,11 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         int32_t uslot = -1, usize = 0;
         uint32_t urun = kInfBits;
         if (merged) {
-            // a pair is stored in the row of its higher-key cluster (the new cluster always has the
-            // highest key, so its distances are one coalesced row write and nothing is mirrored);
-            // rows a and b may live on another rank: peer-mapped loads / stores.
+            // The matrix is kept symmetric: d(k,a) and d(k,b) come from rows a and b (two coalesced reads; gathering
+            // the entries of newer clusters from their own rows cost one 32-byte sector per value on the critical
+            // path, ~6 MB per merge at N = 100k), the result goes to row b (coalesced) and to dm[k][b] (a scattered
+            // store into this block's own row: fire and forget).  Rows a and b may live on another rank:
+            // peer-mapped loads / stores.
             // Work units of 64 slots are handed out dynamically: the warps that scanned rows above join late.
             auto update_slot = [&](int32_t i, int2 kk, float dka, float dkb) {
                 const int32_t k = lo + i;
@@ -996,7 +983,8 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     val = __uint_as_float(kInfBits);  // inadmissible for good: sizes only grow (:228)
                 else
                     val = lance_williams(sa, sb, kk.y, dka, dkb, dab);
-                __stcg(row_b + k, val);
+                __stcg(row_b + k, val);                                              // the new cluster's row (coalesced)
+                __stcg(dm_own + static_cast<int64_t>(k - r_lo) * ld + b, val);       // mirrored entry in this block's own row k
                 const uint64_t cd = pack_cand(val, static_cast<uint32_t>(kk.x));
                 if (cd < ubest) {
                     ubest = cd;
@@ -1048,9 +1036,8 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     const int32_t k = lo + i0;
                     ok0 = k != a && k != b && kk0.x >= 0;
                     if (ok0) {
-                        const float* own = dm_own + static_cast<int64_t>(k - r_lo) * ld;
-                        da0 = __ldcg(kk0.x < key_a ? row_a + k : own + a);
-                        db0 = __ldcg(kk0.x < key_b ? row_b + k : own + b);
+                        da0 = __ldcg(row_a + k);
+                        db0 = __ldcg(row_b + k);
                     }
                 }
                 if (i1 < cnt) {
@@ -1058,9 +1045,8 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     const int32_t k = lo + i1;
                     ok1 = k != a && k != b && kk1.x >= 0;
                     if (ok1) {
-                        const float* own = dm_own + static_cast<int64_t>(k - r_lo) * ld;
-                        da1 = __ldcg(kk1.x < key_a ? row_a + k : own + a);
-                        db1 = __ldcg(kk1.x < key_b ? row_b + k : own + b);
+                        da1 = __ldcg(row_a + k);
+                        db1 = __ldcg(row_b + k);
                     }
                 }
                 if (ok0) update_slot(i0, kk0, da0, db0);
@@ -1082,9 +1068,6 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         }
         if (tid == 0 && s_qtail - s_qhead > qcap) s_err = 1;  // dry queue overflow (cannot happen)
         __syncthreads();
-        if (wpr > 1 && warp < nreq0) push_partial(warp, warp * wpr, wpr);
-        // rare: more requests than scanning warps
-        for (int32_t j = kScanWarps + warp; j < nreq_all; j += kW) scan_part(j, 0, 1);
         const long long t4 = timed ? clock64() : 0;
 
         // rows that ran dry in this update pass will be scanned one or two iterations from now: pull them into L2
