@@ -211,7 +211,7 @@ std::vector<int2> build_tile_list(int64_t n, int64_t row_begin, int64_t row_end)
 int n_ranks(const ic_ctx* c) { return c->shard_world > 1 ? c->shard_world : c->vranks; }
 int n_local(const ic_ctx* c) { return c->shard_world > 1 ? 1 : c->vranks; }
 int rank0(const ic_ctx* c) { return c->shard_world > 1 ? c->shard_rank : 0; }
-int64_t rows_per_rank(const ic_ctx* c) { return (c->n + n_ranks(c) - 1) / n_ranks(c); }
+int64_t rows_per_rank(const ic_ctx* c) { return merge_loop_rows_per_rank(c->n, n_ranks(c)); }
 // rows of the distance matrix resident on this device: [row_begin, row_end)
 int64_t row_begin(const ic_ctx* c) { return c->shard_world > 1 ? std::min(c->n, c->shard_rank * rows_per_rank(c)) : 0; }
 int64_t row_end(const ic_ctx* c) {

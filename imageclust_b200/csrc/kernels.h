@@ -61,7 +61,7 @@ cudaError_t launch_nn_sweep(const float* dm, int64_t row_begin, int64_t row_end,
 
 // ---- K3 persistent merge loop ------------------------------------------------------------
 // The distance matrix is row-block sharded over P "ranks" (SURVEY 8e): rank q owns slots
-// [q*C, (q+1)*C), C = ceil(n / P), i.e. the rows of those slots with ALL their columns.
+// [q*C, (q+1)*C), C = ceil(n / P) rounded up to a multiple of 4, i.e. the rows of those slots with ALL their columns.
 //   * one GPU:            P = 1.
 //   * several GPUs:       one process / GPU / rank; every rank launches the kernel with n_local = 1
 //                         and reaches its peers' rows and rank mailboxes through peer-mapped pointers.
@@ -109,6 +109,8 @@ enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_N
 // CTL_STOP values
 enum { STOP_TARGET = 1, STOP_EXHAUSTED = 2, STOP_MAX_MERGES = 3, STOP_EPOCHS = 4, STOP_ERROR = 5 };
 constexpr int kLoopThreads = 512;
+// C: rows (slots) per rank, ceil(n / P) rounded up to a multiple of 4
+int64_t merge_loop_rows_per_rank(int64_t n, int n_ranks);
 // blocks per rank for a problem of n slots over n_ranks ranks, n_local of them in this launch
 // `replica`: every block keeps the keys of ALL slots in shared memory (needs merge_loop_replica_fits(n))
 bool merge_loop_replica_fits(int64_t n);

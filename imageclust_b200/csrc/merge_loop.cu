@@ -85,6 +85,18 @@ IC_DEVINL void fence_acq_rel() {
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
+// bulk asynchronous stores (TMA, async proxy): shared -> global (possibly a peer's memory over NVLink).  Unlike
+// generic stores they are not waited for by a later fence of the issuing SM; completion is tracked per thread.
+IC_DEVINL void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes of the source first
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+                 "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+IC_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+IC_DEVINL void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 // Lance-Williams update of Ward's distance (clustering.go:141-144 is the closed form it
 // equals): exact integer weights, double arithmetic, one rounding to fp32.  The CPU
 // oracle's LW mode (oracle/ward_fast.c) performs the same operations in the same order.
@@ -251,10 +263,13 @@ size_t merge_loop_rankbox_bytes() { return kRankboxFlagBytes + 2 * kMaxRanks * k
 // streams only the row itself.
 constexpr int64_t kReplicaMaxSlots = 36 * 1024;
 bool merge_loop_replica_fits(int64_t n) { return n <= kReplicaMaxSlots; }
+// rows per rank and slots per block are multiples of 4: every block's slice of a matrix row starts on a 16-byte
+// boundary (bulk stores of the new row's slices)
+int64_t merge_loop_rows_per_rank(int64_t n, int n_ranks) { return ((n + n_ranks - 1) / n_ranks + 3) / 4 * 4; }
 static int64_t slice_slots(int64_t n, int n_ranks, int G) {
-    const int64_t C = (n + n_ranks - 1) / n_ranks;
-    const int64_t c = (C + G - 1) / G;
-    return c > 0 ? c : 1;
+    const int64_t C = merge_loop_rows_per_rank(n, n_ranks);
+    const int64_t c = ((C + G - 1) / G + 3) / 4 * 4;
+    return c > 0 ? c : 4;
 }
 size_t merge_loop_smem_bytes(int64_t n, int n_ranks, int G, bool replica) {
     const int64_t c = slice_slots(n, n_ranks, G);
@@ -262,6 +277,7 @@ size_t merge_loop_smem_bytes(int64_t n, int n_ranks, int G, bool replica) {
     size_t bytes = static_cast<size_t>(c) * (kNNK * sizeof(uint4) + sizeof(int2) + 3 * sizeof(int32_t));
     bytes = (bytes + 15) & ~size_t(15);
     if (replica) bytes += static_cast<size_t>((n + 3) / 4 * 4) * sizeof(int32_t);
+    if (n_ranks > 1) bytes += static_cast<size_t>(c) * sizeof(float);  // staging of the new row's slice
     return bytes;
 }
 
@@ -289,7 +305,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
 
     // slot slice owned by this block (rows of this rank); its state lives in shared memory
     const int32_t r_lo = min(n, rank * C), r_hi = min(n, r_lo + C);
-    const int32_t chunk = (C + G - 1) / G;
+    const int32_t chunk = (((C + G - 1) / G) + 3) & ~3;
     const int32_t lo = min(r_hi, r_lo + blk * chunk), hi = min(r_hi, lo + chunk);
     const int32_t cnt = hi - lo;
     // column window this block scans when a row of its rank is rescanned
@@ -298,14 +314,17 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     const int split = W > 512 ? kMaxSplit : 1;  // warps per (request, block): one batch of 4 x 16-byte loads per lane
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    const size_t c1 = static_cast<size_t>(chunk > 0 ? chunk : 1);
+    const size_t c1 = static_cast<size_t>(chunk > 0 ? chunk : 4);
     uint4* const s_nn = reinterpret_cast<uint4*>(dyn_smem);                                  // [chunk][kNNK]
     int2* const s_ks = reinterpret_cast<int2*>(dyn_smem + c1 * kNNK * sizeof(uint4));        // [chunk]
     uint32_t* const s_more = reinterpret_cast<uint32_t*>(dyn_smem + c1 * (kNNK * sizeof(uint4) + sizeof(int2)));
     int32_t* const s_dryq = reinterpret_cast<int32_t*>(s_more + c1);                         // ring, [2 * chunk]
     const int32_t qcap = static_cast<int32_t>(2 * c1);
-    int32_t* const s_key = reinterpret_cast<int32_t*>(
-        dyn_smem + ((c1 * (kNNK * sizeof(uint4) + sizeof(int2) + 3 * sizeof(int32_t)) + 15) & ~size_t(15)));  // [n4] if kReplica
+    const size_t off_key = (c1 * (kNNK * sizeof(uint4) + sizeof(int2) + 3 * sizeof(int32_t)) + 15) & ~size_t(15);
+    int32_t* const s_key = reinterpret_cast<int32_t*>(dyn_smem + off_key);  // [n4] if kReplica
+    // [chunk] if kMulti: this block's slice of the new row, shipped to the row's owner as ONE bulk store
+    float* const s_newrow = reinterpret_cast<float*>(dyn_smem + off_key + (kReplica ? static_cast<size_t>(n4) * 4 : 0));
+    const int32_t cnt4 = (cnt + 3) & ~3;  // bulk stores move multiples of 16 bytes; columns >= n of a row are padding
 
     __shared__ uint64_t s_m1[kW], s_m2[kW], s_up[kW], s_ur[kW];
     __shared__ Decision s_dec;
@@ -323,6 +342,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     __shared__ PartList s_wl[kW];
     __shared__ int32_t s_err;
     __shared__ int32_t s_uwork;  // next unprocessed slot of the update pass
+    __shared__ __align__(16) uint4 s_rr[2][kMaxRanks][kRecU4];  // leader: staging of the rank records (by epoch parity)
 
     if (tid == 0) {
         s_qhead = 0;
@@ -336,6 +356,8 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         s_more[i] = static_cast<uint32_t>(__ldcg(st.nn_more + lo + i)) & (kMoreBit | kDryBit);
     }
     for (int32_t i = tid; i < cnt * kNNK; i += kT) s_nn[i] = __ldcg(st.nn + static_cast<int64_t>(lo) * kNNK + i);
+    if (kMulti)
+        for (int32_t i = tid; i < static_cast<int32_t>(c1); i += kT) s_newrow[i] = __uint_as_float(kInfBits);
     if (kReplica)
         for (int32_t u = tid; u < n4; u += kT) s_key[u] = __ldcg(g_key + u);
     __syncthreads();
@@ -447,7 +469,14 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             // release: ONE thread fences (every store of the block was ordered before it by the bar.sync above,
             // the pushes below are ordered after it by the next bar.sync -- the grid-barrier idiom); a fence per
             // pushing warp serialises and cost 3x more
-            if (tid == kT - 1) fence_acq_rel<kMulti>();
+            // With P > 1 every store to a peer is a bulk asynchronous store: this thread issued the block's slice of
+            // the new row an iteration ago and only has to see it completed (it long has); everything else the block
+            // wrote lives in this GPU's own memory, so the release stays at gpu scope -- a system-scope fence here
+            // waited ~2.7 us per merge for NVLink acknowledgements.
+            if (tid == kT - 1) {
+                if (kMulti) bulk_wait_all();
+                fence_acq_rel<false>();
+            }
             __syncthreads();
             const long long tb = timed ? clock64() : 0;
             long long tc = 0;
@@ -693,16 +722,19 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     const NewRow nr = s_new;
                     uint4* rec = static_cast<uint4*>(static_cast<void*>(static_cast<uint8_t*>(st.rankbox[tid]) + kRankboxFlagBytes)) +
                                  (static_cast<size_t>(par) * kMaxRanks + rank) * kRecU4;
-                    // what this rank's blocks published was system-visible before their local records were written
-                    // (fence.sys in every block's publish), i.e. before the leader could see them
-                    st_volatile_u4(rec + 0, make_uint4(static_cast<uint32_t>(d.m1), static_cast<uint32_t>(d.m1 >> 32),
-                                                       static_cast<uint32_t>(d.m2 >> 32), tag));
-                    st_volatile_u4(rec + 1, make_uint4(static_cast<uint32_t>(d.a), static_cast<uint32_t>(d.b),
-                                                       static_cast<uint32_t>(d.sa), tag));
-                    st_volatile_u4(rec + 2, make_uint4(static_cast<uint32_t>(d.sb), d.pkey, d.stale, tag));
-                    st_volatile_u4(rec + 3, make_uint4(static_cast<uint32_t>(nr.pack), static_cast<uint32_t>(nr.pack >> 32),
-                                                       static_cast<uint32_t>(nr.slot), tag));
-                    st_volatile_u4(rec + 4, make_uint4(static_cast<uint32_t>(nr.size), nr.runner, 0u, tag));
+                    // what this rank's blocks published was visible in this GPU's L2 before their local records were
+                    // written, i.e. before the leader could see them.  The record travels as one bulk asynchronous
+                    // store per peer, so that the acquire fence below does not wait for NVLink acknowledgements.
+                    bulk_wait_read_1();  // the staging line of two iterations ago has been read
+                    uint4* stg = s_rr[par][tid];
+                    stg[0] = make_uint4(static_cast<uint32_t>(d.m1), static_cast<uint32_t>(d.m1 >> 32),
+                                        static_cast<uint32_t>(d.m2 >> 32), tag);
+                    stg[1] = make_uint4(static_cast<uint32_t>(d.a), static_cast<uint32_t>(d.b), static_cast<uint32_t>(d.sa), tag);
+                    stg[2] = make_uint4(static_cast<uint32_t>(d.sb), d.pkey, d.stale, tag);
+                    stg[3] = make_uint4(static_cast<uint32_t>(nr.pack), static_cast<uint32_t>(nr.pack >> 32),
+                                        static_cast<uint32_t>(nr.slot), tag);
+                    stg[4] = make_uint4(static_cast<uint32_t>(nr.size), nr.runner, 0u, tag);
+                    bulk_store(rec, stg, 5 * sizeof(uint4));
                 }
                 __syncthreads();  // s_dec / s_new were read by the pushing threads
                 if (warp == 0) {
@@ -730,7 +762,11 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                         ft.m2 = (static_cast<uint64_t>(r0.z) << 32) | 0xFFFFFFFFull;
                         best = (static_cast<uint64_t>(r3.y) << 32) | r3.x;
                         run = r4.y;
-                        fence_acq_rel<true>();
+                        // acquire at gpu scope: every data load of the loop is ld.global.cg / volatile, which a B200
+                        // never serves from a copy on the requesting GPU when the address is a peer's (measured:
+                        // experiments/nvlink_pingpong.cu, 3 244 cycles for every re-read), and the peers' bulk stores
+                        // into this GPU's memory land in its own L2.  A system-scope fence here cost 3 400 cycles.
+                        fence_acq_rel<false>();
                     }
                     const uint64_t mine = ft.m1;
                     ft = warp_top2(ft);
@@ -983,7 +1019,10 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     val = __uint_as_float(kInfBits);  // inadmissible for good: sizes only grow (:228)
                 else
                     val = lance_williams(sa, sb, kk.y, dka, dkb, dab);
-                __stcg(row_b + k, val);                                              // the new cluster's row (coalesced)
+                if (kMulti)
+                    s_newrow[i] = val;       // the new cluster's row: staged, shipped to its owner as one bulk store
+                else
+                    __stcg(row_b + k, val);  // the new cluster's row (coalesced)
                 __stcg(dm_own + static_cast<int64_t>(k - r_lo) * ld + b, val);       // mirrored entry in this block's own row k
                 const uint64_t cd = pack_cand(val, static_cast<uint32_t>(kk.x));
                 if (cd < ubest) {
@@ -1049,8 +1088,14 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                         db1 = __ldcg(row_b + k);
                     }
                 }
-                if (ok0) update_slot(i0, kk0, da0, db0);
-                if (ok1) update_slot(i1, kk1, da1, db1);
+                if (ok0)
+                    update_slot(i0, kk0, da0, db0);
+                else if (kMulti && i0 < cnt)
+                    s_newrow[i0] = __uint_as_float(kInfBits);  // columns of retired slots / of a and b: never read
+                if (ok1)
+                    update_slot(i1, kk1, da1, db1);
+                else if (kMulti && i1 < cnt)
+                    s_newrow[i1] = __uint_as_float(kInfBits);
             }
         }
         {  // per-warp part of the new row's minimum; the block's fold happens in the next publish
@@ -1068,6 +1113,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         }
         if (tid == 0 && s_qtail - s_qhead > qcap) s_err = 1;  // dry queue overflow (cannot happen)
         __syncthreads();
+        if (kMulti && merged && tid == kT - 1 && cnt4 > 0) bulk_store(row_b + lo, s_newrow, static_cast<uint32_t>(cnt4) * 4u);
         const long long t4 = timed ? clock64() : 0;
 
         // rows that ran dry in this update pass will be scanned one or two iterations from now: pull them into L2
@@ -1121,6 +1167,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         st.prof[6] = epoch;
         for (int i = 0; i < 6; ++i) st.prof[10 + i] = c_sub[i];
     }
+    if (kMulti && (tid == kT - 1 || (blk == 0 && tid < P))) bulk_wait_all();  // this thread's bulk stores have landed
     // the partner lists live in shared memory during the loop: write the slice back for resume / read-back
     __syncthreads();
     for (int32_t i = tid; i < cnt * kNNK; i += kT) st.nn[static_cast<int64_t>(lo) * kNNK + i] = s_nn[i];
@@ -1189,7 +1236,7 @@ cudaError_t merge_loop_grid(int num_sms, int64_t n, int n_ranks, int n_local, in
                             int* blocks_per_rank) {
     *blocks_per_rank = 0;
     if (n_ranks < 1 || n_ranks > kMaxRanks || n_local < 1 || n_local > n_ranks) return cudaErrorInvalidValue;
-    const int64_t C = (n + n_ranks - 1) / n_ranks;
+    const int64_t C = merge_loop_rows_per_rank(n, n_ranks);
     // the exchange costs grow with the number of blocks: small problems use fewer
     // (measured on B200: 48 blocks at n = 20k, 111 at n = 100k; more blocks make the all-to-all dearer than the
     // per-block work they save)

@@ -18,8 +18,8 @@ from . import _lib
 
 
 def rows_per_rank(n: int, world: int) -> int:
-    """C = ceil(n / world): rank r owns the slots [r*C, (r+1)*C)."""
-    return -(-int(n) // int(world)) if n > 0 else 0
+    """C = ceil(n / world) rounded up to a multiple of 4: rank r owns the slots [r*C, (r+1)*C)."""
+    return (-(-int(n) // int(world)) + 3) // 4 * 4 if n > 0 else 0
 
 
 def row_range(n: int, rank: int, world: int):

@@ -127,7 +127,7 @@ int ic_build_clusters(ic_ctx *ctx, int64_t min_size, int32_t *cluster_offsets, i
  * (BASELINE north_star: "the distance matrix is row-block sharded across the 8 GPUs";
  * the reference has no counterpart: its [][]float32 matrix lives in one process,
  * clustering.go:61-73.)  One process per GPU; rank r keeps the rows of the slots
- * [r*C, (r+1)*C), C = ceil(n / world), with all their columns.  Every rank makes the
+ * [r*C, (r+1)*C), C = ceil(n / world) rounded up to a multiple of 4, with all their columns.  Every rank makes the
  * same calls with the same X, min/max; every rank gets the complete result.
  *   ic_shard_init(ctx, rank, world)            before ic_load
  *   ic_load(ctx, x, ...)                        the whole X on every rank (replicated, <= 2 GB)

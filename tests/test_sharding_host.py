@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("n,world", [(0, 2), (1, 8), (7, 2), (8, 8), (1000, 3), (100_000, 8), (250_000, 8), (20_001, 4)])
 def test_row_ranges_partition_the_slots(n, world):
     c = sharding.rows_per_rank(n, world)
-    assert c * world >= n and (n == 0 or (c - 1) * world < n)
+    assert c % 4 == 0 and c * world >= n and (n == 0 or (c - 4) * world < n)
     covered = []
     for r in range(world):
         lo, hi = sharding.row_range(n, r, world)
