@@ -51,7 +51,7 @@ constexpr int kW = kT / 32;
 constexpr int kMaxBlocks = 160;  // blocks per rank: one record per lane of 5 polling warps, x3 parts
 constexpr int kMaxReqTotal = kMaxBlocks * kReqPerBlock;
 constexpr uint32_t kMoreBit = 1u, kDryBit = 2u, kReqBit = 4u;
-constexpr int kMaxSplit = 2;  // parts a block's scan window may be split into
+constexpr int kMaxSplit = 4;  // parts a block's scan window may be split into
 constexpr int kRankboxFlagBytes = 256;
 
 // block record chunks (uint4 each, .w = tag)
@@ -311,7 +311,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     // column window this block scans when a row of its rank is rescanned
     const int32_t W = (((n4 + G - 1) / G) + 3) & ~3;
     const int32_t w0 = min(n4, blk * W), w1 = min(n4, w0 + W);
-    const int split = W > 512 ? kMaxSplit : 1;  // warps per (request, block): one batch of 4 x 16-byte loads per lane
+    const int split = W > 1024 ? 4 : (W > 512 ? 2 : 1);  // warps per (request, block): ~one batch of 4 x 16-byte loads per lane
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     const size_t c1 = static_cast<size_t>(chunk > 0 ? chunk : 4);
@@ -1242,7 +1242,9 @@ cudaError_t merge_loop_grid(int num_sms, int64_t n, int n_ranks, int n_local, in
     // per-block work they save)
     int64_t G = want_blocks;
     if (G <= 0) {
-        G = (C + 399) / 400;
+        // ~400 slots of the update pass per block, and scan windows (n / G columns of a rescanned row, whatever the
+        // number of ranks) of at most ~900 columns
+        G = std::max<int64_t>((C + 399) / 400, (n + 899) / 900);
         if (G < 8) G = std::min<int64_t>(8, (C + 63) / 64);
         if (G > 111) G = 111;
     }
