@@ -333,7 +333,11 @@ def main():
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "clocks": clocks,
             "roofline": {"kernel": "merge_loop_kernel (K3, persistent)", "bound": "hbm", "achieved": loop_gbs,
-                         "peak": hbm, "unit": "GB/s", "frac": loop_gbs / hbm, "traffic": None,
+                         "peak": hbm, "unit": "GB/s", "frac": loop_gbs / hbm,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full at this exact
+                         # workload (profiles/r01_summary.md); GB per launch like `achieved`'s numerator (60 GB)
+                         "traffic": 971.4 if (args.config == "C" and world == 1 and not args.n) else None,
+                         "traffic_unit": "GB per launch (ncu, profiles/r01_summary.md)",
                          "peak_source": peaks["source"] + " copy bandwidth",
                          "note": "algorithmic bytes 12*n per merge; the loop is a chain of dependent merges bound by one "
                                  "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth",
