@@ -187,6 +187,31 @@ class Engine:
                                     x.strides[0] // 4))
         self.n, self.d = x.shape
 
+    def load_combined(self, image_embeddings, item_labels, label_set):
+        """``GenerateLabelVector`` + ``CombineEmbeddings`` (embeddings.go:166-183, workflow.go:167-168) on the
+        device: ``image_embeddings`` is ``[N x D_img]``, ``item_labels[i]`` the label names of item ``i``,
+        ``label_set`` the ``name -> index`` map (``BuildLabelSet``).  Only the image block and the label indices
+        are uploaded; the ``[N x (D_img + len(label_set))]`` matrix is formed in HBM."""
+        img = self._as_matrix(image_embeddings)
+        n, d_img = img.shape
+        if len(item_labels) != n:
+            raise ValueError("one label list per item")
+        offsets = np.zeros(n + 1, np.int32)
+        ids = []
+        for i, labels in enumerate(item_labels):
+            # the map lookup of embeddings.go:169; a label outside the set becomes -1 and is ignored by the kernel
+            ids.extend(label_set.get(name, -1) for name in labels)
+            offsets[i + 1] = len(ids)
+        ids = np.asarray(ids if ids else [0], np.int32)
+        self._check(self._L.ic_load_combined(self._h, img.ctypes.data_as(C.c_void_p), n, d_img, img.strides[0] // 4,
+                                             _i32p(offsets), _i32p(ids), len(label_set)))
+        self.n, self.d = n, d_img + len(label_set)
+
+    def read_x(self) -> np.ndarray:
+        out = np.zeros((self.n, max(self.d, 1)), np.float32)
+        self._check(self._L.ic_read_x(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), max(self.d, 1)))
+        return out[:, :self.d]
+
     def load_device(self, ptr: int, n: int, d: int, ldx: int):
         self._check(self._L.ic_load_device(self._h, C.c_void_p(ptr), n, d, ldx))
         self.n, self.d = n, d

@@ -757,6 +757,62 @@ int ic_load_device(ic_ctx* ctx, const float* x_dev, int64_t n, int64_t d, int64_
     return load_common(ctx, x_dev, n, d, ldx, cudaMemcpyDeviceToDevice);
 }
 
+int ic_load_combined(ic_ctx* ctx, const float* img_host, int64_t n, int64_t d_img, int64_t ld_img,
+                     const int32_t* label_offsets, const int32_t* label_ids, int64_t n_labels) {
+    if (!ctx) return IC_ERR_BAD_ARG;
+    if (n_labels < 0 || d_img < 0 || (n > 0 && !label_offsets)) return fail(ctx, IC_ERR_BAD_ARG, "bad label arguments");
+    const int64_t d = d_img + n_labels;
+    int rc = validate_sizes(ctx, n, d_img, ld_img);
+    if (rc != IC_OK) return rc;
+    if (n > 0 && d_img > 0 && !img_host) return fail(ctx, IC_ERR_BAD_ARG, "img is NULL");
+    const int64_t nnz = n > 0 ? label_offsets[n] : 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (label_offsets[i] < 0 || label_offsets[i] > label_offsets[i + 1])
+            return fail(ctx, IC_ERR_BAD_ARG, "label_offsets must be non-decreasing");
+    if (nnz > 0 && !label_ids) return fail(ctx, IC_ERR_BAD_ARG, "label_ids is NULL");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    rc = alloc_problem(ctx, n, d);
+    if (rc != IC_OK) return rc;
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.n_items = n;
+    ctx->stats.dim = d;
+    ctx->stats.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
+    ctx->stats.matrix_bytes = static_cast<int64_t>(sizeof(float)) * (row_end(ctx) - row_begin(ctx)) * ctx->ld;
+    int32_t *d_off = nullptr, *d_ids = nullptr;
+    IC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (n > 0) {
+        if (d_img > 0)  // copy(combined, embedding): the image block of every row (embeddings.go:180)
+            IC_CUDA(cudaMemcpy2DAsync(ctx->x, sizeof(float) * d, img_host, sizeof(float) * ld_img, sizeof(float) * d_img, n,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        IC_CUDA(cudaMalloc(&d_off, sizeof(int32_t) * (n + 1)));
+        IC_CUDA(cudaMalloc(&d_ids, sizeof(int32_t) * (nnz > 0 ? nnz : 1)));
+        IC_CUDA(cudaMemcpyAsync(d_off, label_offsets, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz > 0)
+            IC_CUDA(cudaMemcpyAsync(d_ids, label_ids, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+        IC_CUDA(launch_label_block(ctx->x, n, d, d_img, d_off, d_ids, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.h2d_bytes += static_cast<int64_t>(sizeof(float)) * n * d_img + 4 * (n + 1 + nnz);
+    }
+    IC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));  // the host arrays and the two temporaries are done with
+    if (d_off) cudaFree(d_off);
+    if (d_ids) cudaFree(d_ids);
+    ctx->loaded = true;
+    return IC_OK;
+}
+
+int ic_read_x(ic_ctx* ctx, float* out_host, int64_t ld) {
+    if (!ctx || !out_host) return IC_ERR_BAD_ARG;
+    if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no problem loaded");
+    if (ld < ctx->d) return fail(ctx, IC_ERR_BAD_ARG, "ld < d");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->n > 0 && ctx->d > 0)
+        IC_CUDA(cudaMemcpy2DAsync(out_host, sizeof(float) * ld, ctx->x, sizeof(float) * ctx->d, sizeof(float) * ctx->d,
+                                  ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IC_OK;
+}
+
 int ic_initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
     if (!ctx) return IC_ERR_BAD_ARG;
     IC_CUDA(cudaSetDevice(ctx->device));

@@ -29,6 +29,9 @@ cudaError_t launch_colsum(const float* x, int64_t n, int64_t d, int64_t ldx, dou
 cudaError_t launch_split(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
                          float* hi, float* lo, double* norms, int64_t n_pad, int64_t d_pad, cudaStream_t s);
 cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s);
+// label block of the combined feature rows (embeddings.go:166-183): x[i][d_img + id] = 1 for the item's labels, else 0
+cudaError_t launch_label_block(float* x, int64_t n, int64_t d, int64_t d_img, const int32_t* label_offsets,
+                               const int32_t* label_ids, cudaStream_t s);
 // ks[s] = {s, 1}, gkey[s] = s (padding up to a multiple of 4: -1)
 cudaError_t launch_init_slots(SlotKS* ks, int32_t* gkey, int64_t n, cudaStream_t s);
 

@@ -192,37 +192,6 @@ IC_DEVINL int warp_select_scan(const ScanCand& c, uint64_t (&pk)[kNNK], int32_t 
     return m;
 }
 
-// Warp-wide selection of the (up to) kNNK smallest candidates from every lane's two smallest.
-// EXACT: the list is cut right after an entry that was a lane's second smallest while that lane
-// saw more than two candidates (its unseen third could be smaller than what follows).
-IC_DEVINL int warp_select_topk(const Cand2& c, uint64_t (&pk)[kNNK], int32_t (&sl)[kNNK], bool& more) {
-    int total = c.cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    int taken = 0, m = 0;
-#pragma unroll
-    for (int r = 0; r < kNNK; ++r) {
-        pk[r] = kPackInf;
-        sl[r] = -1;
-    }
-#pragma unroll
-    for (int r = 0; r < kNNK; ++r) {
-        const uint64_t cand = taken == 0 ? c.c1 : (taken == 1 ? c.c2 : kPackInf);
-        const uint64_t wm = warp_min_u64(cand);
-        if (wm == kPackInf) break;  // warp uniform
-        const bool win = cand == wm;  // packs are unique: exactly one lane
-        const int src = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
-        const int32_t myslot = taken == 0 ? c.s1 : c.s2;
-        pk[r] = wm;
-        sl[r] = __shfl_sync(0xffffffffu, myslot, src);
-        if (win) ++taken;
-        m = r + 1;
-        if (__ballot_sync(0xffffffffu, win && taken == 2 && c.cnt > 2)) break;
-    }
-    more = total > m;
-    return m;
-}
-
 // Warp-wide merge of one sorted list per lane (m entries, `more`: unlisted entries >= the last one
 // exist).  Same exactness rule: cut right after a list's last entry if that list has more.
 IC_DEVINL void warp_merge_lists(const PartList& in, PartList& out) {

@@ -122,6 +122,30 @@ cudaError_t launch_fill(float* dm, int64_t count, float value, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// GenerateLabelVector + the label half of CombineEmbeddings (embeddings.go:166-183): one block per item writes the
+// zeros of its label block, then 1.0 at every label index of the item that lies inside the label set.
+__global__ void __launch_bounds__(128) label_block_kernel(float* __restrict__ x, int64_t d, int64_t d_img,
+                                                          const int32_t* __restrict__ label_offsets,
+                                                          const int32_t* __restrict__ label_ids) {
+    const int64_t row = blockIdx.x;
+    float* lab = x + row * d + d_img;
+    const int64_t n_labels = d - d_img;
+    for (int64_t j = threadIdx.x; j < n_labels; j += blockDim.x) lab[j] = 0.0f;  // make([]float32, len(labelSet))
+    __syncthreads();
+    const int32_t b = label_offsets[row], e = label_offsets[row + 1];
+    for (int32_t q = b + threadIdx.x; q < e; q += blockDim.x) {
+        const int32_t id = label_ids[q];
+        if (id >= 0 && id < n_labels) lab[id] = 1.0f;  // labelVector[idx] = 1.0 if the label exists in the set
+    }
+}
+
+cudaError_t launch_label_block(float* x, int64_t n, int64_t d, int64_t d_img, const int32_t* label_offsets,
+                               const int32_t* label_ids, cudaStream_t s) {
+    if (n == 0 || d == d_img) return cudaSuccess;
+    label_block_kernel<<<static_cast<unsigned>(n), 128, 0, s>>>(x, d, d_img, label_offsets, label_ids);
+    return cudaGetLastError();
+}
+
 __global__ void init_slots_kernel(SlotKS* __restrict__ ks, int32_t* __restrict__ gkey, int64_t n, int64_t n4) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) ks[i] = make_int2(static_cast<int32_t>(i), 1);  // NewCluster, clustering.go:18-26

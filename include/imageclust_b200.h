@@ -103,6 +103,17 @@ int ic_cluster_with_constraints(ic_ctx *ctx, const float *x, int64_t n, int64_t 
 /* upload X (host pointer) or adopt a device pointer (copied), then K0 prep */
 int ic_load(ic_ctx *ctx, const float *x_host, int64_t n, int64_t d, int64_t ldx);
 int ic_load_device(ic_ctx *ctx, const float *x_dev, int64_t n, int64_t d, int64_t ldx);
+/* Input formation on the device -- the step right before the path:
+ * GenerateLabelVector + CombineEmbeddings, internal/embeddings/embeddings.go:166-183, called per item at
+ * internal/workflow/workflow.go:167-168.  Row i of X = image embedding i (d_img floats) ++ a vector over the label
+ * set (n_labels floats) holding 1.0 at the index of every label of item i that is in the set, 0.0 elsewhere.
+ * label_ids[label_offsets[i] .. label_offsets[i+1]) are item i's labels as indices into the label set (the shim does
+ * the map[string]int lookup of embeddings.go:169); an index outside [0, n_labels) stands for a label that is not in
+ * the set and is ignored, as the reference ignores it.  Only the image block crosses PCIe. */
+int ic_load_combined(ic_ctx *ctx, const float *img_host, int64_t n, int64_t d_img, int64_t ld_img,
+                     const int32_t *label_offsets, const int32_t *label_ids, int64_t n_labels);
+/* the resident X [n x d] back on the host (row stride ld >= d) -- inspection / tests */
+int ic_read_x(ic_ctx *ctx, float *out_host, int64_t ld);
 /* ComputeInitialDistanceMatrix + WardDistance + DotFloat32, clustering.go:61-73,136-157 */
 int ic_initial_distances(ic_ctx *ctx, int mode, int64_t max_size);
 /* replace the resident matrix (host [n x n], row stride ld) -- test hook */

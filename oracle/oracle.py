@@ -207,3 +207,22 @@ def fast_cluster(x, min_size: int, max_size: int, flags: int = 0, n_threads: int
                                       n_threads or (os.cpu_count() or 1), _fp(init_matrix),
                                       _ip(offsets), _ip(members), C.byref(n_out), C.byref(tr), C.byref(st))
     return _finish(rc, st, arrs, offsets, members, n_out)
+
+
+# ---- input formation: literal restatement, plain Python loops (tiny inputs only) ----------------
+
+def generate_label_vector(labels, label_set):
+    """``GenerateLabelVector`` -- /root/reference/internal/embeddings/embeddings.go:166-174."""
+    label_vector = [np.float32(0.0)] * len(label_set)       # make([]float32, len(labelSet))          :167
+    for label in labels:                                    # for _, label := range labels            :168
+        if label in label_set:                              # if idx, exists := labelSet[label]       :169
+            label_vector[label_set[label]] = np.float32(1.0)  # labelVector[idx] = 1.0                :170
+    return np.asarray(label_vector, np.float32)
+
+
+def combine_embeddings(embedding, label_vector):
+    """``CombineEmbeddings`` -- /root/reference/internal/embeddings/embeddings.go:177-183."""
+    combined = np.zeros(len(embedding) + len(label_vector), np.float32)  # make(..., len(e)+len(l))  :179
+    combined[:len(embedding)] = embedding                                 # copy(combined, embedding) :180
+    combined[len(embedding):] = label_vector                              # copy(combined[len(e):], l) :181
+    return combined
