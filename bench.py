@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override N (debug)")
     ap.add_argument("--ref-n", type=int, default=1500, help="sample size of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gram-mode", type=int, default=0)
+    ap.add_argument("--gram-mode", type=int, default=2, help="2: tcgen05 kind::i8 (default), 0: tcgen05 kind::tf32, 1: exact fp32 SIMT")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent clusterings instead of one sharded one")
     args = ap.parse_args()
 
@@ -280,10 +280,8 @@ def main():
     kern = {}
     if rank == 0 and not sharded:
         eng.load(x_host)
-        if args.gram_mode == 0:
-            kern["gram_ms"] = eng.time_kernel("gram", 3)
-        else:
-            kern["gram_ms"] = eng.time_kernel("gram_exact", 1)
+        kern["gram_ms"] = eng.time_kernel({0: "gram", 1: "gram_exact", 2: "gram_i8"}[args.gram_mode],
+                                          1 if args.gram_mode == 1 else 3)
         kern["nn_sweep_ms"] = eng.time_kernel("nn_sweep", 5)
     if world > 1:
         dist.barrier()
@@ -314,14 +312,14 @@ def main():
             "metric": METRIC, "value": sec_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": False,
             "scaling": "strong" if sharded else "weak",
-            "vs_baseline": None, "dtype": "f32" if args.gram_mode else "tf32+f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {0: "tf32+f32", 1: "f32", 2: "i8/i32 (22-bit fixed point) + f32"}[args.gram_mode], "data": "synthetic",
             "config": {"workload": f"config {args.config}: N={n} x {d} Gaussian-mixture fp32 embeddings, "
                                    f"minSize={mn}, maxSize={mx} -> {stats[-1]['n_target']} clusters, {merges} merges",
                        "parallelism": "1 GPU" if world == 1 else (
                            f"one clustering row-block sharded over {world} GPUs (peer-mapped rows + per-merge record "
                            f"exchange over NVLink)" if sharded else f"{world} independent clustering jobs (one per GPU)"),
                        "l2": "inputs larger than L2 (X %.0f MB, distance matrix %.1f GB)" % (4e-6 * n * d, stats[-1]["matrix_bytes"] / 1e9),
-                       "gram": "tcgen05 kind::tf32, exact fixed-point slice + residual (4 products)" if args.gram_mode == 0 else "exact fp32 SIMT"},
+                       "gram": {0: "tcgen05 kind::tf32, exact fixed-point slice + residual (4 products)", 1: "exact fp32 SIMT", 2: "tcgen05 kind::i8, three int8 digits of a 22-bit fixed-point row, exact int32 accumulation (6 products)"}[args.gram_mode]},
             "merges_per_s": merges / (ms_loop * 1e-3) if ms_loop > 0 else None,
             "dist_matrix_gbs": 4.0 * pairs / (ms_gram * 1e-3) / 1e9 if ms_gram > 0 else None,
             "phases_ms": phases,
@@ -343,12 +341,12 @@ def main():
                                  "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth",
                          "dominant_phase": dominant},
             "kernels": None if sharded else {
-                "gram_tcgen05" if args.gram_mode == 0 else "gram_exact": {
+                {0: "gram_tcgen05", 1: "gram_exact", 2: "gram_i8"}[args.gram_mode]: {
                     "bound": "tensor", "achieved": gram_tf, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": gram_tf / tf32_peak, "ms": kern.get("gram_ms"),
-                    "note": "algorithmic flops 2*D per unordered pair; the exact-slice split issues 4 tcgen05.mma "
-                            "kind::tf32 per k-step (4x the algorithmic flops on the pipe); peak = measured sustained "
-                            "bf16 / 2 (TF32 dense)"},
+                    "note": "algorithmic flops 2*D per unordered pair over the fp32-accurate (TF32-equivalent) peak = measured "
+                            "sustained bf16 / 2; the int8 path issues 6 kind::i8 MMAs per k-step (6x the algorithmic "
+                            "flops, on a pipe 4x as fast), the tf32 path 4 kind::tf32 MMAs"},
                 "nn_sweep": {"bound": "hbm", "achieved": sweep_gbs, "peak": hbm, "unit": "GB/s", "frac": sweep_gbs / hbm,
                              "ms": kern.get("nn_sweep_ms"), "note": "algorithmic bytes 4 per pair (lower triangle read once)"},
             },

@@ -25,6 +25,7 @@ IC_ERR_INTERNAL = -9
 
 GRAM_TCGEN05_3XTF32 = 0
 GRAM_EXACT_FP32 = 1
+GRAM_TCGEN05_I8 = 2
 
 # every symbol include/imageclust_b200.h declares
 SYMBOLS = [

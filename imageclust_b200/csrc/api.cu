@@ -29,7 +29,7 @@ struct ic_ctx {
     // options
     double near_tie_tol = 1e-5;
     int center = 1;
-    int gram_mode = IC_GRAM_TCGEN05_3XTF32;
+    int gram_mode = IC_GRAM_TCGEN05_I8;
     int verbose = 0;
     int gram_terms = 23;      // debug: which products of the split K1 issues
     int loop_blocks = 0;      // merge-loop blocks per rank, 0 = auto
@@ -60,7 +60,13 @@ struct ic_ctx {
     double *colsum = nullptr, *norms = nullptr;
     int2* tiles = nullptr;
     int n_tiles = 0;
-    bool prepped = false;
+    // int8 path (IC_GRAM_TCGEN05_I8)
+    int8_t *i8h = nullptr, *i8m = nullptr, *i8l = nullptr;
+    float* quanta = nullptr;
+    int64_t d_pad8 = 0;
+    int2* tiles8 = nullptr;
+    int n_tiles8 = 0;
+    bool prepped = false, prepped_i8 = false;
     float* dm = nullptr;
     SlotKS* ks = nullptr;
     int32_t* gkey = nullptr;
@@ -125,6 +131,11 @@ void release_problem(ic_ctx* c) {
     dev_free(c->colsum);
     dev_free(c->norms);
     dev_free(c->tiles);
+    dev_free(c->i8h);
+    dev_free(c->i8m);
+    dev_free(c->i8l);
+    dev_free(c->quanta);
+    dev_free(c->tiles8);
     dev_free(c->dm);
     dev_free(c->ks);
     dev_free(c->gkey);
@@ -140,7 +151,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->rankbox);
     dev_free(c->prof);
     dev_free(c->ctl);
-    c->loaded = c->have_dm = c->have_nn = c->prepped = false;
+    c->loaded = c->have_dm = c->have_nn = c->prepped = c->prepped_i8 = false;
     c->n = c->d = 0;
     c->trace_on_host = false;
 }
@@ -218,12 +229,44 @@ int64_t row_end(const ic_ctx* c) {
     return c->shard_world > 1 ? std::min(c->n, row_begin(c) + rows_per_rank(c)) : c->n;
 }
 
+// 128 x 128 tiles of the int8 kernel, lower triangle, in 2048 x 2048 super-tiles (operand panels stay in L2)
+std::vector<int2> build_tile_list_i8(int64_t n, int64_t row_begin, int64_t row_end) {
+    std::vector<int2> tiles;
+    const int nb = static_cast<int>((n + kI8Tile - 1) / kI8Tile);
+    const int S = 16;
+    for (int sr = 0; sr * S < nb; ++sr)
+        for (int sc = 0; sc <= sr; ++sc)
+            for (int rb = sr * S; rb < (sr + 1) * S && rb < nb; ++rb)
+                for (int cb = sc * S; cb < (sc + 1) * S && cb <= rb; ++cb) {
+                    const int64_t r0 = static_cast<int64_t>(rb) * kI8Tile, c0 = static_cast<int64_t>(cb) * kI8Tile;
+                    const bool rows_in = !(r0 + kI8Tile <= row_begin || r0 >= row_end);
+                    const bool cols_in = !(c0 + kI8Tile <= row_begin || c0 >= row_end);
+                    if (!rows_in && !cols_in) continue;
+                    tiles.push_back(make_int2(rb, cb));
+                }
+    return tiles;
+}
+
+int make_operand_map_i8(ic_ctx* ctx, CUtensorMap* map, int8_t* base, int64_t rows, int64_t cols) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(ctx, IC_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kI8BK), static_cast<cuuint32_t>(kI8Tile)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, IC_ERR_CUDA, "cuTensorMapEncodeTiled (int8) failed: " + std::to_string(r));
+    return IC_OK;
+}
+
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 && ctx->loop_blocks == ctx->loop_blocks_alloc &&
         ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && ctx->shard_world == ctx->shard_world_alloc &&
         ctx->shard_rank == ctx->shard_rank_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
-        ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = false;
+        ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = ctx->prepped_i8 = false;
         ctx->trace_on_host = false;
         return IC_OK;
     }
@@ -232,6 +275,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     ctx->d = d;
     ctx->n_pad = round_up(n, kGramBN);
     ctx->d_pad = round_up(d, kGramBK);
+    ctx->d_pad8 = round_up(d, kI8BK);
     ctx->ld = round_up(n, 32);
     ctx->vranks_alloc = ctx->vranks;
     ctx->no_replica_alloc = ctx->no_replica;
@@ -246,7 +290,8 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     size_t free_b = 0, total_b = 0;
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const double need = 4.0 * n * d + 4.0 * static_cast<double>(rows) * ctx->ld +
-                        (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) + 160.0 * n +
+                        (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
+                        (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 160.0 * n +
                         (96 << 20);
     if (need > static_cast<double>(free_b))
         return fail(ctx, IC_ERR_OOM, "problem needs " + std::to_string(need / 1e9) + " GB, device has " +
@@ -331,12 +376,38 @@ int loop_state(ic_ctx* c, LoopState* out) {
     return IC_OK;
 }
 
+int do_prep_i8(ic_ctx* ctx) {
+    if (ctx->prepped_i8) return IC_OK;
+    const size_t pad_elems = static_cast<size_t>(ctx->n_pad) * static_cast<size_t>(ctx->d_pad8);
+    if (!ctx->i8h) IC_CUDA(cudaMalloc(&ctx->i8h, pad_elems ? pad_elems : 1));
+    if (!ctx->i8m) IC_CUDA(cudaMalloc(&ctx->i8m, pad_elems ? pad_elems : 1));
+    if (!ctx->i8l) IC_CUDA(cudaMalloc(&ctx->i8l, pad_elems ? pad_elems : 1));
+    if (!ctx->quanta) IC_CUDA(cudaMalloc(&ctx->quanta, sizeof(float) * static_cast<size_t>(ctx->n_pad ? ctx->n_pad : 1)));
+    if (!ctx->colsum) IC_CUDA(cudaMalloc(&ctx->colsum, sizeof(double) * static_cast<size_t>(std::max(ctx->d_pad, ctx->d_pad8))));
+    if (!ctx->norms) IC_CUDA(cudaMalloc(&ctx->norms, sizeof(double) * static_cast<size_t>(ctx->n_pad ? ctx->n_pad : 1)));
+    IC_CUDA(launch_colsum(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->stream));
+    IC_CUDA(launch_split_i8(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->center, ctx->i8h, ctx->i8m, ctx->i8l,
+                            ctx->quanta, ctx->norms, ctx->n_pad, ctx->d_pad8, ctx->stream));
+    ctx->stats.kernel_launches += 2;
+    if (!ctx->tiles8) {
+        const std::vector<int2> tiles = build_tile_list_i8(ctx->n, row_begin(ctx), row_end(ctx));
+        ctx->n_tiles8 = static_cast<int>(tiles.size());
+        IC_CUDA(cudaMalloc(&ctx->tiles8, sizeof(int2) * (tiles.size() ? tiles.size() : 1)));
+        IC_CUDA(cudaMemcpyAsync(ctx->tiles8, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+        IC_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vector goes out of scope
+    }
+    ctx->prepped_i8 = true;
+    ctx->prepped = false;  // norms now belong to the int8 representation
+    return IC_OK;
+}
+
 int do_prep(ic_ctx* ctx) {
     if (ctx->prepped) return IC_OK;
+    ctx->prepped_i8 = false;  // norms will belong to the tf32 representation
     const size_t pad_elems = static_cast<size_t>(ctx->n_pad) * static_cast<size_t>(ctx->d_pad);
     if (!ctx->hi) IC_CUDA(cudaMalloc(&ctx->hi, sizeof(float) * pad_elems));
     if (!ctx->lo) IC_CUDA(cudaMalloc(&ctx->lo, sizeof(float) * pad_elems));
-    if (!ctx->colsum) IC_CUDA(cudaMalloc(&ctx->colsum, sizeof(double) * static_cast<size_t>(ctx->d_pad)));
+    if (!ctx->colsum) IC_CUDA(cudaMalloc(&ctx->colsum, sizeof(double) * static_cast<size_t>(std::max(ctx->d_pad, ctx->d_pad8))));
     if (!ctx->norms) IC_CUDA(cudaMalloc(&ctx->norms, sizeof(double) * static_cast<size_t>(ctx->n_pad)));
     IC_CUDA(launch_colsum(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->stream));
     IC_CUDA(launch_split(ctx->x, ctx->n, ctx->d, ctx->d, ctx->colsum, ctx->center, ctx->hi, ctx->lo, ctx->norms,
@@ -357,6 +428,20 @@ int do_prep(ic_ctx* ctx) {
 int do_gram(ic_ctx* ctx, int mode) {
     if (mode == IC_GRAM_EXACT_FP32) {
         IC_CUDA(launch_gram_exact(ctx->x, ctx->n, ctx->d, ctx->d, ctx->dm, ctx->ld, row_begin(ctx), row_end(ctx), ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        return IC_OK;
+    }
+    if (mode == IC_GRAM_TCGEN05_I8) {
+        GramI8Plan p8{};
+        int rc8 = make_operand_map_i8(ctx, &p8.map_h, ctx->i8h, ctx->n_pad, ctx->d_pad8);
+        if (rc8 == IC_OK) rc8 = make_operand_map_i8(ctx, &p8.map_m, ctx->i8m, ctx->n_pad, ctx->d_pad8);
+        if (rc8 == IC_OK) rc8 = make_operand_map_i8(ctx, &p8.map_l, ctx->i8l, ctx->n_pad, ctx->d_pad8);
+        if (rc8 != IC_OK) return rc8;
+        p8.tiles = ctx->tiles8;
+        p8.n_tiles = ctx->n_tiles8;
+        p8.k_blocks = static_cast<int>(ctx->d_pad8 / kI8BK);
+        IC_CUDA(launch_gram_i8(p8, ctx->norms, ctx->quanta, ctx->dm, ctx->n, ctx->ld, row_begin(ctx), row_end(ctx),
+                               ctx->num_sms, ctx->stream));
         ctx->stats.kernel_launches += 1;
         return IC_OK;
     }
@@ -563,10 +648,14 @@ int load_common(ic_ctx* ctx, const float* x, int64_t n, int64_t d, int64_t ldx, 
 
 int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
     if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no matrix loaded");
-    if (mode != IC_GRAM_TCGEN05_3XTF32 && mode != IC_GRAM_EXACT_FP32) return fail(ctx, IC_ERR_BAD_ARG, "bad gram mode");
+    if (mode != IC_GRAM_TCGEN05_3XTF32 && mode != IC_GRAM_EXACT_FP32 && mode != IC_GRAM_TCGEN05_I8)
+        return fail(ctx, IC_ERR_BAD_ARG, "bad gram mode");
     IC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (mode == IC_GRAM_TCGEN05_3XTF32) {
         const int rc = do_prep(ctx);
+        if (rc != IC_OK) return rc;
+    } else if (mode == IC_GRAM_TCGEN05_I8) {
+        const int rc = do_prep_i8(ctx);
         if (rc != IC_OK) return rc;
     }
     IC_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -615,7 +704,7 @@ int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offse
     int rc = ic_optimal_clusters(ctx->n, min_size, max_size, &n_target);
     if (rc != IC_OK) return fail(ctx, rc, "cluster size constraints cannot be satisfied");
     ctx->n_target = n_target;
-    ctx->prepped = false;  // K0 is part of the path: redo it on every run
+    ctx->prepped = ctx->prepped_i8 = false;  // K0 is part of the path: redo it on every run
     rc = initial_distances(ctx, ctx->gram_mode, max_size);
     if (rc != IC_OK) return rc;
     rc = nn_init(ctx);
@@ -709,7 +798,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         ctx->center = value != 0.0;
     else if (k == "gram_mode") {
         const int m = static_cast<int>(value);
-        if (m != IC_GRAM_TCGEN05_3XTF32 && m != IC_GRAM_EXACT_FP32) return fail(ctx, IC_ERR_BAD_ARG, "bad gram_mode");
+        if (m != IC_GRAM_TCGEN05_3XTF32 && m != IC_GRAM_EXACT_FP32 && m != IC_GRAM_TCGEN05_I8)
+            return fail(ctx, IC_ERR_BAD_ARG, "bad gram_mode");
         ctx->gram_mode = m;
     } else if (k == "loop_threads") {
         const int t = static_cast<int>(value);  // kept for compatibility: the loop kernel has 512 threads
@@ -1062,12 +1152,19 @@ int ic_time_kernel(ic_ctx* ctx, const char* which, int repeats, float* ms_each) 
         const int rc = do_prep(ctx);
         if (rc != IC_OK) return rc;
     }
+    if (k == "gram_i8") {
+        const int rc = do_prep_i8(ctx);
+        if (rc != IC_OK) return rc;
+    }
     if (k == "nn_sweep" && !ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     IC_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
     for (int r = 0; r < repeats; ++r) {
         if (k == "gram") {
             const int rc = do_gram(ctx, IC_GRAM_TCGEN05_3XTF32);
+            if (rc != IC_OK) return rc;
+        } else if (k == "gram_i8") {
+            const int rc = do_gram(ctx, IC_GRAM_TCGEN05_I8);
             if (rc != IC_OK) return rc;
         } else if (k == "gram_exact") {
             const int rc = do_gram(ctx, IC_GRAM_EXACT_FP32);
@@ -1084,7 +1181,7 @@ int ic_time_kernel(ic_ctx* ctx, const char* which, int repeats, float* ms_each) 
     IC_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
     IC_CUDA(cudaEventSynchronize(ctx->ev[9]));
     *ms_each = ev_ms(ctx->ev[8], ctx->ev[9]) / static_cast<float>(repeats);
-    if (k == "gram" || k == "gram_exact") ctx->have_dm = true;
+    if (k == "gram" || k == "gram_exact" || k == "gram_i8") ctx->have_dm = true;
     if (k != "split") ctx->have_nn = false;  // the loop state no longer matches the matrix
     return IC_OK;
 }

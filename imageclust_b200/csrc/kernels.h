@@ -52,6 +52,25 @@ struct GramPlan {
 cudaError_t launch_gram_tcgen05(const GramPlan& plan, const double* norms, float* dm, int64_t n, int64_t ld,
                                 int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s, int terms = 23);
 size_t gram_tcgen05_smem_bytes();
+
+// ---- K1 (int8 Ozaki slices): the same Gram identity with EXACT integer tensor-core arithmetic -----------------
+// K0': x_c = x - mean is rounded to a 21-bit fixed-point value per row, v = rint(x_c / q_i), q_i = 2^(e_i - 20), and cut
+// into three balanced base-128 digits v = h*2^14 + m*2^7 + l (each in [-64, 64]); norm_i = q_i^2 * sum v^2 (double).
+constexpr int kI8Tile = 128;   // tile rows == tile cols (UMMA M = N = 128)
+constexpr int kI8BK = 128;     // int8 elements per 128-byte swizzle row
+cudaError_t launch_split_i8(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
+                            int8_t* h, int8_t* m, int8_t* l, float* quanta, double* norms, int64_t n_pad, int64_t d_pad,
+                            cudaStream_t s);
+struct GramI8Plan {
+    CUtensorMap map_h, map_m, map_l;  // box {128 bytes, 128 rows} over the slice arrays [n_pad x d_pad] (int8)
+    const int2* tiles;                // (row block, col block) of 128 x 128 tiles, L2-friendly order
+    int n_tiles;
+    int k_blocks;                     // d_pad / 128
+};
+// six kind::i8 products per k-step into three int32 TMEM accumulators (weights 2^28, 2^21, 2^14); the three dropped
+// low-order products are below 2^-21 of the Gram value.  Same output contract as launch_gram_tcgen05.
+cudaError_t launch_gram_i8(const GramI8Plan& plan, const double* norms, const float* quanta, float* dm, int64_t n,
+                           int64_t ld, int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s);
 // audit kernel: the reference's own arithmetic (sequential fp32, clustering.go:136-157), bit exact
 cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx, float* dm, int64_t ld,
                               int64_t row_begin, int64_t row_end, cudaStream_t s);

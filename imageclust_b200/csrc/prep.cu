@@ -96,6 +96,93 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
     }
 }
 
+// K0' for the int8 path.  One block per row: 22-bit fixed point relative to the row's largest |x_c|, three balanced
+// base-128 digits (the leading one uses the whole int8 range).  A row with a non-finite value gets norm = NaN: all its distances become NaN, which never win
+// (the reference's strict '<', clustering.go:124).
+__global__ void __launch_bounds__(256) split_i8_kernel(const float* __restrict__ x, int64_t n, int64_t d, int64_t ldx,
+                                                       const double* __restrict__ colsum, int center,
+                                                       int8_t* __restrict__ hs, int8_t* __restrict__ ms,
+                                                       int8_t* __restrict__ ls, float* __restrict__ quanta,
+                                                       double* __restrict__ norms, int64_t d_pad) {
+    const int64_t row = blockIdx.x;
+    const double inv_n = n > 0 ? 1.0 / static_cast<double>(n) : 0.0;
+    __shared__ float redf[8];
+    __shared__ double red[8];
+    __shared__ int bad[8];
+    float amax = 0.0f;
+    int nonfinite = 0;
+    if (row < n)
+        for (int64_t k = threadIdx.x; k < d; k += blockDim.x) {
+            float v = x[row * ldx + k];
+            if (center) v = __fsub_rn(v, static_cast<float>(colsum[k] * inv_n));
+            const float a = fabsf(v);
+            if (!(a <= 3.0e38f)) nonfinite = 1;
+            else if (a > amax) amax = a;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        nonfinite |= __shfl_xor_sync(0xffffffffu, nonfinite, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        redf[threadIdx.x >> 5] = amax;
+        bad[threadIdx.x >> 5] = nonfinite;
+    }
+    __syncthreads();
+    amax = redf[0];
+    nonfinite = bad[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+        amax = fmaxf(amax, redf[w]);
+        nonfinite |= bad[w];
+    }
+    if (amax < 1e-30f) amax = 1e-30f;  // an all-zero row: every digit is 0 whatever the scale
+    int e = 0;
+    const float fr = frexpf(amax, &e);         // amax = fr * 2^e, fr in [0.5, 1)
+    // quantum: 22 bits including the sign, v = h*2^14 + m*2^7 + l with h in [-127, 127], m, l in [-64, 63]; the
+    // largest representable |v| is 127*2^14 + 63*2^7 + 63 = 2088895 < 2^21: rows whose maximum sits in the top 0.4 %
+    // of their binade take the next quantum
+    if (fr * 2097152.0f > 2088000.0f) ++e;
+    const float q = ldexpf(1.0f, e - 21);
+    const float inv_q = ldexpf(1.0f, 21 - e);
+    double acc = 0.0;
+    for (int64_t k = threadIdx.x; k < d_pad; k += blockDim.x) {
+        int hh = 0, mm = 0, ll = 0;
+        if (row < n && k < d && !nonfinite) {
+            float v = x[row * ldx + k];
+            if (center) v = __fsub_rn(v, static_cast<float>(colsum[k] * inv_n));
+            const int iv = __float2int_rn(v * inv_q);  // |iv| <= 2088000 (the product by a power of two is exact)
+            ll = ((iv + 64) & 127) - 64;         // balanced digits in [-64, 63]; the leading one spans [-127, 127]
+            const int v1 = (iv - ll) >> 7;
+            mm = ((v1 + 64) & 127) - 64;
+            hh = (v1 - mm) >> 7;
+            acc += static_cast<double>(iv) * static_cast<double>(iv);
+        }
+        hs[row * d_pad + k] = static_cast<int8_t>(hh);
+        ms[row * d_pad + k] = static_cast<int8_t>(mm);
+        ls[row * d_pad + k] = static_cast<int8_t>(ll);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const double qd = static_cast<double>(q);
+        norms[row] = nonfinite ? __longlong_as_double(0x7FF8000000000000ll) : t * qd * qd;
+        quanta[row] = q;
+    }
+}
+
+cudaError_t launch_split_i8(const float* x, int64_t n, int64_t d, int64_t ldx, const double* colsum, int center,
+                            int8_t* h, int8_t* m, int8_t* l, float* quanta, double* norms, int64_t n_pad, int64_t d_pad,
+                            cudaStream_t s) {
+    if (n_pad == 0) return cudaSuccess;
+    split_i8_kernel<<<static_cast<unsigned>(n_pad), 256, 0, s>>>(x, n, d, ldx, colsum, center, h, m, l, quanta, norms, d_pad);
+    return cudaGetLastError();
+}
+
 int split_slice_bits(int64_t d_pad) {
     int bits = 1;
     while (bits < 10 && (static_cast<int64_t>(d_pad) << (2 * (bits + 1))) <= (int64_t(1) << 24)) ++bits;

@@ -40,8 +40,10 @@ extern "C" {
 #define IC_ERR_INTERNAL (-9)
 
 /* ic_initial_distances modes */
-#define IC_GRAM_TCGEN05_3XTF32 0 /* K1: TMA + tcgen05 3xTF32 Gram GEMM, fp32 TMEM accumulate (product path) */
+#define IC_GRAM_TCGEN05_3XTF32 0 /* K1 (first version): TMA + tcgen05 kind::tf32, exact fixed-point slice + residual, fp32 TMEM */
 #define IC_GRAM_EXACT_FP32 1     /* SIMT kernel with the reference's own sequential fp32 arithmetic (audit path) */
+#define IC_GRAM_TCGEN05_I8 2     /* K1 (default): TMA + tcgen05 kind::i8, three int8 digits of a 21-bit fixed-point row, exact int32
+                                    accumulation in TMEM (6 products per k-step at 4x the TF32 rate) */
 
 typedef struct ic_ctx ic_ctx;
 

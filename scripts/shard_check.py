@@ -27,7 +27,7 @@ eng = clustering.Engine(local)
 sh = sharding.ShardedEngine(eng, rank, world)
 ok = True
 cases = [(600, 48, 3, 10, _lib.GRAM_EXACT_FP32), (3001, 64, 4, 12, _lib.GRAM_TCGEN05_3XTF32),
-         (5000, 256, 6, 8, _lib.GRAM_TCGEN05_3XTF32)]
+         (5000, 256, 6, 8, _lib.GRAM_TCGEN05_I8)]
 for n, d, mn, mx, mode in cases:
     x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=n + d)
     eng.set_option("gram_mode", mode)
@@ -55,7 +55,7 @@ for n, d, mn, mx, mode in cases:
         print(f"shard_check W={world} N={n} D={d} {mn}/{mx}: merges={st['n_merges']} ranks_agree={same} oracle_exact={exact} "
               f"loop {st['ms_loop']:.2f} ms rescans={st['n_rescans']}", flush=True)
         ok = ok and same and exact
-eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
+eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
 
 if big:
     for cfg in sys.argv[2:] or ["B"]:

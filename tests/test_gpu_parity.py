@@ -144,7 +144,7 @@ def test_full_path_exact_mode_equals_golden(eng, oracle, name):
     try:
         res = eng.cluster(g["x"], mn, mx)
     finally:
-        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
     o = oracle.fast_cluster(g["x"], mn, mx, flags=LW_EAGER)
     assert same_clusters(res.clusters, o.clusters)
     _same_trace(eng.merge_trace(), o)
@@ -177,7 +177,7 @@ def test_many_rows_lose_their_partner(eng, oracle):
     try:
         res = eng.cluster(x, 1, 6)
     finally:
-        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
     _same_trace(eng.merge_trace(), o)
     assert same_clusters(res.clusters, o.clusters)
     lit = oracle.literal_cluster(x, 1, 6)
@@ -256,7 +256,7 @@ def test_members_follow_the_reference_order(eng, oracle):
     try:
         res = eng.cluster(g["x"], int(g["min_size"]), int(g["max_size"]))
     finally:
-        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
     for a, b in zip(res.clusters, golden_clusters(g)):
         assert a.tolist() == b.tolist()
 
@@ -300,7 +300,7 @@ def test_sharded_loop_replays_bit_exact(eng, oracle, knobs, n, d, mn, mx, ranks,
     x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=n + d)
     knobs(virtual_ranks=ranks, loop_blocks=blocks, no_replica=no_replica)
     eng.load(x)
-    eng.initial_distances(_lib.GRAM_TCGEN05_3XTF32, mx)
+    eng.initial_distances(_lib.GRAM_TCGEN05_I8 if ranks % 2 else _lib.GRAM_TCGEN05_3XTF32, mx)
     m0 = eng.read_matrix()
     eng.nn_init()
     eng.merge_loop(mn, mx)
@@ -324,7 +324,7 @@ def test_sharded_duplicates_many_dry_rows(eng, oracle, knobs):
     try:
         res = eng.cluster(x, 1, 6)
     finally:
-        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_3XTF32)
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
     _same_trace(eng.merge_trace(), o)
     assert same_clusters(res.clusters, o.clusters)
 
@@ -361,7 +361,7 @@ def test_config_b_full_size_bit_exact_vs_oracle(eng, oracle):
     n, d, mn, mx = synth.CONFIGS["B"]
     x = synth.gaussian_mixture(n, d, mn, mx, seed=20241)
     eng.load(x)
-    eng.initial_distances(_lib.GRAM_TCGEN05_3XTF32, mx)
+    eng.initial_distances(_lib.GRAM_TCGEN05_I8, mx)
     m0 = eng.read_matrix()
     rows = np.arange(0, n, 97)[:200]
     ref = oracle.initial_matrix(np.ascontiguousarray(x[rows]))
@@ -408,3 +408,40 @@ def test_config_c_full_size_properties_and_sharded_identity(eng, knobs):
     eng.load(x)
     eng.run_resident(mn, mx)
     assert _trace_digest(eng.merge_trace()) == want
+
+
+# ---- K1, int8 path: exact integer tensor-core Gram (gram_i8.cu) -------------------------------------------------
+
+def _gram_case_mode(eng, oracle, x, mode):
+    eng.load(x)
+    eng.initial_distances(mode)
+    m = eng.read_matrix()
+    ref = oracle.initial_matrix(x)
+    assert np.array_equal(m, m.T)
+    assert np.all(np.diag(m) == 0)
+    off = ~np.eye(len(x), dtype=bool)
+    return float((np.abs(m[off] - ref[off]) / ref[off]).max())
+
+
+@pytest.mark.parametrize("n,d,relu", [(256, 64, False), (700, 2048, False), (700, 2048, True), (333, 2148, False),
+                                      (1000, 96, False), (129, 40, False), (130, 300, True)])
+def test_i8_gram_within_tolerance(eng, oracle, n, d, relu):
+    x = synth.gaussian_mixture(n, d, 5, 20, seed=100 + n + d, relu_like=relu)
+    assert _gram_case_mode(eng, oracle, x, _lib.GRAM_TCGEN05_I8) <= RTOL
+
+
+def test_i8_gram_config_e_like(eng, oracle):
+    x = synth.combined_features(600, 2048, 100, 2, 8, seed=7)
+    assert _gram_case_mode(eng, oracle, x, _lib.GRAM_TCGEN05_I8) <= RTOL
+
+
+def test_i8_gram_full_path_replays_bit_exact(eng, oracle):
+    n, d, mn, mx = 3000, 64, 4, 12
+    x = synth.gaussian_mixture(n, d, mn, mx, seed=n + d)
+    eng.load(x)
+    eng.initial_distances(_lib.GRAM_TCGEN05_I8, mx)
+    m0 = eng.read_matrix()
+    eng.nn_init()
+    eng.merge_loop(mn, mx)
+    o = oracle.fast_cluster(x, mn, mx, flags=LW_EAGER, init_matrix=m0)
+    _same_trace(eng.merge_trace(), o)
