@@ -35,7 +35,7 @@ SYMBOLS = [
     "ic_run_resident", "ic_build_clusters", "ic_read_matrix", "ic_read_slots", "ic_get_merge_trace",
     "ic_get_stats", "ic_get_loop_profile", "ic_time_kernel",
     "ic_shard_init", "ic_shard_export", "ic_shard_connect", "ic_shard_rows",
-    "ic_load_combined", "ic_read_x",
+    "ic_load_combined", "ic_read_x", "ic_get_loop_block_waits",
 ]
 SHARD_HANDLE_BYTES = 192
 
@@ -105,6 +105,7 @@ def load():
         "ic_shard_rows": (i32, [vp, i64p, i64p]),
         "ic_load_combined": (i32, [vp, vp, i64, i64, i64, i32p, i32p, i64]),
         "ic_read_x": (i32, [vp, fp, i64]),
+        "ic_get_loop_block_waits": (i32, [vp, i64p, i64, i64p]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():

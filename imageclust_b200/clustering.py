@@ -305,6 +305,13 @@ class Engine:
         self._check(self._L.ic_shard_rows(self._h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
+    def loop_block_waits(self) -> np.ndarray:
+        """Cycles every merge-loop block waited in the exchanges of the last launch (option profile_loop=1)."""
+        out = (C.c_int64 * 256)()
+        nb = C.c_int64(0)
+        self._check(self._L.ic_get_loop_block_waits(self._h, out, 256, C.byref(nb)))
+        return np.array(list(out)[:min(nb.value, 240)], np.int64)
+
     def time_kernel(self, which: str, repeats: int = 1) -> float:
         ms = C.c_float(0)
         self._check(self._L.ic_time_kernel(self._h, which.encode(), int(repeats), C.byref(ms)))

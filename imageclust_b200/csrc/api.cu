@@ -35,7 +35,7 @@ struct ic_ctx {
     int loop_blocks = 0;      // merge-loop blocks per rank, 0 = auto
     int loop_blocks_alloc = -1;
     int profile_loop = 0;     // debug: per-phase cycle counters of the merge loop
-    long long h_prof[16] = {0};
+    long long h_prof[256] = {0};  // [0,16): phases of block 0; [16, 16+G): exchange wait of every block
     // row-block sharding.  vranks > 1: P virtual shards emulated on this one GPU by one
     // cooperative launch (same kernel code path as the multi-GPU build; test hook).
     int vranks = 1;
@@ -311,7 +311,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->tr_dist, sizeof(float) * nn1 * NL));
     IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1 * NL));
     IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16 * NL));
-    IC_CUDA(cudaMalloc(&ctx->prof, sizeof(long long) * 16));
+    IC_CUDA(cudaMalloc(&ctx->prof, sizeof(long long) * 256));
     // merge-loop launch geometry and mailboxes (zeroed once: tags carry the launch generation)
     IC_CUDA(merge_loop_grid(ctx->num_sms, n, P, NL, ctx->loop_blocks, ctx->loop_replica, &ctx->loop_grid));
     if (ctx->loop_grid <= 0) return fail(ctx, IC_ERR_OOM, "merge loop slice does not fit an SM's shared memory");
@@ -323,7 +323,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMemsetAsync(ctx->records, 0, rb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->partials, 0, pb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL, ctx->stream));
-    IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 16, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->loop_gen = 0;
     ctx->loop_launches = 0;
@@ -1125,6 +1125,13 @@ int ic_get_merge_trace(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dis
     if (dist) std::memcpy(dist, ctx->h_dist.data(), 4 * m);
     if (size) std::memcpy(size, ctx->h_size.data(), 4 * m);
     if (gap) std::memcpy(gap, ctx->h_gap.data(), 4 * m);
+    return IC_OK;
+}
+
+int ic_get_loop_block_waits(ic_ctx* ctx, int64_t* out, int64_t capacity, int64_t* n_blocks) {
+    if (!ctx || !out || !n_blocks) return IC_ERR_BAD_ARG;
+    *n_blocks = ctx->loop_grid;
+    for (int64_t i = 0; i < capacity && i < ctx->loop_grid && i < 240; ++i) out[i] = ctx->h_prof[16 + i];
     return IC_OK;
 }
 

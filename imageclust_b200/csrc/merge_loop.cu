@@ -52,6 +52,7 @@ constexpr int kMaxBlocks = 160;  // blocks per rank: one record per lane of 5 po
 constexpr int kMaxReqTotal = kMaxBlocks * kReqPerBlock;
 constexpr uint32_t kMoreBit = 1u, kDryBit = 2u, kReqBit = 4u;
 constexpr int kMaxSplit = 4;  // parts a block's scan window may be split into
+constexpr bool kSharedRecords = true;  // block records: one shared line per writer (false: one per reader and writer)
 constexpr int kRankboxFlagBytes = 256;
 
 // block record chunks (uint4 each, .w = tag)
@@ -72,6 +73,11 @@ IC_DEVINL uint4 ld_volatile_u4(const uint4* p) {
     uint4 v;
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
+}
+// weak write-through store: the five chunks of a record are independent (each carries its own tag), and a thread's
+// volatile stores are performed one after the other (measured: 3 000 cycles until the fifth one was visible)
+IC_DEVINL void st_cg_u4(uint4* p, uint4 v) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 IC_DEVINL void st_volatile_u4(uint4* p, uint4 v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -352,6 +358,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
 
     const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long c_pub = 0, c_exch = 0, c_scan = 0, c_upd = 0, c_fold = 0;
+    long long blk_wait = 0;  // cycles this block waited for the slowest record of every exchange (profile_loop)
     long long c_sub[6] = {0, 0, 0, 0, 0, 0};  // publish: argmin, reduce, fence, stores; exchange: poll, fold
     uint32_t epoch = 0;  // iteration index; records of iteration i carry tag (gen, i+1)
     const uint32_t tagbase = st.gen << 20;
@@ -449,11 +456,17 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             __syncthreads();
             const long long tb = timed ? clock64() : 0;
             long long tc = 0;
-            if (tid < G) {  // push to reader `tid`
+            if (kSharedRecords) {
+                // one line per writer, polled by every block of the rank: 5 stores per block instead of 5 * G
+                // (draining G private copies through one SM's store path took ~3 000 cycles at G = 111)
+                const int nch = s_nmine[par] > 0 ? kChunks : kChunks - 2;  // the request chunks travel only when used
+                tc = timed ? clock64() : 0;
+                if (tid < nch) st_cg_u4(records + (static_cast<size_t>(par) * G + blk) * kRecU4 + tid, s_pub[tid]);
+            } else if (tid < G) {  // push to reader `tid`: a private line per (reader, writer) pair
                 uint4* rec = records + ((static_cast<size_t>(tid) * 2 + par) * G + blk) * kRecU4;
                 tc = timed ? clock64() : 0;
                 const int nch = s_nmine[par] > 0 ? kChunks : kChunks - 2;  // the request chunks travel only when used
-                for (int c = 0; c < nch; ++c) st_volatile_u4(rec + c, s_pub[c]);
+                for (int c = 0; c < nch; ++c) st_cg_u4(rec + c, s_pub[c]);
             }
             if (timed) {
 #ifndef IC_SCAN_PROF
@@ -554,27 +567,57 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         const long long t1 = timed ? clock64() : 0;
 
         // ====== exchange: poll every block's record (one record per lane) and fold with shuffles ======
+        const long long t1b = (st.prof != nullptr && tid == 0) ? clock64() : 0;
         {
-            const uint4* base = records + (static_cast<size_t>(blk) * 2 + par) * G * kRecU4;
-            if (warp < npw) {  // A-parts: two smallest candidates + the winner's payload
+            const uint4* base = kSharedRecords ? records + static_cast<size_t>(par) * G * kRecU4
+                                               : records + (static_cast<size_t>(blk) * 2 + par) * G * kRecU4;
+            if (warp < npw) {
+                // One lane per record.  Only the LAST chunk of the record (c4) is polled: three groups of warps
+                // polling five chunks of every record kept ~130 k 16-byte L2 requests in flight per polling round and
+                // every block waited ~7 k cycles per exchange.  Every chunk carries its own tag, so the rest of the
+                // record is read once and re-read in the (never observed) case that it lags behind c4.
                 const int g = warp * 32 + lane;
                 Top2 ft = {kPackInf, kPackInf};
-                uint4 r1 = make_uint4(0, 0, 0, 0), r2 = make_uint4(0, 0, 0, 0);
+                uint4 r1 = make_uint4(0, 0, 0, 0), r2 = r1, r3 = r1, r4 = r1;
+                uint64_t best = kPackInf;
+                uint32_t run = 0xFFFFFFFFu;
                 if (g < G) {
                     const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
                     uint4 r0;
                     uint32_t spins = 0;
                     for (;;) {
+                        r4 = ld_volatile_u4(rec + 4);
+                        if (r4.w == tag) break;
+                        if (++spins > kSpinLimit) __trap();  // a protocol bug must not hang the GPU box
+                    }
+                    if (timed) c_sub[4] += clock64() - t1;
+                    for (;;) {
                         r0 = ld_volatile_u4(rec + 0);
                         r1 = ld_volatile_u4(rec + 1);
                         r2 = ld_volatile_u4(rec + 2);
-                        if (r0.w == tag && r1.w == tag && r2.w == tag) break;
-                        if (++spins > kSpinLimit) __trap();  // a protocol bug must not hang the GPU box
+                        r3 = ld_volatile_u4(rec + 3);
+                        if (r0.w == tag && r1.w == tag && r2.w == tag && r3.w == tag) break;
+                        if (++spins > kSpinLimit) __trap();
                     }
                     ft.m1 = (static_cast<uint64_t>(r0.y) << 32) | r0.x;
                     ft.m2 = (static_cast<uint64_t>(r0.z) << 32) | 0xFFFFFFFFull;  // only its distance matters
-                    if (timed) c_sub[4] += clock64() - t1;
+                    best = (static_cast<uint64_t>(r3.y) << 32) | r3.x;
+                    run = r4.y;
+                    if (r4.z != 0u) {  // rescan requests of that block
+                        uint4 r5, r6;
+                        for (;;) {
+                            r5 = ld_volatile_u4(rec + 5);
+                            r6 = ld_volatile_u4(rec + 6);
+                            if (r5.w == tag && r6.w == tag) break;
+                            if (++spins > kSpinLimit) __trap();
+                        }
+                        if (static_cast<int32_t>(r5.x) >= 0)
+                            s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.x), static_cast<int32_t>(r5.y), g, 0);
+                        if (static_cast<int32_t>(r5.z) >= 0)
+                            s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.z), static_cast<int32_t>(r6.x), g, 1);
+                    }
                 }
+                // A-parts: two smallest candidates + the winner's payload
                 const uint64_t mine = ft.m1;
                 ft = warp_top2(ft);
                 const unsigned who = __ballot_sync(0xffffffffu, mine == ft.m1 && mine != kPackInf);
@@ -596,64 +639,21 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
                     d.stale = r2.z;
                     s_pdec[warp] = d;
                 }
-            } else if (warp < 2 * npw) {  // B-parts: the pending merge's new row: best entry + exact runner-up distance
-                const int g = (warp - npw) * 32 + lane;
-                uint64_t best = kPackInf;
-                uint32_t run = 0xFFFFFFFFu;
-                int32_t bslot = -1, bsize = 0;
-                if (g < G) {
-                    const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
-                    uint4 r3, r4;
-                    uint32_t spins = 0;
-                    for (;;) {
-                        r3 = ld_volatile_u4(rec + 3);
-                        r4 = ld_volatile_u4(rec + 4);
-                        if (r3.w == tag && r4.w == tag) break;
-                        if (++spins > kSpinLimit) __trap();
-                    }
-                    best = (static_cast<uint64_t>(r3.y) << 32) | r3.x;
-                    bslot = static_cast<int32_t>(r3.z);
-                    bsize = static_cast<int32_t>(r4.x);
-                    run = r4.y;
-                }
+                // B-parts: the pending merge's new row: best entry + exact runner-up distance
                 const uint64_t wm = warp_min_u64(best);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) run = min(run, __shfl_xor_sync(0xffffffffu, run, o));
-                const unsigned who = __ballot_sync(0xffffffffu, best == wm);
-                if (lane == __ffs(who) - 1) {
+                run = __reduce_min_sync(0xffffffffu, run);
+                const unsigned whob = __ballot_sync(0xffffffffu, best == wm);
+                if (lane == __ffs(whob) - 1) {
                     NewRow nr;
                     nr.pack = wm;
-                    nr.slot = bslot;
-                    nr.size = bsize;
+                    nr.slot = static_cast<int32_t>(r3.z);
+                    nr.size = static_cast<int32_t>(r4.x);
                     nr.runner = run;
-                    s_pnew[warp - npw] = nr;
-                }
-            } else if (warp < 3 * npw) {  // rescan requests of the rank
-                const int g = (warp - 2 * npw) * 32 + lane;
-                if (g < G) {
-                    const uint4* rec = base + static_cast<size_t>(g) * kRecU4;
-                    uint4 r4, r5 = make_uint4(0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u), r6 = make_uint4(0u, 0u, 0u, 0u);
-                    uint32_t spins = 0;
-                    for (;;) {
-                        r4 = ld_volatile_u4(rec + 4);
-                        if (r4.w == tag) break;
-                        if (++spins > kSpinLimit) __trap();
-                    }
-                    if (r4.z != 0u) {
-                        for (;;) {
-                            r5 = ld_volatile_u4(rec + 5);
-                            r6 = ld_volatile_u4(rec + 6);
-                            if (r5.w == tag && r6.w == tag) break;
-                            if (++spins > kSpinLimit) __trap();
-                        }
-                    }
-                    if (static_cast<int32_t>(r5.x) >= 0)
-                        s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.x), static_cast<int32_t>(r5.y), g, 0);
-                    if (static_cast<int32_t>(r5.z) >= 0)
-                        s_rlist[atomicAdd(&s_nreq, 1)] = make_int4(static_cast<int32_t>(r5.z), static_cast<int32_t>(r6.x), g, 1);
+                    s_pnew[warp] = nr;
                 }
             }
             __syncthreads();
+            if (st.prof != nullptr && tid == 0 && v == 0) blk_wait += clock64() - t1b;
             // acquire: one thread fences after ALL polls of the block completed (ordered by the bar.sync above); the
             // data reads of this iteration come after the bar.sync below
             // With P > 1 nobody fences here: every block of the rank completed a system-scope release fence before
@@ -1126,6 +1126,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             c_upd += t4 - t3;
         }
     }
+    if (st.prof != nullptr && tid == 0 && v == 0 && blk < 240) st.prof[16 + blk] = blk_wait;
     if (timed) {
         st.prof[0] = c_pub;
         st.prof[1] = c_exch;

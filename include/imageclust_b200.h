@@ -170,6 +170,9 @@ int ic_get_stats(ic_ctx *ctx, ic_stats *stats);
  * {publish, exchange poll + fold, decision + update, row scans, partial folds, merges, iterations, rescans,
  *  0, bubbles ...} of the last launch */
 int ic_get_loop_profile(ic_ctx *ctx, int64_t *out16);
+/* debug (profile_loop = 1): SM cycles every block of (local) rank 0 spent waiting for the slowest record of the
+ * exchanges of the last launch -- the block with the smallest wait is the one the others waited for */
+int ic_get_loop_block_waits(ic_ctx *ctx, int64_t *out, int64_t capacity, int64_t *n_blocks);
 
 /* microbenchmarks used by bench.py's roofline legs: one launch of the named
  * kernel on the resident problem, device time in ms */

@@ -3,6 +3,8 @@ usage: python scripts/profile_target.py [config] [n-override] [passes]"""
 import os
 import sys
 
+import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from imageclust_b200 import clustering, synth
 
@@ -29,3 +31,8 @@ with clustering.Engine(0) as eng:
     m = max(p["merges"], 1)
     print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
           + f" | iterations={p["iterations"]} rescans={p["rescans"]} bubbles={p["bubbles"]}")
+    w = eng.loop_block_waits() / max(p["iterations"], 1)
+    if len(w):
+        order = np.argsort(w)
+        print(f"exchange wait per iteration and block: min {w.min():.0f} (block {order[0]}) median {np.median(w):.0f} max {w.max():.0f} "
+              f"(block {order[-1]}); five smallest: " + " ".join(f"{int(b)}:{w[b]:.0f}" for b in order[:5]))
