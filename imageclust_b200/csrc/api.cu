@@ -40,6 +40,7 @@ struct ic_ctx {
     // cooperative launch (same kernel code path as the multi-GPU build; test hook).
     int vranks = 1;
     int vranks_alloc = -1;
+    int scan_every = 4;  // merge loop: rescans are requested every scan_every-th iteration
     int no_replica = 0, no_replica_alloc = -1;  // test hook: stream the keys from L2 even when the replica would fit
     bool loop_replica = false;
     uint32_t loop_gen = 0;    // generation of the last merge-loop launch (mailbox tags)
@@ -492,6 +493,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.max_size = static_cast<int32_t>(max_size > 0x3FFFFFFF ? 0x3FFFFFFF : max_size);
     p.max_merges = static_cast<int32_t>(max_merges < 0 ? -1 : (max_merges > 0x7FFFFFFF ? 0x7FFFFFFF : max_merges));
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
+    p.scan_every = ctx->scan_every;
     ctx->loop_gen = ctx->loop_gen % 4095u + 1u;
     st.gen = ctx->loop_gen;
     if (ctx->loop_gen == 1u && ctx->loop_launches > 0) {  // generation wrapped: forget every old tag
@@ -809,6 +811,10 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         if (r < 1 || r > kMaxRanks) return fail(ctx, IC_ERR_BAD_ARG, "virtual_ranks must be 1..8");
         if (ctx->shard_world > 1) return fail(ctx, IC_ERR_STATE, "virtual_ranks on a sharded context");
         ctx->vranks = r;
+    } else if (k == "scan_every") {
+        const int e = static_cast<int>(value);
+        if (e < 1 || e > 64) return fail(ctx, IC_ERR_BAD_ARG, "scan_every must be 1..64");
+        ctx->scan_every = e;
     } else if (k == "no_replica") {
         ctx->no_replica = value != 0.0;
     } else if (k == "loop_blocks") {

@@ -124,6 +124,7 @@ struct LoopParams {
     int32_t max_size;    // clustering.go:228
     int32_t max_merges;  // stop after this many merges in this launch (<0: unlimited)
     float near_tie_tol;
+    int32_t scan_every;  // rescan requests are published every scan_every-th iteration (batched row scans)
 };
 // ctl[] indices.  N_LIVE and N_MERGES are read at launch (resume) and written at exit.
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,

@@ -362,6 +362,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     long long c_sub[6] = {0, 0, 0, 0, 0, 0};  // publish: argmin, reduce, fence, stores; exchange: poll, fold
     uint32_t epoch = 0;  // iteration index; records of iteration i carry tag (gen, i+1)
     const uint32_t tagbase = st.gen << 20;
+    const uint32_t scan_every = prm.scan_every > 0 ? static_cast<uint32_t>(prm.scan_every) : 1u;
 
     for (;;) {
         const uint32_t tag = tagbase | (epoch + 1u);
@@ -392,7 +393,10 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
             }
             if (tid == 0) {  // rescan requests: oldest dry rows of the slice first
                 int32_t nreq = 0;
-                while (nreq < kReqPerBlock && s_qhead != s_qtail) {
+                // requests go out every scan_every-th iteration only: whenever any row of the rank is rescanned every
+                // block pays the scan phase (~7 k cycles), so the rescans are batched; a row that waits keeps its
+                // lower bound in the reduction (bubbles stay rare: the bound of a dry row is rarely the minimum)
+                while ((epoch % scan_every) == 0u && nreq < kReqPerBlock && s_qhead != s_qtail) {
                     const int32_t i = s_dryq[s_qhead % qcap];
                     ++s_qhead;
                     const int32_t s = lo + i;
@@ -876,7 +880,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
         // warps [0, ns) scan the requested rows while the others update: the two passes are independent.  A wide
         // window is split over kSplit warps, each mailing its own partial list (the owner folds G * split lists one
         // iteration later, off the critical path), so that a scanning warp needs one batch of loads, not two.
-        constexpr int kScanWarps = kW / 2;
+        constexpr int kScanWarps = (3 * kW) / 4;  // the update pass of a block is short: most warps may scan
         const int nparts = nreq_all * split;                 // (request, part) pairs of this iteration
         const int ns = min(nparts, kScanWarps);
 

@@ -85,7 +85,9 @@ void ic_pinned_free(void *p);
 /* knobs: "near_tie_tol" (float, default 1e-5), "center" (0/1, default 1),
  * "gram_mode" (IC_GRAM_*), "loop_blocks" (merge-loop blocks per rank, 0 = auto),
  * "virtual_ranks" (1..8: row-block shards emulated on ONE GPU by one cooperative launch --
- * the same kernel path as the multi-GPU build, for tests), "profile_loop", "verbose" */
+ * the same kernel path as the multi-GPU build, for tests), "scan_every" (row rescans are requested every k-th
+ * merge-loop iteration, default 4: batching them keeps the scan phase out of most iterations), "no_replica",
+ * "profile_loop", "verbose" */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 
 /* ---- CalculateOptimalClusters, clustering.go:168-186 (host, exact) ---- */

@@ -16,6 +16,8 @@ passes = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 x = synth.gaussian_mixture(n, d, mn, mx, seed=20240 + ord(cfg) - ord("A"))
 with clustering.Engine(0) as eng:
     eng.set_option("profile_loop", 1)
+    if os.environ.get("IC_SCAN_EVERY"):
+        eng.set_option("scan_every", int(os.environ["IC_SCAN_EVERY"]))
     if os.environ.get("IC_LOOP_BLOCKS"):
         eng.set_option("loop_blocks", int(os.environ["IC_LOOP_BLOCKS"]))
     eng.load(x)
