@@ -41,6 +41,10 @@ struct ic_ctx {
     int vranks = 1;
     int vranks_alloc = -1;
     int scan_every = 4;  // merge loop: rescans are requested every scan_every-th iteration
+    int loop_mode = 1;   // 1: batched loop (merge_batch.cu) on an unsharded context; 0: one merge per iteration (merge_loop.cu)
+    int batch_grid = 0;
+    uint8_t* batch_scratch = nullptr;  // hdr | cand | counters | dryq | partials | part_cnt | bar
+    size_t batch_scratch_bytes = 0, batch_off[9] = {0};
     int no_replica = 0, no_replica_alloc = -1;  // test hook: stream the keys from L2 even when the replica would fit
     bool loop_replica = false;
     uint32_t loop_gen = 0;    // generation of the last merge-loop launch (mailbox tags)
@@ -150,6 +154,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->records);
     dev_free(c->partials);
     dev_free(c->rankbox);
+    dev_free(c->batch_scratch);
     dev_free(c->prof);
     dev_free(c->ctl);
     c->loaded = c->have_dm = c->have_nn = c->prepped = c->prepped_i8 = false;
@@ -302,7 +307,8 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->x, sizeof(float) * nn1 * static_cast<size_t>(d > 0 ? d : 1)));
     IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * static_cast<size_t>(rows > 0 ? rows : 1) *
                                      static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
-    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * nn1 * NL));
+    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * (nn1 * NL + 4)));  // + padding up to a multiple of 4 slots: key -1
+    IC_CUDA(cudaMemsetAsync(ctx->ks + nn1 * NL, 0xFF, sizeof(SlotKS) * 4, ctx->stream));
     IC_CUDA(cudaMalloc(&ctx->gkey, sizeof(int32_t) * n4 * NL));
     IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1 * kNNK));
     IC_CUDA(cudaMalloc(&ctx->nn_more, sizeof(int32_t) * nn1));
@@ -325,6 +331,22 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMemsetAsync(ctx->partials, 0, pb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
+    ctx->batch_grid = 0;
+    if (P == 1) {  // batched loop: launch geometry and scratch
+        IC_CUDA(merge_batch_grid(ctx->num_sms, n, &ctx->batch_grid));
+        if (ctx->loop_blocks > 0 && ctx->batch_grid > 0) ctx->batch_grid = std::min(ctx->loop_blocks, ctx->num_sms);
+        const size_t sizes[9] = {static_cast<size_t>(kBatchMaxBlocks) * 32, static_cast<size_t>(kBatchMaxBlocks) * kBatchCand * 32,
+                                 3 * 4 * 4, 4 * nn1, static_cast<size_t>(kBatchMaxDry) * kBatchMaxWin * 128,
+                                 static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), 0};
+        size_t off = 0;
+        for (int i = 0; i < 9; ++i) {
+            ctx->batch_off[i] = off;
+            off += (sizes[i] + 255) / 256 * 256;
+        }
+        ctx->batch_scratch_bytes = off;
+        IC_CUDA(cudaMalloc(&ctx->batch_scratch, off));
+        IC_CUDA(cudaMemsetAsync(ctx->batch_scratch, 0, off, ctx->stream));
+    }
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->loop_gen = 0;
     ctx->loop_launches = 0;
@@ -482,6 +504,9 @@ int init_loop_state(ic_ctx* ctx) {
     return IC_OK;
 }
 
+// the batched loop runs on an unsharded context whose slice state fits (it always does below ~1e6 items)
+bool use_batch(const ic_ctx* c) { return c->loop_mode == 1 && n_ranks(c) == 1 && c->batch_grid > 0 && c->n > 0; }
+
 // One launch of the persistent loop (enqueued; sync_loop_result waits and relaunches if the kernel ran out of
 // mailbox epochs, which takes ~1e6 iterations).
 int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges) {
@@ -494,6 +519,45 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.max_merges = static_cast<int32_t>(max_merges < 0 ? -1 : (max_merges > 0x7FFFFFFF ? 0x7FFFFFFF : max_merges));
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
     p.scan_every = ctx->scan_every;
+    if (use_batch(ctx)) {
+        BatchState bs{};
+        uint8_t* sc = ctx->batch_scratch;
+        bs.n = static_cast<int32_t>(ctx->n);
+        bs.ld = ctx->ld;
+        bs.dm = ctx->dm;
+        bs.ks = ctx->ks;
+        bs.gkey = ctx->gkey;
+        bs.nn = ctx->nn;
+        bs.nn_more = ctx->nn_more;
+        bs.tr_key_hi = ctx->tr_key_hi;
+        bs.tr_key_lo = ctx->tr_key_lo;
+        bs.tr_dist = ctx->tr_dist;
+        bs.tr_size = ctx->tr_size;
+        bs.tr_gap = ctx->tr_gap;
+        bs.ctl = ctx->ctl;
+        bs.prof = ctx->profile_loop ? ctx->prof : nullptr;
+        bs.hdr = reinterpret_cast<uint4*>(sc + ctx->batch_off[0]);
+        bs.cand = reinterpret_cast<uint4*>(sc + ctx->batch_off[1]);
+        bs.counters = reinterpret_cast<int32_t*>(sc + ctx->batch_off[2]);
+        bs.dryq = reinterpret_cast<int32_t*>(sc + ctx->batch_off[3]);
+        bs.partials = reinterpret_cast<uint4*>(sc + ctx->batch_off[4]);
+        bs.part_cnt = reinterpret_cast<int32_t*>(sc + ctx->batch_off[5]);
+        bs.bar = reinterpret_cast<uint32_t*>(sc + ctx->batch_off[6]);
+        bs.lsize = reinterpret_cast<int32_t*>(sc + ctx->batch_off[7]);
+        // scratch of a launch: counters and the barrier at zero
+        IC_CUDA(cudaMemsetAsync(bs.counters, 0, 3 * 4 * 4, ctx->stream));
+        IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
+        IC_CUDA(cudaMemsetAsync(bs.bar, 0, 256, ctx->stream));
+        IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
+        IC_CUDA(launch_merge_batch(bs, p, ctx->batch_grid, ctx->stream));
+        ++ctx->loop_launches;
+        ctx->stats.kernel_launches += 1;
+        IC_CUDA(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(ctx->h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
+        if (bs.prof)
+            IC_CUDA(cudaMemcpyAsync(ctx->h_prof, bs.prof, sizeof(ctx->h_prof), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->trace_on_host = false;
+        return IC_OK;
+    }
     ctx->loop_gen = ctx->loop_gen % 4095u + 1u;
     st.gen = ctx->loop_gen;
     if (ctx->loop_gen == 1u && ctx->loop_launches > 0) {  // generation wrapped: forget every old tag
@@ -815,6 +879,10 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         const int e = static_cast<int>(value);
         if (e < 1 || e > 64) return fail(ctx, IC_ERR_BAD_ARG, "scan_every must be 1..64");
         ctx->scan_every = e;
+    } else if (k == "loop_mode") {
+        const int m = static_cast<int>(value);
+        if (m != 0 && m != 1) return fail(ctx, IC_ERR_BAD_ARG, "loop_mode must be 0 (sequential) or 1 (batched)");
+        ctx->loop_mode = m;
     } else if (k == "no_replica") {
         ctx->no_replica = value != 0.0;
     } else if (k == "loop_blocks") {

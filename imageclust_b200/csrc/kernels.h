@@ -145,6 +145,45 @@ size_t merge_loop_partials_bytes(int blocks_per_rank);  // per rank
 size_t merge_loop_rankbox_bytes();                      // per rank (barrier flags + [2][kMaxRanks] records)
 cudaError_t launch_merge_loop(const LoopState& st, const LoopParams& p, int blocks_per_rank, bool replica,
                               cudaStream_t s);
+// ---- K3b batched merge loop (merge_batch.cu): one GPU, several provably consecutive merges per iteration -----
+constexpr int kBatchThreads = 512;
+constexpr int kMaxBatch = 512;        // candidate pairs / merges per iteration (<= kBatchThreads: one per thread)
+constexpr int kBatchCand = 64;        // candidate pairs a block may publish per iteration
+constexpr int kBatchMaxDry = 2048;    // rows rescanned per round of the rescan phase (partial-list buffers)
+constexpr int kBatchWinMin = 2048;    // columns of a row-scan window (at most kBatchMaxWin windows per row)
+constexpr int kBatchMaxWin = 128;
+constexpr int kBatchMaxBlocks = 160;
+constexpr int CTL_ITERS = 12;         // ctl[]: iterations of the batched loop
+struct BatchState {
+    int32_t n;
+    int32_t win_cols, n_win;  // filled in by launch_merge_batch
+    int64_t ld;
+    float* dm;          // [n x ld] symmetric
+    SlotKS* ks;         // [n4] {key, size}; padding key = -1
+    int32_t* gkey;      // [n4]
+    SlotNN* nn;         // [n][kNNK]
+    int32_t* nn_more;   // [n]
+    int32_t* tr_key_hi;
+    int32_t* tr_key_lo;
+    float* tr_dist;
+    int32_t* tr_size;
+    float* tr_gap;
+    int32_t* ctl;       // [16]
+    long long* prof;    // [16] or NULL
+    // scratch (zeroed before every launch)
+    uint4* hdr;         // [kBatchMaxBlocks][2] per block: {candidates, 0, stopper lo, hi} {head minimum lo, hi, 0, 0}
+    uint4* cand;        // [kBatchMaxBlocks][kBatchCand][2] {head lo, head hi, row slot, partner slot} {size, size, partner key, 0}
+    int32_t* counters;  // [3][4] dry rows, per iteration mod 3
+    int32_t* dryq;      // [n]   rows to rescan
+    int32_t* lsize;     // [n4]  size of the live cluster in every slot, 0: retired (rebuilt from ks at launch)
+    uint4* partials;    // [kBatchMaxDry][kBatchMaxWin][8] partial lists of the window scans
+    int32_t* part_cnt;  // [kBatchMaxDry] windows done per row
+    uint32_t* bar;      // grid barrier counter
+};
+size_t merge_batch_smem_bytes(int64_t n);
+int64_t merge_batch_windows(int64_t n);
+cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks);  // *blocks = 0: does not fit
+cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);
 // device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
 cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);
 

@@ -1,0 +1,698 @@
+// merge_batch.cu -- K3b: the agglomeration loop with BATCHES of provably consecutive merges (one GPU).
+//
+// Same reference semantics as merge_loop.cu (clustering.go:220-246; FindClosestClusters :119-133, maxSize branch
+// :228-234, MergeClusters :29-47, UpdateDistanceMatrix :76-96), same state (slots, keys, static sorted partner
+// lists, eager admissibility, Lance-Williams in double) and the SAME merge sequence, but one iteration of this kernel
+// takes every merge that is certain to be the next one, the one after it, ... of the sequential algorithm:
+//
+//   Every live row r has a head h_r = (d, key_r) -- its smallest pair with a lower-key partner -- and the pairs
+//   of the matrix in scan order are the k-way merge of the rows' sorted lists.  Ward's update is reducible:
+//   d(k, a u b) >= min(d(k,a), d(k,b)), so a merge only ever creates distances that are >= every pair that
+//   touched one of its two clusters.  Walk the pairs in scan order and stop at the first pair that touches a
+//   cluster of an earlier pair (the "stopper" T).  Every pair before T is disjoint from the others, is a row head,
+//   and every distance the earlier merges create is >= T (a tie goes to the older pair: new clusters carry the
+//   highest keys).  Hence the sequential algorithm performs exactly those merges, in that order.
+//   T = min( second list entry of any row,  any head that is not the first head at both of its slots ).
+//
+//   Batch sizes grow like ~0.3 * sqrt(n live) on the benchmark mixtures: ~2 000 iterations instead of 97 250
+//   at config C, which turns the loop from a latency chain into a bandwidth problem.
+//
+// One iteration = three grid-wide phases of a persistent cooperative kernel (one CTA per SM):
+//   P1 rescans    rows whose cached partners all died (and the rows of the clusters just created) are scanned
+//                 by 2048-column windows, one warp each; the warp that finishes a row's last window folds the
+//                 partial lists (exact cut rule)
+//   P2 heads      per row: head + stopper; every block publishes its heads below its own stopper minimum
+//                 (any value >= T is a valid filter) and that minimum
+//   P3 batch      every block reads all published candidates (a few dozen), derives T -- stopper minimum and
+//                 slot conflicts, pairwise in shared memory -- and ranks the pairs below T; then: Lance-Williams
+//                 rows (coalesced row reads / writes + mirrored column stores), the m x m cross terms of the
+//                 batch (two chained updates from the four old entries), trace / slot bookkeeping, validation
+//                 of the partner lists
+// HBM roofline: algorithmic bytes = 12*n per merge.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "loop_common.cuh"
+
+namespace ic {
+
+namespace {
+
+constexpr int kBT = kBatchThreads;
+constexpr int kBW = kBT / 32;
+constexpr uint32_t kMoreBit = 1u, kDryBit = 2u;
+constexpr uint32_t kBarSpin = 1u << 24;
+constexpr int kUpdCols = 512;  // columns of one update unit (one warp: 4 x 32 lanes x 4, all loads in flight at once)
+constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead of the update pass
+
+// counters[slot][*]
+enum { CN_DRY = 0 };
+
+// grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
+IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G) {
+    __syncthreads();
+    ++phase;
+    if (threadIdx.x == 0) {
+        red_release_add_u32(bar, 1u);
+        const uint32_t target = phase * G;
+        uint32_t spins = 0;
+        while (ld_acquire_u32(bar) < target)
+            if (++spins > kBarSpin) __trap();  // a protocol bug must not hang the GPU box
+    }
+    __syncthreads();
+}
+
+IC_DEVINL uint64_t block_min_u64(uint64_t v, uint64_t* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t w = warp_min_u64(v);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = w;
+    __syncthreads();
+    uint64_t r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < kBW; ++i) r = umin64(r, s_red[i]);
+    return r;
+}
+IC_DEVINL int block_sum_i32(int v, int* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < kBW; ++i) r += s_red[i];
+    return r;
+}
+
+// head and stopper of a row from its list.  Lists are compacted: valid entries first, then (if entries were
+// removed and more partners may exist) one bound placeholder, then empty entries.  The distance of the last
+// non-empty entry is a lower bound of every unlisted partner.
+struct RowHead {
+    uint64_t head;  // (dist bits << 32 | row key), kPackInf: none
+    uint64_t stop;  // smallest pack a second pair of this row may have, +1 (see P2); kPackInf: none
+    uint32_t partner_slot, partner_key;
+};
+IC_DEVINL RowHead row_head(const SlotNN* nn, const int32_t* nn_more, int32_t r, uint32_t key_r) {
+    RowHead h;
+    h.head = h.stop = kPackInf;
+    h.partner_slot = h.partner_key = kNoPartner;
+    const uint4 e0 = __ldcg(nn + static_cast<int64_t>(r) * kNNK);
+    if (e0.z == kNoPartner) return h;  // no partner (a bound cannot be here: dry rows were rescanned in P1)
+    const uint4 e1 = __ldcg(nn + static_cast<int64_t>(r) * kNNK + 1);
+    h.head = (static_cast<uint64_t>(e0.y) << 32) | key_r;
+    h.partner_slot = e0.z;
+    h.partner_key = e0.x;
+    if (e1.y != kNoPartner)  // a second partner, or the bound of the unlisted ones
+        h.stop = ((static_cast<uint64_t>(e1.y) << 32) | key_r) + 1ull;
+    else if ((static_cast<uint32_t>(__ldcg(nn_more + r)) & kMoreBit) != 0u)
+        h.stop = h.head + 1ull;  // list cut after the head: the rest is >= the head's distance
+    return h;
+}
+
+}  // namespace
+
+size_t merge_batch_smem_bytes(int64_t n) {
+    const size_t n4 = static_cast<size_t>((n + 3) / 4 * 4);
+    const size_t bitmap = ((n4 + 31) / 32 + 3) / 4 * 4 * sizeof(uint32_t);
+    return bitmap;
+}
+static int64_t batch_window_cols(int64_t n) {  // at most kBatchMaxWin windows per row: <= 4 partial lists per lane in the fold
+    const int64_t n4 = (n + 3) / 4 * 4;
+    return std::max<int64_t>(kBatchWinMin, ((n4 + kBatchMaxWin - 1) / kBatchMaxWin + 127) / 128 * 128);
+}
+int64_t merge_batch_windows(int64_t n) {
+    const int64_t n4 = (n + 3) / 4 * 4, win = batch_window_cols(n);
+    return std::max<int64_t>(1, (n4 + win - 1) / win);
+}
+
+__global__ void __launch_bounds__(kBT, 1)
+merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant__ LoopParams prm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t G = gridDim.x;
+    const int32_t n = st.n;
+    const int32_t n4 = (n + 3) & ~3;
+    const int64_t ld = st.ld;
+    const int32_t gtid = static_cast<int32_t>(blockIdx.x) * kBT + tid, GT = static_cast<int32_t>(G) * kBT;
+    const int32_t gw = static_cast<int32_t>(blockIdx.x) * kBW + warp, GW = static_cast<int32_t>(G) * kBW;
+    const int32_t win = st.win_cols, nwin = st.n_win;
+    float* const dm = st.dm;
+    int32_t* const ctl = st.ctl;
+
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem);  // merged-slot bitmap of the current batch
+    const int32_t n_words = (n4 + 31) >> 5;
+
+    __shared__ uint64_t s_red[kBW];
+    __shared__ int s_redi[kBW];
+    __shared__ int32_t s_bcnt[kBatchMaxBlocks];
+    // candidate pairs as collected (unordered) ...
+    __shared__ uint64_t s_hp[kMaxBatch];
+    __shared__ int32_t s_ca[kMaxBatch], s_cb[kMaxBatch], s_idx[kMaxBatch];
+    // ... and the batch in scan order
+    __shared__ int32_t s_a[kMaxBatch], s_b[kMaxBatch], s_sa[kMaxBatch], s_sb[kMaxBatch], s_ka[kMaxBatch], s_kb[kMaxBatch];
+    __shared__ uint32_t s_d[kMaxBatch + 1];
+    __shared__ int32_t s_m, s_pub;
+
+    uint32_t phase = 0;
+    int32_t n_live = __ldcg(ctl + CTL_N_LIVE);
+    int32_t t = __ldcg(ctl + CTL_N_MERGES);
+    int32_t launched = 0, stop_reason = 0, iters = 0;
+    long long n_rescans = 0;
+    const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long c_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // rows that were dry when the previous launch stopped (or rows the other loop left dry): queue slot 0
+    for (int32_t r = gtid; r < n; r += GT)
+        if ((static_cast<uint32_t>(__ldcg(st.nn_more + r)) & kDryBit) != 0u && __ldcg(st.ks + r).x >= 0)
+            st.dryq[atomicAdd(st.counters + 0 * 4 + CN_DRY, 1)] = r;
+    // live size of every slot (0: retired / padding): what the update pass streams beside the two rows
+    for (int32_t r = gtid; r < n4; r += GT) {
+        const int2 k = __ldcg(st.ks + r);
+        st.lsize[r] = (r < n && k.x >= 0) ? k.y : 0;
+    }
+    grid_sync(st.bar, phase, G);
+
+    for (uint32_t it = 0;; ++it) {
+        const int sl = static_cast<int>(it % 3u), sl1 = static_cast<int>((it + 1u) % 3u), sl2 = static_cast<int>((it + 2u) % 3u);
+        const long long tp0 = timed ? clock64() : 0;
+
+        // ================= P1: row rescans (cooperative, one warp per window) =================
+        const int32_t Q = __ldcg(st.counters + sl * 4 + CN_DRY);
+        n_rescans += Q;
+        for (int32_t base = 0; base < Q; base += kBatchMaxDry) {
+            const int32_t rows = min(Q - base, kBatchMaxDry);
+            const int64_t units = static_cast<int64_t>(rows) * nwin;
+            for (int64_t u = gw; u < units; u += GW) {
+                // windows of one row go to warps of different blocks: q = u % rows
+                const int32_t w = static_cast<int32_t>(u / rows), q = static_cast<int32_t>(u - static_cast<int64_t>(w) * rows);
+                const int32_t r = __ldcg(st.dryq + base + q);
+                const uint32_t ukr = static_cast<uint32_t>(__ldcg(st.gkey + r));
+                const float* rowp = dm + static_cast<int64_t>(r) * ld;
+                const int32_t sw0 = min(n4, w * win), sw1 = min(n4, sw0 + win);
+                ScanCand c;
+                scan_init(c);
+                constexpr int kU = 8;  // 16-byte loads of the row and of the keys in flight per lane
+                for (int32_t b0 = sw0; b0 < sw1; b0 += 128 * kU) {
+                    float4 vv[kU];
+                    int4 kq[kU];
+#pragma unroll
+                    for (int x = 0; x < kU; ++x) {
+                        const int32_t u0 = b0 + (x * 32 + lane) * 4;
+                        vv[x] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                        kq[x] = make_int4(-1, -1, -1, -1);
+                        if (u0 < sw1) {
+                            vv[x] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
+                            kq[x] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
+                        }
+                    }
+#pragma unroll
+                    for (int x = 0; x < kU; ++x) {
+                        const int32_t u0 = b0 + (x * 32 + lane) * 4;
+                        const uint32_t vs4[4] = {__float_as_uint(vv[x].x), __float_as_uint(vv[x].y), __float_as_uint(vv[x].z),
+                                                 __float_as_uint(vv[x].w)};
+                        const uint32_t ks4[4] = {static_cast<uint32_t>(kq[x].x), static_cast<uint32_t>(kq[x].y),
+                                                 static_cast<uint32_t>(kq[x].z), static_cast<uint32_t>(kq[x].w)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)  // retired slots and padding hold key -1 == 0xFFFFFFFF: never below the row's key
+                            if (ks4[e] < ukr && vs4[e] < kMaxFloatBits)
+                                scan_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ks4[e], u0 + e);
+                    }
+                }
+                PartList out;
+                bool more = false;
+                out.m = warp_select_scan(c, out.pk, out.sl, more);
+                out.more = more ? 1 : 0;
+#pragma unroll
+                for (int x = 0; x < kNNK; ++x) out.sz[x] = 0;
+                bool folder = nwin == 1;
+                if (nwin > 1) {
+                    uint4* prec = st.partials + (static_cast<size_t>(q) * kBatchMaxWin + w) * 8;
+                    if (lane < kNNK) {
+                        const uint64_t myp = sel4(out.pk, lane);
+                        __stcg(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                                      static_cast<uint32_t>(sel4(out.sl, lane)), 0u)
+                                                         : nn_none());
+                    } else if (lane == kNNK) {
+                        __stcg(prec + kNNK, make_uint4(static_cast<uint32_t>(out.m), static_cast<uint32_t>(out.more), 0u, 0u));
+                    }
+                    __syncwarp();
+                    int old = 0;
+                    if (lane == 0) {
+                        __threadfence();
+                        old = atomicAdd(st.part_cnt + q, 1);
+                        __threadfence();
+                    }
+                    old = __shfl_sync(0xffffffffu, old, 0);
+                    folder = old == nwin - 1;
+                    if (folder) {  // last window of the row: fold the nwin partial lists (up to four per lane)
+                        PartList acc;
+                        acc.m = 0;
+                        acc.more = 0;
+#pragma unroll
+                        for (int x = 0; x < kNNK; ++x) {
+                            acc.pk[x] = kPackInf;
+                            acc.sl[x] = -1;
+                            acc.sz[x] = 0;
+                        }
+                        for (int32_t ww = lane; ww < nwin; ww += 32) {
+                            const uint4* rec = st.partials + (static_cast<size_t>(q) * kBatchMaxWin + ww) * 8;
+                            PartList in;
+                            const uint4 hd = __ldcg(rec + kNNK);
+                            in.m = static_cast<int32_t>(hd.x);
+                            in.more = static_cast<int32_t>(hd.y);
+#pragma unroll
+                            for (int x = 0; x < kNNK; ++x) {
+                                const uint4 e = __ldcg(rec + x);
+                                in.pk[x] = x < in.m ? ((static_cast<uint64_t>(e.y) << 32) | e.x) : kPackInf;
+                                in.sl[x] = x < in.m ? static_cast<int32_t>(e.z) : -1;
+                                in.sz[x] = 0;
+                            }
+                            if (ww == lane)
+                                acc = in;
+                            else
+                                lane_merge2(acc, in);
+                        }
+                        warp_merge_lists(acc, out);
+                        if (lane == 0) st.part_cnt[q] = 0;
+                    }
+                }
+                if (folder) {
+                    if (lane < kNNK) {
+                        const uint64_t myp = sel4(out.pk, lane);
+                        __stcg(st.nn + static_cast<int64_t>(r) * kNNK + lane,
+                               lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                         static_cast<uint32_t>(sel4(out.sl, lane)), 0u)
+                                            : nn_none());
+                    } else if (lane == kNNK) {
+                        __stcg(st.nn_more + r, out.more ? static_cast<int32_t>(kMoreBit) : 0);
+                    }
+                }
+            }
+            if (base + kBatchMaxDry < Q) grid_sync(st.bar, phase, G);  // the partial buffers are reused
+        }
+        grid_sync(st.bar, phase, G);
+        const long long tp1 = timed ? clock64() : 0;
+
+        // ================= P2: heads and stoppers; every block publishes its candidates =================
+        {
+            uint64_t bstop = kPackInf, bhead = kPackInf, dropped = kPackInf;
+            if (tid == 0) s_pub = 0;
+            __syncthreads();
+            for (int32_t r0 = 0; r0 < n; r0 += GT) {
+                const int32_t r = r0 + gtid;
+                RowHead h;
+                h.head = h.stop = kPackInf;
+                h.partner_slot = h.partner_key = kNoPartner;
+                if (r < n) {
+                    const int32_t key_r = __ldcg(st.gkey + r);
+                    if (key_r >= 0) h = row_head(st.nn, st.nn_more, r, static_cast<uint32_t>(key_r));
+                }
+                bstop = umin64(bstop, block_min_u64(h.stop, s_red));  // running minimum: any value >= T is a valid filter
+                bhead = umin64(bhead, h.head);
+                if (h.head < bstop) {
+                    const int k = atomicAdd(&s_pub, 1);
+                    if (k < kBatchCand) {
+                        const int32_t u = static_cast<int32_t>(h.partner_slot);
+                        const int32_t sr = __ldcg(st.ks + r).y, su = __ldcg(st.ks + u).y;
+                        uint4* dst = st.cand + (static_cast<size_t>(blockIdx.x) * kBatchCand + k) * 2;
+                        __stcg(dst, make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
+                                               static_cast<uint32_t>(r), h.partner_slot));
+                        __stcg(dst + 1, make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(su), h.partner_key, 0u));
+                    } else {
+                        dropped = umin64(dropped, h.head);  // does not fit: nothing at or above it may be taken
+                    }
+                }
+            }
+            bhead = block_min_u64(bhead, s_red);
+            dropped = block_min_u64(dropped, s_red);
+            if (tid == 0) {
+                const uint64_t bs = umin64(bstop, dropped);
+                __stcg(st.hdr + 2 * blockIdx.x, make_uint4(static_cast<uint32_t>(min(s_pub, kBatchCand)), 0u,
+                                                          static_cast<uint32_t>(bs), static_cast<uint32_t>(bs >> 32)));
+                __stcg(st.hdr + 2 * blockIdx.x + 1, make_uint4(static_cast<uint32_t>(bhead), static_cast<uint32_t>(bhead >> 32), 0u, 0u));
+            }
+        }
+        grid_sync(st.bar, phase, G);
+        const long long tp2 = timed ? clock64() : 0;
+
+        // ================= P3: the batch =================
+        // lists of this thread's first rows: loaded now, validated after the update pass (one DRAM round trip less)
+        uint4 ve[kVR][kNNK];
+#pragma unroll
+        for (int x = 0; x < kVR; ++x) {
+            const int32_t r = gtid + x * GT;
+#pragma unroll
+            for (int y = 0; y < kNNK; ++y)
+                ve[x][y] = r < n ? __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y) : nn_none();
+        }
+        uint64_t tstop = kPackInf, H = kPackInf;
+        if (tid < static_cast<int>(G)) {
+            const uint4 h0 = __ldcg(st.hdr + 2 * tid), h1 = __ldcg(st.hdr + 2 * tid + 1);
+            s_bcnt[tid] = static_cast<int32_t>(h0.x);
+            tstop = (static_cast<uint64_t>(h0.w) << 32) | h0.z;
+            H = (static_cast<uint64_t>(h1.y) << 32) | h1.x;
+        }
+        tstop = block_min_u64(tstop, s_red);  // (the barriers inside also publish s_bcnt)
+        H = block_min_u64(H, s_red);
+        // termination (clustering.go:220 loop condition, :222-225 exhaustion)
+        if (n_live <= prm.n_target)
+            stop_reason = STOP_TARGET;
+        else if (!pack_selectable(H))
+            stop_reason = STOP_EXHAUSTED;
+        else if (prm.max_merges >= 0 && launched >= prm.max_merges)
+            stop_reason = STOP_MAX_MERGES;
+        else if (it + 8u >= (1u << 22))
+            stop_reason = STOP_EPOCHS;
+        const int32_t n_slots_c = static_cast<int32_t>(G) * kBatchCand;
+        if (stop_reason != 0) {
+            if (blockIdx.x == 0) {  // what FindClosestClusters would return now
+                if (!pack_selectable(H)) {
+                    if (tid == 0) {
+                        ctl[CTL_NEXT_HI] = -1;
+                        ctl[CTL_NEXT_LO] = -1;
+                        ctl[CTL_NEXT_DIST] = static_cast<int32_t>(kInfBits);
+                    }
+                } else {
+                    for (int32_t i = tid; i < n_slots_c; i += kBT) {
+                        if ((i % kBatchCand) >= s_bcnt[i / kBatchCand]) continue;
+                        const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+                        if (((static_cast<uint64_t>(p.y) << 32) | p.x) == H) {
+                            ctl[CTL_NEXT_HI] = static_cast<int32_t>(p.x);
+                            ctl[CTL_NEXT_LO] = static_cast<int32_t>(__ldcg(st.cand + 2 * static_cast<int64_t>(i) + 1).z);
+                            ctl[CTL_NEXT_DIST] = static_cast<int32_t>(p.y);
+                        }
+                    }
+                }
+            }
+            break;
+        }
+        int32_t limit = n_live - prm.n_target;
+        if (prm.max_merges >= 0) limit = min(limit, prm.max_merges - launched);
+        limit = min(limit, kMaxBatch);
+
+        // candidate pairs below theta are examined; theta = the stopper minimum unless more than kMaxBatch pairs are
+        // below it (any prefix of a valid batch is a valid batch): bisection on the packed value, packs are unique
+        uint64_t theta = tstop;
+        {
+            auto count_lt = [&](uint64_t th) {
+                int c = 0;
+                for (int32_t i = tid; i < n_slots_c; i += kBT) {
+                    if ((i % kBatchCand) >= s_bcnt[i / kBatchCand]) continue;
+                    const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+                    c += ((static_cast<uint64_t>(p.y) << 32) | p.x) < th ? 1 : 0;
+                }
+                return block_sum_i32(c, s_redi);
+            };
+            int total = 0;
+            for (int32_t b = tid; b < static_cast<int32_t>(G); b += kBT) total += s_bcnt[b];
+            total = block_sum_i32(total, s_redi);
+            if (total > kMaxBatch && count_lt(tstop) > kMaxBatch) {
+                uint64_t lo_t = 0, hi_t = tstop;  // count(lo) <= kMaxBatch < count(hi)
+                while (hi_t - lo_t > 1) {
+                    const uint64_t mid = lo_t + (hi_t - lo_t) / 2;
+                    if (count_lt(mid) <= kMaxBatch)
+                        lo_t = mid;
+                    else
+                        hi_t = mid;
+                }
+                theta = lo_t;
+            }
+        }
+        if (tid == 0) s_m = 0;
+        for (int32_t w = tid; w < n_words; w += kBT) s_bits[w] = 0u;
+        __syncthreads();
+        for (int32_t i = tid; i < n_slots_c; i += kBT) {
+            if ((i % kBatchCand) >= s_bcnt[i / kBatchCand]) continue;
+            const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+            const uint64_t hp = (static_cast<uint64_t>(p.y) << 32) | p.x;
+            if (hp < theta) {
+                const int k = atomicAdd(&s_m, 1);
+                s_hp[k] = hp;
+                s_ca[k] = static_cast<int32_t>(p.z);
+                s_cb[k] = static_cast<int32_t>(p.w);
+                s_idx[k] = i;
+            }
+        }
+        __syncthreads();
+        const int32_t n_cand = s_m;  // <= kMaxBatch
+        // slot conflicts: a pair that shares a cluster with an earlier pair is a stopper
+        uint64_t mine = kPackInf, conf = kPackInf;
+        if (tid < n_cand) {
+            mine = s_hp[tid];
+            const int32_t a = s_ca[tid], b = s_cb[tid];
+            bool hit = false;
+            for (int j = 0; j < n_cand; ++j) {
+                const int32_t aj = s_ca[j], bj = s_cb[j];
+                hit = hit || (s_hp[j] < mine && (aj == a || aj == b || bj == a || bj == b));
+            }
+            if (hit) conf = mine;
+        }
+        const uint64_t T = umin64(theta, block_min_u64(conf, s_red));
+        int rank = -1;
+        if (tid < n_cand && mine < T) {
+            rank = 0;
+            for (int j = 0; j < n_cand; ++j) rank += s_hp[j] < mine ? 1 : 0;  // everything below an accepted pair is accepted
+        }
+        const int32_t m_all = block_sum_i32(rank >= 0 ? 1 : 0, s_redi);  // >= 1: the global minimum head is always among them
+        const int32_t m = min(m_all, limit);                              // merges of this iteration
+        if (rank >= 0) {
+            s_d[rank] = static_cast<uint32_t>(mine >> 32);
+            if (rank < m) {
+                const uint4 p1 = __ldcg(st.cand + 2 * static_cast<int64_t>(s_idx[tid]) + 1);
+                const uint32_t a = static_cast<uint32_t>(s_ca[tid]), b = static_cast<uint32_t>(s_cb[tid]);
+                s_a[rank] = static_cast<int32_t>(a);
+                s_b[rank] = static_cast<int32_t>(b);
+                s_sa[rank] = static_cast<int32_t>(p1.x);
+                s_sb[rank] = static_cast<int32_t>(p1.y);
+                s_ka[rank] = static_cast<int32_t>(pack_key(mine));
+                s_kb[rank] = static_cast<int32_t>(p1.z);
+                atomicOr(&s_bits[a >> 5], 1u << (a & 31u));
+                atomicOr(&s_bits[b >> 5], 1u << (b & 31u));
+            }
+        }
+        if (tid == 0) {  // runner-up of the last pair: the stopper (a lower bound of what comes next)
+            const uint32_t tb = static_cast<uint32_t>(T >> 32);
+            s_d[m_all] = tb < kInfBits ? tb : kInfBits;
+        }
+        __syncthreads();
+        const long long tp3 = timed ? clock64() : 0;
+
+        // ---- bookkeeping (block 0): trace, slot table; counters of the next iterations ----
+        if (blockIdx.x == 0) {
+            if (tid < m) {
+                const int32_t a = s_a[tid], b = s_b[tid], snew = s_sa[tid] + s_sb[tid], new_key = n + t + tid;
+                const float d = __uint_as_float(s_d[tid]), sd = __uint_as_float(s_d[tid + 1]);
+                const float gap = (sd - d) / fmaxf(d, 1e-30f);
+                st.tr_key_hi[t + tid] = s_ka[tid];
+                st.tr_key_lo[t + tid] = s_kb[tid];
+                st.tr_dist[t + tid] = d;
+                st.tr_size[t + tid] = snew;
+                st.tr_gap[t + tid] = gap;
+                if (gap < prm.near_tie_tol) atomicAdd(ctl + CTL_NEAR_TIES, 1);
+                __stcg(st.ks + a, make_int2(-1, 0));
+                __stcg(st.gkey + a, -1);
+                __stcg(st.ks + b, make_int2(new_key, snew));
+                __stcg(st.gkey + b, new_key);
+                __stcg(st.lsize + a, 0);
+                __stcg(st.lsize + b, snew);
+                // the new cluster's row: queued for a scan (all live clusters have a lower key)
+                __stcg(st.nn + static_cast<int64_t>(b) * kNNK, nn_bound(0u));
+#pragma unroll
+                for (int x = 1; x < kNNK; ++x) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + x, nn_none());
+                __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit | kDryBit));
+                __stcg(st.nn_more + a, 0);
+                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = b;
+            }
+            if (tid == kBT - 1) st.counters[sl2 * 4 + CN_DRY] = 0;
+        }
+
+        // ---- Lance-Williams rows: unit = (merge, 512 columns), one warp each, all loads of a unit in flight ----
+        {
+            const int32_t n_chunks = (n4 + kUpdCols - 1) / kUpdCols;
+            const int64_t units = static_cast<int64_t>(m) * n_chunks;
+            for (int64_t u = gw; u < units; u += GW) {
+                const int32_t ch = static_cast<int32_t>(u / m), i = static_cast<int32_t>(u - static_cast<int64_t>(ch) * m);
+                const int32_t a = s_a[i], b = s_b[i], sa = s_sa[i], sb = s_sb[i], snew = sa + sb;
+                const float dab = __uint_as_float(s_d[i]);
+                const float* row_a = dm + static_cast<int64_t>(a) * ld;
+                float* row_b = dm + static_cast<int64_t>(b) * ld;
+                constexpr int kI = kUpdCols / 128;
+                int4 sz4[kI];
+                float4 va[kI], vb[kI];
+#pragma unroll
+                for (int x = 0; x < kI; ++x) {
+                    const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
+                    sz4[x] = make_int4(0, 0, 0, 0);
+                    va[x] = vb[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c0 < n4) {
+                        sz4[x] = __ldcg(reinterpret_cast<const int4*>(st.lsize + c0));
+                        va[x] = __ldcg(reinterpret_cast<const float4*>(row_a + c0));
+                        vb[x] = __ldcg(reinterpret_cast<const float4*>(row_b + c0));
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < kI; ++x) {
+                    const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
+                    if (c0 >= n4) continue;
+                    const uint32_t bits = (s_bits[c0 >> 5] >> (c0 & 31)) & 0xFu;  // c0 % 4 == 0: the four bits share a word
+                    const int32_t sizes[4] = {sz4[x].x, sz4[x].y, sz4[x].z, sz4[x].w};
+                    const float da[4] = {va[x].x, va[x].y, va[x].z, va[x].w};
+                    const float db[4] = {vb[x].x, vb[x].y, vb[x].z, vb[x].w};
+                    float out[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool live = sizes[e] > 0 && ((bits >> e) & 1u) == 0u;
+                        float val = __uint_as_float(kInfBits);
+                        if (live) {
+                            if (sizes[e] + snew <= prm.max_size)  // else inadmissible for good: sizes only grow (:228)
+                                val = lance_williams(sa, sb, sizes[e], da[e], db[e], dab);
+                            __stcg(dm + static_cast<int64_t>(c0 + e) * ld + b, val);  // mirrored entry
+                        }
+                        out[e] = val;
+                    }
+                    if (bits == 0u) {
+                        __stcg(reinterpret_cast<float4*>(row_b + c0), make_float4(out[0], out[1], out[2], out[3]));
+                    } else {  // columns of this batch's clusters belong to the cross-term pass
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (((bits >> e) & 1u) == 0u) __stcg(row_b + c0 + e, out[e]);
+                    }
+                }
+            }
+        }
+        // ---- cross terms: d(new_i, new_j), i < j, two chained updates from the four old entries ----
+        for (int32_t j = gw; j < m; j += GW) {
+            const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
+            const float dj = __uint_as_float(s_d[j]);
+            for (int32_t i = lane; i < j; i += 32) {
+                const int32_t ai = s_a[i], bi = s_b[i], sai = s_sa[i], sbi = s_sb[i], si = sai + sbi;
+                const float di = __uint_as_float(s_d[i]);
+                const float* ra = dm + static_cast<int64_t>(ai) * ld;
+                const float* rb = dm + static_cast<int64_t>(bi) * ld;
+                const float x1 = __ldcg(ra + aj), x2 = __ldcg(rb + aj), x3 = __ldcg(ra + bj), x4 = __ldcg(rb + bj);
+                // merge i seen from k = a_j and k = b_j
+                float t1 = __uint_as_float(kInfBits), t2 = __uint_as_float(kInfBits);
+                if (saj + si <= prm.max_size) t1 = lance_williams(sai, sbi, saj, x1, x2, di);
+                if (sbj + si <= prm.max_size) t2 = lance_williams(sai, sbi, sbj, x3, x4, di);
+                // merge j seen from k = new_i (slot b_i, size si)
+                float val = __uint_as_float(kInfBits);
+                if (si + saj + sbj <= prm.max_size) val = lance_williams(saj, sbj, si, t1, t2, dj);
+                __stcg(dm + static_cast<int64_t>(bi) * ld + bj, val);
+                __stcg(dm + static_cast<int64_t>(bj) * ld + bi, val);
+            }
+        }
+        // ---- list validation: partners merged in this batch are dead ----
+        auto validate = [&](int32_t r, const uint4 (&e)[kNNK]) {
+            if ((s_bits[r >> 5] >> (r & 31)) & 1u) return;  // merged rows: handled by block 0
+            bool dead = false;
+#pragma unroll
+            for (int x = 0; x < kNNK; ++x)
+                if (e[x].z != kNoPartner && ((s_bits[e[x].z >> 5] >> (e[x].z & 31u)) & 1u)) dead = true;
+            if (!dead) return;
+            if (__ldcg(st.gkey + r) < 0) return;
+            uint4 keep[kNNK];
+            int kept = 0;
+            uint32_t last = 0u;
+#pragma unroll
+            for (int x = 0; x < kNNK; ++x) {
+                if (e[x].y == kNoPartner) continue;  // empty
+                last = e[x].y;                        // distance of the last listed entry (valid, dead or bound)
+                if (e[x].z == kNoPartner) continue;  // an old bound
+                if ((s_bits[e[x].z >> 5] >> (e[x].z & 31u)) & 1u) continue;
+#pragma unroll
+                for (int y = 0; y < kNNK; ++y)
+                    if (y == kept) keep[y] = e[x];
+                ++kept;
+            }
+            const bool more = (static_cast<uint32_t>(__ldcg(st.nn_more + r)) & kMoreBit) != 0u;
+#pragma unroll
+            for (int x = 0; x < kNNK; ++x) {
+                uint4 v = nn_none();
+                if (x < kept)
+                    v = keep[x];
+                else if (x == kept && more)
+                    v = nn_bound(last);
+                __stcg(st.nn + static_cast<int64_t>(r) * kNNK + x, v);
+            }
+            if (kept == 0 && more) {
+                __stcg(st.nn_more + r, static_cast<int32_t>(kMoreBit | kDryBit));
+                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = r;
+            }
+        };
+#pragma unroll
+        for (int x = 0; x < kVR; ++x)
+            if (gtid + x * GT < n) validate(gtid + x * GT, ve[x]);
+        for (int32_t r = gtid + kVR * GT; r < n; r += GT) {
+            uint4 e[kNNK];
+#pragma unroll
+            for (int y = 0; y < kNNK; ++y) e[y] = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y);
+            validate(r, e);
+        }
+        t += m;
+        launched += m;
+        n_live -= m;
+        ++iters;
+        grid_sync(st.bar, phase, G);
+        if (timed) {
+            const long long tp4 = clock64();
+            c_ph[0] += tp1 - tp0;
+            c_ph[1] += tp2 - tp1;
+            c_ph[2] += tp3 - tp2;
+            c_ph[3] += tp4 - tp3;
+        }
+    }
+    if (timed) {
+        st.prof[0] = c_ph[0];
+        st.prof[1] = c_ph[1];
+        st.prof[2] = c_ph[2];
+        st.prof[3] = c_ph[3];
+        st.prof[5] = launched;
+        st.prof[6] = iters;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        ctl[CTL_N_LIVE] = n_live;
+        ctl[CTL_N_MERGES] = t;
+        ctl[CTL_EXHAUSTED] = stop_reason == STOP_EXHAUSTED ? 1 : 0;
+        ctl[CTL_ITERS] = ctl[CTL_ITERS] + iters;
+        ctl[CTL_RESCANS] = ctl[CTL_RESCANS] + static_cast<int32_t>(n_rescans);
+        ctl[CTL_STOP] = stop_reason;
+        __threadfence();
+        ctl[CTL_DONE] = 1;
+    }
+}
+
+cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks) {
+    *blocks = 0;
+    const size_t smem = merge_batch_smem_bytes(n);
+    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return cudaSuccess;  // does not fit: *blocks stays 0
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_batch_kernel, kBT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaSuccess;
+    // small problems: fewer blocks make the grid barriers cheaper
+    int64_t want = std::max<int64_t>(8, (n + 127) / 128);
+    *blocks = static_cast<int>(std::min<int64_t>(std::min(num_sms, kBatchMaxBlocks), want));
+    return cudaSuccess;
+}
+
+cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s) {
+    if (blocks <= 0) return cudaErrorInvalidConfiguration;
+    BatchState st_copy = st;
+    st_copy.win_cols = static_cast<int32_t>(batch_window_cols(st.n));
+    st_copy.n_win = static_cast<int32_t>(merge_batch_windows(st.n));
+    LoopParams p_copy = p;
+    void* args[] = {&st_copy, &p_copy};
+    const size_t smem = merge_batch_smem_bytes(st.n);
+    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(merge_batch_kernel), dim3(blocks), dim3(kBT), args, smem, s);
+}
+
+}  // namespace ic

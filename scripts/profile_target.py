@@ -18,6 +18,8 @@ with clustering.Engine(0) as eng:
     eng.set_option("profile_loop", 1)
     if os.environ.get("IC_SCAN_EVERY"):
         eng.set_option("scan_every", int(os.environ["IC_SCAN_EVERY"]))
+    mode = int(os.environ.get("IC_LOOP_MODE", "1"))
+    eng.set_option("loop_mode", mode)
     if os.environ.get("IC_LOOP_BLOCKS"):
         eng.set_option("loop_blocks", int(os.environ["IC_LOOP_BLOCKS"]))
     eng.load(x)
@@ -31,6 +33,11 @@ with clustering.Engine(0) as eng:
     print("trace_sha=" + hashlib.sha256(tr.key_hi.tobytes() + tr.key_lo.tobytes() + tr.dist.tobytes()).hexdigest()[:12])
     p = eng.loop_profile()
     m = max(p["merges"], 1)
+    if mode == 1:  # batched loop: cycles of block 0 per phase
+        it = max(p["iterations"], 1)
+        print(f"batched loop: iterations={p['iterations']} merges/iteration={p['merges'] / it:.1f} cycles per iteration: "
+              f"rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} conflicts={p['update'] / it:.0f} apply={p['scan'] / it:.0f}")
+        sys.exit(0)
     print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
           + f" | iterations={p["iterations"]} rescans={p["rescans"]} bubbles={p["bubbles"]}")
     w = eng.loop_block_waits() / max(p["iterations"], 1)

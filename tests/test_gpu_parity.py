@@ -272,8 +272,8 @@ def knobs(eng):
         for k, v in kw.items():
             eng.set_option(k, v)
     yield set_
-    for k in ("virtual_ranks", "loop_blocks", "no_replica"):
-        eng.set_option(k, 1 if k == "virtual_ranks" else 0)
+    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode"):
+        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode") else 0)
 
 
 @pytest.mark.parametrize("name", SMALL_GOLDENS)
@@ -445,3 +445,65 @@ def test_i8_gram_full_path_replays_bit_exact(eng, oracle):
     eng.merge_loop(mn, mx)
     o = oracle.fast_cluster(x, mn, mx, flags=LW_EAGER, init_matrix=m0)
     _same_trace(eng.merge_trace(), o)
+
+
+# ---- K3b: batched merge loop (merge_batch.cu, the default on one GPU) vs the one-merge-per-iteration loop ----------
+
+@pytest.mark.parametrize("name", SMALL_GOLDENS)
+def test_sequential_loop_mode_goldens_bit_exact(eng, oracle, knobs, name):
+    """loop_mode=0 keeps the one-merge-per-iteration kernel covered on a single rank (the default is batched)."""
+    g = load_golden(name)
+    mn, mx = int(g["min_size"]), int(g["max_size"])
+    o = oracle.fast_cluster(g["x"], mn, mx, flags=LW_EAGER, init_matrix=g["init_matrix"])
+    knobs(loop_mode=0)
+    eng.load(g["x"])
+    eng.set_matrix(g["init_matrix"])
+    eng.nn_init()
+    eng.merge_loop(mn, mx)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(eng.build_clusters(mn), o.clusters)
+
+
+@pytest.mark.parametrize("n,d,mn,mx", [(3000, 64, 4, 12), (6000, 256, 10, 50), (5000, 32, 6, 8)])
+def test_batched_and_sequential_loops_agree(eng, knobs, n, d, mn, mx):
+    """The batch rule only ever takes merges the sequential algorithm would take next, in the same order."""
+    x = synth.gaussian_mixture(n, d, mn, mx, seed=7 * n + d)
+    digests, iters = [], []
+    for mode in (1, 0):
+        knobs(loop_mode=mode)
+        eng.load(x)
+        res = eng.run_resident(mn, mx)
+        digests.append(_trace_digest(eng.merge_trace()))
+        iters.append(res.stats["n_merges"])
+    assert digests[0] == digests[1]
+
+
+def test_batched_more_disjoint_pairs_than_the_batch_capacity(eng, oracle, knobs):
+    """1 500 exact duplicate pairs: every pair is a head at distance 0 and none conflicts, so far more than
+    kMaxBatch (512) pairs sit below the stopper; the batch is cut to a prefix by bisection on the packed value."""
+    rng = np.random.default_rng(11)
+    base = (rng.standard_normal((1500, 8)) * 50).astype(np.float32)
+    x = np.concatenate([base, base])[rng.permutation(3000)]
+    o = oracle.fast_cluster(x, 1, 4, flags=LW_EAGER)
+    knobs(gram_mode=_lib.GRAM_EXACT_FP32)
+    try:
+        res = eng.cluster(x, 1, 4)
+    finally:
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(res.clusters, o.clusters)
+
+
+def test_batched_loop_exhaustion_and_tight_max(eng, oracle, knobs):
+    """maxSize = 8 with minSize = 6 ends by exhaustion (clustering.go:222-225): the batched loop must stop at the
+    same merge as the oracle."""
+    x = synth.gaussian_mixture(2000, 32, 6, 8, seed=5)
+    o = oracle.fast_cluster(x, 6, 8, flags=LW_EAGER)
+    knobs(gram_mode=_lib.GRAM_EXACT_FP32)
+    try:
+        res = eng.cluster(x, 6, 8)
+    finally:
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
+    _same_trace(eng.merge_trace(), o)
+    assert bool(res.stats["exhausted"]) == o.exhausted
+    assert same_clusters(res.clusters, o.clusters)
