@@ -41,6 +41,7 @@ struct ic_ctx {
     int vranks = 1;
     int vranks_alloc = -1;
     int scan_every = 4;  // merge loop: rescans are requested every scan_every-th iteration
+    int loop_debug = 0;  // experiments only
     int loop_mode = 1;   // 1: batched loop (merge_batch.cu) on an unsharded context; 0: one merge per iteration (merge_loop.cu)
     int batch_grid = 0;
     uint8_t* batch_scratch = nullptr;  // hdr | cand | counters | dryq | partials | part_cnt | bar
@@ -335,7 +336,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (P == 1) {  // batched loop: launch geometry and scratch
         IC_CUDA(merge_batch_grid(ctx->num_sms, n, &ctx->batch_grid));
         if (ctx->loop_blocks > 0 && ctx->batch_grid > 0) ctx->batch_grid = std::min(ctx->loop_blocks, ctx->num_sms);
-        const size_t sizes[9] = {static_cast<size_t>(kBatchMaxBlocks) * 32, static_cast<size_t>(kBatchMaxBlocks) * kBatchCand * 32,
+        const size_t sizes[9] = {static_cast<size_t>(kBatchMaxBlocks) * 32, 32 * nn1,
                                  3 * 4 * 4, 4 * nn1, static_cast<size_t>(kBatchMaxDry) * kBatchMaxWin * 128,
                                  static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), 0};
         size_t off = 0;
@@ -519,6 +520,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.max_merges = static_cast<int32_t>(max_merges < 0 ? -1 : (max_merges > 0x7FFFFFFF ? 0x7FFFFFFF : max_merges));
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
     p.scan_every = ctx->scan_every;
+    p.debug = ctx->loop_debug;
     if (use_batch(ctx)) {
         BatchState bs{};
         uint8_t* sc = ctx->batch_scratch;
@@ -883,6 +885,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         const int m = static_cast<int>(value);
         if (m != 0 && m != 1) return fail(ctx, IC_ERR_BAD_ARG, "loop_mode must be 0 (sequential) or 1 (batched)");
         ctx->loop_mode = m;
+    } else if (k == "loop_debug") {
+        ctx->loop_debug = static_cast<int>(value);
     } else if (k == "no_replica") {
         ctx->no_replica = value != 0.0;
     } else if (k == "loop_blocks") {

@@ -125,6 +125,7 @@ struct LoopParams {
     int32_t max_merges;  // stop after this many merges in this launch (<0: unlimited)
     float near_tie_tol;
     int32_t scan_every;  // rescan requests are published every scan_every-th iteration (batched row scans)
+    int32_t debug;       // experiments only (bit 0: batched loop skips the mirrored column stores -> wrong results)
 };
 // ctl[] indices.  N_LIVE and N_MERGES are read at launch (resume) and written at exit.
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,
@@ -171,9 +172,9 @@ struct BatchState {
     int32_t* ctl;       // [16]
     long long* prof;    // [16] or NULL
     // scratch (zeroed before every launch)
-    uint4* hdr;         // [kBatchMaxBlocks][2] per block: {candidates, 0, stopper lo, hi} {head minimum lo, hi, 0, 0}
-    uint4* cand;        // [kBatchMaxBlocks][kBatchCand][2] {head lo, head hi, row slot, partner slot} {size, size, partner key, 0}
-    int32_t* counters;  // [3][4] dry rows, per iteration mod 3
+    uint4* hdr;         // [kBatchMaxBlocks] per block: {stopper minimum lo, hi, head minimum lo, hi}
+    uint4* cand;        // [n][2] candidate pairs {head lo, head hi, row slot, partner slot} {size, size, partner key, 0}
+    int32_t* counters;  // [3][4] dry rows, candidate pairs; per iteration mod 3
     int32_t* dryq;      // [n]   rows to rescan
     int32_t* lsize;     // [n4]  size of the live cluster in every slot, 0: retired (rebuilt from ks at launch)
     uint4* partials;    // [kBatchMaxDry][kBatchMaxWin][8] partial lists of the window scans

@@ -41,14 +41,18 @@ IC_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: 
 IC_DEVINL void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // Lance-Williams update of Ward's distance (clustering.go:141-144 is the closed form it
-// equals): exact integer weights, double arithmetic, one rounding to fp32.  The CPU
+// equals): exact integer weights, double arithmetic, the quotient as a product with the
+// correctly rounded reciprocal of the (small integer) size sum, one rounding to fp32.  The CPU
 // oracle's LW mode (oracle/ward_fast.c) performs the same operations in the same order.
-IC_DEVINL float lance_williams(int sa, int sb, int sk, float dka, float dkb, float dab) {
+IC_DEVINL float lance_williams_rcp(int sa, int sb, int sk, float dka, float dkb, float dab, double rcp_den) {
     const double t1 = static_cast<double>(sa + sk) * static_cast<double>(dka);
     const double t2 = static_cast<double>(sb + sk) * static_cast<double>(dkb);
     const double t3 = static_cast<double>(sk) * static_cast<double>(dab);
     const double num = (t1 + t2) - t3;
-    return canon_dist(static_cast<float>(num / static_cast<double>(sa + sb + sk)));
+    return canon_dist(static_cast<float>(num * rcp_den));
+}
+IC_DEVINL float lance_williams(int sa, int sb, int sk, float dka, float dkb, float dab) {
+    return lance_williams_rcp(sa, sb, sk, dka, dkb, dab, 1.0 / static_cast<double>(sa + sb + sk));
 }
 
 IC_DEVINL uint4 nn_none() { return make_uint4(kNoPartner, kNoPartner, kNoPartner, 0u); }

@@ -44,10 +44,11 @@ constexpr int kBW = kBT / 32;
 constexpr uint32_t kMoreBit = 1u, kDryBit = 2u;
 constexpr uint32_t kBarSpin = 1u << 24;
 constexpr int kUpdCols = 512;  // columns of one update unit (one warp: 4 x 32 lanes x 4, all loads in flight at once)
+constexpr int kRcpTab = 1024;
 constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead of the update pass
 
 // counters[slot][*]
-enum { CN_DRY = 0 };
+enum { CN_DRY = 0, CN_CAND = 1 };
 
 // grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
 IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G) {
@@ -94,20 +95,21 @@ struct RowHead {
     uint64_t head;  // (dist bits << 32 | row key), kPackInf: none
     uint64_t stop;  // smallest pack a second pair of this row may have, +1 (see P2); kPackInf: none
     uint32_t partner_slot, partner_key;
+    int32_t partner_size;
 };
-IC_DEVINL RowHead row_head(const SlotNN* nn, const int32_t* nn_more, int32_t r, uint32_t key_r) {
+IC_DEVINL RowHead row_head(uint4 e0, uint4 e1, uint32_t more_bits, uint32_t key_r) {
     RowHead h;
     h.head = h.stop = kPackInf;
     h.partner_slot = h.partner_key = kNoPartner;
-    const uint4 e0 = __ldcg(nn + static_cast<int64_t>(r) * kNNK);
+    h.partner_size = 0;
     if (e0.z == kNoPartner) return h;  // no partner (a bound cannot be here: dry rows were rescanned in P1)
-    const uint4 e1 = __ldcg(nn + static_cast<int64_t>(r) * kNNK + 1);
     h.head = (static_cast<uint64_t>(e0.y) << 32) | key_r;
     h.partner_slot = e0.z;
     h.partner_key = e0.x;
+    h.partner_size = static_cast<int32_t>(e0.w);
     if (e1.y != kNoPartner)  // a second partner, or the bound of the unlisted ones
         h.stop = ((static_cast<uint64_t>(e1.y) << 32) | key_r) + 1ull;
-    else if ((static_cast<uint32_t>(__ldcg(nn_more + r)) & kMoreBit) != 0u)
+    else if ((more_bits & kMoreBit) != 0u)
         h.stop = h.head + 1ull;  // list cut after the head: the rest is >= the head's distance
     return h;
 }
@@ -136,7 +138,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     const int32_t n4 = (n + 3) & ~3;
     const int64_t ld = st.ld;
     const int32_t gtid = static_cast<int32_t>(blockIdx.x) * kBT + tid, GT = static_cast<int32_t>(G) * kBT;
-    const int32_t gw = static_cast<int32_t>(blockIdx.x) * kBW + warp, GW = static_cast<int32_t>(G) * kBW;
+    // work units go to warps block-interleaved: consecutive units run on different SMs
+    const int32_t gw = warp * static_cast<int32_t>(G) + static_cast<int32_t>(blockIdx.x), GW = static_cast<int32_t>(G) * kBW;
     const int32_t win = st.win_cols, nwin = st.n_win;
     float* const dm = st.dm;
     int32_t* const ctl = st.ctl;
@@ -147,14 +150,14 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
 
     __shared__ uint64_t s_red[kBW];
     __shared__ int s_redi[kBW];
-    __shared__ int32_t s_bcnt[kBatchMaxBlocks];
     // candidate pairs as collected (unordered) ...
     __shared__ uint64_t s_hp[kMaxBatch];
     __shared__ int32_t s_ca[kMaxBatch], s_cb[kMaxBatch], s_idx[kMaxBatch];
     // ... and the batch in scan order
     __shared__ int32_t s_a[kMaxBatch], s_b[kMaxBatch], s_sa[kMaxBatch], s_sb[kMaxBatch], s_ka[kMaxBatch], s_kb[kMaxBatch];
     __shared__ uint32_t s_d[kMaxBatch + 1];
-    __shared__ int32_t s_m, s_pub;
+    __shared__ int32_t s_m;
+    __shared__ double s_rcp[kRcpTab];  // 1.0 / size sum, correctly rounded (what lance_williams() computes inline)
 
     uint32_t phase = 0;
     int32_t n_live = __ldcg(ctl + CTL_N_LIVE);
@@ -164,6 +167,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long c_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+    for (int i = tid; i < kRcpTab; i += kBT) s_rcp[i] = 1.0 / static_cast<double>(i > 0 ? i : 1);
+    __syncthreads();
     // rows that were dry when the previous launch stopped (or rows the other loop left dry): queue slot 0
     for (int32_t r = gtid; r < n; r += GT)
         if ((static_cast<uint32_t>(__ldcg(st.nn_more + r)) & kDryBit) != 0u && __ldcg(st.ks + r).x >= 0)
@@ -280,11 +285,13 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     }
                 }
                 if (folder) {
-                    if (lane < kNNK) {
+                    if (lane < kNNK) {  // entry: {partner key, distance bits, partner slot, partner size}
                         const uint64_t myp = sel4(out.pk, lane);
+                        const int32_t ps = sel4(out.sl, lane);
+                        const int32_t psz = lane < out.m ? __ldcg(st.lsize + ps) : 0;
                         __stcg(st.nn + static_cast<int64_t>(r) * kNNK + lane,
                                lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
-                                                         static_cast<uint32_t>(sel4(out.sl, lane)), 0u)
+                                                         static_cast<uint32_t>(ps), static_cast<uint32_t>(psz))
                                             : nn_none());
                     } else if (lane == kNNK) {
                         __stcg(st.nn_more + r, out.more ? static_cast<int32_t>(kMoreBit) : 0);
@@ -296,44 +303,39 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         grid_sync(st.bar, phase, G);
         const long long tp1 = timed ? clock64() : 0;
 
-        // ================= P2: heads and stoppers; every block publishes its candidates =================
+        // ================= P2: heads and stoppers; candidates go to one global list =================
         {
-            uint64_t bstop = kPackInf, bhead = kPackInf, dropped = kPackInf;
-            if (tid == 0) s_pub = 0;
-            __syncthreads();
+            uint64_t bstop = kPackInf, bhead = kPackInf;
+            int32_t* const cnt_cand = st.counters + sl * 4 + CN_CAND;
             for (int32_t r0 = 0; r0 < n; r0 += GT) {
                 const int32_t r = r0 + gtid;
                 RowHead h;
                 h.head = h.stop = kPackInf;
                 h.partner_slot = h.partner_key = kNoPartner;
-                if (r < n) {
+                h.partner_size = 0;
+                int32_t sr = 0;
+                if (r < n) {  // one round trip: key, own size, list flags and the first two entries
                     const int32_t key_r = __ldcg(st.gkey + r);
-                    if (key_r >= 0) h = row_head(st.nn, st.nn_more, r, static_cast<uint32_t>(key_r));
+                    sr = __ldcg(st.lsize + r);
+                    const uint32_t mb = static_cast<uint32_t>(__ldcg(st.nn_more + r));
+                    const uint4 e0 = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK);
+                    const uint4 e1 = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + 1);
+                    if (key_r >= 0) h = row_head(e0, e1, mb, static_cast<uint32_t>(key_r));
                 }
                 bstop = umin64(bstop, block_min_u64(h.stop, s_red));  // running minimum: any value >= T is a valid filter
                 bhead = umin64(bhead, h.head);
                 if (h.head < bstop) {
-                    const int k = atomicAdd(&s_pub, 1);
-                    if (k < kBatchCand) {
-                        const int32_t u = static_cast<int32_t>(h.partner_slot);
-                        const int32_t sr = __ldcg(st.ks + r).y, su = __ldcg(st.ks + u).y;
-                        uint4* dst = st.cand + (static_cast<size_t>(blockIdx.x) * kBatchCand + k) * 2;
-                        __stcg(dst, make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
-                                               static_cast<uint32_t>(r), h.partner_slot));
-                        __stcg(dst + 1, make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(su), h.partner_key, 0u));
-                    } else {
-                        dropped = umin64(dropped, h.head);  // does not fit: nothing at or above it may be taken
-                    }
+                    const int32_t k = atomicAdd(cnt_cand, 1);
+                    uint4* dst = st.cand + 2 * static_cast<int64_t>(k);
+                    __stcg(dst, make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
+                                           static_cast<uint32_t>(r), h.partner_slot));
+                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(h.partner_size), h.partner_key, 0u));
                 }
             }
             bhead = block_min_u64(bhead, s_red);
-            dropped = block_min_u64(dropped, s_red);
-            if (tid == 0) {
-                const uint64_t bs = umin64(bstop, dropped);
-                __stcg(st.hdr + 2 * blockIdx.x, make_uint4(static_cast<uint32_t>(min(s_pub, kBatchCand)), 0u,
-                                                          static_cast<uint32_t>(bs), static_cast<uint32_t>(bs >> 32)));
-                __stcg(st.hdr + 2 * blockIdx.x + 1, make_uint4(static_cast<uint32_t>(bhead), static_cast<uint32_t>(bhead >> 32), 0u, 0u));
-            }
+            if (tid == 0)
+                __stcg(st.hdr + blockIdx.x, make_uint4(static_cast<uint32_t>(bstop), static_cast<uint32_t>(bstop >> 32),
+                                                       static_cast<uint32_t>(bhead), static_cast<uint32_t>(bhead >> 32)));
         }
         grid_sync(st.bar, phase, G);
         const long long tp2 = timed ? clock64() : 0;
@@ -349,13 +351,15 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 ve[x][y] = r < n ? __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y) : nn_none();
         }
         uint64_t tstop = kPackInf, H = kPackInf;
+        const int32_t n_pub = __ldcg(st.counters + sl * 4 + CN_CAND);  // heads below their block's stopper minimum
+        uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        if (tid < n_pub) c0 = __ldcg(st.cand + 2 * static_cast<int64_t>(tid));
         if (tid < static_cast<int>(G)) {
-            const uint4 h0 = __ldcg(st.hdr + 2 * tid), h1 = __ldcg(st.hdr + 2 * tid + 1);
-            s_bcnt[tid] = static_cast<int32_t>(h0.x);
-            tstop = (static_cast<uint64_t>(h0.w) << 32) | h0.z;
-            H = (static_cast<uint64_t>(h1.y) << 32) | h1.x;
+            const uint4 h0 = __ldcg(st.hdr + tid);
+            tstop = (static_cast<uint64_t>(h0.y) << 32) | h0.x;
+            H = (static_cast<uint64_t>(h0.w) << 32) | h0.z;
         }
-        tstop = block_min_u64(tstop, s_red);  // (the barriers inside also publish s_bcnt)
+        tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
         if (n_live <= prm.n_target)
@@ -366,7 +370,6 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             stop_reason = STOP_MAX_MERGES;
         else if (it + 8u >= (1u << 22))
             stop_reason = STOP_EPOCHS;
-        const int32_t n_slots_c = static_cast<int32_t>(G) * kBatchCand;
         if (stop_reason != 0) {
             if (blockIdx.x == 0) {  // what FindClosestClusters would return now
                 if (!pack_selectable(H)) {
@@ -376,8 +379,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                         ctl[CTL_NEXT_DIST] = static_cast<int32_t>(kInfBits);
                     }
                 } else {
-                    for (int32_t i = tid; i < n_slots_c; i += kBT) {
-                        if ((i % kBatchCand) >= s_bcnt[i / kBatchCand]) continue;
+                    for (int32_t i = tid; i < n_pub; i += kBT) {
                         const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
                         if (((static_cast<uint64_t>(p.y) << 32) | p.x) == H) {
                             ctl[CTL_NEXT_HI] = static_cast<int32_t>(p.x);
@@ -396,20 +398,16 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         // candidate pairs below theta are examined; theta = the stopper minimum unless more than kMaxBatch pairs are
         // below it (any prefix of a valid batch is a valid batch): bisection on the packed value, packs are unique
         uint64_t theta = tstop;
-        {
+        if (n_pub > kMaxBatch) {
             auto count_lt = [&](uint64_t th) {
                 int c = 0;
-                for (int32_t i = tid; i < n_slots_c; i += kBT) {
-                    if ((i % kBatchCand) >= s_bcnt[i / kBatchCand]) continue;
+                for (int32_t i = tid; i < n_pub; i += kBT) {
                     const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
                     c += ((static_cast<uint64_t>(p.y) << 32) | p.x) < th ? 1 : 0;
                 }
                 return block_sum_i32(c, s_redi);
             };
-            int total = 0;
-            for (int32_t b = tid; b < static_cast<int32_t>(G); b += kBT) total += s_bcnt[b];
-            total = block_sum_i32(total, s_redi);
-            if (total > kMaxBatch && count_lt(tstop) > kMaxBatch) {
+            if (count_lt(tstop) > kMaxBatch) {
                 uint64_t lo_t = 0, hi_t = tstop;  // count(lo) <= kMaxBatch < count(hi)
                 while (hi_t - lo_t > 1) {
                     const uint64_t mid = lo_t + (hi_t - lo_t) / 2;
@@ -424,9 +422,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         if (tid == 0) s_m = 0;
         for (int32_t w = tid; w < n_words; w += kBT) s_bits[w] = 0u;
         __syncthreads();
-        for (int32_t i = tid; i < n_slots_c; i += kBT) {
-            if ((i % kBatchCand) >= s_bcnt[i / kBatchCand]) continue;
-            const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+        for (int32_t i = tid; i < n_pub; i += kBT) {
+            const uint4 p = i == tid ? c0 : __ldcg(st.cand + 2 * static_cast<int64_t>(i));
             const uint64_t hp = (static_cast<uint64_t>(p.y) << 32) | p.x;
             if (hp < theta) {
                 const int k = atomicAdd(&s_m, 1);
@@ -506,53 +503,82 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 __stcg(st.nn_more + a, 0);
                 st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = b;
             }
-            if (tid == kBT - 1) st.counters[sl2 * 4 + CN_DRY] = 0;
+            if (tid == kBT - 1) {
+                st.counters[sl2 * 4 + CN_DRY] = 0;
+                st.counters[sl1 * 4 + CN_CAND] = 0;
+            }
         }
 
-        // ---- Lance-Williams rows: unit = (merge, 512 columns), one warp each, all loads of a unit in flight ----
+        // ---- Lance-Williams rows: unit = (merge, kUpdCols columns), one warp each, all loads of a unit in flight ----
+        // A pair's distance lives in the row of its HIGHER-key cluster (the new cluster's row is written in full, nothing
+        // is mirrored into the older rows: that cost one scattered sector per live cluster and merge).  d(c,a) of a
+        // cluster c newer than a is therefore gathered from row c; early in the loop almost every column is older.
         {
             const int32_t n_chunks = (n4 + kUpdCols - 1) / kUpdCols;
             const int64_t units = static_cast<int64_t>(m) * n_chunks;
             for (int64_t u = gw; u < units; u += GW) {
                 const int32_t ch = static_cast<int32_t>(u / m), i = static_cast<int32_t>(u - static_cast<int64_t>(ch) * m);
                 const int32_t a = s_a[i], b = s_b[i], sa = s_sa[i], sb = s_sb[i], snew = sa + sb;
+                const int32_t ka = s_ka[i], kb = s_kb[i];
                 const float dab = __uint_as_float(s_d[i]);
                 const float* row_a = dm + static_cast<int64_t>(a) * ld;
                 float* row_b = dm + static_cast<int64_t>(b) * ld;
                 constexpr int kI = kUpdCols / 128;
-                int4 sz4[kI];
+                int4 k01[kI], k23[kI];
                 float4 va[kI], vb[kI];
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
                     const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
-                    sz4[x] = make_int4(0, 0, 0, 0);
+                    k01[x] = k23[x] = make_int4(-1, 0, -1, 0);
                     va[x] = vb[x] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (c0 < n4) {
-                        sz4[x] = __ldcg(reinterpret_cast<const int4*>(st.lsize + c0));
+                        k01[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0));
+                        k23[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0 + 2));
                         va[x] = __ldcg(reinterpret_cast<const float4*>(row_a + c0));
                         vb[x] = __ldcg(reinterpret_cast<const float4*>(row_b + c0));
                     }
+                }
+                float da[kI][4], db[kI][4];
+                uint32_t livem[kI];
+#pragma unroll
+                for (int x = 0; x < kI; ++x) {  // second round trip, only for the columns of newer clusters
+                    const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
+                    const uint32_t bits = c0 < n4 ? (s_bits[c0 >> 5] >> (c0 & 31)) & 0xFu : 0xFu;  // c0 % 4 == 0: one word
+                    const int32_t keys[4] = {k01[x].x, k01[x].z, k23[x].x, k23[x].z};
+                    const float ra[4] = {va[x].x, va[x].y, va[x].z, va[x].w};
+                    const float rb[4] = {vb[x].x, vb[x].y, vb[x].z, vb[x].w};
+                    livem[x] = 0u;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool live = keys[e] >= 0 && ((bits >> e) & 1u) == 0u;
+                        livem[x] |= live ? (1u << e) : 0u;
+                        da[x][e] = ra[e];
+                        db[x][e] = rb[e];
+                        if (live && keys[e] > kb) {
+                            const float* rc = dm + static_cast<int64_t>(c0 + e) * ld;
+                            db[x][e] = __ldcg(rc + b);
+                            if (keys[e] > ka) da[x][e] = __ldcg(rc + a);
+                        }
+                    }
+                    livem[x] |= bits << 4;
                 }
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
                     const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
                     if (c0 >= n4) continue;
-                    const uint32_t bits = (s_bits[c0 >> 5] >> (c0 & 31)) & 0xFu;  // c0 % 4 == 0: the four bits share a word
-                    const int32_t sizes[4] = {sz4[x].x, sz4[x].y, sz4[x].z, sz4[x].w};
-                    const float da[4] = {va[x].x, va[x].y, va[x].z, va[x].w};
-                    const float db[4] = {vb[x].x, vb[x].y, vb[x].z, vb[x].w};
+                    const int32_t sizes[4] = {k01[x].y, k01[x].w, k23[x].y, k23[x].w};
                     float out[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const bool live = sizes[e] > 0 && ((bits >> e) & 1u) == 0u;
                         float val = __uint_as_float(kInfBits);
-                        if (live) {
-                            if (sizes[e] + snew <= prm.max_size)  // else inadmissible for good: sizes only grow (:228)
-                                val = lance_williams(sa, sb, sizes[e], da[e], db[e], dab);
-                            __stcg(dm + static_cast<int64_t>(c0 + e) * ld + b, val);  // mirrored entry
+                        if (((livem[x] >> e) & 1u) != 0u && sizes[e] + snew <= prm.max_size) {  // else inadmissible for good (:228)
+                            const int den = snew + sizes[e];
+                            val = lance_williams_rcp(sa, sb, sizes[e], da[x][e], db[x][e], dab,
+                                                     den < kRcpTab ? s_rcp[den] : 1.0 / static_cast<double>(den));
                         }
                         out[e] = val;
                     }
+                    const uint32_t bits = livem[x] >> 4;
                     if (bits == 0u) {
                         __stcg(reinterpret_cast<float4*>(row_b + c0), make_float4(out[0], out[1], out[2], out[3]));
                     } else {  // columns of this batch's clusters belong to the cross-term pass
@@ -563,16 +589,19 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 }
             }
         }
+        const long long tq1 = timed ? clock64() : 0;
         // ---- cross terms: d(new_i, new_j), i < j, two chained updates from the four old entries ----
         for (int32_t j = gw; j < m; j += GW) {
-            const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
+            const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j], kaj = s_ka[j], kbj = s_kb[j];
             const float dj = __uint_as_float(s_d[j]);
             for (int32_t i = lane; i < j; i += 32) {
-                const int32_t ai = s_a[i], bi = s_b[i], sai = s_sa[i], sbi = s_sb[i], si = sai + sbi;
+                const int32_t ai = s_a[i], bi = s_b[i], sai = s_sa[i], sbi = s_sb[i], si = sai + sbi, kai = s_ka[i], kbi = s_kb[i];
                 const float di = __uint_as_float(s_d[i]);
-                const float* ra = dm + static_cast<int64_t>(ai) * ld;
-                const float* rb = dm + static_cast<int64_t>(bi) * ld;
-                const float x1 = __ldcg(ra + aj), x2 = __ldcg(rb + aj), x3 = __ldcg(ra + bj), x4 = __ldcg(rb + bj);
+                auto pair = [&](int32_t p, int32_t kp, int32_t q, int32_t kq) {  // row of the higher key
+                    return kp > kq ? __ldcg(dm + static_cast<int64_t>(p) * ld + q) : __ldcg(dm + static_cast<int64_t>(q) * ld + p);
+                };
+                const float x1 = pair(ai, kai, aj, kaj), x2 = pair(bi, kbi, aj, kaj), x3 = pair(ai, kai, bj, kbj),
+                            x4 = pair(bi, kbi, bj, kbj);
                 // merge i seen from k = a_j and k = b_j
                 float t1 = __uint_as_float(kInfBits), t2 = __uint_as_float(kInfBits);
                 if (saj + si <= prm.max_size) t1 = lance_williams(sai, sbi, saj, x1, x2, di);
@@ -580,10 +609,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 // merge j seen from k = new_i (slot b_i, size si)
                 float val = __uint_as_float(kInfBits);
                 if (si + saj + sbj <= prm.max_size) val = lance_williams(saj, sbj, si, t1, t2, dj);
-                __stcg(dm + static_cast<int64_t>(bi) * ld + bj, val);
-                __stcg(dm + static_cast<int64_t>(bj) * ld + bi, val);
+                __stcg(dm + static_cast<int64_t>(bj) * ld + bi, val);  // new_j carries the higher key
             }
         }
+        const long long tq2 = timed ? clock64() : 0;
         // ---- list validation: partners merged in this batch are dead ----
         auto validate = [&](int32_t r, const uint4 (&e)[kNNK]) {
             if ((s_bits[r >> 5] >> (r & 31)) & 1u) return;  // merged rows: handled by block 0
@@ -635,6 +664,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         launched += m;
         n_live -= m;
         ++iters;
+        const long long tq3 = timed ? clock64() : 0;
         grid_sync(st.bar, phase, G);
         if (timed) {
             const long long tp4 = clock64();
@@ -642,6 +672,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             c_ph[1] += tp2 - tp1;
             c_ph[2] += tp3 - tp2;
             c_ph[3] += tp4 - tp3;
+            c_ph[4] += tq1 - tp3;
+            c_ph[5] += tq2 - tq1;
+            c_ph[6] += tq3 - tq2;
+            c_ph[7] += tp4 - tq3;
         }
     }
     if (timed) {
@@ -651,6 +685,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         st.prof[3] = c_ph[3];
         st.prof[5] = launched;
         st.prof[6] = iters;
+        for (int i = 0; i < 4; ++i) st.prof[10 + i] = c_ph[4 + i];
     }
     if (blockIdx.x == 0 && tid == 0) {
         ctl[CTL_N_LIVE] = n_live;

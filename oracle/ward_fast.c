@@ -284,7 +284,8 @@ int oracle_fast_cluster_ex(const float *x, int n, int d, int min_size, int max_s
                     double t2 = (double)(sb + sk) * (double)rb[k];
                     double t3 = (double)sk * (double)bd;
                     double num = (t1 + t2) - t3;
-                    v = (float)(num / (double)(snew + sk));
+                    /* product with the correctly rounded reciprocal: the device keeps a table of 1.0 / size sum */
+                    v = (float)(num * (1.0 / (double)(snew + sk)));
                 }
                 if (!(v >= 0.0f))
                     v = (v != v) ? INFINITY : 0.0f;

@@ -20,6 +20,8 @@ with clustering.Engine(0) as eng:
         eng.set_option("scan_every", int(os.environ["IC_SCAN_EVERY"]))
     mode = int(os.environ.get("IC_LOOP_MODE", "1"))
     eng.set_option("loop_mode", mode)
+    if os.environ.get("IC_LOOP_DEBUG"):
+        eng.set_option("loop_debug", int(os.environ["IC_LOOP_DEBUG"]))
     if os.environ.get("IC_LOOP_BLOCKS"):
         eng.set_option("loop_blocks", int(os.environ["IC_LOOP_BLOCKS"]))
     eng.load(x)
@@ -36,7 +38,8 @@ with clustering.Engine(0) as eng:
     if mode == 1:  # batched loop: cycles of block 0 per phase
         it = max(p["iterations"], 1)
         print(f"batched loop: iterations={p['iterations']} merges/iteration={p['merges'] / it:.1f} cycles per iteration: "
-              f"rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} conflicts={p['update'] / it:.0f} apply={p['scan'] / it:.0f}")
+              f"rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} select={p['update'] / it:.0f} apply={p['scan'] / it:.0f} "
+              f"(rows={p['pub_argmin'] / it:.0f} cross={p['pub_reduce'] / it:.0f} validate={p['pub_fence'] / it:.0f} barrier={p['pub_stores'] / it:.0f})")
         sys.exit(0)
     print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
           + f" | iterations={p["iterations"]} rescans={p["rescans"]} bubbles={p["bubbles"]}")
