@@ -50,7 +50,7 @@ class Stats(C.Structure):
         ("ms_h2d", C.c_float), ("ms_prep", C.c_float), ("ms_gram", C.c_float), ("ms_nn_init", C.c_float),
         ("ms_loop", C.c_float), ("ms_d2h", C.c_float), ("ms_host", C.c_float), ("ms_total", C.c_float),
         ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-        ("matrix_bytes", C.c_int64),
+        ("matrix_bytes", C.c_int64), ("n_iterations", C.c_int32), ("loop_mode", C.c_int32),
     ]
 
     def as_dict(self):

@@ -42,10 +42,12 @@ struct ic_ctx {
     int vranks_alloc = -1;
     int scan_every = 4;  // merge loop: rescans are requested every scan_every-th iteration
     int loop_debug = 0;  // experiments only
+    int loop_mode_alloc = -1, loop_mode_used = -1;  // layout the allocation was made for; loop that touched the matrix
+    bool batch_layout = false;  // scratch of the batched loop is allocated
     int loop_mode = 1;   // 1: batched loop (merge_batch.cu) on an unsharded context; 0: one merge per iteration (merge_loop.cu)
     int batch_grid = 0;
     uint8_t* batch_scratch = nullptr;  // hdr | cand | counters | dryq | partials | part_cnt | bar
-    size_t batch_scratch_bytes = 0, batch_off[9] = {0};
+    size_t batch_scratch_bytes = 0, batch_off[12] = {0};
     int no_replica = 0, no_replica_alloc = -1;  // test hook: stream the keys from L2 even when the replica would fit
     bool loop_replica = false;
     uint32_t loop_gen = 0;    // generation of the last merge-loop launch (mailbox tags)
@@ -270,7 +272,7 @@ int make_operand_map_i8(ic_ctx* ctx, CUtensorMap* map, int8_t* base, int64_t row
 
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 && ctx->loop_blocks == ctx->loop_blocks_alloc &&
-        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && ctx->shard_world == ctx->shard_world_alloc &&
+        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
         ctx->shard_rank == ctx->shard_rank_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
         ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = ctx->prepped_i8 = false;
@@ -284,6 +286,9 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     ctx->d_pad = round_up(d, kGramBK);
     ctx->d_pad8 = round_up(d, kI8BK);
     ctx->ld = round_up(n, 32);
+    ctx->loop_mode_alloc = ctx->loop_mode;
+    ctx->batch_layout = false;
+    ctx->batch_grid = 0;
     ctx->vranks_alloc = ctx->vranks;
     ctx->no_replica_alloc = ctx->no_replica;
     ctx->loop_replica = merge_loop_replica_fits(n) && !ctx->no_replica;
@@ -296,10 +301,17 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     const int64_t rows = ctx->shard_world > 1 ? rows_per_rank(ctx) : n;
     size_t free_b = 0, total_b = 0;
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const double need = 4.0 * n * d + 4.0 * static_cast<double>(rows) * ctx->ld +
-                        (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
-                        (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 160.0 * n +
-                        (96 << 20);
+    const double other = 4.0 * n * d + (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
+                         (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20);
+    if (P == 1 && ctx->loop_mode == 1 && n > 0) {  // batched loop (one unsharded GPU)
+        int grid = 0;
+        IC_CUDA(merge_batch_grid(ctx->num_sms, n, &grid));
+        if (grid > 0) {
+            ctx->batch_layout = true;
+            ctx->batch_grid = ctx->loop_blocks > 0 ? std::min(ctx->loop_blocks, ctx->num_sms) : grid;
+        }
+    }
+    const double need = other + 4.0 * static_cast<double>(rows) * ctx->ld;
     if (need > static_cast<double>(free_b))
         return fail(ctx, IC_ERR_OOM, "problem needs " + std::to_string(need / 1e9) + " GB, device has " +
                                          std::to_string(free_b / 1e9) + " GB free");
@@ -332,15 +344,12 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMemsetAsync(ctx->partials, 0, pb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
-    ctx->batch_grid = 0;
-    if (P == 1) {  // batched loop: launch geometry and scratch
-        IC_CUDA(merge_batch_grid(ctx->num_sms, n, &ctx->batch_grid));
-        if (ctx->loop_blocks > 0 && ctx->batch_grid > 0) ctx->batch_grid = std::min(ctx->loop_blocks, ctx->num_sms);
-        const size_t sizes[9] = {static_cast<size_t>(kBatchMaxBlocks) * 32, 32 * nn1,
-                                 3 * 4 * 4, 4 * nn1, static_cast<size_t>(kBatchMaxDry) * kBatchMaxWin * 128,
-                                 static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), 0};
+    if (ctx->batch_layout) {  // batched loop: scratch
+        const size_t sizes[11] = {static_cast<size_t>(kBatchMaxBlocks) * 32, 32 * nn1,
+                                  3 * 4 * 4, 8 * nn1, static_cast<size_t>(kBatchMaxDry) * kBatchMaxWin * 128,
+                                  static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), 0, 0, 0};
         size_t off = 0;
-        for (int i = 0; i < 9; ++i) {
+        for (int i = 0; i < 11; ++i) {
             ctx->batch_off[i] = off;
             off += (sizes[i] + 255) / 256 * 256;
         }
@@ -489,6 +498,7 @@ int init_loop_state(ic_ctx* ctx) {
     IC_CUDA(launch_init_slots(ctx->ks, ctx->gkey, ctx->n, ctx->stream));
     ctx->stats.kernel_launches += 1;
     ctx->n_live = static_cast<int32_t>(ctx->n);
+    ctx->loop_mode_used = -1;
     ctx->n_merges = 0;
     ctx->exhausted = 0;
     ctx->trace_on_host = false;
@@ -506,7 +516,7 @@ int init_loop_state(ic_ctx* ctx) {
 }
 
 // the batched loop runs on an unsharded context whose slice state fits (it always does below ~1e6 items)
-bool use_batch(const ic_ctx* c) { return c->loop_mode == 1 && n_ranks(c) == 1 && c->batch_grid > 0 && c->n > 0; }
+bool use_batch(const ic_ctx* c) { return c->loop_mode == 1 && c->batch_layout && n_ranks(c) == 1 && c->batch_grid > 0 && c->n > 0; }
 
 // One launch of the persistent loop (enqueued; sync_loop_result waits and relaunches if the kernel ran out of
 // mailbox epochs, which takes ~1e6 iterations).
@@ -521,6 +531,12 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
     p.scan_every = ctx->scan_every;
     p.debug = ctx->loop_debug;
+    {   // the batched loop stops mirroring distances into the older clusters' rows: one loop per clustering
+        const int mode = use_batch(ctx) ? 1 : 0;
+        if (ctx->loop_mode_used >= 0 && ctx->loop_mode_used != mode && ctx->n_merges > 0)
+            return fail(ctx, IC_ERR_STATE, "loop_mode changed in the middle of a clustering");
+        ctx->loop_mode_used = mode;
+    }
     if (use_batch(ctx)) {
         BatchState bs{};
         uint8_t* sc = ctx->batch_scratch;
@@ -541,7 +557,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         bs.hdr = reinterpret_cast<uint4*>(sc + ctx->batch_off[0]);
         bs.cand = reinterpret_cast<uint4*>(sc + ctx->batch_off[1]);
         bs.counters = reinterpret_cast<int32_t*>(sc + ctx->batch_off[2]);
-        bs.dryq = reinterpret_cast<int32_t*>(sc + ctx->batch_off[3]);
+        bs.dryq = reinterpret_cast<int2*>(sc + ctx->batch_off[3]);
         bs.partials = reinterpret_cast<uint4*>(sc + ctx->batch_off[4]);
         bs.part_cnt = reinterpret_cast<int32_t*>(sc + ctx->batch_off[5]);
         bs.bar = reinterpret_cast<uint32_t*>(sc + ctx->batch_off[6]);
@@ -762,6 +778,8 @@ void fill_stats(ic_ctx* ctx) {
     s.exhausted = ctx->exhausted;
     s.n_near_ties = ctx->h_ctl[CTL_NEAR_TIES];
     s.n_rescans = ctx->h_ctl[CTL_RESCANS];
+    s.loop_mode = ctx->loop_mode_used > 0 ? 1 : 0;
+    s.n_iterations = s.loop_mode ? ctx->h_ctl[CTL_ITERS] : ctx->n_merges + ctx->h_ctl[CTL_BUBBLES];
 }
 
 int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offsets, int32_t* members,

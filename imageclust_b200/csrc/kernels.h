@@ -159,7 +159,7 @@ struct BatchState {
     int32_t n;
     int32_t win_cols, n_win;  // filled in by launch_merge_batch
     int64_t ld;
-    float* dm;          // [n x ld] symmetric
+    float* dm;          // [n x ld]; symmetric at launch, then a pair lives in the row of its higher-key cluster
     SlotKS* ks;         // [n4] {key, size}; padding key = -1
     int32_t* gkey;      // [n4]
     SlotNN* nn;         // [n][kNNK]
@@ -175,7 +175,7 @@ struct BatchState {
     uint4* hdr;         // [kBatchMaxBlocks] per block: {stopper minimum lo, hi, head minimum lo, hi}
     uint4* cand;        // [n][2] candidate pairs {head lo, head hi, row slot, partner slot} {size, size, partner key, 0}
     int32_t* counters;  // [3][4] dry rows, candidate pairs; per iteration mod 3
-    int32_t* dryq;      // [n]   rows to rescan
+    int2* dryq;         // [n]   rows to rescan {slot, key}
     int32_t* lsize;     // [n4]  size of the live cluster in every slot, 0: retired (rebuilt from ks at launch)
     uint4* partials;    // [kBatchMaxDry][kBatchMaxWin][8] partial lists of the window scans
     int32_t* part_cnt;  // [kBatchMaxDry] windows done per row

@@ -51,15 +51,17 @@ constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead o
 enum { CN_DRY = 0, CN_CAND = 1 };
 
 // grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
-IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G) {
+IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* wait_acc = nullptr) {
     __syncthreads();
     ++phase;
     if (threadIdx.x == 0) {
+        const long long t_arrive = wait_acc ? clock64() : 0;
         red_release_add_u32(bar, 1u);
         const uint32_t target = phase * G;
         uint32_t spins = 0;
         while (ld_acquire_u32(bar) < target)
             if (++spins > kBarSpin) __trap();  // a protocol bug must not hang the GPU box
+        if (wait_acc) *wait_acc += clock64() - t_arrive;
     }
     __syncthreads();
 }
@@ -165,14 +167,15 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     int32_t launched = 0, stop_reason = 0, iters = 0;
     long long n_rescans = 0;
     const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
-    long long c_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __shared__ long long c_ph[8];  // cycles of block 0 per phase (profile_loop)
+    if (tid < 8) c_ph[tid] = 0;
 
     for (int i = tid; i < kRcpTab; i += kBT) s_rcp[i] = 1.0 / static_cast<double>(i > 0 ? i : 1);
     __syncthreads();
     // rows that were dry when the previous launch stopped (or rows the other loop left dry): queue slot 0
     for (int32_t r = gtid; r < n; r += GT)
         if ((static_cast<uint32_t>(__ldcg(st.nn_more + r)) & kDryBit) != 0u && __ldcg(st.ks + r).x >= 0)
-            st.dryq[atomicAdd(st.counters + 0 * 4 + CN_DRY, 1)] = r;
+            st.dryq[atomicAdd(st.counters + 0 * 4 + CN_DRY, 1)] = make_int2(r, __ldcg(st.ks + r).x);
     // live size of every slot (0: retired / padding): what the update pass streams beside the two rows
     for (int32_t r = gtid; r < n4; r += GT) {
         const int2 k = __ldcg(st.ks + r);
@@ -193,8 +196,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             for (int64_t u = gw; u < units; u += GW) {
                 // windows of one row go to warps of different blocks: q = u % rows
                 const int32_t w = static_cast<int32_t>(u / rows), q = static_cast<int32_t>(u - static_cast<int64_t>(w) * rows);
-                const int32_t r = __ldcg(st.dryq + base + q);
-                const uint32_t ukr = static_cast<uint32_t>(__ldcg(st.gkey + r));
+                const int2 rq = __ldcg(st.dryq + base + q);
+                const int32_t r = rq.x;
+                const uint32_t ukr = static_cast<uint32_t>(rq.y);
                 const float* rowp = dm + static_cast<int64_t>(r) * ld;
                 const int32_t sw0 = min(n4, w * win), sw1 = min(n4, sw0 + win);
                 ScanCand c;
@@ -300,7 +304,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             }
             if (base + kBatchMaxDry < Q) grid_sync(st.bar, phase, G);  // the partial buffers are reused
         }
-        grid_sync(st.bar, phase, G);
+        grid_sync(st.bar, phase, G, timed ? &c_ph[5] : nullptr);
         const long long tp1 = timed ? clock64() : 0;
 
         // ================= P2: heads and stoppers; candidates go to one global list =================
@@ -337,7 +341,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 __stcg(st.hdr + blockIdx.x, make_uint4(static_cast<uint32_t>(bstop), static_cast<uint32_t>(bstop >> 32),
                                                        static_cast<uint32_t>(bhead), static_cast<uint32_t>(bhead >> 32)));
         }
-        grid_sync(st.bar, phase, G);
+        grid_sync(st.bar, phase, G, timed ? &c_ph[6] : nullptr);
         const long long tp2 = timed ? clock64() : 0;
 
         // ================= P3: the batch =================
@@ -501,7 +505,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 for (int x = 1; x < kNNK; ++x) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + x, nn_none());
                 __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit | kDryBit));
                 __stcg(st.nn_more + a, 0);
-                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = b;
+                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(b, new_key);
             }
             if (tid == kBT - 1) {
                 st.counters[sl2 * 4 + CN_DRY] = 0;
@@ -521,6 +525,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 const int32_t a = s_a[i], b = s_b[i], sa = s_sa[i], sb = s_sb[i], snew = sa + sb;
                 const int32_t ka = s_ka[i], kb = s_kb[i];
                 const float dab = __uint_as_float(s_d[i]);
+                const double sad = static_cast<double>(sa), sbd = static_cast<double>(sb), dabd = static_cast<double>(dab);
                 const float* row_a = dm + static_cast<int64_t>(a) * ld;
                 float* row_b = dm + static_cast<int64_t>(b) * ld;
                 constexpr int kI = kUpdCols / 128;
@@ -572,9 +577,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     for (int e = 0; e < 4; ++e) {
                         float val = __uint_as_float(kInfBits);
                         if (((livem[x] >> e) & 1u) != 0u && sizes[e] + snew <= prm.max_size) {  // else inadmissible for good (:228)
+                            // lance_williams_rcp() with the integer -> double conversions hoisted (sums of small integers are exact)
                             const int den = snew + sizes[e];
-                            val = lance_williams_rcp(sa, sb, sizes[e], da[x][e], db[x][e], dab,
-                                                     den < kRcpTab ? s_rcp[den] : 1.0 / static_cast<double>(den));
+                            const double skd = static_cast<double>(sizes[e]);
+                            const double num = ((sad + skd) * static_cast<double>(da[x][e]) + (sbd + skd) * static_cast<double>(db[x][e])) - skd * dabd;
+                            val = canon_dist(static_cast<float>(num * (den < kRcpTab ? s_rcp[den] : 1.0 / static_cast<double>(den))));
                         }
                         out[e] = val;
                     }
@@ -621,7 +628,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             for (int x = 0; x < kNNK; ++x)
                 if (e[x].z != kNoPartner && ((s_bits[e[x].z >> 5] >> (e[x].z & 31u)) & 1u)) dead = true;
             if (!dead) return;
-            if (__ldcg(st.gkey + r) < 0) return;
+            const int32_t key_r = __ldcg(st.gkey + r);
+            if (key_r < 0) return;
             uint4 keep[kNNK];
             int kept = 0;
             uint32_t last = 0u;
@@ -648,7 +656,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             }
             if (kept == 0 && more) {
                 __stcg(st.nn_more + r, static_cast<int32_t>(kMoreBit | kDryBit));
-                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = r;
+                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(r, key_r);
             }
         };
 #pragma unroll
@@ -673,8 +681,6 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             c_ph[2] += tp3 - tp2;
             c_ph[3] += tp4 - tp3;
             c_ph[4] += tq1 - tp3;
-            c_ph[5] += tq2 - tq1;
-            c_ph[6] += tq3 - tq2;
             c_ph[7] += tp4 - tq3;
         }
     }

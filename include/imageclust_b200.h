@@ -72,6 +72,8 @@ typedef struct ic_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     int64_t matrix_bytes;  /* bytes of the distance matrix resident in HBM */
+    int32_t n_iterations;  /* iterations of the merge loop (batched loop: several merges each) */
+    int32_t loop_mode;     /* 1: batched loop (merge_batch.cu), 0: one merge per iteration (merge_loop.cu) */
 } ic_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -86,7 +88,9 @@ void ic_pinned_free(void *p);
  * "gram_mode" (IC_GRAM_*), "loop_blocks" (merge-loop blocks per rank, 0 = auto),
  * "virtual_ranks" (1..8: row-block shards emulated on ONE GPU by one cooperative launch --
  * the same kernel path as the multi-GPU build, for tests), "scan_every" (row rescans are requested every k-th
- * merge-loop iteration, default 4: batching them keeps the scan phase out of most iterations), "no_replica",
+ * merge-loop iteration, default 4: batching them keeps the scan phase out of most iterations), "loop_mode" (1, default:
+ * batched loop on an unsharded context -- every iteration takes all merges that are provably the next ones; needs rows
+ * of 2N columns, falls back to 0 when they do not fit; 0: one merge per iteration; set it before ic_load), "no_replica",
  * "profile_loop", "verbose" */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 

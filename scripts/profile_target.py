@@ -39,7 +39,7 @@ with clustering.Engine(0) as eng:
         it = max(p["iterations"], 1)
         print(f"batched loop: iterations={p['iterations']} merges/iteration={p['merges'] / it:.1f} cycles per iteration: "
               f"rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} select={p['update'] / it:.0f} apply={p['scan'] / it:.0f} "
-              f"(rows={p['pub_argmin'] / it:.0f} cross={p['pub_reduce'] / it:.0f} validate={p['pub_fence'] / it:.0f} barrier={p['pub_stores'] / it:.0f})")
+              f"(rows={p['pub_argmin'] / it:.0f}) | block 0 waits at the barriers: after rescans={p['pub_reduce'] / it:.0f} after heads={p['pub_fence'] / it:.0f} after apply={p['pub_stores'] / it:.0f}")
         sys.exit(0)
     print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
           + f" | iterations={p["iterations"]} rescans={p["rescans"]} bubbles={p["bubbles"]}")
