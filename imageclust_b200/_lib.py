@@ -72,7 +72,7 @@ def load():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise LibraryMissing(f"{LIB_PATH} not built: run `python -m imageclust_b200.build` (needs nvcc)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("IC_LIB_PATH", LIB_PATH))  # IC_LIB_PATH: tuning builds of the same library
     vp, i32p, i64p, fp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_float)
     i64, i32 = C.c_int64, C.c_int
     sig = {

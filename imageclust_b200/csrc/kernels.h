@@ -151,7 +151,10 @@ constexpr int kBatchThreads = 512;
 constexpr int kMaxBatch = 512;        // candidate pairs / merges per iteration (<= kBatchThreads: one per thread)
 constexpr int kBatchCand = 64;        // candidate pairs a block may publish per iteration
 constexpr int kBatchMaxDry = 2048;    // rows rescanned per round of the rescan phase (partial-list buffers)
-constexpr int kBatchWinMin = 2048;    // columns of a row-scan window (at most kBatchMaxWin windows per row)
+#ifndef IC_WIN_MIN
+#define IC_WIN_MIN 2048
+#endif
+constexpr int kBatchWinMin = IC_WIN_MIN;    // columns of a row-scan window (at most kBatchMaxWin windows per row)
 constexpr int kBatchMaxWin = 128;
 constexpr int kBatchMaxBlocks = 160;
 constexpr int CTL_ITERS = 12;         // ctl[]: iterations of the batched loop
