@@ -36,6 +36,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# dram__bytes_read.sum + dram__bytes_write.sum of the merge-loop launch (ncu --set full, profiles/r01_summary.md), GB
+LOOP_TRAFFIC_GB = {("C", False): 971.4}
 sys.path.insert(0, ROOT)
 
 from imageclust_b200 import synth  # noqa: E402
@@ -291,6 +293,7 @@ def main():
             return sum(s[key] for s in src) / len(src)
 
         merges = stats[-1]["n_merges"]
+        batched = bool(stats[-1].get("loop_mode", 0))
         n_final = stats[-1]["n_final"]
         pairs = n * (n - 1) / 2
         ms_loop = avg("ms_loop")
@@ -330,15 +333,23 @@ def main():
                     "ms_h2d": sum(s["ms_h2d"] for s in e2e_stats) / len(e2e_stats)},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "clocks": clocks,
-            "roofline": {"kernel": "merge_loop_kernel (K3, persistent)", "bound": "hbm", "achieved": loop_gbs,
+            "loop": {"mode": "batched (merge_batch_kernel)" if batched else "one merge per iteration (merge_loop_kernel)",
+                     "iterations": stats[-1]["n_iterations"],
+                     "merges_per_iteration": merges / max(stats[-1]["n_iterations"], 1)},
+            "roofline": {"kernel": "merge_batch_kernel (K3b, persistent, batched)" if batched else "merge_loop_kernel (K3, persistent)",
+                         "bound": "hbm", "achieved": loop_gbs,
                          "peak": hbm, "unit": "GB/s", "frac": loop_gbs / hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full at this exact
-                         # workload (profiles/r01_summary.md); GB per launch like `achieved`'s numerator (60 GB)
-                         "traffic": 971.4 if (args.config == "C" and world == 1 and not args.n) else None,
+                         # workload (profiles/); GB per launch like `achieved`'s numerator (60 GB at config C)
+                         "traffic": LOOP_TRAFFIC_GB.get((args.config, batched)) if (world == 1 and not args.n) else None,
                          "traffic_unit": "GB per launch (ncu, profiles/r01_summary.md)",
                          "peak_source": peaks["source"] + " copy bandwidth",
-                         "note": "algorithmic bytes 12*n per merge; the loop is a chain of dependent merges bound by one "
-                                 "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth",
+                         "note": ("algorithmic bytes 12*n per merge; the batched loop takes ~10 provably consecutive merges per "
+                                  "iteration, each iteration is three grid-wide phases of dependent DRAM round trips: bound by "
+                                  "latency and by per-SM request throughput of the scattered column gathers, not by bandwidth"
+                                  if batched else
+                                  "algorithmic bytes 12*n per merge; the loop is a chain of dependent merges bound by one "
+                                  "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth"),
                          "dominant_phase": dominant},
             "kernels": None if sharded else {
                 {0: "gram_tcgen05", 1: "gram_exact", 2: "gram_i8"}[args.gram_mode]: {
