@@ -355,6 +355,10 @@ def main():
                 {0: "gram_tcgen05", 1: "gram_exact", 2: "gram_i8"}[args.gram_mode]: {
                     "bound": "tensor", "achieved": gram_tf, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": gram_tf / tf32_peak, "ms": kern.get("gram_ms"),
+                    # what the pipe itself executes: 6 int8 products (4 TF32 products) per algorithmic product, against
+                    # the int8 (TF32) dense peak = measured sustained bf16 x 2 (/ 2)
+                    "pipe_frac": (gram_tf * 6.0 / (peaks["bf16_tflops_sustained"] * 2.0) if args.gram_mode == 2 else
+                                  gram_tf * 4.0 / tf32_peak if args.gram_mode == 0 else None),
                     "note": "algorithmic flops 2*D per unordered pair over the fp32-accurate (TF32-equivalent) peak = measured "
                             "sustained bf16 / 2; the int8 path issues 6 kind::i8 MMAs per k-step (6x the algorithmic "
                             "flops, on a pipe 4x as fast), the tf32 path 4 kind::tf32 MMAs"},

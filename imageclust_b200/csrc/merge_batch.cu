@@ -169,6 +169,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     __shared__ int32_t s_a[kMaxBatch], s_b[kMaxBatch], s_sa[kMaxBatch], s_sb[kMaxBatch], s_ka[kMaxBatch], s_kb[kMaxBatch];
     __shared__ uint32_t s_d[kMaxBatch + 1];
     __shared__ int32_t s_m;
+    __shared__ uint64_t s_ppk[kBW][kNNK];  // row-per-block rescans: the warps' partial lists
+    __shared__ int32_t s_psl[kBW][kNNK];
+    __shared__ int2 s_pm[kBW];
     __shared__ double s_rcp[kRcpTab];  // 1.0 / size sum, correctly rounded (what lance_williams() computes inline)
 
     uint32_t phase = 0;
@@ -198,10 +201,97 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         const int sl = static_cast<int>(it % 3u), sl1 = static_cast<int>((it + 1u) % 3u), sl2 = static_cast<int>((it + 2u) % 3u);
         const long long tp0 = timed ? clock64() : 0;
 
-        // ================= P1: row rescans (cooperative, one warp per window) =================
+        // ================= P1: row rescans =================
         const int32_t Q = __ldcg(st.counters + sl * 4 + CN_DRY);
         n_rescans += Q;
-        for (int32_t base = 0; base < Q; base += kBatchMaxDry) {
+        // Short rows, a few dozen of them: ONE BLOCK PER ROW.  Its sixteen warps scan a sixteenth of the row each and the
+        // partial lists are folded in shared memory -- no partial records in global memory, no fence / atomic / re-read
+        // chain.  Long rows must be spread over many SMs: one SM streams a 400 KB row (+ its keys) in ~50 k cycles
+        // (measured at config C; the window mode below takes 32 k per iteration for ~28 rows).
+        const bool row_per_block = Q <= 2 * static_cast<int32_t>(G) && n4 <= 32768;
+        for (int32_t q = blockIdx.x; row_per_block && q < Q; q += static_cast<int32_t>(G)) {
+            const int2 rq = __ldcg(st.dryq + q);
+            const int32_t r = rq.x;
+            const uint32_t ukr = static_cast<uint32_t>(rq.y);
+            const float* rowp = dm + static_cast<int64_t>(r) * ld;
+            const int32_t seg = (((n4 + kBW - 1) / kBW) + 127) & ~127;
+            const int32_t sw0 = min(n4, warp * seg), sw1 = min(n4, sw0 + seg);
+            ScanCand c;
+            scan_init(c);
+            constexpr int kU = 8;
+            for (int32_t b0 = sw0; b0 < sw1; b0 += 128 * kU) {
+                float4 vv[kU];
+                int4 kq[kU];
+#pragma unroll
+                for (int x = 0; x < kU; ++x) {
+                    const int32_t u0 = b0 + (x * 32 + lane) * 4;
+                    vv[x] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                    kq[x] = make_int4(-1, -1, -1, -1);
+                    if (u0 < sw1) {
+                        vv[x] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
+                        kq[x] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < kU; ++x) {
+                    const int32_t u0 = b0 + (x * 32 + lane) * 4;
+                    const uint32_t vs4[4] = {__float_as_uint(vv[x].x), __float_as_uint(vv[x].y), __float_as_uint(vv[x].z),
+                                             __float_as_uint(vv[x].w)};
+                    const uint32_t ks4[4] = {static_cast<uint32_t>(kq[x].x), static_cast<uint32_t>(kq[x].y),
+                                             static_cast<uint32_t>(kq[x].z), static_cast<uint32_t>(kq[x].w)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (ks4[e] < ukr && vs4[e] < kMaxFloatBits)
+                            scan_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ks4[e], u0 + e);
+                }
+            }
+            PartList out;
+            bool more = false;
+            out.m = warp_select_scan(c, out.pk, out.sl, more);
+            out.more = more ? 1 : 0;
+            if (lane < kNNK) {
+                s_ppk[warp][lane] = sel4(out.pk, lane);
+                s_psl[warp][lane] = sel4(out.sl, lane);
+            } else if (lane == kNNK) {
+                s_pm[warp] = make_int2(out.m, out.more);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                PartList in;
+                in.m = 0;
+                in.more = 0;
+#pragma unroll
+                for (int x = 0; x < kNNK; ++x) {
+                    in.pk[x] = kPackInf;
+                    in.sl[x] = -1;
+                    in.sz[x] = 0;
+                }
+                if (lane < kBW) {
+                    in.m = s_pm[lane].x;
+                    in.more = s_pm[lane].y;
+#pragma unroll
+                    for (int x = 0; x < kNNK; ++x) {
+                        in.pk[x] = x < in.m ? s_ppk[lane][x] : kPackInf;
+                        in.sl[x] = x < in.m ? s_psl[lane][x] : -1;
+                    }
+                }
+                warp_merge_lists(in, out);
+                if (lane < kNNK) {  // entry: {partner key, distance bits, partner slot, partner size}
+                    const uint64_t myp = sel4(out.pk, lane);
+                    const int32_t ps = sel4(out.sl, lane);
+                    const int32_t psz = lane < out.m ? __ldcg(st.lsize + ps) : 0;
+                    __stcg(st.nn + static_cast<int64_t>(r) * kNNK + lane,
+                           lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32), static_cast<uint32_t>(ps),
+                                                     static_cast<uint32_t>(psz))
+                                        : nn_none());
+                } else if (lane == kNNK) {
+                    __stcg(st.nn_more + r, out.more ? static_cast<int32_t>(kMoreBit) : 0);
+                }
+            }
+            __syncthreads();
+        }
+        // Many rows at once (thousands of duplicates, ...): cooperative, one warp per (row, window)
+        for (int32_t base = 0; !row_per_block && base < Q; base += kBatchMaxDry) {
             const int32_t rows = min(Q - base, kBatchMaxDry);
             const int64_t units = static_cast<int64_t>(rows) * nwin;
             for (int64_t u = gw; u < units; u += GW) {
