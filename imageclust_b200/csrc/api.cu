@@ -42,6 +42,8 @@ struct ic_ctx {
     int vranks_alloc = -1;
     int scan_every = 4;  // merge loop: rescans are requested every scan_every-th iteration
     int loop_debug = 0;  // experiments only
+    int gram_debug = 0;  // experiments only (gram_i8.cu)
+    bool dm_lower_only = false;  // K1 stored dm[i][j] for j <= i only (batched loop: the upper triangle is never read)
     int loop_mode_alloc = -1, loop_mode_used = -1;  // layout the allocation was made for; loop that touched the matrix
     bool batch_layout = false;  // scratch of the batched loop is allocated
     int loop_mode = 1;   // 1: batched loop (merge_batch.cu) on an unsharded context; 0: one merge per iteration (merge_loop.cu)
@@ -458,7 +460,10 @@ int do_prep(ic_ctx* ctx) {
     return IC_OK;
 }
 
+bool use_batch(const ic_ctx* c);
+
 int do_gram(ic_ctx* ctx, int mode) {
+    ctx->dm_lower_only = false;
     if (mode == IC_GRAM_EXACT_FP32) {
         IC_CUDA(launch_gram_exact(ctx->x, ctx->n, ctx->d, ctx->d, ctx->dm, ctx->ld, row_begin(ctx), row_end(ctx), ctx->stream));
         ctx->stats.kernel_launches += 1;
@@ -473,8 +478,9 @@ int do_gram(ic_ctx* ctx, int mode) {
         p8.tiles = ctx->tiles8;
         p8.n_tiles = ctx->n_tiles8;
         p8.k_blocks = static_cast<int>(ctx->d_pad8 / kI8BK);
+        ctx->dm_lower_only = use_batch(ctx);
         IC_CUDA(launch_gram_i8(p8, ctx->norms, ctx->quanta, ctx->dm, ctx->n, ctx->ld, row_begin(ctx), row_end(ctx),
-                               ctx->num_sms, ctx->stream));
+                               ctx->num_sms, ctx->stream, ctx->gram_debug | (ctx->dm_lower_only ? 8 : 0)));
         ctx->stats.kernel_launches += 1;
         return IC_OK;
     }
@@ -535,6 +541,8 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         const int mode = use_batch(ctx) ? 1 : 0;
         if (ctx->loop_mode_used >= 0 && ctx->loop_mode_used != mode && ctx->n_merges > 0)
             return fail(ctx, IC_ERR_STATE, "loop_mode changed in the middle of a clustering");
+        if (mode == 0 && ctx->dm_lower_only)
+            return fail(ctx, IC_ERR_STATE, "loop_mode changed after ic_initial_distances (the matrix holds the lower triangle only)");
         ctx->loop_mode_used = mode;
     }
     if (use_batch(ctx)) {
@@ -747,6 +755,7 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
         const int rc = do_gram(ctx, mode);
         if (rc != IC_OK) return rc;
     } else {
+        ctx->dm_lower_only = false;
         // 1 + 1 > maxSize: every pair is inadmissible from the start (clustering.go:228)
         IC_CUDA(launch_fill(ctx->dm, (row_end(ctx) - row_begin(ctx)) * ctx->ld, INFINITY, ctx->stream));
         ctx->stats.kernel_launches += 1;
@@ -903,6 +912,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         const int m = static_cast<int>(value);
         if (m != 0 && m != 1) return fail(ctx, IC_ERR_BAD_ARG, "loop_mode must be 0 (sequential) or 1 (batched)");
         ctx->loop_mode = m;
+    } else if (k == "gram_debug") {
+        ctx->gram_debug = static_cast<int>(value);
     } else if (k == "loop_debug") {
         ctx->loop_debug = static_cast<int>(value);
     } else if (k == "no_replica") {
@@ -1016,6 +1027,7 @@ int ic_set_matrix(ic_ctx* ctx, const float* m_host, int64_t ld) {
     if (ld < ctx->n) return fail(ctx, IC_ERR_BAD_ARG, "ld < n");
     IC_CUDA(cudaSetDevice(ctx->device));
     const int64_t r0 = row_begin(ctx), r1 = row_end(ctx);  // a sharded context keeps its own row block
+    ctx->dm_lower_only = false;
     if (r1 > r0)
         IC_CUDA(cudaMemcpy2DAsync(ctx->dm, sizeof(float) * ctx->ld, m_host + r0 * ld, sizeof(float) * ld,
                                   sizeof(float) * ctx->n, r1 - r0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1188,6 +1200,9 @@ int ic_read_matrix(ic_ctx* ctx, float* out_host, int64_t ld) {
         IC_CUDA(cudaMemcpy2DAsync(out_host + r0 * ld, sizeof(float) * ld, ctx->dm, sizeof(float) * ctx->ld,
                                   sizeof(float) * ctx->n, r1 - r0, cudaMemcpyDeviceToHost, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->dm_lower_only)  // K1 skipped the mirrored triangle: the caller still gets the symmetric matrix
+        for (int64_t i = 0; i < ctx->n; ++i)
+            for (int64_t j = i + 1; j < ctx->n; ++j) out_host[i * ld + j] = out_host[j * ld + i];
     return IC_OK;
 }
 

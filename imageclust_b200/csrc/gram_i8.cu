@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_m,
                const __grid_constant__ CUtensorMap map_l, const int2* __restrict__ tiles, int n_tiles, int k_blocks,
                const double* __restrict__ norms, const float* __restrict__ quanta, float* __restrict__ dm, int64_t n,
-               int64_t ld, int64_t row_begin, int64_t row_end) {
+               int64_t ld, int64_t row_begin, int64_t row_end, int debug) {
+    // flags: bit 3 = store the lower triangle only (the batched merge loop never reads dm[j][i], j < i: half the stores);
+    // experiments only, wrong results: bit 0 = no TMA loads, bit 1 = no MMAs, bit 2 = no epilogue stores
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     SmemTail* tail = reinterpret_cast<SmemTail*>(smem + static_cast<size_t>(kStages) * kStageBytes);
@@ -112,6 +114,14 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&tail->empty[stage], phase ^ 1u);
                     uint8_t* sb = smem + static_cast<size_t>(stage) * kStageBytes;
+                    if (debug & 1) {
+                        mbar_arrive(&tail->full[stage]);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&tail->full[stage], kStageBytes);
                     const int kc = kb * kI8BK;
                     tma_load_2d(sb + 0 * kTileBytes, &map_h, &tail->full[stage], kc, row0);
@@ -146,7 +156,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
                     const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
                     const uint32_t sbb = sa + 3 * kTileBytes;
 #pragma unroll
-                    for (int k = 0; k < kI8BK / 32; ++k) {  // UMMA_K = 32 for 8-bit operands = 32 bytes along K
+                    for (int k = 0; k < ((debug & 2) ? 0 : kI8BK / 32); ++k) {  // UMMA_K = 32 for 8-bit operands = 32 bytes along K
                         const uint32_t off = static_cast<uint32_t>(k) * 32u;
                         const uint64_t a_h = umma_desc_k_sw128(sa + 0 * kTileBytes + off);
                         const uint64_t a_m = umma_desc_k_sw128(sa + 1 * kTileBytes + off);
@@ -206,7 +216,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
                 if (kLow) tmem_ld_32x16(taddr0 + 3 * T + c * kChunk, reinterpret_cast<uint32_t(&)[kChunk]>(r7));
                 tmem_ld_wait();
                 const int64_t gj0 = col0 + c * kChunk;
-                if (gj0 > row0 + T - 1) continue;  // chunk entirely above the diagonal (warp uniform)
+                if (gj0 > row0 + T - 1 || (debug & 4)) continue;  // chunk entirely above the diagonal (warp uniform)
                 float v[kChunk];
 #pragma unroll
                 for (int q = 0; q < kChunk; ++q) {
@@ -222,7 +232,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
                 }
                 // mirrored entries dm[j][i]: for a fixed column j the 32 lanes hold consecutive i
 #pragma unroll
-                for (int q = 0; q < kChunk; ++q) {
+                for (int q = 0; q < ((debug & 8) ? 0 : kChunk); ++q) {
                     const int64_t gj = gj0 + q;
                     if (gj < gi && gi < n && gj >= row_begin && gj < row_end) __stcs(dm + (gj - row_begin) * ld + gi, v[q]);
                 }
@@ -254,7 +264,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
 }
 
 cudaError_t launch_gram_i8(const GramI8Plan& plan, const double* norms, const float* quanta, float* dm, int64_t n,
-                           int64_t ld, int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s) {
+                           int64_t ld, int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s, int debug) {
     if (plan.n_tiles == 0) return cudaSuccess;
     const size_t smem = gram_i8_smem_bytes();
     const int grid = plan.n_tiles < num_sms ? plan.n_tiles : num_sms;
@@ -264,10 +274,10 @@ cudaError_t launch_gram_i8(const GramI8Plan& plan, const double* norms, const fl
     if (e != cudaSuccess) return e;
     if (low)
         gram_i8_kernel<true><<<grid, kThreads, smem, s>>>(plan.map_h, plan.map_m, plan.map_l, plan.tiles, plan.n_tiles,
-                                                          plan.k_blocks, norms, quanta, dm, n, ld, row_begin, row_end);
+                                                          plan.k_blocks, norms, quanta, dm, n, ld, row_begin, row_end, debug);
     else
         gram_i8_kernel<false><<<grid, kThreads, smem, s>>>(plan.map_h, plan.map_m, plan.map_l, plan.tiles, plan.n_tiles,
-                                                           plan.k_blocks, norms, quanta, dm, n, ld, row_begin, row_end);
+                                                           plan.k_blocks, norms, quanta, dm, n, ld, row_begin, row_end, debug);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,7 @@ struct GramI8Plan {
 // six kind::i8 products per k-step into three int32 TMEM accumulators (weights 2^28, 2^21, 2^14); the three dropped
 // low-order products are below 2^-21 of the Gram value.  Same output contract as launch_gram_tcgen05.
 cudaError_t launch_gram_i8(const GramI8Plan& plan, const double* norms, const float* quanta, float* dm, int64_t n,
-                           int64_t ld, int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s);
+                           int64_t ld, int64_t row_begin, int64_t row_end, int num_sms, cudaStream_t s, int debug = 0);
 // audit kernel: the reference's own arithmetic (sequential fp32, clustering.go:136-157), bit exact
 cudaError_t launch_gram_exact(const float* x, int64_t n, int64_t d, int64_t ldx, float* dm, int64_t ld,
                               int64_t row_begin, int64_t row_end, cudaStream_t s);
