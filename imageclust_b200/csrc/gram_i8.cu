@@ -28,7 +28,8 @@ constexpr int kStages = 2;
 constexpr int kTileBytes = T * kI8BK;          // 16 KB: one digit of one operand
 constexpr int kStageBytes = 6 * kTileBytes;    // A{h,m,l} + B{h,m,l}
 constexpr int kTmemCols = 512;                 // 3 accumulators x 128 columns (allocation is a power of two)
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;                   // two per TMEM lane quadrant: each drains one half of the columns
+constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kEpiWarp0 = 4;
 constexpr int kChunk = 16;                     // accumulator columns per epilogue step
 
@@ -42,7 +43,7 @@ struct __align__(8) SmemTail {
     double norm_b[T];
     float qa[T];
     float qb[T];
-    float stage[4][32 * (kChunk + 1)];
+    float stage[kEpiWarps][32 * (kChunk + 1)];
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint64_t tfull[1];
@@ -91,7 +92,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
             mbar_init(&tail->empty[s], 1);
         }
         mbar_init(&tail->tfull[0], 1);
-        mbar_init(&tail->tempty[0], 4);  // one arrive per epilogue warp
+        mbar_init(&tail->tempty[0], kEpiWarps);  // one arrive per epilogue warp
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -188,19 +189,23 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
         }
     } else if (warp >= kEpiWarp0) {
         // ===== epilogue: TMEM -> registers -> Ward distance -> both triangles =====
-        const int ew = warp - kEpiWarp0;              // TMEM lane quadrant of this warp
-        const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
-        float* stg = tail->stage[ew];
+        const int ew = warp & 3;                      // TMEM lane quadrant of this warp (hardware: warp id % 4)
+        const int eh = (warp - kEpiWarp0) >> 2;       // which half of the tile's columns
+        const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+        float* stg = tail->stage[warp - kEpiWarp0];
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int2 tile = tiles[t];
             const int64_t row0 = static_cast<int64_t>(tile.x) * T, col0 = static_cast<int64_t>(tile.y) * T;
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's norm reads are done
-            tail->norm_a[et] = norms[row0 + et];
-            tail->norm_b[et] = norms[col0 + et];
-            tail->qa[et] = quanta[row0 + et];
-            tail->qb[et] = quanta[col0 + et];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's norm reads are done
+            if (et < T) {
+                tail->norm_a[et] = norms[row0 + et];
+                tail->qa[et] = quanta[row0 + et];
+            } else {
+                tail->norm_b[et - T] = norms[col0 + et - T];
+                tail->qb[et - T] = quanta[col0 + et - T];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tail->tfull[0], acc_phase);
             tc_fence_after();
             const int64_t gi = row0 + ew * 32 + lane;  // this thread's matrix row
@@ -208,7 +213,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
             const double qi = static_cast<double>(tail->qa[ew * 32 + lane]);
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < T / kChunk; ++c) {
+            for (int c = eh * (T / kChunk / 2); c < (eh + 1) * (T / kChunk / 2); ++c) {
                 uint32_t r28[kChunk], r21[kChunk], r14[kChunk], r7[kLow ? kChunk : 1];
                 tmem_ld_32x16(taddr0 + c * kChunk, r28);
                 tmem_ld_32x16(taddr0 + T + c * kChunk, r21);
