@@ -305,7 +305,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const double other = 4.0 * n * d + (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
                          (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20);
-    if (P == 1 && ctx->loop_mode == 1 && n > 0) {  // batched loop (one unsharded GPU)
+    if ((P == 1 || ctx->shard_world > 1) && ctx->loop_mode == 1 && n > 0) {  // batched loop: one GPU, or real shards
         int grid = 0;
         IC_CUDA(merge_batch_grid(ctx->num_sms, n, &grid));
         if (grid > 0) {
@@ -341,10 +341,11 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
                  xb = merge_loop_rankbox_bytes();
     IC_CUDA(cudaMalloc(&ctx->records, rb * NL));
     IC_CUDA(cudaMalloc(&ctx->partials, pb * NL));
-    IC_CUDA(cudaMalloc(&ctx->rankbox, xb * NL));
+    // (+ the exchange box of the sharded batched loop, behind the rank mailboxes: one IPC handle covers both)
+    IC_CUDA(cudaMalloc(&ctx->rankbox, xb * NL + kBatchXBoxBytes));
     IC_CUDA(cudaMemsetAsync(ctx->records, 0, rb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->partials, 0, pb * NL, ctx->stream));
-    IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL + kBatchXBoxBytes, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
     if (ctx->batch_layout) {  // batched loop: scratch
         const size_t sizes[11] = {static_cast<size_t>(kBatchMaxBlocks) * 32, 32 * nn1,
@@ -522,7 +523,9 @@ int init_loop_state(ic_ctx* ctx) {
 }
 
 // the batched loop runs on an unsharded context whose slice state fits (it always does below ~1e6 items)
-bool use_batch(const ic_ctx* c) { return c->loop_mode == 1 && c->batch_layout && n_ranks(c) == 1 && c->batch_grid > 0 && c->n > 0; }
+bool use_batch(const ic_ctx* c) {
+    return c->loop_mode == 1 && c->batch_layout && (n_ranks(c) == 1 || c->shard_world > 1) && c->batch_grid > 0 && c->n > 0;
+}
 
 // One launch of the persistent loop (enqueued; sync_loop_result waits and relaunches if the kernel ran out of
 // mailbox epochs, which takes ~1e6 iterations).
@@ -549,6 +552,18 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         BatchState bs{};
         uint8_t* sc = ctx->batch_scratch;
         bs.n = static_cast<int32_t>(ctx->n);
+        bs.n_ranks = 1;
+        bs.rank = 0;
+        bs.rows_per_rank = static_cast<int32_t>(rows_per_rank(ctx));
+        if (ctx->shard_world > 1) {  // real shards: peer-mapped row blocks and exchange boxes
+            if (!ctx->peers_open) return fail(ctx, IC_ERR_STATE, "sharded context: ic_shard_connect has not run");
+            bs.n_ranks = ctx->shard_world;
+            bs.rank = ctx->shard_rank;
+            for (int q = 0; q < ctx->shard_world; ++q) {
+                bs.dm_rank[q] = static_cast<float*>(ctx->peer_dm[q]);
+                bs.xbox[q] = static_cast<uint8_t*>(ctx->peer_box[q]) + merge_loop_rankbox_bytes();
+            }
+        }
         bs.ld = ctx->ld;
         bs.dm = ctx->dm;
         bs.ks = ctx->ks;
@@ -575,6 +590,17 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
         IC_CUDA(cudaMemsetAsync(bs.bar, 0, 256, ctx->stream));
         IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
+        if (ctx->shard_world > 1) {
+            // this rank's exchange-box slots: no candidates, no minima (the flags keep counting up across launches);
+            // then all ranks line up: nobody starts before every box is reset
+            uint8_t* xb = ctx->rankbox + merge_loop_rankbox_bytes();
+            IC_CUDA(cudaMemsetAsync(xb + 256, 0xFF, 48, ctx->stream));
+            IC_CUDA(cudaMemsetAsync(xb + 256 + 48, 0, 16, ctx->stream));
+            ++ctx->barrier_seq;
+            bs.gen = static_cast<uint32_t>(ctx->barrier_seq);
+            IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
+            ctx->stats.kernel_launches += 1;
+        }
         IC_CUDA(launch_merge_batch(bs, p, ctx->batch_grid, ctx->stream));
         ++ctx->loop_launches;
         ctx->stats.kernel_launches += 1;
@@ -1200,7 +1226,7 @@ int ic_read_matrix(ic_ctx* ctx, float* out_host, int64_t ld) {
         IC_CUDA(cudaMemcpy2DAsync(out_host + r0 * ld, sizeof(float) * ld, ctx->dm, sizeof(float) * ctx->ld,
                                   sizeof(float) * ctx->n, r1 - r0, cudaMemcpyDeviceToHost, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->dm_lower_only)  // K1 skipped the mirrored triangle: the caller still gets the symmetric matrix
+    if (ctx->dm_lower_only && ctx->shard_world <= 1)  // K1 skipped the mirrored triangle: the caller still gets the symmetric matrix
         for (int64_t i = 0; i < ctx->n; ++i)
             for (int64_t j = i + 1; j < ctx->n; ++j) out_host[i * ld + j] = out_host[j * ld + i];
     return IC_OK;

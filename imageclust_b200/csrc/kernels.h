@@ -158,11 +158,23 @@ constexpr int kBatchWinMin = IC_WIN_MIN;    // columns of a row-scan window (at 
 constexpr int kBatchMaxWin = 128;
 constexpr int kBatchMaxBlocks = 160;
 constexpr int CTL_ITERS = 12;         // ctl[]: iterations of the batched loop
+// Sharded runs (one process per GPU, row-block shards like merge_loop.cu): every rank runs the kernel on its own row
+// block; the ranks exchange their candidate pairs once per iteration through peer-mapped "exchange boxes":
+//   [0, 256)    u64 flags[kMaxRanks]        cross-rank barrier: flags[q] is written by rank q
+//   [256, 512)  u64 stop[3], head[3]; i32 cnt[3]   per iteration mod 3: stopper / head minimum, candidate pairs
+//   [512, ...)  uint4 cand[kBatchXCand][2]  the rank's candidate pairs of the current iteration
+constexpr int kBatchXCand = 2048;
+constexpr size_t kBatchXBoxBytes = 512 + static_cast<size_t>(kBatchXCand) * 32;
 struct BatchState {
     int32_t n;
+    int32_t n_ranks, rank, rows_per_rank;  // 1, 0, - on one GPU
+    uint32_t gen;                          // launch generation (cross-rank barrier sequence numbers)
+    float* dm_rank[kMaxRanks];             // sharded: first row of every rank's row block (peer mapped)
+    uint8_t* xbox[kMaxRanks];              // sharded: every rank's exchange box (peer mapped)
     int32_t win_cols, n_win;  // filled in by launch_merge_batch
     int64_t ld;
-    float* dm;          // [n x ld]; symmetric at launch, then a pair lives in the row of its higher-key cluster
+    float* dm;          // [rows x ld] (rows = n, or the rank's row block); lower triangle valid at launch, then a pair lives in
+                        // the row of its higher-key cluster
     SlotKS* ks;         // [n4] {key, size}; padding key = -1
     int32_t* gkey;      // [n4]
     SlotNN* nn;         // [n][kNNK]
@@ -187,7 +199,7 @@ struct BatchState {
 size_t merge_batch_smem_bytes(int64_t n);
 int64_t merge_batch_windows(int64_t n);
 cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks);  // *blocks = 0: does not fit
-cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);
+cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);  // n_ranks > 1: sharded
 // device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
 cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);
 

@@ -53,6 +53,8 @@ constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead o
 // counters[slot][*]
 enum { CN_DRY = 0, CN_CAND = 1 };
 
+IC_DEVINL uint64_t ldcg_u64(const uint64_t* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
+
 // grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
 IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* wait_acc = nullptr) {
     __syncthreads();
@@ -64,6 +66,51 @@ IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* 
         uint32_t spins = 0;
         while (ld_acquire_u32(bar) < target)
             if (++spins > kBarSpin) __trap();  // a protocol bug must not hang the GPU box
+        if (wait_acc) *wait_acc += clock64() - t_arrive;
+    }
+    __syncthreads();
+}
+
+// Barrier of all blocks of ALL ranks (sharded runs): every block fences its stores to peer memory at system scope and
+// arrives on the local counter; block 0 waits for its rank, exchanges a sequence number with every peer through the
+// peer-mapped flags, and releases the local blocks.
+// `remote_stores`: the blocks wrote to peer memory in this phase (their stores must be performed at system scope before
+// the rank reports; stores to the rank's own memory only need the gpu-scope release of the arrival -- block 0's system
+// fence after it has acquired all arrivals is cumulative).
+IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& xcount, uint32_t G, bool remote_stores,
+                               long long* wait_acc = nullptr) {
+    __syncthreads();
+    ++phase;
+    ++xcount;
+    if (threadIdx.x == 0) {
+        const long long t_arrive = wait_acc ? clock64() : 0;
+        if (remote_stores) asm volatile("fence.acq_rel.sys;" ::: "memory");
+        red_release_add_u32(st.bar, 1u);
+        uint32_t spins = 0;
+        if (blockIdx.x == 0) {
+            const uint32_t target = phase * G;
+            while (ld_acquire_u32(st.bar) < target)
+                if (++spins > kBarSpin) __trap();
+            const unsigned long long seq = (static_cast<unsigned long long>(st.gen) << 32) | xcount;
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int q = 0; q < st.n_ranks; ++q)
+                if (q != st.rank)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(st.xbox[q]) + st.rank), "l"(seq) : "memory");
+            for (int q = 0; q < st.n_ranks; ++q) {
+                if (q == st.rank) continue;
+                unsigned long long seen = 0;
+                for (spins = 0;; ++spins) {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(reinterpret_cast<unsigned long long*>(st.xbox[st.rank]) + q) : "memory");
+                    if (seen >= seq) break;
+                    if (spins > kBarSpin) __trap();  // a missing peer must not hang the GPU box
+                }
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(st.bar + 32), "r"(phase) : "memory");
+        } else {
+            while (ld_acquire_u32(st.bar + 32) < phase)
+                if (++spins > kBarSpin) __trap();
+        }
         if (wait_acc) *wait_acc += clock64() - t_arrive;
     }
     __syncthreads();
@@ -142,6 +189,7 @@ int64_t merge_batch_windows(int64_t n) {
     return std::max<int64_t>(1, (n4 + win - 1) / win);
 }
 
+template <bool kMulti>
 __global__ void __launch_bounds__(kBT, 1)
 merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant__ LoopParams prm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -153,8 +201,22 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     // work units go to warps block-interleaved: consecutive units run on different SMs
     const int32_t gw = warp * static_cast<int32_t>(G) + static_cast<int32_t>(blockIdx.x), GW = static_cast<int32_t>(G) * kBW;
     const int32_t win = st.win_cols, nwin = st.n_win;
-    float* const dm = st.dm;
+    float* const dm = st.dm;  // first row of this rank's row block (row 0 on one GPU)
     int32_t* const ctl = st.ctl;
+    // row-block shard of this rank (sharded runs): rows [r_lo, r_hi) live here, with all their columns
+    const int32_t C = kMulti ? st.rows_per_rank : n4;
+    const int32_t r_lo = kMulti ? min(n, st.rank * C) : 0, r_hi = kMulti ? min(n, r_lo + C) : n;
+    auto row_of = [&](int32_t slot) -> float* {  // any cluster's row (peer mapped when it lives on another rank)
+        if (!kMulti) return dm + static_cast<int64_t>(slot) * ld;
+        const int32_t q = slot / C;
+        return st.dm_rank[q] + static_cast<int64_t>(slot - q * C) * ld;
+    };
+    uint8_t* const xb = kMulti ? st.xbox[st.rank] : nullptr;  // this rank's exchange box
+    unsigned long long* const xb_stop = reinterpret_cast<unsigned long long*>(xb + 256);
+    unsigned long long* const xb_head = xb_stop + 3;
+    int32_t* const xb_cnt = reinterpret_cast<int32_t*>(xb_head + 3);
+    uint32_t xcount = 0;
+    __shared__ int32_t s_xcnt[kMaxRanks + 1];  // candidate pairs per rank (prefix sums)
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem);  // merged-slot bitmap of the current batch
@@ -187,7 +249,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     for (int i = tid; i < kRcpTab; i += kBT) s_rcp[i] = 1.0 / static_cast<double>(i > 0 ? i : 1);
     __syncthreads();
     // rows that were dry when the previous launch stopped (or rows the other loop left dry): queue slot 0
-    for (int32_t r = gtid; r < n; r += GT)
+    for (int32_t r = r_lo + gtid; r < r_hi; r += GT)
         if ((static_cast<uint32_t>(__ldcg(st.nn_more + r)) & kDryBit) != 0u && __ldcg(st.ks + r).x >= 0)
             st.dryq[atomicAdd(st.counters + 0 * 4 + CN_DRY, 1)] = make_int2(r, __ldcg(st.ks + r).x);
     // live size of every slot (0: retired / padding): what the update pass streams beside the two rows
@@ -213,7 +275,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             const int2 rq = __ldcg(st.dryq + q);
             const int32_t r = rq.x;
             const uint32_t ukr = static_cast<uint32_t>(rq.y);
-            const float* rowp = dm + static_cast<int64_t>(r) * ld;
+            const float* rowp = dm + static_cast<int64_t>(r - r_lo) * ld;
             const int32_t seg = (((n4 + kBW - 1) / kBW) + 127) & ~127;
             const int32_t sw0 = min(n4, warp * seg), sw1 = min(n4, sw0 + seg);
             ScanCand c;
@@ -300,7 +362,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 const int2 rq = __ldcg(st.dryq + base + q);
                 const int32_t r = rq.x;
                 const uint32_t ukr = static_cast<uint32_t>(rq.y);
-                const float* rowp = dm + static_cast<int64_t>(r) * ld;
+                const float* rowp = dm + static_cast<int64_t>(r - r_lo) * ld;
                 const int32_t sw0 = min(n4, w * win), sw1 = min(n4, sw0 + win);
                 ScanCand c;
                 scan_init(c);
@@ -410,16 +472,17 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
 
         // ================= P2: heads and stoppers; candidates go to one global list =================
         {
-            uint64_t bstop = kPackInf, bhead = kPackInf;
-            int32_t* const cnt_cand = st.counters + sl * 4 + CN_CAND;
-            for (int32_t r0 = 0; r0 < n; r0 += GT) {
+            uint64_t bstop = kPackInf, bhead = kPackInf, dropped = kPackInf;
+            int32_t* const cnt_cand = kMulti ? xb_cnt + sl : st.counters + sl * 4 + CN_CAND;
+            uint4* const cand_out = kMulti ? reinterpret_cast<uint4*>(xb + 512) : st.cand;
+            for (int32_t r0 = r_lo; r0 < r_hi; r0 += GT) {
                 const int32_t r = r0 + gtid;
                 RowHead h;
                 h.head = h.stop = kPackInf;
                 h.partner_slot = h.partner_key = kNoPartner;
                 h.partner_size = 0;
                 int32_t sr = 0;
-                if (r < n) {  // one round trip: key, own size, list flags and the first two entries
+                if (r < r_hi) {  // one round trip: key, own size, list flags and the first two entries
                     const int32_t key_r = __ldcg(st.gkey + r);
                     sr = __ldcg(st.lsize + r);
                     const uint32_t mb = static_cast<uint32_t>(__ldcg(st.nn_more + r));
@@ -431,18 +494,33 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 bhead = umin64(bhead, h.head);
                 if (h.head < bstop) {
                     const int32_t k = atomicAdd(cnt_cand, 1);
-                    uint4* dst = st.cand + 2 * static_cast<int64_t>(k);
-                    __stcg(dst, make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
-                                           static_cast<uint32_t>(r), h.partner_slot));
-                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(h.partner_size), h.partner_key, 0u));
+                    if (!kMulti || k < kBatchXCand) {
+                        uint4* dst = cand_out + 2 * static_cast<int64_t>(k);
+                        __stcg(dst, make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
+                                               static_cast<uint32_t>(r), h.partner_slot));
+                        __stcg(dst + 1, make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(h.partner_size), h.partner_key, 0u));
+                    } else {
+                        dropped = umin64(dropped, h.head);  // does not fit the exchange box: nothing at or above it may be taken
+                    }
                 }
             }
             bhead = block_min_u64(bhead, s_red);
-            if (tid == 0)
+            if (kMulti) {  // rank-wide minima in the exchange box
+                dropped = block_min_u64(dropped, s_red);
+                if (tid == 0) {
+                    const uint64_t bs = umin64(bstop, dropped);
+                    if (bs != kPackInf) atomicMin(xb_stop + sl, static_cast<unsigned long long>(bs));
+                    if (bhead != kPackInf) atomicMin(xb_head + sl, static_cast<unsigned long long>(bhead));
+                }
+            } else if (tid == 0) {
                 __stcg(st.hdr + blockIdx.x, make_uint4(static_cast<uint32_t>(bstop), static_cast<uint32_t>(bstop >> 32),
                                                        static_cast<uint32_t>(bhead), static_cast<uint32_t>(bhead >> 32)));
+            }
         }
-        grid_sync(st.bar, phase, G, timed ? &c_ph[6] : nullptr);
+        if (kMulti)
+            grid_sync_ranks(st, phase, xcount, G, false, timed ? &c_ph[6] : nullptr);
+        else
+            grid_sync(st.bar, phase, G, timed ? &c_ph[6] : nullptr);
         const long long tp2 = timed ? clock64() : 0;
 
         // ================= P3: the batch =================
@@ -450,20 +528,43 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         uint4 ve[kVR][kNNK];
 #pragma unroll
         for (int x = 0; x < kVR; ++x) {
-            const int32_t r = gtid + x * GT;
+            const int32_t r = r_lo + gtid + x * GT;
 #pragma unroll
             for (int y = 0; y < kNNK; ++y)
-                ve[x][y] = r < n ? __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y) : nn_none();
+                ve[x][y] = r < r_hi ? __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y) : nn_none();
         }
         uint64_t tstop = kPackInf, H = kPackInf;
-        const int32_t n_pub = __ldcg(st.counters + sl * 4 + CN_CAND);  // heads below their block's stopper minimum
-        uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-        if (tid < n_pub) c0 = __ldcg(st.cand + 2 * static_cast<int64_t>(tid));
-        if (tid < static_cast<int>(G)) {
-            const uint4 h0 = __ldcg(st.hdr + tid);
-            tstop = (static_cast<uint64_t>(h0.y) << 32) | h0.x;
-            H = (static_cast<uint64_t>(h0.w) << 32) | h0.z;
+        int32_t n_pub;  // heads below their block's stopper minimum, all ranks
+        if (kMulti) {   // every rank's minima and candidate count, read from its exchange box
+            if (tid < st.n_ranks) {
+                const uint8_t* pb = st.xbox[tid];
+                tstop = ldcg_u64(reinterpret_cast<const uint64_t*>(pb + 256) + sl);
+                H = ldcg_u64(reinterpret_cast<const uint64_t*>(pb + 256) + 3 + sl);
+                s_xcnt[tid + 1] = min(__ldcg(reinterpret_cast<const int32_t*>(pb + 256 + 48) + sl), kBatchXCand);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_xcnt[0] = 0;
+                for (int q = 0; q < st.n_ranks; ++q) s_xcnt[q + 1] += s_xcnt[q];
+            }
+            __syncthreads();
+            n_pub = s_xcnt[st.n_ranks];
+        } else {
+            n_pub = __ldcg(st.counters + sl * 4 + CN_CAND);
+            if (tid < static_cast<int>(G)) {
+                const uint4 h0 = __ldcg(st.hdr + tid);
+                tstop = (static_cast<uint64_t>(h0.y) << 32) | h0.x;
+                H = (static_cast<uint64_t>(h0.w) << 32) | h0.z;
+            }
         }
+        auto cand_ptr = [&](int32_t i) -> const uint4* {  // candidate pair i of the concatenated lists
+            if (!kMulti) return st.cand + 2 * static_cast<int64_t>(i);
+            int q = 0;
+            while (i >= s_xcnt[q + 1]) ++q;
+            return reinterpret_cast<const uint4*>(st.xbox[q] + 512) + 2 * static_cast<int64_t>(i - s_xcnt[q]);
+        };
+        uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        if (tid < n_pub) c0 = __ldcg(cand_ptr(tid));
         tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
@@ -485,10 +586,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     }
                 } else {
                     for (int32_t i = tid; i < n_pub; i += kBT) {
-                        const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+                        const uint4 p = __ldcg(cand_ptr(i));
                         if (((static_cast<uint64_t>(p.y) << 32) | p.x) == H) {
                             ctl[CTL_NEXT_HI] = static_cast<int32_t>(p.x);
-                            ctl[CTL_NEXT_LO] = static_cast<int32_t>(__ldcg(st.cand + 2 * static_cast<int64_t>(i) + 1).z);
+                            ctl[CTL_NEXT_LO] = static_cast<int32_t>(__ldcg(cand_ptr(i) + 1).z);
                             ctl[CTL_NEXT_DIST] = static_cast<int32_t>(p.y);
                         }
                     }
@@ -507,7 +608,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             auto count_lt = [&](uint64_t th) {
                 int c = 0;
                 for (int32_t i = tid; i < n_pub; i += kBT) {
-                    const uint4 p = __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+                    const uint4 p = __ldcg(cand_ptr(i));
                     c += ((static_cast<uint64_t>(p.y) << 32) | p.x) < th ? 1 : 0;
                 }
                 return block_sum_i32(c, s_redi);
@@ -528,7 +629,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         for (int32_t w = tid; w < n_words; w += kBT) s_bits[w] = 0u;
         __syncthreads();
         for (int32_t i = tid; i < n_pub; i += kBT) {
-            const uint4 p = i == tid ? c0 : __ldcg(st.cand + 2 * static_cast<int64_t>(i));
+            const uint4 p = i == tid ? c0 : __ldcg(cand_ptr(i));
             const uint64_t hp = (static_cast<uint64_t>(p.y) << 32) | p.x;
             if (hp < theta) {
                 const int k = atomicAdd(&s_m, 1);
@@ -563,7 +664,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         if (rank >= 0) {
             s_d[rank] = static_cast<uint32_t>(mine >> 32);
             if (rank < m) {
-                const uint4 p1 = __ldcg(st.cand + 2 * static_cast<int64_t>(s_idx[tid]) + 1);
+                const uint4 p1 = __ldcg(cand_ptr(s_idx[tid]) + 1);
                 const uint32_t a = static_cast<uint32_t>(s_ca[tid]), b = static_cast<uint32_t>(s_cb[tid]);
                 s_a[rank] = static_cast<int32_t>(a);
                 s_b[rank] = static_cast<int32_t>(b);
@@ -606,11 +707,16 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 for (int x = 1; x < kNNK; ++x) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + x, nn_none());
                 __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit | kDryBit));
                 __stcg(st.nn_more + a, 0);
-                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(b, new_key);
+                if (b >= r_lo && b < r_hi) st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(b, new_key);
             }
             if (tid == kBT - 1) {
                 st.counters[sl2 * 4 + CN_DRY] = 0;
                 st.counters[sl1 * 4 + CN_CAND] = 0;
+                if (kMulti) {  // this rank's exchange-box slot of the next iteration (last read two iterations ago)
+                    xb_cnt[sl1] = 0;
+                    xb_stop[sl1] = kPackInf;
+                    xb_head[sl1] = kPackInf;
+                }
             }
         }
 
@@ -619,7 +725,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         // is mirrored into the older rows: that cost one scattered sector per live cluster and merge).  d(c,a) of a
         // cluster c newer than a is therefore gathered from row c; early in the loop almost every column is older.
         {
-            const int32_t n_chunks = (n4 + kUpdCols - 1) / kUpdCols;
+            // sharded: a rank updates the columns of its own row block -- rows a and b are coalesced (possibly remote) reads,
+            // the gathers from the rows of newer clusters c are local, its part of the new row is a coalesced remote store
+            const int32_t c_lo = r_lo, c_hi = kMulti ? min(n4, r_lo + C) : n4;
+            const int32_t n_chunks = (c_hi - c_lo + kUpdCols - 1) / kUpdCols;
             const int64_t units = static_cast<int64_t>(m) * n_chunks;
             for (int64_t u = gw; u < units; u += GW) {
                 const int32_t ch = static_cast<int32_t>(u / m), i = static_cast<int32_t>(u - static_cast<int64_t>(ch) * m);
@@ -627,17 +736,17 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 const int32_t ka = s_ka[i], kb = s_kb[i];
                 const float dab = __uint_as_float(s_d[i]);
                 const double sad = static_cast<double>(sa), sbd = static_cast<double>(sb), dabd = static_cast<double>(dab);
-                const float* row_a = dm + static_cast<int64_t>(a) * ld;
-                float* row_b = dm + static_cast<int64_t>(b) * ld;
+                const float* row_a = row_of(a);
+                float* row_b = row_of(b);
                 constexpr int kI = kUpdCols / 128;
                 int4 k01[kI], k23[kI];
                 float4 va[kI], vb[kI];
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
-                    const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
+                    const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
                     k01[x] = k23[x] = make_int4(-1, 0, -1, 0);
                     va[x] = vb[x] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c0 < n4) {
+                    if (c0 < c_hi) {
                         k01[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0));
                         k23[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0 + 2));
                         va[x] = __ldcg(reinterpret_cast<const float4*>(row_a + c0));
@@ -650,8 +759,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 uint32_t livem[kI];
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {  // second round trip, only for the columns of newer clusters
-                    const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
-                    const uint32_t bits = c0 < n4 ? (s_bits[c0 >> 5] >> (c0 & 31)) & 0xFu : 0xFu;  // c0 % 4 == 0: one word
+                    const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
+                    const uint32_t bits = c0 < c_hi ? (s_bits[c0 >> 5] >> (c0 & 31)) & 0xFu : 0xFu;  // c0 % 4 == 0: one word
                     const int32_t keys[4] = {k01[x].x, k01[x].z, k23[x].x, k23[x].z};
                     const float ra[4] = {va[x].x, va[x].y, va[x].z, va[x].w};
                     const float rb[4] = {vb[x].x, vb[x].y, vb[x].z, vb[x].w};
@@ -660,7 +769,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     for (int e = 0; e < 4; ++e) {
                         const bool live = keys[e] >= 0 && ((bits >> e) & 1u) == 0u;
                         livem[x] |= live ? (1u << e) : 0u;
-                        const float* rc = dm + static_cast<int64_t>(c0 + e) * ld;
+                        const float* rc = dm + static_cast<int64_t>(c0 + e - r_lo) * ld;  // row of cluster c: local
                         db[x][e] = ldcg_if(rc + b, live && keys[e] > kb, rb[e]);
                         da[x][e] = ldcg_if(rc + a, live && keys[e] > ka, ra[e]);
                     }
@@ -668,7 +777,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 }
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
-                    const int32_t c0 = ch * kUpdCols + x * 128 + lane * 4;
+                    const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
                     const int32_t sizes[4] = {k01[x].y, k01[x].w, k23[x].y, k23[x].w};
                     float out[4];
 #pragma unroll
@@ -682,7 +791,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                         const float lw = canon_dist(static_cast<float>(num * rcp));
                         out[e] = (((livem[x] >> e) & 1u) != 0u && den <= prm.max_size) ? lw : __uint_as_float(kInfBits);
                     }
-                    if (c0 >= n4) continue;
+                    if (c0 >= c_hi) continue;
                     const uint32_t bits = livem[x] >> 4;
                     if (bits == 0u) {
                         __stcg(reinterpret_cast<float4*>(row_b + c0), make_float4(out[0], out[1], out[2], out[3]));
@@ -699,11 +808,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         for (int32_t j = gw; j < m; j += GW) {
             const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j], kaj = s_ka[j], kbj = s_kb[j];
             const float dj = __uint_as_float(s_d[j]);
+            if (kMulti && (bj < r_lo || bj >= r_hi)) continue;  // the owner of new cluster j's row computes its cross terms
             for (int32_t i = lane; i < j; i += 32) {
                 const int32_t ai = s_a[i], bi = s_b[i], sai = s_sa[i], sbi = s_sb[i], si = sai + sbi, kai = s_ka[i], kbi = s_kb[i];
                 const float di = __uint_as_float(s_d[i]);
                 auto pair = [&](int32_t p, int32_t kp, int32_t q, int32_t kq) {  // row of the higher key
-                    return kp > kq ? __ldcg(dm + static_cast<int64_t>(p) * ld + q) : __ldcg(dm + static_cast<int64_t>(q) * ld + p);
+                    return kp > kq ? __ldcg(row_of(p) + q) : __ldcg(row_of(q) + p);
                 };
                 const float x1 = pair(ai, kai, aj, kaj), x2 = pair(bi, kbi, aj, kaj), x3 = pair(ai, kai, bj, kbj),
                             x4 = pair(bi, kbi, bj, kbj);
@@ -714,7 +824,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 // merge j seen from k = new_i (slot b_i, size si)
                 float val = __uint_as_float(kInfBits);
                 if (si + saj + sbj <= prm.max_size) val = lance_williams(saj, sbj, si, t1, t2, dj);
-                __stcg(dm + static_cast<int64_t>(bj) * ld + bi, val);  // new_j carries the higher key
+                __stcg(row_of(bj) + bi, val);  // new_j carries the higher key
             }
         }
         const long long tq2 = timed ? clock64() : 0;
@@ -759,8 +869,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         };
 #pragma unroll
         for (int x = 0; x < kVR; ++x)
-            if (gtid + x * GT < n) validate(gtid + x * GT, ve[x]);
-        for (int32_t r = gtid + kVR * GT; r < n; r += GT) {
+            if (r_lo + gtid + x * GT < r_hi) validate(r_lo + gtid + x * GT, ve[x]);
+        for (int32_t r = r_lo + gtid + kVR * GT; r < r_hi; r += GT) {
             uint4 e[kNNK];
 #pragma unroll
             for (int y = 0; y < kNNK; ++y) e[y] = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y);
@@ -771,7 +881,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         n_live -= m;
         ++iters;
         const long long tq3 = timed ? clock64() : 0;
-        grid_sync(st.bar, phase, G);
+        if (kMulti)
+            grid_sync_ranks(st, phase, xcount, G, true);
+        else
+            grid_sync(st.bar, phase, G);
         if (timed) {
             const long long tp4 = clock64();
             c_ph[0] += tp1 - tp0;
@@ -806,13 +919,15 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
 cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks) {
     *blocks = 0;
     const size_t smem = merge_batch_smem_bytes(n);
-    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(merge_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return cudaSuccess;  // does not fit: *blocks stays 0
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_batch_kernel, kBT, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_batch_kernel<true>, kBT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaSuccess;
     // small problems: fewer blocks make the grid barriers cheaper
@@ -829,9 +944,12 @@ cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int bl
     LoopParams p_copy = p;
     void* args[] = {&st_copy, &p_copy};
     const size_t smem = merge_batch_smem_bytes(st.n);
-    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const bool multi = st.n_ranks > 1;
+    void* fn = multi ? reinterpret_cast<void*>(merge_batch_kernel<true>) : reinterpret_cast<void*>(merge_batch_kernel<false>);
+    cudaError_t e = multi ? cudaFuncSetAttribute(merge_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                          : cudaFuncSetAttribute(merge_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(merge_batch_kernel), dim3(blocks), dim3(kBT), args, smem, s);
+    return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kBT), args, smem, s);
 }
 
 }  // namespace ic

@@ -24,6 +24,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 big = len(sys.argv) > 1 and sys.argv[1] == "big"
 
 eng = clustering.Engine(local)
+eng.set_option("loop_mode", int(os.environ.get("IC_LOOP_MODE", "1")))  # 1: batched loop across the ranks, 0: one merge per iteration
 sh = sharding.ShardedEngine(eng, rank, world)
 ok = True
 cases = [(600, 48, 3, 10, _lib.GRAM_EXACT_FP32), (3001, 64, 4, 12, _lib.GRAM_TCGEN05_3XTF32),
@@ -53,7 +54,7 @@ for n, d, mn, mx, mode in cases:
                  and len(cl) == len(o.clusters) and all(np.array_equal(a, b) for a, b in zip(cl, o.clusters)))
         st = eng.stats()
         print(f"shard_check W={world} N={n} D={d} {mn}/{mx}: merges={st['n_merges']} ranks_agree={same} oracle_exact={exact} "
-              f"loop {st['ms_loop']:.2f} ms rescans={st['n_rescans']}", flush=True)
+              f"loop {st['ms_loop']:.2f} ms rescans={st['n_rescans']} iterations={st['n_iterations']} loop_mode={st['loop_mode']}", flush=True)
         ok = ok and same and exact
 eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
 
@@ -80,7 +81,7 @@ if big:
                 mg = max(p["merges"], 1)
                 print(f"config {cfg} W={world}: {dt:.3f} s  merges={s['n_merges']} out={s['n_out']} ranks_agree={len(set(digests)) == 1} "
                       f"prep {s['ms_prep']:.2f} gram {s['ms_gram']:.2f} nn {s['ms_nn_init']:.2f} loop {s['ms_loop']:.2f} ms "
-                      f"rescans={s['n_rescans']} trace_sha={digest[:12]} | cycles/merge "
+                      f"rescans={s['n_rescans']} iterations={s['n_iterations']} loop_mode={s['loop_mode']} trace_sha={digest[:12]} | cycles/merge "
                       + " ".join(f"{k}={v / mg:.0f}" for k, v in p.items() if k in ("publish", "exchange", "update", "scan", "fold", "pub_fence", "pub_stores", "exch_poll", "exch_rank"))
                       + f" bubbles={p['bubbles']}", flush=True)
                 ok = ok and len(set(digests)) == 1
