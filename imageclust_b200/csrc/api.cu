@@ -594,8 +594,8 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             // this rank's exchange-box slots: no candidates, no minima (the flags keep counting up across launches);
             // then all ranks line up: nobody starts before every box is reset
             uint8_t* xb = ctx->rankbox + merge_loop_rankbox_bytes();
-            IC_CUDA(cudaMemsetAsync(xb + 256, 0xFF, 48, ctx->stream));
-            IC_CUDA(cudaMemsetAsync(xb + 256 + 48, 0, 16, ctx->stream));
+            IC_CUDA(cudaMemsetAsync(xb + kBatchXAccum, 0xFF, 48, ctx->stream));
+            IC_CUDA(cudaMemsetAsync(xb + kBatchXAccum + 48, 0, 16, ctx->stream));
             ++ctx->barrier_seq;
             bs.gen = static_cast<uint32_t>(ctx->barrier_seq);
             IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));

@@ -160,11 +160,16 @@ constexpr int kBatchMaxBlocks = 160;
 constexpr int CTL_ITERS = 12;         // ctl[]: iterations of the batched loop
 // Sharded runs (one process per GPU, row-block shards like merge_loop.cu): every rank runs the kernel on its own row
 // block; the ranks exchange their candidate pairs once per iteration through peer-mapped "exchange boxes":
-//   [0, 256)    u64 flags[kMaxRanks]        cross-rank barrier: flags[q] is written by rank q
-//   [256, 512)  u64 stop[3], head[3]; i32 cnt[3]   per iteration mod 3: stopper / head minimum, candidate pairs
-//   [512, ...)  uint4 cand[kBatchXCand][2]  the rank's candidate pairs of the current iteration
+// Everything a rank needs for the batch selection is PUSHED into its box by the peers (stores over NVLink are fire and
+// forget; a remote load costs ~3 000 cycles):
+//   [0, 256)        u64 flags[kMaxRanks]            cross-rank barrier: flags[q] is written by rank q
+//   [256, 1280)     summary[src][slot] of 32 bytes   {u64 stopper minimum, u64 head minimum, i32 candidate pairs} of rank
+//                                                    src in iteration slot (iteration mod 3), written by src's block 0
+//   [1280, 1344)    u64 stop[3], head[3]; i32 cnt[3] this rank's own accumulators (local atomics)
+//   [2048, ...)     uint4 cand[src][kBatchXCand][2]  candidate pairs of rank src in the current iteration
 constexpr int kBatchXCand = 2048;
-constexpr size_t kBatchXBoxBytes = 512 + static_cast<size_t>(kBatchXCand) * 32;
+constexpr size_t kBatchXSummary = 256, kBatchXAccum = 1280, kBatchXCandBase = 2048;
+constexpr size_t kBatchXBoxBytes = kBatchXCandBase + static_cast<size_t>(kMaxRanks) * kBatchXCand * 32;
 struct BatchState {
     int32_t n;
     int32_t n_ranks, rank, rows_per_rank;  // 1, 0, - on one GPU

@@ -78,7 +78,7 @@ IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* 
 // the rank reports; stores to the rank's own memory only need the gpu-scope release of the arrival -- block 0's system
 // fence after it has acquired all arrivals is cumulative).
 IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& xcount, uint32_t G, bool remote_stores,
-                               long long* wait_acc = nullptr) {
+                               int publish_slot, long long* wait_acc = nullptr) {
     __syncthreads();
     ++phase;
     ++xcount;
@@ -92,6 +92,18 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
             while (ld_acquire_u32(st.bar) < target)
                 if (++spins > kBarSpin) __trap();
             const unsigned long long seq = (static_cast<unsigned long long>(st.gen) << 32) | xcount;
+            if (publish_slot >= 0) {  // this rank's minima and candidate count of the iteration go into every rank's box
+                const uint8_t* acc = st.xbox[st.rank] + kBatchXAccum;
+                const unsigned long long sstop = __ldcg(reinterpret_cast<const unsigned long long*>(acc) + publish_slot);
+                const unsigned long long shead = __ldcg(reinterpret_cast<const unsigned long long*>(acc) + 3 + publish_slot);
+                const int32_t scnt = __ldcg(reinterpret_cast<const int32_t*>(acc + 48) + publish_slot);
+                for (int q = 0; q < st.n_ranks; ++q) {
+                    uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXSummary + (static_cast<size_t>(st.rank) * 3 + publish_slot) * 32);
+                    __stcg(dst, make_uint4(static_cast<uint32_t>(sstop), static_cast<uint32_t>(sstop >> 32),
+                                           static_cast<uint32_t>(shead), static_cast<uint32_t>(shead >> 32)));
+                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(scnt), 0u, 0u, 0u));
+                }
+            }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (int q = 0; q < st.n_ranks; ++q)
                 if (q != st.rank)
@@ -105,7 +117,8 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
                     if (spins > kBarSpin) __trap();  // a missing peer must not hang the GPU box
                 }
             }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            // acquire at gpu scope: what the peers pushed landed in THIS GPU's L2, and everything read after the barrier
+            // is read with ld.global.cg (never from a stale L1 line); a system-scope fence here cost ~3 400 cycles
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(st.bar + 32), "r"(phase) : "memory");
         } else {
             while (ld_acquire_u32(st.bar + 32) < phase)
@@ -212,7 +225,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         return st.dm_rank[q] + static_cast<int64_t>(slot - q * C) * ld;
     };
     uint8_t* const xb = kMulti ? st.xbox[st.rank] : nullptr;  // this rank's exchange box
-    unsigned long long* const xb_stop = reinterpret_cast<unsigned long long*>(xb + 256);
+    unsigned long long* const xb_stop = reinterpret_cast<unsigned long long*>(xb + kBatchXAccum);
     unsigned long long* const xb_head = xb_stop + 3;
     int32_t* const xb_cnt = reinterpret_cast<int32_t*>(xb_head + 3);
     uint32_t xcount = 0;
@@ -471,10 +484,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         const long long tp1 = timed ? clock64() : 0;
 
         // ================= P2: heads and stoppers; candidates go to one global list =================
+        int p2_remote = 0;  // this block pushed candidates into the peers' boxes
         {
             uint64_t bstop = kPackInf, bhead = kPackInf, dropped = kPackInf;
+            bool pushed = false;
             int32_t* const cnt_cand = kMulti ? xb_cnt + sl : st.counters + sl * 4 + CN_CAND;
-            uint4* const cand_out = kMulti ? reinterpret_cast<uint4*>(xb + 512) : st.cand;
+            uint4* const cand_out = st.cand;
             for (int32_t r0 = r_lo; r0 < r_hi; r0 += GT) {
                 const int32_t r = r0 + gtid;
                 RowHead h;
@@ -495,16 +510,29 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 if (h.head < bstop) {
                     const int32_t k = atomicAdd(cnt_cand, 1);
                     if (!kMulti || k < kBatchXCand) {
-                        uint4* dst = cand_out + 2 * static_cast<int64_t>(k);
-                        __stcg(dst, make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
-                                               static_cast<uint32_t>(r), h.partner_slot));
-                        __stcg(dst + 1, make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(h.partner_size), h.partner_key, 0u));
+                        const uint4 w0 = make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
+                                                    static_cast<uint32_t>(r), h.partner_slot);
+                        const uint4 w1 = make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(h.partner_size), h.partner_key, 0u);
+                        pushed = true;
+                        if (kMulti) {  // into every rank's box (region of this rank)
+                            for (int q = 0; q < st.n_ranks; ++q) {
+                                uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXCandBase) +
+                                             2 * (static_cast<int64_t>(st.rank) * kBatchXCand + k);
+                                __stcg(dst, w0);
+                                __stcg(dst + 1, w1);
+                            }
+                        } else {
+                            uint4* dst = cand_out + 2 * static_cast<int64_t>(k);
+                            __stcg(dst, w0);
+                            __stcg(dst + 1, w1);
+                        }
                     } else {
                         dropped = umin64(dropped, h.head);  // does not fit the exchange box: nothing at or above it may be taken
                     }
                 }
             }
             bhead = block_min_u64(bhead, s_red);
+            if (kMulti) p2_remote = __syncthreads_or(pushed ? 1 : 0);
             if (kMulti) {  // rank-wide minima in the exchange box
                 dropped = block_min_u64(dropped, s_red);
                 if (tid == 0) {
@@ -518,7 +546,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             }
         }
         if (kMulti)
-            grid_sync_ranks(st, phase, xcount, G, false, timed ? &c_ph[6] : nullptr);
+            grid_sync_ranks(st, phase, xcount, G, p2_remote != 0, sl, timed ? &c_ph[6] : nullptr);
         else
             grid_sync(st.bar, phase, G, timed ? &c_ph[6] : nullptr);
         const long long tp2 = timed ? clock64() : 0;
@@ -536,11 +564,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         uint64_t tstop = kPackInf, H = kPackInf;
         int32_t n_pub;  // heads below their block's stopper minimum, all ranks
         if (kMulti) {   // every rank's minima and candidate count, read from its exchange box
-            if (tid < st.n_ranks) {
-                const uint8_t* pb = st.xbox[tid];
-                tstop = ldcg_u64(reinterpret_cast<const uint64_t*>(pb + 256) + sl);
-                H = ldcg_u64(reinterpret_cast<const uint64_t*>(pb + 256) + 3 + sl);
-                s_xcnt[tid + 1] = min(__ldcg(reinterpret_cast<const int32_t*>(pb + 256 + 48) + sl), kBatchXCand);
+            if (tid < st.n_ranks) {  // summary of rank `tid`, pushed into this rank's box
+                const uint4* sm = reinterpret_cast<const uint4*>(xb + kBatchXSummary + (static_cast<size_t>(tid) * 3 + sl) * 32);
+                const uint4 s0 = __ldcg(sm), s1 = __ldcg(sm + 1);
+                tstop = (static_cast<uint64_t>(s0.y) << 32) | s0.x;
+                H = (static_cast<uint64_t>(s0.w) << 32) | s0.z;
+                s_xcnt[tid + 1] = min(static_cast<int32_t>(s1.x), kBatchXCand);
             }
             __syncthreads();
             if (tid == 0) {
@@ -561,7 +590,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             if (!kMulti) return st.cand + 2 * static_cast<int64_t>(i);
             int q = 0;
             while (i >= s_xcnt[q + 1]) ++q;
-            return reinterpret_cast<const uint4*>(st.xbox[q] + 512) + 2 * static_cast<int64_t>(i - s_xcnt[q]);
+            return reinterpret_cast<const uint4*>(xb + kBatchXCandBase) + 2 * (static_cast<int64_t>(q) * kBatchXCand + (i - s_xcnt[q]));
         };
         uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
         if (tid < n_pub) c0 = __ldcg(cand_ptr(tid));
@@ -882,7 +911,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         ++iters;
         const long long tq3 = timed ? clock64() : 0;
         if (kMulti)
-            grid_sync_ranks(st, phase, xcount, G, true);
+            grid_sync_ranks(st, phase, xcount, G, true, -1);
         else
             grid_sync(st.bar, phase, G);
         if (timed) {
