@@ -17,8 +17,8 @@ cpu_baseline  the CPU oracle (C restatement of the Go reference) on a bounded sa
 
 With --gpus N > 1 (torchrun) the SAME clustering is row-block sharded over the N GPUs
 (BASELINE config "N=100,000 x 2048 on 1 x B200 vs 8 x B200 row-block sharded"): rank r keeps
-the rows of its slot block, the ranks' persistent kernels exchange one record per merge
-through peer-mapped memory over NVLink (imageclust_b200/sharding.py).
+the rows of its slot block, the ranks' persistent kernels exchange their candidate pairs once per
+iteration (~10 merges) through peer-mapped memory over NVLink (imageclust_b200/sharding.py).
 Total work is fixed => "scaling": "strong".  --replicas runs N independent clusterings
 instead (one per GPU, "weak").
 """
@@ -319,8 +319,8 @@ def main():
             "config": {"workload": f"config {args.config}: N={n} x {d} Gaussian-mixture fp32 embeddings, "
                                    f"minSize={mn}, maxSize={mx} -> {stats[-1]['n_target']} clusters, {merges} merges",
                        "parallelism": "1 GPU" if world == 1 else (
-                           f"one clustering row-block sharded over {world} GPUs (peer-mapped rows + per-merge record "
-                           f"exchange over NVLink)" if sharded else f"{world} independent clustering jobs (one per GPU)"),
+                           f"one clustering row-block sharded over {world} GPUs (peer-mapped rows; the ranks' persistent kernels "
+                           f"exchange their candidate pairs once per iteration of ~10 merges over NVLink)" if sharded else f"{world} independent clustering jobs (one per GPU)"),
                        "l2": "inputs larger than L2 (X %.0f MB, distance matrix %.1f GB)" % (4e-6 * n * d, stats[-1]["matrix_bytes"] / 1e9),
                        "gram": {0: "tcgen05 kind::tf32, exact fixed-point slice + residual (4 products)", 1: "exact fp32 SIMT", 2: "tcgen05 kind::i8, three int8 digits of a 22-bit fixed-point row, exact int32 accumulation (6 products)"}[args.gram_mode]},
             "merges_per_s": merges / (ms_loop * 1e-3) if ms_loop > 0 else None,
