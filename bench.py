@@ -37,7 +37,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 # dram__bytes_read.sum + dram__bytes_write.sum of the merge-loop launch (ncu --set full, profiles/r01_summary.md), GB
-LOOP_TRAFFIC_GB = {("C", False): 971.4}
+LOOP_TRAFFIC_GB = {("C", False): 971.4, ("C", True): 1016.2}
 sys.path.insert(0, ROOT)
 
 from imageclust_b200 import synth  # noqa: E402

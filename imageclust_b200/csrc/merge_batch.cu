@@ -104,7 +104,8 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
                     __stcg(dst + 1, make_uint4(static_cast<uint32_t>(scnt), 0u, 0u, 0u));
                 }
             }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            // block 0's own pushes (the summary) must be performed before the flags; the other blocks fenced theirs
+            if (publish_slot >= 0 || remote_stores) asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (int q = 0; q < st.n_ranks; ++q)
                 if (q != st.rank)
                     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(st.xbox[q]) + st.rank), "l"(seq) : "memory");
@@ -749,6 +750,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             }
         }
 
+        bool wrote_remote = false;
         // ---- Lance-Williams rows: unit = (merge, kUpdCols columns), one warp each, all loads of a unit in flight ----
         // A pair's distance lives in the row of its HIGHER-key cluster (the new cluster's row is written in full, nothing
         // is mirrored into the older rows: that cost one scattered sector per live cluster and merge).  d(c,a) of a
@@ -763,6 +765,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 const int32_t ch = static_cast<int32_t>(u / m), i = static_cast<int32_t>(u - static_cast<int64_t>(ch) * m);
                 const int32_t a = s_a[i], b = s_b[i], sa = s_sa[i], sb = s_sb[i], snew = sa + sb;
                 const int32_t ka = s_ka[i], kb = s_kb[i];
+                if (kMulti && (b < r_lo || b >= r_hi)) wrote_remote = true;  // this unit's slice of the new row goes to a peer
                 const float dab = __uint_as_float(s_d[i]);
                 const double sad = static_cast<double>(sa), sbd = static_cast<double>(sb), dabd = static_cast<double>(dab);
                 const float* row_a = row_of(a);
@@ -911,7 +914,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         ++iters;
         const long long tq3 = timed ? clock64() : 0;
         if (kMulti)
-            grid_sync_ranks(st, phase, xcount, G, true, -1);
+            grid_sync_ranks(st, phase, xcount, G, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
         else
             grid_sync(st.bar, phase, G);
         if (timed) {

@@ -507,3 +507,28 @@ def test_batched_loop_exhaustion_and_tight_max(eng, oracle, knobs):
     _same_trace(eng.merge_trace(), o)
     assert bool(res.stats["exhausted"]) == o.exhausted
     assert same_clusters(res.clusters, o.clusters)
+
+
+def test_batched_loop_stats_and_mode_guard(eng, knobs):
+    """ic_stats reports the loop that ran and its iterations; the loop mode cannot change once the batched path's
+    lower-triangle-only initial matrix exists (the one-merge-per-iteration loop needs the mirrored entries)."""
+    x = synth.gaussian_mixture(1500, 64, 4, 12, seed=77)
+    res = eng.cluster(x, 4, 12)
+    assert res.stats["loop_mode"] == 1
+    assert 0 < res.stats["n_iterations"] < res.stats["n_merges"]
+    eng.load(x)
+    eng.initial_distances(_lib.GRAM_TCGEN05_I8, 12)
+    m0 = eng.read_matrix()
+    assert np.array_equal(m0, m0.T)  # K1 stored the lower triangle only; the caller still gets the symmetric matrix
+    eng.nn_init()
+    eng.set_option("loop_mode", 0)
+    try:
+        with pytest.raises(Exception):
+            eng.merge_loop(4, 12)
+    finally:
+        eng.set_option("loop_mode", 1)
+    knobs(loop_mode=0)
+    eng.load(x)
+    res0 = eng.run_resident(4, 12)
+    assert res0.stats["loop_mode"] == 0 and res0.stats["n_iterations"] >= res0.stats["n_merges"]
+    assert same_clusters(res0.clusters, res.clusters)
