@@ -125,7 +125,7 @@ struct LoopParams {
     int32_t max_merges;  // stop after this many merges in this launch (<0: unlimited)
     float near_tie_tol;
     int32_t scan_every;  // rescan requests are published every scan_every-th iteration (batched row scans)
-    int32_t debug;       // experiments only (bit 0: batched loop skips the mirrored column stores -> wrong results)
+    int32_t debug;       // experiments only (currently unused by the kernels)
 };
 // ctl[] indices.  N_LIVE and N_MERGES are read at launch (resume) and written at exit.
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,

@@ -14,20 +14,25 @@
 //   highest keys).  Hence the sequential algorithm performs exactly those merges, in that order.
 //   T = min( second list entry of any row,  any head that is not the first head at both of its slots ).
 //
-//   Batch sizes grow like ~0.3 * sqrt(n live) on the benchmark mixtures: ~2 000 iterations instead of 97 250
-//   at config C, which turns the loop from a latency chain into a bandwidth problem.
+//   Measured batch sizes: 10.2 merges per iteration at config C (N = 100 000), 12.4 at B, 60 at E (maxSize 8): 9 511
+//   iterations instead of 97 250.  The stopper is almost always a second list entry, so batches do not grow with N.
 //
 // One iteration = three grid-wide phases of a persistent cooperative kernel (one CTA per SM):
 //   P1 rescans    rows whose cached partners all died (and the rows of the clusters just created) are scanned
 //                 by 2048-column windows, one warp each; the warp that finishes a row's last window folds the
-//                 partial lists (exact cut rule)
+//                 partial lists (exact cut rule).  Short rows (n <= 32k): one block per row, fold in shared memory
 //   P2 heads      per row: head + stopper; every block publishes its heads below its own stopper minimum
 //                 (any value >= T is a valid filter) and that minimum
 //   P3 batch      every block reads all published candidates (a few dozen), derives T -- stopper minimum and
-//                 slot conflicts, pairwise in shared memory -- and ranks the pairs below T; then: Lance-Williams
-//                 rows (coalesced row reads / writes + mirrored column stores), the m x m cross terms of the
-//                 batch (two chained updates from the four old entries), trace / slot bookkeeping, validation
-//                 of the partner lists
+//                 slot conflicts, pairwise in shared memory -- and ranks the pairs below T; then: trace / slot
+//                 bookkeeping, validation of the partner lists, Lance-Williams rows (the new cluster's row is written
+//                 in full; a pair lives in the row of its HIGHER-key cluster, entries of newer clusters are gathered
+//                 with predicated loads), the m x m cross terms of the batch (two chained updates from the four old
+//                 entries)
+// Sharded runs (template parameter kMulti, one process per GPU): every rank runs the kernel on its row block -- own rows
+// in P1 / P2 / validation, the columns of its own row block in the rows phase (rows a, b: coalesced peer loads; gathers:
+// local; its slice of the new row: coalesced peer store) -- candidates and rank minima are pushed into every rank's
+// exchange box, and two cross-rank barriers per iteration (after P2, after the rows) replace the grid barriers.
 // HBM roofline: algorithmic bytes = 12*n per merge.
 #include <algorithm>
 

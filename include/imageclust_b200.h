@@ -89,8 +89,9 @@ void ic_pinned_free(void *p);
  * "virtual_ranks" (1..8: row-block shards emulated on ONE GPU by one cooperative launch --
  * the same kernel path as the multi-GPU build, for tests), "scan_every" (row rescans are requested every k-th
  * merge-loop iteration, default 4: batching them keeps the scan phase out of most iterations), "loop_mode" (1, default:
- * batched loop on an unsharded context -- every iteration takes all merges that are provably the next ones; needs rows
- * of 2N columns, falls back to 0 when they do not fit; 0: one merge per iteration; set it before ic_load), "no_replica",
+ * batched loop -- every iteration takes all merges that are provably the next ones of the reference's sequence, on one
+ * GPU or across the ranks of a sharded context; 0: one merge per iteration, also what "virtual_ranks" runs; set it
+ * before ic_load, it cannot change once ic_initial_distances has run), "no_replica",
  * "profile_loop", "verbose" */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 
