@@ -245,6 +245,20 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
 #pragma unroll
                 for (int q = 0; q < kChunk; ++q) stg[lane * (kChunk + 1) + q] = v[q];
                 __syncwarp();
+                // a chunk wholly below the diagonal and inside the matrix: 16-byte stores, 8 rows per instruction
+                const int64_t wr0 = row0 + ew * 32;  // first row of this warp
+                if (gj0 + kChunk - 1 < wr0 && wr0 >= row_begin && wr0 + 32 <= row_end && wr0 + 32 <= n) {
+                    const int c4 = (lane & 3) * 4;
+#pragma unroll
+                    for (int rr = 0; rr < 32; rr += 8) {
+                        const int rloc = rr + (lane >> 2);
+                        const float* sp = stg + rloc * (kChunk + 1) + c4;
+                        __stcs(reinterpret_cast<float4*>(dm + (wr0 + rloc - row_begin) * ld + gj0 + c4),
+                               make_float4(sp[0], sp[1], sp[2], sp[3]));
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 const int64_t gj = gj0 + (lane & (kChunk - 1));
 #pragma unroll 4
                 for (int rr = 0; rr < 32; rr += 2) {
