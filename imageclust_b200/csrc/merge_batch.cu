@@ -245,7 +245,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     __shared__ int s_redi[kBW];
     // candidate pairs as collected (unordered) ...
     __shared__ uint64_t s_hp[kMaxBatch];
-    __shared__ int32_t s_ca[kMaxBatch], s_cb[kMaxBatch], s_idx[kMaxBatch];
+    __shared__ int32_t s_ca[kMaxBatch], s_cb[kMaxBatch], s_csa[kMaxBatch], s_csb[kMaxBatch], s_ckb[kMaxBatch];
     // ... and the batch in scan order
     __shared__ int32_t s_a[kMaxBatch], s_b[kMaxBatch], s_sa[kMaxBatch], s_sb[kMaxBatch], s_ka[kMaxBatch], s_kb[kMaxBatch];
     __shared__ uint32_t s_d[kMaxBatch + 1];
@@ -496,44 +496,57 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             bool pushed = false;
             int32_t* const cnt_cand = kMulti ? xb_cnt + sl : st.counters + sl * 4 + CN_CAND;
             uint4* const cand_out = st.cand;
-            for (int32_t r0 = r_lo; r0 < r_hi; r0 += GT) {
-                const int32_t r = r0 + gtid;
-                RowHead h;
-                h.head = h.stop = kPackInf;
-                h.partner_slot = h.partner_key = kNoPartner;
-                h.partner_size = 0;
-                int32_t sr = 0;
-                if (r < r_hi) {  // one round trip: key, own size, list flags and the first two entries
-                    const int32_t key_r = __ldcg(st.gkey + r);
-                    sr = __ldcg(st.lsize + r);
-                    const uint32_t mb = static_cast<uint32_t>(__ldcg(st.nn_more + r));
-                    const uint4 e0 = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK);
-                    const uint4 e1 = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + 1);
-                    if (key_r >= 0) h = row_head(e0, e1, mb, static_cast<uint32_t>(key_r));
+            constexpr int kP2R = 2;  // rows per thread and tile: one round trip and one block reduction for both
+            for (int32_t r0 = r_lo; r0 < r_hi; r0 += kP2R * GT) {
+                RowHead h[kP2R];
+                int32_t sr[kP2R], rr[kP2R];
+#pragma unroll
+                for (int x = 0; x < kP2R; ++x) {
+                    const int32_t r = r0 + x * GT + gtid;
+                    rr[x] = r;
+                    h[x].head = h[x].stop = kPackInf;
+                    h[x].partner_slot = h[x].partner_key = kNoPartner;
+                    h[x].partner_size = 0;
+                    sr[x] = 0;
+                    if (r < r_hi) {  // one round trip: key, own size, list flags and the first two entries
+                        const int32_t key_r = __ldcg(st.gkey + r);
+                        sr[x] = __ldcg(st.lsize + r);
+                        const uint32_t mb = static_cast<uint32_t>(__ldcg(st.nn_more + r));
+                        const uint4 e0 = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK);
+                        const uint4 e1 = __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + 1);
+                        if (key_r >= 0) h[x] = row_head(e0, e1, mb, static_cast<uint32_t>(key_r));
+                    }
                 }
-                bstop = umin64(bstop, block_min_u64(h.stop, s_red));  // running minimum: any value >= T is a valid filter
-                bhead = umin64(bhead, h.head);
-                if (h.head < bstop) {
-                    const int32_t k = atomicAdd(cnt_cand, 1);
-                    if (!kMulti || k < kBatchXCand) {
-                        const uint4 w0 = make_uint4(static_cast<uint32_t>(h.head), static_cast<uint32_t>(h.head >> 32),
-                                                    static_cast<uint32_t>(r), h.partner_slot);
-                        const uint4 w1 = make_uint4(static_cast<uint32_t>(sr), static_cast<uint32_t>(h.partner_size), h.partner_key, 0u);
-                        pushed = true;
-                        if (kMulti) {  // into every rank's box (region of this rank)
-                            for (int q = 0; q < st.n_ranks; ++q) {
-                                uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXCandBase) +
-                                             2 * (static_cast<int64_t>(st.rank) * kBatchXCand + k);
+                uint64_t tstop_min = h[0].stop;
+#pragma unroll
+                for (int x = 1; x < kP2R; ++x) tstop_min = umin64(tstop_min, h[x].stop);
+                bstop = umin64(bstop, block_min_u64(tstop_min, s_red));  // running minimum: any value >= T is a valid filter
+#pragma unroll
+                for (int x = 0; x < kP2R; ++x) {
+                    bhead = umin64(bhead, h[x].head);
+                    if (h[x].head < bstop) {
+                        const int32_t k = atomicAdd(cnt_cand, 1);
+                        if (!kMulti || k < kBatchXCand) {
+                            const uint4 w0 = make_uint4(static_cast<uint32_t>(h[x].head), static_cast<uint32_t>(h[x].head >> 32),
+                                                        static_cast<uint32_t>(rr[x]), h[x].partner_slot);
+                            const uint4 w1 = make_uint4(static_cast<uint32_t>(sr[x]), static_cast<uint32_t>(h[x].partner_size),
+                                                        h[x].partner_key, 0u);
+                            pushed = true;
+                            if (kMulti) {  // into every rank's box (region of this rank)
+                                for (int q = 0; q < st.n_ranks; ++q) {
+                                    uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXCandBase) +
+                                                 2 * (static_cast<int64_t>(st.rank) * kBatchXCand + k);
+                                    __stcg(dst, w0);
+                                    __stcg(dst + 1, w1);
+                                }
+                            } else {
+                                uint4* dst = cand_out + 2 * static_cast<int64_t>(k);
                                 __stcg(dst, w0);
                                 __stcg(dst + 1, w1);
                             }
                         } else {
-                            uint4* dst = cand_out + 2 * static_cast<int64_t>(k);
-                            __stcg(dst, w0);
-                            __stcg(dst + 1, w1);
+                            dropped = umin64(dropped, h[x].head);  // does not fit the exchange box: nothing at or above it may be taken
                         }
-                    } else {
-                        dropped = umin64(dropped, h.head);  // does not fit the exchange box: nothing at or above it may be taken
                     }
                 }
             }
@@ -598,8 +611,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             while (i >= s_xcnt[q + 1]) ++q;
             return reinterpret_cast<const uint4*>(xb + kBatchXCandBase) + 2 * (static_cast<int64_t>(q) * kBatchXCand + (i - s_xcnt[q]));
         };
-        uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-        if (tid < n_pub) c0 = __ldcg(cand_ptr(tid));
+        uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < n_pub) {
+            c0 = __ldcg(cand_ptr(tid));
+            c1 = __ldcg(cand_ptr(tid) + 1);
+        }
         tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
@@ -667,46 +683,47 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             const uint4 p = i == tid ? c0 : __ldcg(cand_ptr(i));
             const uint64_t hp = (static_cast<uint64_t>(p.y) << 32) | p.x;
             if (hp < theta) {
+                const uint4 p1 = i == tid ? c1 : __ldcg(cand_ptr(i) + 1);
                 const int k = atomicAdd(&s_m, 1);
                 s_hp[k] = hp;
                 s_ca[k] = static_cast<int32_t>(p.z);
                 s_cb[k] = static_cast<int32_t>(p.w);
-                s_idx[k] = i;
+                s_csa[k] = static_cast<int32_t>(p1.x);
+                s_csb[k] = static_cast<int32_t>(p1.y);
+                s_ckb[k] = static_cast<int32_t>(p1.z);
             }
         }
         __syncthreads();
         const int32_t n_cand = s_m;  // <= kMaxBatch
         // slot conflicts: a pair that shares a cluster with an earlier pair is a stopper
         uint64_t mine = kPackInf, conf = kPackInf;
+        int n_less = 0;
         if (tid < n_cand) {
             mine = s_hp[tid];
             const int32_t a = s_ca[tid], b = s_cb[tid];
             bool hit = false;
             for (int j = 0; j < n_cand; ++j) {
                 const int32_t aj = s_ca[j], bj = s_cb[j];
-                hit = hit || (s_hp[j] < mine && (aj == a || aj == b || bj == a || bj == b));
+                const bool less = s_hp[j] < mine;
+                n_less += less ? 1 : 0;
+                hit = hit || (less && (aj == a || aj == b || bj == a || bj == b));
             }
             if (hit) conf = mine;
         }
         const uint64_t T = umin64(theta, block_min_u64(conf, s_red));
-        int rank = -1;
-        if (tid < n_cand && mine < T) {
-            rank = 0;
-            for (int j = 0; j < n_cand; ++j) rank += s_hp[j] < mine ? 1 : 0;  // everything below an accepted pair is accepted
-        }
+        const int rank = (tid < n_cand && mine < T) ? n_less : -1;  // everything below an accepted pair is accepted
         const int32_t m_all = block_sum_i32(rank >= 0 ? 1 : 0, s_redi);  // >= 1: the global minimum head is always among them
         const int32_t m = min(m_all, limit);                              // merges of this iteration
         if (rank >= 0) {
             s_d[rank] = static_cast<uint32_t>(mine >> 32);
             if (rank < m) {
-                const uint4 p1 = __ldcg(cand_ptr(s_idx[tid]) + 1);
                 const uint32_t a = static_cast<uint32_t>(s_ca[tid]), b = static_cast<uint32_t>(s_cb[tid]);
                 s_a[rank] = static_cast<int32_t>(a);
                 s_b[rank] = static_cast<int32_t>(b);
-                s_sa[rank] = static_cast<int32_t>(p1.x);
-                s_sb[rank] = static_cast<int32_t>(p1.y);
+                s_sa[rank] = s_csa[tid];
+                s_sb[rank] = s_csb[tid];
                 s_ka[rank] = static_cast<int32_t>(pack_key(mine));
-                s_kb[rank] = static_cast<int32_t>(p1.z);
+                s_kb[rank] = s_ckb[tid];
                 atomicOr(&s_bits[a >> 5], 1u << (a & 31u));
                 atomicOr(&s_bits[b >> 5], 1u << (b & 31u));
             }
