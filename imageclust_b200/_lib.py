@@ -35,7 +35,7 @@ SYMBOLS = [
     "ic_run_resident", "ic_build_clusters", "ic_read_matrix", "ic_read_slots", "ic_get_merge_trace",
     "ic_get_stats", "ic_get_loop_profile", "ic_time_kernel",
     "ic_shard_init", "ic_shard_export", "ic_shard_connect", "ic_shard_rows",
-    "ic_load_combined", "ic_read_x", "ic_get_loop_block_waits",
+    "ic_load_combined", "ic_read_x", "ic_get_loop_block_waits", "ic_get_linkage",
 ]
 SHARD_HANDLE_BYTES = 192
 
@@ -96,6 +96,7 @@ def load():
         "ic_read_matrix": (i32, [vp, fp, i64]),
         "ic_read_slots": (i32, [vp, i32p, i32p]),
         "ic_get_merge_trace": (i32, [vp, i32p, i32p, fp, i32p, fp, i64, i64p]),
+        "ic_get_linkage": (i32, [vp, C.POINTER(C.c_double), i64, i64p]),
         "ic_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "ic_get_loop_profile": (i32, [vp, i64p]),
         "ic_time_kernel": (i32, [vp, C.c_char_p, i32, fp]),

@@ -268,6 +268,15 @@ class Engine:
         k = m.value
         return MergeTrace(hi[:k], lo[:k], dist[:k], sz[:k], gap[:k])
 
+    def linkage(self) -> np.ndarray:
+        """The merge trace as a scipy-style linkage matrix ``[n_merges x 4]`` (``ic_get_linkage``): rows
+        ``{key_lo, key_hi, sqrt(2 d), size}``; an unconstrained run equals ``scipy.cluster.hierarchy.linkage(X, "ward")``."""
+        cap = max(self.n, 1)
+        z = np.zeros((cap, 4), np.float64)
+        m = C.c_int64(0)
+        self._check(self._L.ic_get_linkage(self._h, z.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(m)))
+        return z[:int(m.value)].copy()
+
     def stats(self) -> dict:
         st = _lib.Stats()
         self._check(self._L.ic_get_stats(self._h, C.byref(st)))
@@ -316,6 +325,31 @@ class Engine:
         ms = C.c_float(0)
         self._check(self._L.ic_time_kernel(self._h, which.encode(), int(repeats), C.byref(ms)))
         return ms.value
+
+
+def trace_to_linkage(trace) -> np.ndarray:
+    """Host-side twin of ``ic_get_linkage`` for any merge trace with ``key_hi / key_lo / dist / size`` arrays (the
+    device's :class:`MergeTrace` or an oracle result)."""
+    m = len(trace.key_hi)
+    z = np.zeros((m, 4), np.float64)
+    z[:, 0] = np.asarray(trace.key_lo[:m], np.float64)
+    z[:, 1] = np.asarray(trace.key_hi[:m], np.float64)
+    z[:, 2] = np.sqrt(2.0 * np.asarray(trace.dist[:m], np.float64))
+    z[:, 3] = np.asarray(trace.size[:m], np.float64)
+    return z
+
+
+def clustering_report(n_items: int, clusters, stats: dict | None = None) -> dict:
+    """What the reference's caller cannot see today (workflow.go:89-97): the items that vanished because
+    their cluster stayed below ``minSize`` (clustering.go:268-271), and the near-tie count of the run."""
+    seen = np.zeros(int(n_items), bool)
+    for c in clusters:
+        seen[np.asarray(c, np.int64)] = True
+    rep = {"n_items": int(n_items), "n_clusters": len(clusters), "dropped_items": np.flatnonzero(~seen).astype(np.int32)}
+    if stats is not None:
+        rep.update(n_near_ties=stats.get("n_near_ties"), near_tie_tol=stats.get("near_tie_tol"),
+                   exhausted=bool(stats.get("exhausted")), n_final=stats.get("n_final"))
+    return rep
 
 
 def _i32p(a):

@@ -1265,6 +1265,24 @@ int ic_get_merge_trace(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dis
     return IC_OK;
 }
 
+int ic_get_linkage(ic_ctx* ctx, double* z, int64_t capacity, int64_t* n_rows) {
+    if (!ctx || !n_rows) return IC_ERR_BAD_ARG;
+    if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "no merge state");
+    IC_CUDA(cudaSetDevice(ctx->device));
+    const int rc = fetch_trace(ctx);
+    if (rc != IC_OK) return rc;
+    const int64_t m = ctx->n_merges;
+    *n_rows = m;
+    if (capacity < m || (m > 0 && !z)) return fail(ctx, IC_ERR_BAD_ARG, "linkage capacity too small");
+    for (int64_t t = 0; t < m; ++t) {
+        z[4 * t + 0] = static_cast<double>(ctx->h_key_lo[t]);
+        z[4 * t + 1] = static_cast<double>(ctx->h_key_hi[t]);
+        z[4 * t + 2] = std::sqrt(2.0 * static_cast<double>(ctx->h_dist[t]));  // Ward distance d = h^2 / 2
+        z[4 * t + 3] = static_cast<double>(ctx->h_size[t]);
+    }
+    return IC_OK;
+}
+
 int ic_get_loop_block_waits(ic_ctx* ctx, int64_t* out, int64_t capacity, int64_t* n_blocks) {
     if (!ctx || !out || !n_blocks) return IC_ERR_BAD_ARG;
     *n_blocks = ctx->loop_grid;

@@ -172,6 +172,12 @@ int ic_read_slots(ic_ctx *ctx, int32_t *key, int32_t *size);
  * merge distance, the new size, and the relative gap to the runner-up candidate */
 int ic_get_merge_trace(ic_ctx *ctx, int32_t *key_hi, int32_t *key_lo, float *dist, int32_t *size,
                        float *gap, int64_t capacity, int64_t *n_merges);
+/* the same trace as a dendrogram in the layout of scipy.cluster.hierarchy.linkage (the reference has no
+ * on-disk format): row t = {key_lo, key_hi, sqrt(2 * dist), size} as doubles, z[capacity][4].  Keys are item indices
+ * (< n) or n + t' for the cluster made by merge t' -- scipy's own numbering -- and sqrt(2 d) is scipy's Ward height, so
+ * an unconstrained run reproduces linkage(X, "ward"); with constraints it is the forest the path built (n_final roots),
+ * which a caller can re-cut at other min / max sizes without clustering again. */
+int ic_get_linkage(ic_ctx *ctx, double *z, int64_t capacity, int64_t *n_rows);
 int ic_get_stats(ic_ctx *ctx, ic_stats *stats);
 /* debug (option "profile_loop" = 1): SM cycles block 0 spent in each phase of the merge loop
  * {publish, exchange poll + fold, decision + update, row scans, partial folds, merges, iterations, rescans,
