@@ -345,6 +345,11 @@ def main():
                          # workload (profiles/); GB per launch like `achieved`'s numerator (60 GB at config C)
                          "traffic": LOOP_TRAFFIC_GB.get((args.config, batched)) if (world == 1 and not args.n) else None,
                          "traffic_unit": "GB per launch (ncu, profiles/r01_summary.md)",
+                         # what the launch actually moves over its measured time, against the same peak (information:
+                         # the gap to `frac` is re-read rows, retired columns, partner lists, sector-granular gathers)
+                         "traffic_frac": (LOOP_TRAFFIC_GB[(args.config, batched)] / (ms_loop * 1e-3) / hbm
+                                          if (world == 1 and not args.n and (args.config, batched) in LOOP_TRAFFIC_GB and ms_loop > 0)
+                                          else None),
                          "peak_source": peaks["source"] + " copy bandwidth",
                          "note": ("algorithmic bytes 12*n per merge; the batched loop takes ~10 provably consecutive merges per "
                                   "iteration, each iteration is three grid-wide phases of dependent DRAM round trips: bound by "
