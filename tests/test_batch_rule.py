@@ -51,3 +51,28 @@ def test_batch_rule_capacity_cut_is_a_prefix(oracle):
         assert np.array_equal(hi, o.key_hi) and np.array_equal(lo, o.key_lo)
         assert np.array_equal(dist.view(np.uint32), o.dist.view(np.uint32))
         assert batches.max() <= cap
+
+
+# ---- property test: integer-grid points (masses of exact ties), random constraints ------------------------------
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(4, 28), d=st.integers(1, 3), grid=st.integers(2, 5), mn=st.integers(1, 4), extra=st.integers(0, 6),
+       seed=st.integers(0, 10**6))
+def test_batch_rule_property_exact_ties(oracle, n, d, grid, mn, extra, seed):
+    """Points on a small integer grid: many pairs at exactly the same distance, duplicates, chains of equal heads.  The
+    tie-break (d, key_hi, key_lo) and the 'ties go to the older pair' argument of the batch rule are what is tested."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, grid, size=(n, d)).astype(np.float32)
+    mx = mn + extra
+    n_target, err = clustering.calculate_optimal_clusters(n, mn, mx)
+    if err is not None:
+        return
+    o = oracle.fast_cluster(x, mn, mx, flags=LW_EAGER)
+    m0 = oracle.initial_matrix(x)
+    hi, lo, dist, s, batches = batch_rule.batched_cluster(m0, n_target, mx)
+    assert len(hi) == o.n_merges
+    assert np.array_equal(hi, o.key_hi) and np.array_equal(lo, o.key_lo)
+    assert np.array_equal(dist.view(np.uint32), o.dist.view(np.uint32)) and np.array_equal(s, o.size)
