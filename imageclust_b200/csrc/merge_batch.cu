@@ -282,6 +282,121 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         const int sl = static_cast<int>(it % 3u), sl1 = static_cast<int>((it + 1u) % 3u), sl2 = static_cast<int>((it + 2u) % 3u);
         const long long tp0 = timed ? clock64() : 0;
 
+        // One (row, window) unit of a rescan: a warp scans 2048 columns of a queued row; the warp that delivers a row's last
+        // window folds the partial lists and writes the row's list.  `during_batch`: the unit runs inside the rows phase of
+        // the batch that follows the one the row ran dry in -- clusters of the current batch are excluded through the
+        // bitmap (their slots are being rewritten), and a queued row that was itself merged is skipped.
+        auto scan_window_unit = [&](int32_t base, int32_t rows, int64_t u, bool during_batch) {
+                // windows of one row go to warps of different blocks: q = u % rows
+                const int32_t w = static_cast<int32_t>(u / rows), q = static_cast<int32_t>(u - static_cast<int64_t>(w) * rows);
+                const int2 rq = __ldcg(st.dryq + base + q);
+                const int32_t r = rq.x;
+                if (during_batch && ((s_bits[r >> 5] >> (r & 31)) & 1u)) return;  // merged in this batch: no list to rebuild
+                const uint32_t ukr = static_cast<uint32_t>(rq.y);
+                const float* rowp = dm + static_cast<int64_t>(r - r_lo) * ld;
+                const int32_t sw0 = min(n4, w * win), sw1 = min(n4, sw0 + win);
+                ScanCand c;
+                scan_init(c);
+                constexpr int kU = 8;  // 16-byte loads of the row and of the keys in flight per lane
+                for (int32_t b0 = sw0; b0 < sw1; b0 += 128 * kU) {
+                    float4 vv[kU];
+                    int4 kq[kU];
+#pragma unroll
+                    for (int x = 0; x < kU; ++x) {
+                        const int32_t u0 = b0 + (x * 32 + lane) * 4;
+                        vv[x] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                        kq[x] = make_int4(-1, -1, -1, -1);
+                        if (u0 < sw1) {
+                            vv[x] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
+                            kq[x] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
+                        }
+                    }
+#pragma unroll
+                    for (int x = 0; x < kU; ++x) {
+                        const int32_t u0 = b0 + (x * 32 + lane) * 4;
+                        const uint32_t vs4[4] = {__float_as_uint(vv[x].x), __float_as_uint(vv[x].y), __float_as_uint(vv[x].z),
+                                                 __float_as_uint(vv[x].w)};
+                        const uint32_t ks4[4] = {static_cast<uint32_t>(kq[x].x), static_cast<uint32_t>(kq[x].y),
+                                                 static_cast<uint32_t>(kq[x].z), static_cast<uint32_t>(kq[x].w)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)  // retired slots and padding hold key -1 == 0xFFFFFFFF: never below the row's key
+                            if (ks4[e] < ukr && vs4[e] < kMaxFloatBits &&
+                                !(during_batch && ((s_bits[(u0 + e) >> 5] >> ((u0 + e) & 31)) & 1u)))
+                                scan_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ks4[e], u0 + e);
+                    }
+                }
+                PartList out;
+                bool more = false;
+                out.m = warp_select_scan(c, out.pk, out.sl, more);
+                out.more = more ? 1 : 0;
+#pragma unroll
+                for (int x = 0; x < kNNK; ++x) out.sz[x] = 0;
+                bool folder = nwin == 1;
+                if (nwin > 1) {
+                    uint4* prec = st.partials + (static_cast<size_t>(q) * kBatchMaxWin + w) * 8;
+                    if (lane < kNNK) {
+                        const uint64_t myp = sel4(out.pk, lane);
+                        __stcg(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                                      static_cast<uint32_t>(sel4(out.sl, lane)), 0u)
+                                                         : nn_none());
+                    } else if (lane == kNNK) {
+                        __stcg(prec + kNNK, make_uint4(static_cast<uint32_t>(out.m), static_cast<uint32_t>(out.more), 0u, 0u));
+                    }
+                    __syncwarp();
+                    int old = 0;
+                    if (lane == 0) {
+                        __threadfence();
+                        old = atomicAdd(st.part_cnt + q, 1);
+                        __threadfence();
+                    }
+                    old = __shfl_sync(0xffffffffu, old, 0);
+                    folder = old == nwin - 1;
+                    if (folder) {  // last window of the row: fold the nwin partial lists (up to four per lane)
+                        PartList acc;
+                        acc.m = 0;
+                        acc.more = 0;
+#pragma unroll
+                        for (int x = 0; x < kNNK; ++x) {
+                            acc.pk[x] = kPackInf;
+                            acc.sl[x] = -1;
+                            acc.sz[x] = 0;
+                        }
+                        for (int32_t ww = lane; ww < nwin; ww += 32) {
+                            const uint4* rec = st.partials + (static_cast<size_t>(q) * kBatchMaxWin + ww) * 8;
+                            PartList in;
+                            const uint4 hd = __ldcg(rec + kNNK);
+                            in.m = static_cast<int32_t>(hd.x);
+                            in.more = static_cast<int32_t>(hd.y);
+#pragma unroll
+                            for (int x = 0; x < kNNK; ++x) {
+                                const uint4 e = __ldcg(rec + x);
+                                in.pk[x] = x < in.m ? ((static_cast<uint64_t>(e.y) << 32) | e.x) : kPackInf;
+                                in.sl[x] = x < in.m ? static_cast<int32_t>(e.z) : -1;
+                                in.sz[x] = 0;
+                            }
+                            if (ww == lane)
+                                acc = in;
+                            else
+                                lane_merge2(acc, in);
+                        }
+                        warp_merge_lists(acc, out);
+                        if (lane == 0) st.part_cnt[q] = 0;
+                    }
+                }
+                if (folder) {
+                    if (lane < kNNK) {  // entry: {partner key, distance bits, partner slot, partner size}
+                        const uint64_t myp = sel4(out.pk, lane);
+                        const int32_t ps = sel4(out.sl, lane);
+                        const int32_t psz = lane < out.m ? __ldcg(st.lsize + ps) : 0;
+                        __stcg(st.nn + static_cast<int64_t>(r) * kNNK + lane,
+                               lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
+                                                         static_cast<uint32_t>(ps), static_cast<uint32_t>(psz))
+                                            : nn_none());
+                    } else if (lane == kNNK) {
+                        __stcg(st.nn_more + r, out.more ? static_cast<int32_t>(kMoreBit) : 0);
+                    }
+                }
+        };
         // ================= P1: row rescans =================
         const int32_t Q = __ldcg(st.counters + sl * 4 + CN_DRY);
         n_rescans += Q;
@@ -375,115 +490,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         for (int32_t base = 0; !row_per_block && base < Q; base += kBatchMaxDry) {
             const int32_t rows = min(Q - base, kBatchMaxDry);
             const int64_t units = static_cast<int64_t>(rows) * nwin;
-            for (int64_t u = gw; u < units; u += GW) {
-                // windows of one row go to warps of different blocks: q = u % rows
-                const int32_t w = static_cast<int32_t>(u / rows), q = static_cast<int32_t>(u - static_cast<int64_t>(w) * rows);
-                const int2 rq = __ldcg(st.dryq + base + q);
-                const int32_t r = rq.x;
-                const uint32_t ukr = static_cast<uint32_t>(rq.y);
-                const float* rowp = dm + static_cast<int64_t>(r - r_lo) * ld;
-                const int32_t sw0 = min(n4, w * win), sw1 = min(n4, sw0 + win);
-                ScanCand c;
-                scan_init(c);
-                constexpr int kU = 8;  // 16-byte loads of the row and of the keys in flight per lane
-                for (int32_t b0 = sw0; b0 < sw1; b0 += 128 * kU) {
-                    float4 vv[kU];
-                    int4 kq[kU];
-#pragma unroll
-                    for (int x = 0; x < kU; ++x) {
-                        const int32_t u0 = b0 + (x * 32 + lane) * 4;
-                        vv[x] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-                        kq[x] = make_int4(-1, -1, -1, -1);
-                        if (u0 < sw1) {
-                            vv[x] = __ldcg(reinterpret_cast<const float4*>(rowp + u0));
-                            kq[x] = __ldcg(reinterpret_cast<const int4*>(st.gkey + u0));
-                        }
-                    }
-#pragma unroll
-                    for (int x = 0; x < kU; ++x) {
-                        const int32_t u0 = b0 + (x * 32 + lane) * 4;
-                        const uint32_t vs4[4] = {__float_as_uint(vv[x].x), __float_as_uint(vv[x].y), __float_as_uint(vv[x].z),
-                                                 __float_as_uint(vv[x].w)};
-                        const uint32_t ks4[4] = {static_cast<uint32_t>(kq[x].x), static_cast<uint32_t>(kq[x].y),
-                                                 static_cast<uint32_t>(kq[x].z), static_cast<uint32_t>(kq[x].w)};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)  // retired slots and padding hold key -1 == 0xFFFFFFFF: never below the row's key
-                            if (ks4[e] < ukr && vs4[e] < kMaxFloatBits)
-                                scan_insert(c, (static_cast<uint64_t>(vs4[e]) << 32) | ks4[e], u0 + e);
-                    }
-                }
-                PartList out;
-                bool more = false;
-                out.m = warp_select_scan(c, out.pk, out.sl, more);
-                out.more = more ? 1 : 0;
-#pragma unroll
-                for (int x = 0; x < kNNK; ++x) out.sz[x] = 0;
-                bool folder = nwin == 1;
-                if (nwin > 1) {
-                    uint4* prec = st.partials + (static_cast<size_t>(q) * kBatchMaxWin + w) * 8;
-                    if (lane < kNNK) {
-                        const uint64_t myp = sel4(out.pk, lane);
-                        __stcg(prec + lane, lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
-                                                                      static_cast<uint32_t>(sel4(out.sl, lane)), 0u)
-                                                         : nn_none());
-                    } else if (lane == kNNK) {
-                        __stcg(prec + kNNK, make_uint4(static_cast<uint32_t>(out.m), static_cast<uint32_t>(out.more), 0u, 0u));
-                    }
-                    __syncwarp();
-                    int old = 0;
-                    if (lane == 0) {
-                        __threadfence();
-                        old = atomicAdd(st.part_cnt + q, 1);
-                        __threadfence();
-                    }
-                    old = __shfl_sync(0xffffffffu, old, 0);
-                    folder = old == nwin - 1;
-                    if (folder) {  // last window of the row: fold the nwin partial lists (up to four per lane)
-                        PartList acc;
-                        acc.m = 0;
-                        acc.more = 0;
-#pragma unroll
-                        for (int x = 0; x < kNNK; ++x) {
-                            acc.pk[x] = kPackInf;
-                            acc.sl[x] = -1;
-                            acc.sz[x] = 0;
-                        }
-                        for (int32_t ww = lane; ww < nwin; ww += 32) {
-                            const uint4* rec = st.partials + (static_cast<size_t>(q) * kBatchMaxWin + ww) * 8;
-                            PartList in;
-                            const uint4 hd = __ldcg(rec + kNNK);
-                            in.m = static_cast<int32_t>(hd.x);
-                            in.more = static_cast<int32_t>(hd.y);
-#pragma unroll
-                            for (int x = 0; x < kNNK; ++x) {
-                                const uint4 e = __ldcg(rec + x);
-                                in.pk[x] = x < in.m ? ((static_cast<uint64_t>(e.y) << 32) | e.x) : kPackInf;
-                                in.sl[x] = x < in.m ? static_cast<int32_t>(e.z) : -1;
-                                in.sz[x] = 0;
-                            }
-                            if (ww == lane)
-                                acc = in;
-                            else
-                                lane_merge2(acc, in);
-                        }
-                        warp_merge_lists(acc, out);
-                        if (lane == 0) st.part_cnt[q] = 0;
-                    }
-                }
-                if (folder) {
-                    if (lane < kNNK) {  // entry: {partner key, distance bits, partner slot, partner size}
-                        const uint64_t myp = sel4(out.pk, lane);
-                        const int32_t ps = sel4(out.sl, lane);
-                        const int32_t psz = lane < out.m ? __ldcg(st.lsize + ps) : 0;
-                        __stcg(st.nn + static_cast<int64_t>(r) * kNNK + lane,
-                               lane < out.m ? make_uint4(pack_key(myp), static_cast<uint32_t>(myp >> 32),
-                                                         static_cast<uint32_t>(ps), static_cast<uint32_t>(psz))
-                                            : nn_none());
-                    } else if (lane == kNNK) {
-                        __stcg(st.nn_more + r, out.more ? static_cast<int32_t>(kMoreBit) : 0);
-                    }
-                }
-            }
+            for (int64_t u = gw; u < units; u += GW) scan_window_unit(base, rows, u, false);
             if (base + kBatchMaxDry < Q) grid_sync(st.bar, phase, G);  // the partial buffers are reused
         }
         grid_sync(st.bar, phase, G, timed ? &c_ph[5] : nullptr);
