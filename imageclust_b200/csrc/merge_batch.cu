@@ -58,8 +58,6 @@ constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead o
 // counters[slot][*]
 enum { CN_DRY = 0, CN_CAND = 1 };
 
-IC_DEVINL uint64_t ldcg_u64(const uint64_t* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
-
 // grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
 IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* wait_acc = nullptr) {
     __syncthreads();
