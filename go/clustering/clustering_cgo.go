@@ -132,6 +132,36 @@ func PerformClusteringWithConstraints(embeddings [][]float32, productReferenceID
 	if st.n_near_ties > 0 {
 		log.Printf("%d of %d merges had a runner-up within %g relative (near-ties)", int(st.n_near_ties), int(st.n_merges), float32(st.near_tie_tol))
 	}
+	// what workflow.go:89-97 cannot see in the map: items whose cluster stayed below minSize are absent (clustering.go:268-271)
+	if kept := int(offsets[int(k)]); kept < n {
+		log.Printf("%d of %d items are in no cluster (their clusters stayed below minSize %d)", n-kept, n, minSize)
+	}
 	log.Printf("Clustering successful. Formed %d valid clusters.", len(clusterMap))
 	return clusterMap, true
+}
+
+// Linkage returns the merge trace of the LAST clustering as a dendrogram in the layout of
+// scipy.cluster.hierarchy.linkage: rows {keyLo, keyHi, sqrt(2*dist), size}; keys are item indices or n + t for the
+// cluster made by merge t.  The reference has no persistent form of its result (workflow.go:99 keeps the map only);
+// a caller that stores the linkage can re-cut it at other minSize / maxSize without clustering again.
+func Linkage(n int) ([][4]float64, bool) {
+	c, err := engine()
+	if err != nil || n <= 0 {
+		return nil, false
+	}
+	z := make([]C.double, 4*n)
+	var rows C.int64_t
+	ctxMu.Lock()
+	rc := C.ic_get_linkage(c, &z[0], C.int64_t(n), &rows)
+	ctxMu.Unlock()
+	if rc != C.IC_OK {
+		return nil, false
+	}
+	out := make([][4]float64, int(rows))
+	for t := range out {
+		for j := 0; j < 4; j++ {
+			out[t][j] = float64(z[4*t+j])
+		}
+	}
+	return out, true
 }
