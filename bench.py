@@ -373,6 +373,21 @@ def main():
                              "ms": kern.get("nn_sweep_ms"), "note": "algorithmic bytes 4 per pair (lower triangle read once)"},
             },
         }
+        # the SAME bounded sample the reference arm times per step (--impl reference: N = --ref-n items of this config,
+        # seed 20241), through the reference-facing call with host buffers: the like-for-like number beside that arm
+        if world == 1 and not sharded:
+            n_s = min(n, args.ref_n)
+            mn_s, mx_s = (mn, mx) if n_s >= 4 * mx else (5, 20)
+            xs = eng.pinned_empty((n_s, d))
+            synth.gaussian_mixture(n_s, d, mn_s, mx_s, seed=20241, out=xs)
+            eng.cluster(xs, mn_s, mx_s)
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                rs = eng.cluster(xs, mn_s, mx_s)
+            torch.cuda.synchronize()
+            line["reference_sample"] = {"workload": f"N={n_s} x {d}, min/max {mn_s}/{mx_s} (one step of --impl reference)",
+                                        "value": (time.perf_counter() - t0) / reps, "unit": UNIT, "merges": rs.stats["n_merges"]}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg(d)
         else:
