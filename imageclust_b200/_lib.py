@@ -51,6 +51,9 @@ class Stats(C.Structure):
         ("ms_loop", C.c_float), ("ms_d2h", C.c_float), ("ms_host", C.c_float), ("ms_total", C.c_float),
         ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("matrix_bytes", C.c_int64), ("n_iterations", C.c_int32), ("loop_mode", C.c_int32),
+        ("exact", C.c_int32), ("n_horizon_raises", C.c_int32), ("n_exact", C.c_int64),
+        ("n_filter_viol", C.c_int32), ("n_order_viol", C.c_int32), ("n_cut", C.c_int32), ("filter_max_err", C.c_float),
+        ("horizon", C.c_double), ("ms_refine", C.c_float), ("pad0", C.c_float),
     ]
 
     def as_dict(self):

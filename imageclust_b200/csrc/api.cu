@@ -93,7 +93,23 @@ struct ic_ctx {
     // loop state mirrored on the host
     int64_t n_target = 0;
     int32_t n_live = 0, n_merges = 0, exhausted = 0;
-    int32_t h_ctl[16] = {0};
+    int32_t h_ctl[kCtlWords] = {0};
+    // reference arithmetic: centroids, horizon, queues of refine.cu and of the loop's exact phase
+    int exact_opt = 1;            // option "exact": 0 off (Lance-Williams values only), 1 auto, 2 on even for ic_set_matrix
+    bool exact_on = false;        // this clustering runs with the horizon
+    bool dm_is_reference = false; // the initial matrix already holds the reference's values (gram_mode 1)
+    double hz_factor = 1.25, eps_filter = 3e-5, delta_cut = 8e-6, abs_slack_opt = -1.0;
+    double horizon = -1.0, abs_slack = 0.0, hz_factor_cur = 1.25;
+    int32_t merges_at_raise = 0;
+    float* cen = nullptr;
+    int64_t ldc = 0;
+    int4* xq = nullptr;
+    int32_t xq_cap = 0;
+    int2* rq = nullptr;
+    int32_t rq_cap = 0;
+    int32_t* rq_cnt = nullptr;
+    double ms_refine = 0.0;
+    int32_t n_raises = 0;
     std::vector<int32_t> h_key_hi, h_key_lo, h_size;
     std::vector<float> h_dist, h_gap;
     bool trace_on_host = false;
@@ -160,6 +176,10 @@ void release_problem(ic_ctx* c) {
     dev_free(c->partials);
     dev_free(c->rankbox);
     dev_free(c->batch_scratch);
+    dev_free(c->cen);
+    dev_free(c->xq);
+    dev_free(c->rq);
+    dev_free(c->rq_cnt);
     dev_free(c->prof);
     dev_free(c->ctl);
     c->loaded = c->have_dm = c->have_nn = c->prepped = c->prepped_i8 = false;
@@ -274,7 +294,7 @@ int make_operand_map_i8(ic_ctx* ctx, CUtensorMap* map, int8_t* base, int64_t row
 
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 && ctx->loop_blocks == ctx->loop_blocks_alloc &&
-        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
+        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && (ctx->exact_opt != 0) == (ctx->cen != nullptr) && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
         ctx->shard_rank == ctx->shard_rank_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
         ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = ctx->prepped_i8 = false;
@@ -304,7 +324,8 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     size_t free_b = 0, total_b = 0;
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const double other = 4.0 * n * d + (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
-                         (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20);
+                         (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20) +
+                         (ctx->exact_opt ? 4.0 * n * round_up(d, 4) + 16.0 * std::max<int64_t>(1 << 20, 16 * n) + 8.0 * (16 << 20) : 0.0);
     if ((P == 1 || ctx->shard_world > 1) && ctx->loop_mode == 1 && n > 0) {  // batched loop: one GPU, or real shards
         int grid = 0;
         IC_CUDA(merge_batch_grid(ctx->num_sms, n, &grid));
@@ -332,7 +353,16 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->tr_size, sizeof(int32_t) * nn1 * NL));
     IC_CUDA(cudaMalloc(&ctx->tr_dist, sizeof(float) * nn1 * NL));
     IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1 * NL));
-    IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * 16 * NL));
+    IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * kCtlWords * NL));
+    ctx->ldc = round_up(d > 0 ? d : 1, 4);
+    if (ctx->exact_opt) {
+        ctx->xq_cap = static_cast<int32_t>(std::max<int64_t>(1 << 20, 16 * static_cast<int64_t>(nn1)));
+        ctx->rq_cap = static_cast<int32_t>(std::min<int64_t>(16 << 20, std::max<int64_t>(1024, static_cast<int64_t>(nn1) * static_cast<int64_t>(nn1) / 2)));
+        IC_CUDA(cudaMalloc(&ctx->cen, sizeof(float) * nn1 * static_cast<size_t>(ctx->ldc)));
+        IC_CUDA(cudaMalloc(&ctx->xq, sizeof(int4) * static_cast<size_t>(ctx->xq_cap)));
+        IC_CUDA(cudaMalloc(&ctx->rq, sizeof(int2) * static_cast<size_t>(ctx->rq_cap)));
+        IC_CUDA(cudaMalloc(&ctx->rq_cnt, sizeof(int32_t) * 4));
+    }
     IC_CUDA(cudaMalloc(&ctx->prof, sizeof(long long) * 256));
     // merge-loop launch geometry and mailboxes (zeroed once: tags carry the launch generation)
     IC_CUDA(merge_loop_grid(ctx->num_sms, n, P, NL, ctx->loop_blocks, ctx->loop_replica, &ctx->loop_grid));
@@ -504,6 +534,16 @@ int init_loop_state(ic_ctx* ctx) {
     const size_t n = static_cast<size_t>(ctx->n), n4 = (n + 3) / 4 * 4;
     IC_CUDA(launch_init_slots(ctx->ks, ctx->gkey, ctx->n, ctx->stream));
     ctx->stats.kernel_launches += 1;
+    if (ctx->exact_on && ctx->cen) {  // singleton centroids (clustering.go:19-20)
+        IC_CUDA(launch_init_centroids(ctx->x, ctx->n, ctx->d, ctx->d, ctx->cen, ctx->ldc, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    ctx->horizon = -1.0;
+    ctx->abs_slack = ctx->abs_slack_opt >= 0.0 ? ctx->abs_slack_opt : 0.0;
+    ctx->hz_factor_cur = ctx->hz_factor;
+    ctx->merges_at_raise = 0;
+    ctx->n_raises = 0;
+    ctx->ms_refine = 0.0;
     ctx->n_live = static_cast<int32_t>(ctx->n);
     ctx->loop_mode_used = -1;
     ctx->n_merges = 0;
@@ -517,7 +557,7 @@ int init_loop_state(ic_ctx* ctx) {
             IC_CUDA(cudaMemcpyAsync(ctx->gkey + v * n4, ctx->gkey, sizeof(int32_t) * n4, cudaMemcpyDeviceToDevice,
                                     ctx->stream));
         }
-        IC_CUDA(cudaMemcpyAsync(ctx->ctl + 16 * v, ctx->h_ctl, sizeof(ctx->h_ctl), cudaMemcpyHostToDevice, ctx->stream));
+        IC_CUDA(cudaMemcpyAsync(ctx->ctl + kCtlWords * v, ctx->h_ctl, sizeof(ctx->h_ctl), cudaMemcpyHostToDevice, ctx->stream));
     }
     return IC_OK;
 }
@@ -540,6 +580,12 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
     p.scan_every = ctx->scan_every;
     p.debug = ctx->loop_debug;
+    p.exact = (ctx->exact_on && use_batch(ctx) && ctx->cen) ? 1 : 0;
+    p.eps_filter = static_cast<float>(ctx->eps_filter);
+    p.abs_slack = static_cast<float>(ctx->abs_slack);
+    p.horizon = ctx->horizon;
+    p.safe = ctx->horizon < 0.0 ? -1.0 : (ctx->horizon - ctx->abs_slack) / (1.0 + 2.0 * ctx->eps_filter);
+    p.delta_cut = ctx->delta_cut;
     {   // the batched loop stops mirroring distances into the older clusters' rows: one loop per clustering
         const int mode = use_batch(ctx) ? 1 : 0;
         if (ctx->loop_mode_used >= 0 && ctx->loop_mode_used != mode && ctx->n_merges > 0)
@@ -585,6 +631,10 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         bs.part_cnt = reinterpret_cast<int32_t*>(sc + ctx->batch_off[5]);
         bs.bar = reinterpret_cast<uint32_t*>(sc + ctx->batch_off[6]);
         bs.lsize = reinterpret_cast<int32_t*>(sc + ctx->batch_off[7]);
+        bs.cen = ctx->cen;
+        bs.ldc = ctx->ldc;
+        bs.xq = ctx->xq;
+        bs.xq_cap = ctx->xq_cap;
         // scratch of a launch: counters and the barrier at zero
         IC_CUDA(cudaMemsetAsync(bs.counters, 0, 3 * 4 * 4, ctx->stream));
         IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
@@ -620,7 +670,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
                                 ctx->stream));
     }
     for (int v = 0; v < n_local(ctx); ++v)
-        IC_CUDA(cudaMemsetAsync(ctx->ctl + 16 * v + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
+        IC_CUDA(cudaMemsetAsync(ctx->ctl + kCtlWords * v + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
     if (ctx->shard_world > 1) {
         // all ranks have left their previous launch (and cleared what they had to) before anyone talks
         ++ctx->barrier_seq;
@@ -634,6 +684,95 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     if (st.prof)
         IC_CUDA(cudaMemcpyAsync(ctx->h_prof, st.prof, sizeof(ctx->h_prof), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->trace_on_host = false;
+    return IC_OK;
+}
+
+// Pairs of the resident rows whose stored value lies in (lo, hi] get the reference's own value (refine.cu).  Rows are
+// swept in one go; if the queue overflows, in row chunks sized from the count.
+int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
+    const double t0 = now_ms();
+    RefineArgs a{};
+    a.dm = ctx->dm;
+    a.ld = ctx->ld;
+    a.n_slots = static_cast<int32_t>(ctx->n);
+    a.r_lo = static_cast<int32_t>(row_begin(ctx));
+    a.r_hi = static_cast<int32_t>(row_end(ctx));
+    a.ks = ctx->ks;
+    a.gkey = ctx->gkey;
+    a.cen = ctx->cen;
+    a.ldc = ctx->ldc;
+    a.lo = lo;
+    a.hi = hi;
+    a.min_row_key = min_row_key;
+    a.lower_only = ctx->n_merges == 0 ? 1 : 0;
+    a.q = ctx->rq;
+    a.cap = ctx->rq_cap;
+    a.cnt = ctx->rq_cnt;
+    a.ctl = ctx->ctl;
+    a.nn_more = ctx->nn_more;
+    a.eps_filter = static_cast<float>(ctx->eps_filter);
+    a.abs_slack = static_cast<float>(ctx->abs_slack);
+    int64_t r = a.r_lo, step = std::max<int64_t>(1, a.r_hi - a.r_lo);
+    while (r < a.r_hi) {
+        a.row0 = static_cast<int32_t>(r);
+        a.row1 = static_cast<int32_t>(std::min<int64_t>(a.r_hi, r + step));
+        int32_t cnt = 0;
+        IC_CUDA(cudaMemsetAsync(ctx->rq_cnt, 0, sizeof(int32_t) * 4, ctx->stream));
+        IC_CUDA(launch_refine_collect(a, ctx->stream));
+        IC_CUDA(cudaMemcpyAsync(&cnt, ctx->rq_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        if (cnt > a.cap) {
+            if (step == 1) return fail(ctx, IC_ERR_INTERNAL, "refine: one row holds more pairs than the queue");
+            step = std::max<int64_t>(1, step * a.cap / cnt / 2);
+            continue;
+        }
+        if (cnt > 0) {
+            IC_CUDA(launch_refine_eval(a, ctx->num_sms, ctx->stream));
+            ctx->stats.kernel_launches += 1;
+        }
+        r = a.row1;
+    }
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ms_refine += now_ms() - t0;
+    return IC_OK;
+}
+
+// STOP_HORIZON: the smallest candidate H is above the range in which stored values are guaranteed to be the reference's.
+// New horizon = factor * (H (1 + 2 eps) + 2 slack); the band between the old and the new one is re-evaluated.  The factor
+// escalates while a horizon buys fewer than 64 merges (isolated tiny distances below the bulk).
+int raise_horizon(ic_ctx* ctx) {
+    float h = 0.0f;
+    const uint32_t hb = static_cast<uint32_t>(ctx->h_ctl[CTL_NEXT_DIST]);
+    std::memcpy(&h, &hb, 4);
+    const bool first = ctx->horizon < 0.0;
+    if (first && ctx->abs_slack_opt < 0.0 && !ctx->dm_is_reference && ctx->norms && ctx->gram_mode_used != IC_GRAM_EXACT_FP32 &&
+        ctx->gram_mode_used >= 0) {
+        // absolute error of a tensor-core Gram value: 2^-20 of the largest centred squared norm
+        std::vector<double> hn(static_cast<size_t>(ctx->n));
+        IC_CUDA(cudaMemcpyAsync(hn.data(), ctx->norms, sizeof(double) * hn.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        IC_CUDA(cudaStreamSynchronize(ctx->stream));
+        double mx = 0.0;
+        for (double v : hn) mx = std::max(mx, v);
+        ctx->abs_slack = mx * (1.0 / 1048576.0);
+    }
+    if (!first && ctx->n_merges - ctx->merges_at_raise < 64)
+        ctx->hz_factor_cur = std::min(ctx->hz_factor_cur * ctx->hz_factor_cur, 1e6);
+    else
+        ctx->hz_factor_cur = ctx->hz_factor;
+    const double base = std::max(static_cast<double>(h), ctx->horizon);
+    const double hi = ctx->hz_factor_cur * (base * (1.0 + 2.0 * ctx->eps_filter) + 2.0 * ctx->abs_slack);
+    if (!(first && ctx->dm_is_reference)) {
+        const int rc = refine_band(ctx, first ? -1.0 : ctx->horizon, hi, 0);
+        if (rc != IC_OK) return rc;
+        if (ctx->n_merges == 0) {  // keys are still the slot indices: the first sweep kernel rebuilds every partner list
+            IC_CUDA(launch_nn_sweep(ctx->dm, row_begin(ctx), row_end(ctx), ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
+            ctx->stats.kernel_launches += 1;
+        }
+    }
+    ctx->horizon = hi;
+    ctx->merges_at_raise = ctx->n_merges;
+    ++ctx->n_raises;
     return IC_OK;
 }
 
@@ -654,7 +793,17 @@ int sync_loop_result(ic_ctx* ctx) {
         ctx->n_live = ctx->h_ctl[CTL_N_LIVE];
         ctx->n_merges = ctx->h_ctl[CTL_N_MERGES];
         ctx->exhausted = ctx->h_ctl[CTL_EXHAUSTED];
-        if (ctx->h_ctl[CTL_STOP] != STOP_EPOCHS) return IC_OK;
+        const int stop = ctx->h_ctl[CTL_STOP];
+        if (stop == STOP_HORIZON) {  // the minimum reached the horizon: raise it, re-evaluate the band (refine.cu)
+            const int rc = raise_horizon(ctx);
+            if (rc != IC_OK) return rc;
+        } else if (stop == STOP_XQ) {  // the exact-evaluation queue of the last iteration overflowed: redo its rows
+            int rc = refine_band(ctx, -1.0, ctx->horizon, ctx->h_ctl[CTL_XQ_FIRST_KEY]);
+            if (rc != IC_OK) return rc;
+            IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_XQ_OVERFLOW, 0, sizeof(int32_t), ctx->stream));
+        } else if (stop != STOP_EPOCHS) {
+            return IC_OK;
+        }
         int64_t left = ctx->loop_max_merges;
         if (left >= 0) left -= ctx->n_merges - ctx->loop_merges_at_start;
         const int rc = enqueue_loop(ctx, ctx->loop_n_target, ctx->loop_max_size, left < 0 ? -1 : left);
@@ -791,6 +940,8 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
     ctx->have_nn = false;
     ctx->gram_mode_used = mode;
     ctx->stats.gram_mode = mode;
+    ctx->exact_on = ctx->exact_opt != 0 && ctx->cen != nullptr;
+    ctx->dm_is_reference = mode == IC_GRAM_EXACT_FP32 || max_size < 2;
     return IC_OK;
 }
 
@@ -814,6 +965,18 @@ void fill_stats(ic_ctx* ctx) {
     s.n_near_ties = ctx->h_ctl[CTL_NEAR_TIES];
     s.n_rescans = ctx->h_ctl[CTL_RESCANS];
     s.loop_mode = ctx->loop_mode_used > 0 ? 1 : 0;
+    s.exact = (ctx->exact_on && use_batch(ctx) && ctx->cen) ? 1 : 0;
+    s.n_horizon_raises = ctx->n_raises;
+    s.n_exact = ctx->h_ctl[CTL_N_EXACT];
+    s.n_filter_viol = ctx->h_ctl[CTL_FILTER_VIOL];
+    s.n_order_viol = ctx->h_ctl[CTL_ORDER_VIOL];
+    s.n_cut = ctx->h_ctl[CTL_N_CUT];
+    {
+        const uint32_t eb = static_cast<uint32_t>(ctx->h_ctl[CTL_FILTER_MAXERR]);
+        std::memcpy(&s.filter_max_err, &eb, 4);
+    }
+    s.horizon = ctx->horizon;
+    s.ms_refine = static_cast<float>(ctx->ms_refine);
     s.n_iterations = s.loop_mode ? ctx->h_ctl[CTL_ITERS] : ctx->n_merges + ctx->h_ctl[CTL_BUBBLES];
 }
 
@@ -832,9 +995,9 @@ int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offse
     if (rc != IC_OK) return rc;
     rc = run_loop(ctx, n_target, max_size, -1);
     if (rc != IC_OK) return rc;
-    IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
-    rc = sync_loop_result(ctx);
+    rc = sync_loop_result(ctx);  // (relaunches after a horizon raise: the loop's time includes the sweeps)
     if (rc != IC_OK) return rc;
+    IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     rc = fetch_trace(ctx);
     if (rc != IC_OK) return rc;
     IC_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
@@ -946,6 +1109,21 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         ctx->no_replica = value != 0.0;
     } else if (k == "loop_blocks") {
         ctx->loop_blocks = static_cast<int>(value);
+    } else if (k == "exact") {
+        const int m = static_cast<int>(value);
+        if (m < 0 || m > 2) return fail(ctx, IC_ERR_BAD_ARG, "exact must be 0, 1 or 2");
+        ctx->exact_opt = m;
+    } else if (k == "horizon_factor") {
+        if (!(value > 1.0)) return fail(ctx, IC_ERR_BAD_ARG, "horizon_factor must be > 1");
+        ctx->hz_factor = value;
+    } else if (k == "eps_filter") {
+        if (!(value >= 0.0 && value < 0.1)) return fail(ctx, IC_ERR_BAD_ARG, "eps_filter must be in [0, 0.1)");
+        ctx->eps_filter = value;
+    } else if (k == "delta_cut") {
+        if (!(value >= 0.0 && value < 0.1)) return fail(ctx, IC_ERR_BAD_ARG, "delta_cut must be in [0, 0.1)");
+        ctx->delta_cut = value;
+    } else if (k == "abs_slack") {
+        ctx->abs_slack_opt = value;
     } else if (k == "profile_loop") {
         ctx->profile_loop = value != 0.0;
     } else if (k == "gram_terms") {
@@ -1060,6 +1238,10 @@ int ic_set_matrix(ic_ctx* ctx, const float* m_host, int64_t ld) {
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_dm = true;
     ctx->have_nn = false;
+    // a supplied matrix need not be the distances of the resident X: Lance-Williams values only, unless "exact" = 2
+    ctx->exact_on = ctx->exact_opt == 2 && ctx->cen != nullptr;
+    ctx->dm_is_reference = false;
+    ctx->gram_mode_used = -1;
     return IC_OK;
 }
 
@@ -1100,9 +1282,10 @@ int ic_merge_loop(ic_ctx* ctx, int64_t min_size, int64_t max_size, int64_t max_m
     IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
     rc = run_loop(ctx, n_target, max_size, max_merges);
     if (rc != IC_OK) return rc;
-    IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     rc = sync_loop_result(ctx);
     if (rc != IC_OK) return rc;
+    IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    IC_CUDA(cudaEventSynchronize(ctx->ev[6]));
     ctx->stats.ms_loop = ev_ms(ctx->ev[5], ctx->ev[6]);
     fill_stats(ctx);
     return IC_OK;

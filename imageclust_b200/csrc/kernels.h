@@ -126,12 +126,32 @@ struct LoopParams {
     float near_tie_tol;
     int32_t scan_every;  // rescan requests are published every scan_every-th iteration (batched row scans)
     int32_t debug;       // experiments only (currently unused by the kernels)
+    // Reference arithmetic (batched loop only).  exact != 0: every stored pair <= horizon holds the reference's own value
+    // (WardDistance of the two fp32 centroids, clustering.go:136-145); pairs above it are Lance-Williams values, known to
+    // within eps_filter.  Merges are only taken among values <= safe = horizon / (1 + 2 eps_filter); when the minimum
+    // gets there the kernel stops (STOP_HORIZON) and the host raises the horizon.  Members of a batch after the first
+    // must be below T (1 - delta_cut): fp32 centroid distances are reducible only up to rounding.
+    int32_t exact;
+    float eps_filter;
+    float abs_slack;     // absolute error a never re-evaluated tensor-core Gram value may carry (monitor only; safe includes it)
+    double horizon, safe, delta_cut;
 };
 // ctl[] indices.  N_LIVE and N_MERGES are read at launch (resume) and written at exit.
+constexpr int kCtlWords = 32;
 enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_NEAR_TIES = 4, CTL_RESCANS = 5,
-       CTL_DONE = 6, CTL_BUBBLES = 7, CTL_NEXT_HI = 8, CTL_NEXT_LO = 9, CTL_NEXT_DIST = 10, CTL_STOP = 11 };
+       CTL_DONE = 6, CTL_BUBBLES = 7, CTL_NEXT_HI = 8, CTL_NEXT_LO = 9, CTL_NEXT_DIST = 10, CTL_STOP = 11,
+       // (12 = CTL_ITERS, below) reference-arithmetic bookkeeping of the batched loop and of refine.cu:
+       CTL_XQ_OVERFLOW = 13,   // the exact-evaluation queue of an iteration overflowed (the host re-evaluates the new rows)
+       CTL_FILTER_VIOL = 14,   // re-evaluated pairs whose stored value was off by more than eps_filter (must stay 0)
+       CTL_FILTER_MAXERR = 15, // largest |stored - reference| / reference seen (float bits)
+       CTL_N_EXACT = 16,       // pairs evaluated with the reference's arithmetic
+       CTL_ORDER_VIOL = 17,    // pairs created inside a batch that came out below a later member of it (must stay 0)
+       CTL_N_CUT = 18,         // batches shortened by delta_cut
+       CTL_XQ_FIRST_KEY = 19   // key of the first cluster created by the iteration whose queue overflowed
+};
 // CTL_STOP values
-enum { STOP_TARGET = 1, STOP_EXHAUSTED = 2, STOP_MAX_MERGES = 3, STOP_EPOCHS = 4, STOP_ERROR = 5 };
+enum { STOP_TARGET = 1, STOP_EXHAUSTED = 2, STOP_MAX_MERGES = 3, STOP_EPOCHS = 4, STOP_ERROR = 5, STOP_HORIZON = 6,
+       STOP_XQ = 7 };
 constexpr int kLoopThreads = 512;
 // C: rows (slots) per rank, ceil(n / P) rounded up to a multiple of 4
 int64_t merge_loop_rows_per_rank(int64_t n, int n_ranks);
@@ -200,11 +220,45 @@ struct BatchState {
     uint4* partials;    // [kBatchMaxDry][kBatchMaxWin][8] partial lists of the window scans
     int32_t* part_cnt;  // [kBatchMaxDry] windows done per row
     uint32_t* bar;      // grid barrier counter
+    // reference arithmetic (LoopParams::exact): fp32 centroid of every slot's cluster (replicated on every rank), and
+    // the queue of the pairs an iteration wrote at or below the horizon {index of the merge in the batch, column slot or
+    // 0x80000000 | index of an earlier merge of the batch (cross term)}
+    float* cen;         // [n x ldc], ldc = d rounded up to 4, zero padded
+    int64_t ldc;
+    int4* xq;           // [xq_cap] {merge, column | cross, Lance-Williams value bits, 0}
+    int32_t xq_cap;
 };
 size_t merge_batch_smem_bytes(int64_t n);
 int64_t merge_batch_windows(int64_t n);
 cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks);  // *blocks = 0: does not fit
 cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);  // n_ranks > 1: sharded
+// ---- reference arithmetic for selected pairs (refine.cu) ---------------------------------------------------------
+// cen[s] = x[s] (zero padded to ldc floats per row): the singleton centroids (clustering.go:19-20)
+cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, cudaStream_t s);
+struct RefineArgs {
+    float* dm;            // resident rows [r_lo, r_hi) x ld
+    int64_t ld;
+    int32_t n_slots, r_lo, r_hi;
+    const SlotKS* ks;     // {key, size} per slot
+    const int32_t* gkey;  // [n4] keys, padding -1
+    const float* cen;
+    int64_t ldc;
+    double lo, hi;        // band: lo < stored value <= hi
+    int32_t min_row_key;  // only rows whose cluster key is >= this
+    int32_t lower_only;   // keys are still the slot indices: row r only has partners in the columns u < r
+    int32_t row0, row1;   // rows collected by this launch (within [r_lo, r_hi))
+    int2* q;              // [cap] collected pairs {row slot, column slot}
+    int32_t cap;
+    int32_t* cnt;         // [2]: pairs collected (may exceed cap: overflow), unused
+    int32_t* ctl;         // monitors (CTL_FILTER_*, CTL_N_EXACT)
+    int32_t* nn_more;     // rows whose values changed get their partner list queued for a rescan (dry bit)
+    float eps_filter, abs_slack;
+};
+// pairs (r, u), key_u < key_r, both live, whose stored value lies in the band -> q
+cudaError_t launch_refine_collect(const RefineArgs& a, cudaStream_t s);
+// dm[r][u] = WardDistance(centroid r, centroid u) for the first min(*cnt, cap) collected pairs, one warp per pair
+cudaError_t launch_refine_eval(const RefineArgs& a, int num_sms, cudaStream_t s);
+
 // device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
 cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);
 

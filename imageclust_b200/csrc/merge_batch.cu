@@ -37,6 +37,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact.cuh"
 #include "kernels.h"
 #include "loop_common.cuh"
 
@@ -56,7 +57,22 @@ constexpr int kRcpTab = 1024;
 constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead of the update pass
 
 // counters[slot][*]
-enum { CN_DRY = 0, CN_CAND = 1 };
+enum { CN_DRY = 0, CN_CAND = 1, CN_XQ = 2 };
+
+// Every lane reserves `cnt` consecutive entries of a global queue with one atomic per warp; returns the lane's first index.
+IC_DEVINL int32_t warp_reserve(int32_t* counter, int cnt, int lane) {
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    int32_t base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - cnt;
+}
 
 // grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
 IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* wait_acc = nullptr) {
@@ -104,7 +120,7 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
                     uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXSummary + (static_cast<size_t>(st.rank) * 3 + publish_slot) * 32);
                     __stcg(dst, make_uint4(static_cast<uint32_t>(sstop), static_cast<uint32_t>(sstop >> 32),
                                            static_cast<uint32_t>(shead), static_cast<uint32_t>(shead >> 32)));
-                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(scnt), 0u, 0u, 0u));
+                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(scnt), static_cast<uint32_t>(__ldcg(st.ctl + CTL_XQ_OVERFLOW)), 0u, 0u));
                 }
             }
             // block 0's own pushes (the summary) must be performed before the flags; the other blocks fenced theirs
@@ -195,7 +211,7 @@ IC_DEVINL RowHead row_head(uint4 e0, uint4 e1, uint32_t more_bits, uint32_t key_
 size_t merge_batch_smem_bytes(int64_t n) {
     const size_t n4 = static_cast<size_t>((n + 3) / 4 * 4);
     const size_t bitmap = ((n4 + 31) / 32 + 3) / 4 * 4 * sizeof(uint32_t);
-    return bitmap;
+    return bitmap + sizeof(float) * kBW * kExChunk;  // + the warps' chunk buffers of the exact phase
 }
 static int64_t batch_window_cols(int64_t n) {  // at most kBatchMaxWin windows per row: <= 4 partial lists per lane in the fold
     const int64_t n4 = (n + 3) / 4 * 4;
@@ -236,7 +252,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     __shared__ int32_t s_xcnt[kMaxRanks + 1];  // candidate pairs per rank (prefix sums)
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem);  // merged-slot bitmap of the current batch
+    float (*const s_ex)[kExChunk] = reinterpret_cast<float (*)[kExChunk]>(dyn_smem);  // exact phase: one chunk of squared differences per warp
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kBW * kExChunk);  // merged-slot bitmap of the current batch
     const int32_t n_words = (n4 + 31) >> 5;
 
     __shared__ uint64_t s_red[kBW];
@@ -252,6 +269,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     __shared__ int32_t s_psl[kBW][kNNK];
     __shared__ int2 s_pm[kBW];
     __shared__ double s_rcp[kRcpTab];  // 1.0 / size sum, correctly rounded (what lance_williams() computes inline)
+    const bool exact = prm.exact != 0;
+    const int d4 = static_cast<int>(st.ldc);
 
     uint32_t phase = 0;
     int32_t n_live = __ldcg(ctl + CTL_N_LIVE);
@@ -587,6 +606,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         }
         uint64_t tstop = kPackInf, H = kPackInf;
         int32_t n_pub;  // heads below their block's stopper minimum, all ranks
+        int over_local = 0;  // some rank's exact-evaluation queue overflowed in the previous iteration
         if (kMulti) {   // every rank's minima and candidate count, read from its exchange box
             if (tid < st.n_ranks) {  // summary of rank `tid`, pushed into this rank's box
                 const uint4* sm = reinterpret_cast<const uint4*>(xb + kBatchXSummary + (static_cast<size_t>(tid) * 3 + sl) * 32);
@@ -594,6 +614,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 tstop = (static_cast<uint64_t>(s0.y) << 32) | s0.x;
                 H = (static_cast<uint64_t>(s0.w) << 32) | s0.z;
                 s_xcnt[tid + 1] = min(static_cast<int32_t>(s1.x), kBatchXCand);
+                over_local = static_cast<int>(s1.y);
             }
             __syncthreads();
             if (tid == 0) {
@@ -604,6 +625,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             n_pub = s_xcnt[st.n_ranks];
         } else {
             n_pub = __ldcg(st.counters + sl * 4 + CN_CAND);
+            if (tid == 0) over_local = __ldcg(ctl + CTL_XQ_OVERFLOW);
             if (tid < static_cast<int>(G)) {
                 const uint4 h0 = __ldcg(st.hdr + tid);
                 tstop = (static_cast<uint64_t>(h0.y) << 32) | h0.x;
@@ -623,6 +645,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         }
         tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
+        const bool xq_over = __syncthreads_or(over_local) != 0;
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
         if (n_live <= prm.n_target)
             stop_reason = STOP_TARGET;
@@ -632,6 +655,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             stop_reason = STOP_MAX_MERGES;
         else if (it + 8u >= (1u << 22))
             stop_reason = STOP_EPOCHS;
+        else if (exact && xq_over)
+            stop_reason = STOP_XQ;  // the previous iteration could not queue all its pairs: the host re-evaluates its rows
+        else if (exact && static_cast<double>(pack_dist(H)) > prm.safe)
+            stop_reason = STOP_HORIZON;  // the minimum reached the horizon: the host raises it (refine.cu)
         if (stop_reason != 0) {
             if (blockIdx.x == 0) {  // what FindClosestClusters would return now
                 if (!pack_selectable(H)) {
@@ -716,9 +743,27 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             if (hit) conf = mine;
         }
         const uint64_t T = umin64(theta, block_min_u64(conf, s_red));
-        const int rank = (tid < n_cand && mine < T) ? n_less : -1;  // everything below an accepted pair is accepted
+        bool take = tid < n_cand && mine < T;
+        int was_cut = 0;
+        if (exact && take) {
+            // decisions only among values the horizon guarantees to be the reference's own; and because fp32 centroid
+            // distances are reducible only up to rounding, a pair after the first must stay clear of the stopper: every
+            // distance the earlier merges create is >= T (1 - rounding) (both predicates are thresholds on the distance, so
+            // the accepted pairs remain a prefix of the scan order)
+            const uint32_t tb = static_cast<uint32_t>(T >> 32);
+            const double dmine = static_cast<double>(pack_dist(mine));
+            const double dT = tb < kInfBits ? static_cast<double>(__uint_as_float(tb)) : static_cast<double>(INFINITY);
+            if (dmine > prm.safe) {
+                take = false;
+            } else if (n_less > 0 && prm.delta_cut > 0.0 && !(dmine <= dT * (1.0 - prm.delta_cut))) {
+                take = false;
+                was_cut = 1;
+            }
+        }
+        const int rank = take ? n_less : -1;  // everything below an accepted pair is accepted
         const int32_t m_all = block_sum_i32(rank >= 0 ? 1 : 0, s_redi);  // >= 1: the global minimum head is always among them
         const int32_t m = min(m_all, limit);                              // merges of this iteration
+        if (exact && blockIdx.x == 0 && __syncthreads_or(was_cut) != 0 && tid == 0) atomicAdd(ctl + CTL_N_CUT, 1);
         if (rank >= 0) {
             s_d[rank] = static_cast<uint32_t>(mine >> 32);
             if (rank < m) {
@@ -769,6 +814,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             if (tid == kBT - 1) {
                 st.counters[sl2 * 4 + CN_DRY] = 0;
                 st.counters[sl1 * 4 + CN_CAND] = 0;
+                st.counters[sl2 * 4 + CN_XQ] = 0;   // last read in the exact phase of the previous iteration
+                ctl[CTL_XQ_FIRST_KEY] = n + t;      // the clusters this iteration creates carry the keys n + t ...
                 if (kMulti) {  // this rank's exchange-box slot of the next iteration (last read two iterations ago)
                     xb_cnt[sl1] = 0;
                     xb_stop[sl1] = kPackInf;
@@ -834,11 +881,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     }
                     livem[x] |= bits << 4;
                 }
+                float outv[kI][4];
+                uint32_t hitm = 0u;  // elements written at or below the horizon: the exact phase owns them
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
-                    const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
                     const int32_t sizes[4] = {k01[x].y, k01[x].w, k23[x].y, k23[x].w};
-                    float out[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         // lance_williams_rcp() with the integer -> double conversions hoisted (sums of small integers are exact);
@@ -848,16 +895,38 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                         const double num = ((sad + skd) * static_cast<double>(da[x][e]) + (sbd + skd) * static_cast<double>(db[x][e])) - skd * dabd;
                         const double rcp = small_sizes ? s_rcp[min(max(den, 0), kRcpTab - 1)] : 1.0 / static_cast<double>(max(den, 1));
                         const float lw = canon_dist(static_cast<float>(num * rcp));
-                        out[e] = (((livem[x] >> e) & 1u) != 0u && den <= prm.max_size) ? lw : __uint_as_float(kInfBits);
+                        const bool keep = ((livem[x] >> e) & 1u) != 0u && den <= prm.max_size;
+                        outv[x][e] = keep ? lw : __uint_as_float(kInfBits);
+                        if (exact && keep && static_cast<double>(lw) <= prm.horizon) hitm |= 1u << (x * 4 + e);
                     }
-                    if (c0 >= c_hi) continue;
-                    const uint32_t bits = livem[x] >> 4;
-                    if (bits == 0u) {
-                        __stcg(reinterpret_cast<float4*>(row_b + c0), make_float4(out[0], out[1], out[2], out[3]));
-                    } else {  // columns of this batch's clusters belong to the cross-term pass
+                }
+                if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // queue {merge, column, Lance-Williams value}
+                    int32_t idx = warp_reserve(st.counters + sl * 4 + CN_XQ, __popc(hitm), lane);
+#pragma unroll
+                    for (int x = 0; x < kI; ++x)
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (((bits >> e) & 1u) == 0u) __stcg(row_b + c0 + e, out[e]);
+                            if ((hitm >> (x * 4 + e)) & 1u) {
+                                if (idx < st.xq_cap)
+                                    st.xq[idx] = make_int4(i, c_lo + ch * kUpdCols + x * 128 + lane * 4 + e,
+                                                           static_cast<int32_t>(__float_as_uint(outv[x][e])), 0);
+                                else
+                                    ctl[CTL_XQ_OVERFLOW] = 1;
+                                ++idx;
+                            }
+                }
+#pragma unroll
+                for (int x = 0; x < kI; ++x) {
+                    const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
+                    if (c0 >= c_hi) continue;
+                    // columns of this batch's clusters belong to the cross-term pass, queued pairs to the exact phase
+                    const uint32_t bits = (livem[x] >> 4) | ((hitm >> (x * 4)) & 0xFu);
+                    if (bits == 0u) {
+                        __stcg(reinterpret_cast<float4*>(row_b + c0), make_float4(outv[x][0], outv[x][1], outv[x][2], outv[x][3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (((bits >> e) & 1u) == 0u) __stcg(row_b + c0 + e, outv[x][e]);
                     }
                 }
             }
@@ -883,7 +952,16 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 // merge j seen from k = new_i (slot b_i, size si)
                 float val = __uint_as_float(kInfBits);
                 if (si + saj + sbj <= prm.max_size) val = lance_williams(saj, sbj, si, t1, t2, dj);
-                __stcg(row_of(bj) + bi, val);  // new_j carries the higher key
+                if (exact && static_cast<double>(val) <= prm.horizon) {  // (lanes diverge here: rare)
+                    const int32_t idx = atomicAdd(st.counters + sl * 4 + CN_XQ, 1);
+                    if (idx < st.xq_cap)
+                        st.xq[idx] = make_int4(j, static_cast<int32_t>(0x80000000u | static_cast<uint32_t>(i)),
+                                               static_cast<int32_t>(__float_as_uint(val)), 0);
+                    else
+                        ctl[CTL_XQ_OVERFLOW] = 1;
+                } else {
+                    __stcg(row_of(bj) + bi, val);  // new_j carries the higher key
+                }
             }
         }
         const long long tq2 = timed ? clock64() : 0;
@@ -940,10 +1018,61 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         n_live -= m;
         ++iters;
         const long long tq3 = timed ? clock64() : 0;
+        // ---- exact phase: the pairs this iteration wrote at or below the horizon get the reference's own value ----
+        // WardDistance(centroid k, centroid of the new cluster), clustering.go:83-86; the new centroid (clustering.go:39) is
+        // formed on the fly from the two stored ones, which are only overwritten after the barrier that ends this phase.
+        if (exact) {
+            grid_sync(st.bar, phase, G);  // gpu scope: every queue is local to its rank
+            const int32_t nx = min(__ldcg(st.counters + sl * 4 + CN_XQ), st.xq_cap);
+            const float d_last = __uint_as_float(s_d[m > 0 ? m - 1 : 0]);
+            int32_t my_exact = 0;
+            for (int32_t q = gw; q < nx; q += GW) {
+                const int4 ent = __ldcg(st.xq + q);
+                const int32_t j = ent.x;
+                const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
+                const ExSide A = ex_merged(st.cen + static_cast<int64_t>(aj) * st.ldc, saj, st.cen + static_cast<int64_t>(bj) * st.ldc, sbj);
+                ExSide B;
+                int32_t size_b, col;
+                if (ent.y < 0) {  // cross term: the other cluster is being created by this batch, too
+                    const int32_t i = ent.y & 0x7FFFFFFF;
+                    B = ex_merged(st.cen + static_cast<int64_t>(s_a[i]) * st.ldc, s_sa[i], st.cen + static_cast<int64_t>(s_b[i]) * st.ldc, s_sb[i]);
+                    size_b = s_sa[i] + s_sb[i];
+                    col = s_b[i];
+                } else {
+                    col = ent.y;
+                    B = ex_plain(st.cen + static_cast<int64_t>(col) * st.ldc);
+                    size_b = __ldcg(st.lsize + col);
+                }
+                const float dsq = warp_exact_dsq(A, B, d4, s_ex[warp]);
+                if (lane == 0) {
+                    const float w = ward_weight(saj + sbj, size_b, dsq);
+                    exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(ent.z)), w, prm.eps_filter, prm.abs_slack);
+                    if (j + 1 < m && w < d_last) atomicAdd(ctl + CTL_ORDER_VIOL, 1);  // would have preceded a later pair of the batch
+                    __stcg(row_of(bj) + col, w);
+                    if (kMulti && (bj < r_lo || bj >= r_hi)) wrote_remote = true;
+                    ++my_exact;
+                }
+            }
+            if (lane == 0 && my_exact > 0) atomicAdd(ctl + CTL_N_EXACT, my_exact);
+        }
         if (kMulti)
             grid_sync_ranks(st, phase, xcount, G, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
         else
             grid_sync(st.bar, phase, G);
+        if (exact) {  // centroids of the new clusters (clustering.go:36-40) replace those of their slots b; every rank keeps a replica
+            const int32_t nch = (d4 + 127) / 128;
+            for (int32_t u = gw; u < m * nch; u += GW) {
+                const int32_t j = u / nch, e = ((u - j * nch) * 32 + lane) * 4;
+                if (e < d4) {
+                    const float* pa = st.cen + static_cast<int64_t>(s_a[j]) * st.ldc + e;
+                    float* pb = st.cen + static_cast<int64_t>(s_b[j]) * st.ldc + e;
+                    const float4 ca = __ldcg(reinterpret_cast<const float4*>(pa)), cb = __ldcg(reinterpret_cast<const float4*>(pb));
+                    const float fa = static_cast<float>(s_sa[j]), fb = static_cast<float>(s_sb[j]), fs = static_cast<float>(s_sa[j] + s_sb[j]);
+                    __stcg(reinterpret_cast<float4*>(pb), make_float4(ex_merge1(fa, ca.x, fb, cb.x, fs), ex_merge1(fa, ca.y, fb, cb.y, fs),
+                                                                     ex_merge1(fa, ca.z, fb, cb.z, fs), ex_merge1(fa, ca.w, fb, cb.w, fs)));
+                }
+            }
+        }
         if (timed) {
             const long long tp4 = clock64();
             c_ph[0] += tp1 - tp0;

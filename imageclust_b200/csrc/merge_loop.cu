@@ -128,7 +128,7 @@ merge_loop_kernel(const __grid_constant__ LoopState st, const __grid_constant__ 
     // this rank's views
     SlotKS* const g_ks = st.ks + static_cast<size_t>(v) * n;
     int32_t* const g_key = st.gkey + static_cast<size_t>(v) * n4;
-    int32_t* const ctl = st.ctl + v * 16;
+    int32_t* const ctl = st.ctl + v * kCtlWords;
     // mailboxes: every writer pushes its record into a private line of every reader, so a polled
     // line has exactly one reader and one writer (148 blocks polling shared lines was 3x slower)
     uint4* const records = reinterpret_cast<uint4*>(static_cast<uint8_t*>(st.records) + v * st.records_stride);

@@ -74,6 +74,19 @@ typedef struct ic_stats {
     int64_t matrix_bytes;  /* bytes of the distance matrix resident in HBM */
     int32_t n_iterations;  /* iterations of the merge loop (batched loop: several merges each) */
     int32_t loop_mode;     /* 1: batched loop (merge_batch.cu), 0: one merge per iteration (merge_loop.cu) */
+    /* reference arithmetic (option "exact"): the loop keeps Lance-Williams values and re-evaluates every pair at or below
+     * a horizon as WardDistance of the two fp32 centroids, clustering.go:83-86,136-157 */
+    int32_t exact;            /* 1: the run used the horizon (merge sequence = the reference's arithmetic) */
+    int32_t n_horizon_raises; /* times the horizon was set / raised (each: one sweep of refine.cu) */
+    int64_t n_exact;          /* pairs evaluated with the reference's arithmetic */
+    int32_t n_filter_viol;    /* re-evaluated pairs whose stored value was off by more than eps_filter: must be 0, else the
+                                 horizon's guarantee does not hold and the sequence may differ from the reference's */
+    int32_t n_order_viol;     /* pairs created inside a batch that came out below a later pair of it: must be 0 */
+    int32_t n_cut;            /* iterations whose batch was shortened by delta_cut */
+    float filter_max_err;     /* largest relative error of a stored value seen at re-evaluation */
+    double horizon;           /* last horizon */
+    float ms_refine;          /* host wall time of the horizon sweeps (inside ms_loop) */
+    float pad0;
 } ic_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -69,6 +69,23 @@ int oracle_fast_cluster_ex(const float *x, int n_items, int d, int min_size, int
  * multi-threaded, full symmetric N x N, bit-identical to the literal path. */
 int oracle_initial_matrix(const float *x, int n_items, int d, int n_threads, float *out);
 
+/* CPU restatement of the DEVICE's merge-loop algorithm (ward_device.c): Lance-Williams values above a horizon, the
+ * reference's own centroid values below it, batches of consecutive merges.  Must reproduce oracle_fast_cluster(flags=0). */
+typedef struct {
+    long n_iterations;    /* batches */
+    long n_exact;         /* pairs evaluated with the reference's arithmetic (WardDistance of two centroids) */
+    long n_raises;        /* horizon raises */
+    long n_cut;           /* batches shortened by delta_cut */
+    long n_violations;    /* pairs created inside a batch that came out below a later member of it (must be 0) */
+    double max_filter_err; /* largest |stored - reference| / reference seen when a pair was re-evaluated */
+    double horizon;
+} oracle_device_stats;
+
+int oracle_device_cluster(const float *x, int n_items, int d, int min_size, int max_size, const float *init_matrix,
+                          double horizon_factor, double eps_filter, double delta_cut, int max_batch, int n_threads,
+                          int *offsets, int *members, int *n_out, oracle_trace *tr, oracle_stats *st,
+                          oracle_device_stats *ds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,11 @@ class _Stats(C.Structure):
                 ("exhausted", C.c_int), ("n_final", C.c_int), ("n_out", C.c_int)]
 
 
+class _DeviceStats(C.Structure):
+    _fields_ = [("n_iterations", C.c_long), ("n_exact", C.c_long), ("n_raises", C.c_long), ("n_cut", C.c_long),
+                ("n_violations", C.c_long), ("max_filter_err", C.c_double), ("horizon", C.c_double)]
+
+
 class _Trace(C.Structure):
     _fields_ = [("key_hi", C.POINTER(C.c_int)), ("key_lo", C.POINTER(C.c_int)),
                 ("pos_i", C.POINTER(C.c_int)), ("pos_j", C.POINTER(C.c_int)),
@@ -38,7 +43,7 @@ class _Trace(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so if missing or stale. Returns its path."""
-    srcs = [os.path.join(_HERE, f) for f in ("ward_literal.c", "ward_fast.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("ward_literal.c", "ward_fast.c", "ward_device.c", "oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
@@ -71,6 +76,10 @@ def lib():
         L.oracle_fast_cluster_ex.restype = C.c_int
         L.oracle_fast_cluster_ex.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                              ip, ip, ip, C.POINTER(_Trace), C.POINTER(_Stats)]
+        L.oracle_device_cluster.restype = C.c_int
+        L.oracle_device_cluster.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_double, C.c_double,
+                                            C.c_double, C.c_int, C.c_int, ip, ip, ip, C.POINTER(_Trace),
+                                            C.POINTER(_Stats), C.POINTER(_DeviceStats)]
         L.oracle_initial_matrix.restype = C.c_int
         L.oracle_initial_matrix.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp]
         _lib = L
@@ -207,6 +216,26 @@ def fast_cluster(x, min_size: int, max_size: int, flags: int = 0, n_threads: int
                                       n_threads or (os.cpu_count() or 1), _fp(init_matrix),
                                       _ip(offsets), _ip(members), C.byref(n_out), C.byref(tr), C.byref(st))
     return _finish(rc, st, arrs, offsets, members, n_out)
+
+
+def device_cluster(x, min_size: int, max_size: int, init_matrix=None, horizon_factor: float = 1.25,
+                   eps_filter: float = 3e-5, delta_cut: float = 8e-6, max_batch: int = 512, n_threads: int = 0):
+    """CPU restatement of the device's merge loop (ward_device.c) -> (OracleResult, device-stats dict)."""
+    x = np.ascontiguousarray(x, np.float32)
+    n, d = x.shape
+    offsets = np.zeros(n + 1, np.int32)
+    members = np.zeros(max(n, 1), np.int32)
+    n_out = C.c_int(0)
+    st = _Stats()
+    ds = _DeviceStats()
+    arrs, tr = _alloc_trace(max(n, 1), True)
+    if init_matrix is not None:
+        init_matrix = np.ascontiguousarray(init_matrix, np.float32)
+        assert init_matrix.shape == (n, n)
+    rc = lib().oracle_device_cluster(_fp(x), n, d, min_size, max_size, _fp(init_matrix), horizon_factor, eps_filter,
+                                     delta_cut, max_batch, n_threads or (os.cpu_count() or 1), _ip(offsets),
+                                     _ip(members), C.byref(n_out), C.byref(tr), C.byref(st), C.byref(ds))
+    return _finish(rc, st, arrs, offsets, members, n_out), {f: getattr(ds, f) for f, _ in _DeviceStats._fields_}
 
 
 # ---- input formation (SURVEY 8f-1): literal restatement, plain Python loops (tiny inputs only) ----------------
