@@ -98,13 +98,34 @@ struct ic_ctx {
     int exact_opt = 1;            // option "exact": 0 off (Lance-Williams values only), 1 auto, 2 on even for ic_set_matrix
     bool exact_on = false;        // this clustering runs with the horizon
     bool dm_is_reference = false; // the initial matrix already holds the reference's values (gram_mode 1)
-    double hz_factor = 1.25, eps_filter = 3e-5, delta_cut = 8e-6, abs_slack_opt = -1.0;
+    // delta_cut = 0: batches are taken optimistically and CHECKED (every pair a batch creates is compared with the batch's
+    // later members, CTL_ORDER_VIOL); a failed check restarts the clustering with delta_cut_fallback
+    double hz_factor = 1.25, eps_filter = 3e-5, delta_cut = 0.0, delta_cut_fallback = 1e-5, abs_slack_opt = -1.0;
+    double delta_cut_cur = 0.0;
+    int32_t n_restarts = 0;
     double horizon = -1.0, abs_slack = 0.0, hz_factor_cur = 1.25;
     int32_t merges_at_raise = 0;
     float* cen = nullptr;
     int64_t ldc = 0;
     int4* xq = nullptr;
     int32_t xq_cap = 0;
+    uint4* xres = nullptr;
+    int32_t* xhit = nullptr;
+    int32_t* crow = nullptr;      // centroid row of every slot
+    // K4 compaction (compact.cu): current epoch's geometry, second copies of the per-slot state and of the matrix
+    int compact_opt = 1, compact_opt_alloc = -1;  // option "compact"
+    int64_t compact_min = 4096;   // no compaction below this many slots
+    int64_t n_cur = 0, ld_cur = 0;
+    float* dm_cur = nullptr;      // dm (buffer A) or dm_b
+    float* dm_b = nullptr;
+    size_t dm_b_floats = 0;
+    SlotKS* ks_b = nullptr;
+    int32_t *gkey_b = nullptr, *nn_more_b = nullptr, *crow_b = nullptr;
+    SlotNN* nn_b = nullptr;
+    int32_t *keymap = nullptr, *newslot = nullptr, *oldslot = nullptr, *nlive_dev = nullptr;
+    int32_t order_key = 0, mirror_key = 0;
+    int32_t n_compactions = 0;
+    double ms_compact = 0.0;
     int2* rq = nullptr;
     int32_t rq_cap = 0;
     int32_t* rq_cnt = nullptr;
@@ -178,6 +199,20 @@ void release_problem(ic_ctx* c) {
     dev_free(c->batch_scratch);
     dev_free(c->cen);
     dev_free(c->xq);
+    dev_free(c->xres);
+    dev_free(c->xhit);
+    dev_free(c->crow);
+    dev_free(c->dm_b);
+    dev_free(c->ks_b);
+    dev_free(c->gkey_b);
+    dev_free(c->nn_more_b);
+    dev_free(c->crow_b);
+    dev_free(c->nn_b);
+    dev_free(c->keymap);
+    dev_free(c->newslot);
+    dev_free(c->oldslot);
+    dev_free(c->nlive_dev);
+    c->dm_cur = nullptr;
     dev_free(c->rq);
     dev_free(c->rq_cnt);
     dev_free(c->prof);
@@ -294,7 +329,7 @@ int make_operand_map_i8(ic_ctx* ctx, CUtensorMap* map, int8_t* base, int64_t row
 
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 && ctx->loop_blocks == ctx->loop_blocks_alloc &&
-        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && (ctx->exact_opt != 0) == (ctx->cen != nullptr) && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
+        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && (ctx->exact_opt != 0) == (ctx->cen != nullptr) && ctx->compact_opt == ctx->compact_opt_alloc && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
         ctx->shard_rank == ctx->shard_rank_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
         ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = ctx->prepped_i8 = false;
@@ -355,11 +390,15 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1 * NL));
     IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * kCtlWords * NL));
     ctx->ldc = round_up(d > 0 ? d : 1, 4);
+    IC_CUDA(cudaMalloc(&ctx->crow, sizeof(int32_t) * (nn1 + 4)));
+    ctx->compact_opt_alloc = ctx->compact_opt;
     if (ctx->exact_opt) {
         ctx->xq_cap = static_cast<int32_t>(std::max<int64_t>(1 << 20, 16 * static_cast<int64_t>(nn1)));
         ctx->rq_cap = static_cast<int32_t>(std::min<int64_t>(16 << 20, std::max<int64_t>(1024, static_cast<int64_t>(nn1) * static_cast<int64_t>(nn1) / 2)));
         IC_CUDA(cudaMalloc(&ctx->cen, sizeof(float) * nn1 * static_cast<size_t>(ctx->ldc)));
         IC_CUDA(cudaMalloc(&ctx->xq, sizeof(int4) * static_cast<size_t>(ctx->xq_cap)));
+        IC_CUDA(cudaMalloc(&ctx->xres, sizeof(uint4) * static_cast<size_t>(kMaxBatch) * kXResCap));
+        IC_CUDA(cudaMalloc(&ctx->xhit, sizeof(int32_t) * kMaxBatch));
         IC_CUDA(cudaMalloc(&ctx->rq, sizeof(int2) * static_cast<size_t>(ctx->rq_cap)));
         IC_CUDA(cudaMalloc(&ctx->rq_cnt, sizeof(int32_t) * 4));
     }
@@ -389,6 +428,26 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
         ctx->batch_scratch_bytes = off;
         IC_CUDA(cudaMalloc(&ctx->batch_scratch, off));
         IC_CUDA(cudaMemsetAsync(ctx->batch_scratch, 0, off, ctx->stream));
+    }
+    // K4: second matrix buffer (a quarter of the first) and second copies of the per-slot state; one GPU, batched loop
+    if (ctx->compact_opt && ctx->batch_layout && ctx->shard_world <= 1 && P == 1 && n >= ctx->compact_min) {
+        const size_t half = static_cast<size_t>(n / 2 + 32);
+        const size_t want = half * static_cast<size_t>(round_up(static_cast<int64_t>(half), 32));
+        size_t fb = 0, tb = 0;
+        IC_CUDA(cudaMemGetInfo(&fb, &tb));
+        if (static_cast<double>(want) * 4.0 + 64.0 * nn1 + (256 << 20) < static_cast<double>(fb)) {
+            ctx->dm_b_floats = want;
+            IC_CUDA(cudaMalloc(&ctx->dm_b, sizeof(float) * want));
+            IC_CUDA(cudaMalloc(&ctx->ks_b, sizeof(SlotKS) * (nn1 + 4)));
+            IC_CUDA(cudaMalloc(&ctx->gkey_b, sizeof(int32_t) * n4));
+            IC_CUDA(cudaMalloc(&ctx->nn_b, sizeof(SlotNN) * nn1 * kNNK));
+            IC_CUDA(cudaMalloc(&ctx->nn_more_b, sizeof(int32_t) * nn1));
+            IC_CUDA(cudaMalloc(&ctx->crow_b, sizeof(int32_t) * (nn1 + 4)));
+            IC_CUDA(cudaMalloc(&ctx->keymap, sizeof(int32_t) * (2 * nn1 + 4)));
+            IC_CUDA(cudaMalloc(&ctx->newslot, sizeof(int32_t) * (nn1 + 4)));
+            IC_CUDA(cudaMalloc(&ctx->oldslot, sizeof(int32_t) * (nn1 + 4)));
+            IC_CUDA(cudaMalloc(&ctx->nlive_dev, sizeof(int32_t) * 4));
+        }
     }
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->loop_gen = 0;
@@ -534,10 +593,16 @@ int init_loop_state(ic_ctx* ctx) {
     const size_t n = static_cast<size_t>(ctx->n), n4 = (n + 3) / 4 * 4;
     IC_CUDA(launch_init_slots(ctx->ks, ctx->gkey, ctx->n, ctx->stream));
     ctx->stats.kernel_launches += 1;
-    if (ctx->exact_on && ctx->cen) {  // singleton centroids (clustering.go:19-20)
-        IC_CUDA(launch_init_centroids(ctx->x, ctx->n, ctx->d, ctx->d, ctx->cen, ctx->ldc, ctx->stream));
-        ctx->stats.kernel_launches += 1;
-    }
+    // singleton centroids (clustering.go:19-20) when the run keeps them; centroid row of slot s = s
+    IC_CUDA(launch_init_centroids(ctx->x, ctx->n, ctx->d, ctx->d, ctx->exact_on ? ctx->cen : nullptr, ctx->ldc, ctx->crow, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    ctx->n_cur = ctx->n;
+    ctx->ld_cur = ctx->ld;
+    ctx->dm_cur = ctx->dm;
+    ctx->order_key = static_cast<int32_t>(ctx->n);  // singletons: key == slot
+    ctx->mirror_key = 0;                            // K1 stores a pair in the row of its higher key only
+    ctx->n_compactions = 0;
+    ctx->ms_compact = 0.0;
     ctx->horizon = -1.0;
     ctx->abs_slack = ctx->abs_slack_opt >= 0.0 ? ctx->abs_slack_opt : 0.0;
     ctx->hz_factor_cur = ctx->hz_factor;
@@ -585,7 +650,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.abs_slack = static_cast<float>(ctx->abs_slack);
     p.horizon = ctx->horizon;
     p.safe = ctx->horizon < 0.0 ? -1.0 : (ctx->horizon - ctx->abs_slack) / (1.0 + 2.0 * ctx->eps_filter);
-    p.delta_cut = ctx->delta_cut;
+    p.delta_cut = ctx->delta_cut_cur;
     {   // the batched loop stops mirroring distances into the older clusters' rows: one loop per clustering
         const int mode = use_batch(ctx) ? 1 : 0;
         if (ctx->loop_mode_used >= 0 && ctx->loop_mode_used != mode && ctx->n_merges > 0)
@@ -597,7 +662,12 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     if (use_batch(ctx)) {
         BatchState bs{};
         uint8_t* sc = ctx->batch_scratch;
-        bs.n = static_cast<int32_t>(ctx->n);
+        bs.n = static_cast<int32_t>(ctx->n_cur);
+        bs.key_base = static_cast<int32_t>(ctx->n);
+        bs.order_key = ctx->order_key;
+        bs.mirror_key = ctx->mirror_key;
+        bs.compact_at = (ctx->dm_b && ctx->n_cur >= ctx->compact_min) ? static_cast<int32_t>(ctx->n_cur / 2) : 0;
+        bs.crow = ctx->crow;
         bs.n_ranks = 1;
         bs.rank = 0;
         bs.rows_per_rank = static_cast<int32_t>(rows_per_rank(ctx));
@@ -610,8 +680,8 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
                 bs.xbox[q] = static_cast<uint8_t*>(ctx->peer_box[q]) + merge_loop_rankbox_bytes();
             }
         }
-        bs.ld = ctx->ld;
-        bs.dm = ctx->dm;
+        bs.ld = ctx->ld_cur;
+        bs.dm = ctx->dm_cur;
         bs.ks = ctx->ks;
         bs.gkey = ctx->gkey;
         bs.nn = ctx->nn;
@@ -635,6 +705,9 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         bs.ldc = ctx->ldc;
         bs.xq = ctx->xq;
         bs.xq_cap = ctx->xq_cap;
+        bs.xres = ctx->xres;
+        bs.xhit = ctx->xhit;
+        if (ctx->xhit) IC_CUDA(cudaMemsetAsync(ctx->xhit, 0, sizeof(int32_t) * kMaxBatch, ctx->stream));
         // scratch of a launch: counters and the barrier at zero
         IC_CUDA(cudaMemsetAsync(bs.counters, 0, 3 * 4 * 4, ctx->stream));
         IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
@@ -692,9 +765,14 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
 int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
     const double t0 = now_ms();
     RefineArgs a{};
-    a.dm = ctx->dm;
-    a.ld = ctx->ld;
-    a.n_slots = static_cast<int32_t>(ctx->n);
+    a.dm = ctx->dm_cur;
+    a.ld = ctx->ld_cur;
+    a.n_slots = static_cast<int32_t>(ctx->n_cur);
+    a.crow = ctx->crow;
+    a.mirror_key = ctx->mirror_key;
+    a.rows_per_rank = ctx->shard_world > 1 ? static_cast<int32_t>(rows_per_rank(ctx)) : 0x40000000;
+    for (int q = 0; q < kMaxRanks; ++q)
+        a.dm_rank[q] = ctx->shard_world > 1 ? static_cast<float*>(ctx->peer_dm[q]) : ctx->dm_cur;
     a.r_lo = static_cast<int32_t>(row_begin(ctx));
     a.r_hi = static_cast<int32_t>(row_end(ctx));
     a.ks = ctx->ks;
@@ -776,6 +854,68 @@ int raise_horizon(ic_ctx* ctx) {
     return IC_OK;
 }
 
+// K4 (compact.cu): renumber the live clusters densely in key order, move the matrix into the other buffer (both
+// triangles), permute the per-slot state.  Host-driven: the loop kernel stopped with STOP_COMPACT.
+int do_compact(ic_ctx* ctx) {
+    const double t0 = now_ms();
+    const int32_t n_old = static_cast<int32_t>(ctx->n_cur), n_new = ctx->n_live, n_new4 = (n_new + 3) & ~3;
+    const int64_t ld_new = round_up(n_new, 32);
+    float* target = ctx->dm_cur == ctx->dm ? ctx->dm_b : ctx->dm;
+    const size_t cap = ctx->dm_cur == ctx->dm ? ctx->dm_b_floats : static_cast<size_t>(ctx->n) * static_cast<size_t>(ctx->ld);
+    if (static_cast<size_t>(n_new4) * static_cast<size_t>(ld_new) > cap)
+        return fail(ctx, IC_ERR_INTERNAL, "compaction target buffer too small");
+    IC_CUDA(launch_compact_map(ctx->ks, n_old, ctx->keymap, static_cast<int32_t>(ctx->n + ctx->n_merges), ctx->newslot,
+                               ctx->oldslot, n_new4, ctx->nlive_dev, ctx->stream));
+    CompactArgs a{};
+    a.n_old = n_old;
+    a.n_new = n_new;
+    a.n_new4 = n_new4;
+    a.oldslot = ctx->oldslot;
+    a.newslot = ctx->newslot;
+    a.ks_old = ctx->ks;
+    a.nn_old = ctx->nn;
+    a.nn_more_old = ctx->nn_more;
+    a.crow_old = ctx->crow;
+    a.ks_new = ctx->ks_b;
+    a.gkey_new = ctx->gkey_b;
+    a.nn_new = ctx->nn_b;
+    a.nn_more_new = ctx->nn_more_b;
+    a.crow_new = ctx->crow_b;
+    for (int q = 0; q < kMaxRanks; ++q) {
+        a.dm_old[q] = ctx->dm_cur;
+        a.dm_new_rank[q] = target;
+    }
+    a.rows_per_rank_old = a.rows_per_rank_new = 0x40000000;
+    a.ld_old = ctx->ld_cur;
+    a.dm_new = target;
+    a.row_base_new = 0;
+    a.row0 = 0;
+    a.row1 = n_new;
+    a.ld_new = ld_new;
+    IC_CUDA(launch_compact_state(a, ctx->stream));
+    IC_CUDA(launch_compact_rows(a, ctx->stream));
+    IC_CUDA(launch_mirror_lower(a, ctx->stream));
+    ctx->stats.kernel_launches += 5;
+    int32_t found = 0;
+    IC_CUDA(cudaMemcpyAsync(&found, ctx->nlive_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (found != n_new) return fail(ctx, IC_ERR_INTERNAL, "compaction found " + std::to_string(found) + " live clusters, expected " + std::to_string(n_new));
+    std::swap(ctx->ks, ctx->ks_b);
+    std::swap(ctx->gkey, ctx->gkey_b);
+    std::swap(ctx->nn, ctx->nn_b);
+    std::swap(ctx->nn_more, ctx->nn_more_b);
+    std::swap(ctx->crow, ctx->crow_b);
+    ctx->dm_cur = target;
+    ctx->n_cur = n_new;
+    ctx->ld_cur = ld_new;
+    ctx->order_key = ctx->mirror_key = static_cast<int32_t>(ctx->n + ctx->n_merges);
+    ++ctx->n_compactions;
+    ctx->ms_compact += now_ms() - t0;
+    return IC_OK;
+}
+
+constexpr int kRestart = 1;  // sync_loop_result: an optimistic batch failed its check (STOP_ORDER)
+
 int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges) {
     ctx->loop_n_target = n_target;
     ctx->loop_max_size = max_size;
@@ -801,6 +941,11 @@ int sync_loop_result(ic_ctx* ctx) {
             int rc = refine_band(ctx, -1.0, ctx->horizon, ctx->h_ctl[CTL_XQ_FIRST_KEY]);
             if (rc != IC_OK) return rc;
             IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_XQ_OVERFLOW, 0, sizeof(int32_t), ctx->stream));
+        } else if (stop == STOP_COMPACT) {
+            const int rc = do_compact(ctx);
+            if (rc != IC_OK) return rc;
+        } else if (stop == STOP_ORDER) {
+            return kRestart;
         } else if (stop != STOP_EPOCHS) {
             return IC_OK;
         }
@@ -977,6 +1122,9 @@ void fill_stats(ic_ctx* ctx) {
     }
     s.horizon = ctx->horizon;
     s.ms_refine = static_cast<float>(ctx->ms_refine);
+    s.n_restarts = ctx->n_restarts;
+    s.n_compactions = ctx->n_compactions;
+    s.ms_compact = static_cast<float>(ctx->ms_compact);
     s.n_iterations = s.loop_mode ? ctx->h_ctl[CTL_ITERS] : ctx->n_merges + ctx->h_ctl[CTL_BUBBLES];
 }
 
@@ -988,15 +1136,28 @@ int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offse
     int rc = ic_optimal_clusters(ctx->n, min_size, max_size, &n_target);
     if (rc != IC_OK) return fail(ctx, rc, "cluster size constraints cannot be satisfied");
     ctx->n_target = n_target;
-    ctx->prepped = ctx->prepped_i8 = false;  // K0 is part of the path: redo it on every run
-    rc = initial_distances(ctx, ctx->gram_mode, max_size);
-    if (rc != IC_OK) return rc;
-    rc = nn_init(ctx);
-    if (rc != IC_OK) return rc;
-    rc = run_loop(ctx, n_target, max_size, -1);
-    if (rc != IC_OK) return rc;
-    rc = sync_loop_result(ctx);  // (relaunches after a horizon raise: the loop's time includes the sweeps)
-    if (rc != IC_OK) return rc;
+    ctx->delta_cut_cur = ctx->delta_cut;
+    ctx->n_restarts = 0;
+    for (int attempt = 0;; ++attempt) {
+        ctx->prepped = ctx->prepped_i8 = false;  // K0 is part of the path: redo it on every run
+        rc = initial_distances(ctx, ctx->gram_mode, max_size);
+        if (rc != IC_OK) return rc;
+        rc = nn_init(ctx);
+        if (rc != IC_OK) return rc;
+        rc = run_loop(ctx, n_target, max_size, -1);
+        if (rc != IC_OK) return rc;
+        rc = sync_loop_result(ctx);  // (relaunches after a horizon raise: the loop's time includes the sweeps)
+        if (rc == kRestart && attempt == 0 && ctx->delta_cut_cur < ctx->delta_cut_fallback) {
+            // a pair created inside an optimistic batch came out below a later member of it (fp32 centroid distances
+            // are reducible only up to rounding): start over, keeping every batch clear of its stopper
+            ctx->delta_cut_cur = ctx->delta_cut_fallback;
+            ++ctx->n_restarts;
+            continue;
+        }
+        if (rc == kRestart) return fail(ctx, IC_ERR_INTERNAL, "batch order check failed even with delta_cut_fallback");
+        if (rc != IC_OK) return rc;
+        break;
+    }
     IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     rc = fetch_trace(ctx);
     if (rc != IC_OK) return rc;
@@ -1122,6 +1283,13 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
     } else if (k == "delta_cut") {
         if (!(value >= 0.0 && value < 0.1)) return fail(ctx, IC_ERR_BAD_ARG, "delta_cut must be in [0, 0.1)");
         ctx->delta_cut = value;
+    } else if (k == "compact") {
+        ctx->compact_opt = value != 0.0;
+    } else if (k == "compact_min") {
+        ctx->compact_min = std::max<int64_t>(64, static_cast<int64_t>(value));
+    } else if (k == "delta_cut_fallback") {
+        if (!(value >= 0.0 && value < 0.1)) return fail(ctx, IC_ERR_BAD_ARG, "delta_cut_fallback must be in [0, 0.1)");
+        ctx->delta_cut_fallback = value;
     } else if (k == "abs_slack") {
         ctx->abs_slack_opt = value;
     } else if (k == "profile_loop") {
@@ -1280,9 +1448,12 @@ int ic_merge_loop(ic_ctx* ctx, int64_t min_size, int64_t max_size, int64_t max_m
     ctx->n_target = n_target;
     IC_CUDA(cudaSetDevice(ctx->device));
     IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->delta_cut_cur = ctx->delta_cut;
     rc = run_loop(ctx, n_target, max_size, max_merges);
     if (rc != IC_OK) return rc;
     rc = sync_loop_result(ctx);
+    if (rc == kRestart)
+        return fail(ctx, IC_ERR_INTERNAL, "batch order check failed: set option delta_cut (e.g. 1e-5) and start again from ic_initial_distances");
     if (rc != IC_OK) return rc;
     IC_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     IC_CUDA(cudaEventSynchronize(ctx->ev[6]));
@@ -1403,6 +1574,7 @@ int ic_read_matrix(ic_ctx* ctx, float* out_host, int64_t ld) {
     if (!ctx || !out_host) return IC_ERR_BAD_ARG;
     if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
     if (ld < ctx->n) return fail(ctx, IC_ERR_BAD_ARG, "ld < n");
+    if (ctx->n_compactions > 0) return fail(ctx, IC_ERR_STATE, "the matrix has been compacted (option \"compact\" = 0 keeps the slot layout)");
     IC_CUDA(cudaSetDevice(ctx->device));
     const int64_t r0 = row_begin(ctx), r1 = row_end(ctx);  // a sharded context fills its own rows only
     if (r1 > r0)
@@ -1419,9 +1591,9 @@ int ic_read_slots(ic_ctx* ctx, int32_t* key, int32_t* size) {
     if (!ctx || !key || !size) return IC_ERR_BAD_ARG;
     if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "no merge state");
     IC_CUDA(cudaSetDevice(ctx->device));
-    std::vector<int2> h(static_cast<size_t>(ctx->n));
-    if (ctx->n > 0)
-        IC_CUDA(cudaMemcpyAsync(h.data(), ctx->ks, sizeof(int2) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int2> h(static_cast<size_t>(ctx->n), make_int2(-1, 0));  // (after a compaction: n_cur dense slots, the rest retired)
+    if (ctx->n_cur > 0)
+        IC_CUDA(cudaMemcpyAsync(h.data(), ctx->ks, sizeof(int2) * ctx->n_cur, cudaMemcpyDeviceToHost, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int64_t i = 0; i < ctx->n; ++i) {
         key[i] = h[i].x;

@@ -1,0 +1,177 @@
+// compact.cu -- K4: active-cluster compaction.
+//
+// The reference physically deletes two rows and two columns per merge and appends the new cluster last
+// (RemoveClusters clustering.go:51-58, RemoveRowsAndColumns :100-116, append :90-93,241): its matrix is always dense and
+// in slice order.  The device loop retires slots instead (no per-merge data movement), so between compactions the live
+// clusters thin out: every row scan and every Lance-Williams row streams retired columns, and distances of clusters
+// created since the matrix was laid out are gathered one sector at a time.  Whenever the live count has fallen to half
+// of the slot count the host stops the loop and runs this file:
+//   * the live clusters are renumbered densely IN KEY ORDER (== the reference's slice order at that moment);
+//   * the matrix moves out of place into a buffer of a quarter of the size, lower triangle from the rows of the
+//     higher-key clusters (where a pair lives), then mirrored, so every row holds ALL its partners contiguously;
+//   * slot tables, partner lists and the centroid row index follow the renumbering.  Keys never change: the merge trace,
+//     tie-breaks and output order are untouched.
+// HBM-bound: reads ~n_old * n_live * 2 bytes (every other column of the old rows is live), writes 4 n_live^2.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ic {
+
+namespace {
+
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const SlotKS* __restrict__ ks, int32_t n_old,
+                                                              int32_t* __restrict__ keymap) {
+    const int32_t s = static_cast<int32_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (s >= n_old) return;
+    const int32_t key = ks[s].x;
+    if (key >= 0) keymap[key] = s;
+}
+
+// one block: rank of every present key (ascending) = new slot
+__global__ void __launch_bounds__(1024) compact_rank_kernel(const int32_t* __restrict__ keymap, int32_t key_cap,
+                                                            int32_t* __restrict__ newslot, int32_t* __restrict__ oldslot,
+                                                            int32_t n_new4, int32_t* __restrict__ n_live_out) {
+    __shared__ int32_t s_cnt[1024];
+    const int tid = threadIdx.x;
+    const int32_t per = (key_cap + 1023) / 1024;
+    const int32_t k0 = min(key_cap, tid * per), k1 = min(key_cap, k0 + per);
+    int32_t c = 0;
+    for (int32_t k = k0; k < k1; ++k) c += keymap[k] >= 0 ? 1 : 0;
+    s_cnt[tid] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan
+        const int32_t v = tid >= o ? s_cnt[tid - o] : 0;
+        __syncthreads();
+        s_cnt[tid] += v;
+        __syncthreads();
+    }
+    int32_t rank = s_cnt[tid] - c;
+    for (int32_t k = k0; k < k1; ++k) {
+        const int32_t s = keymap[k];
+        if (s >= 0) {
+            newslot[s] = rank;
+            oldslot[rank] = s;
+            ++rank;
+        }
+    }
+    const int32_t total = s_cnt[1023];
+    for (int32_t r = total + tid; r < n_new4; r += 1024) oldslot[r] = -1;
+    if (tid == 0) *n_live_out = total;
+}
+
+__global__ void __launch_bounds__(256) compact_state_kernel(const CompactArgs a) {
+    const int32_t s = static_cast<int32_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (s >= a.n_new4) return;
+    const int32_t o = s < a.n_new ? a.oldslot[s] : -1;
+    if (o < 0) {
+        a.ks_new[s] = make_int2(-1, 0);
+        a.gkey_new[s] = -1;
+        if (s < a.n_new) {  // (cannot happen: fewer live keys than the host counted)
+            a.nn_more_new[s] = 0;
+            a.crow_new[s] = 0;
+        }
+        return;
+    }
+    const int2 k = a.ks_old[o];
+    a.ks_new[s] = k;
+    a.gkey_new[s] = k.x;
+    a.crow_new[s] = a.crow_old[o];
+    int32_t more = a.nn_more_old[o];
+#pragma unroll
+    for (int e = 0; e < kNNK; ++e) {
+        uint4 v = a.nn_old[static_cast<int64_t>(o) * kNNK + e];
+        if (v.z != kNoPartner) {
+            const int32_t p = a.newslot[v.z];
+            if (p < 0) {  // a listed partner that is not alive: rebuild the list before it is used
+                v = make_uint4(kNoPartner, v.y, kNoPartner, 0u);
+                more |= 3;
+            } else {
+                v.z = static_cast<uint32_t>(p);
+            }
+        }
+        a.nn_new[static_cast<int64_t>(s) * kNNK + e] = v;
+    }
+    a.nn_more_new[s] = more;
+}
+
+// new row s' <- the live lower-key partners of its cluster, from the cluster's old row (a pair lives in the row of its
+// higher-key cluster; lower key == lower new slot).  One block per new row.
+__global__ void __launch_bounds__(256) compact_rows_kernel(const CompactArgs a) {
+    const int32_t s = a.row0 + static_cast<int32_t>(blockIdx.x);
+    if (s >= a.row1) return;
+    const int32_t o = a.oldslot[s];
+    const int32_t q = o / a.rows_per_rank_old;
+    const float* src = a.dm_old[q] + static_cast<int64_t>(o - q * a.rows_per_rank_old) * a.ld_old;
+    float* dst = a.dm_new + static_cast<int64_t>(s - a.row_base_new) * a.ld_new;
+    for (int32_t u = threadIdx.x; u < a.n_new4; u += 256) {
+        float v = INFINITY;
+        if (u < s)
+            v = __ldg(src + a.oldslot[u]);
+        else if (u == s)
+            v = 0.0f;
+        dst[u] = v;
+    }
+}
+
+// upper triangle <- lower triangle, 32 x 32 tiles through shared memory (both sides coalesced)
+__global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a) {
+    __shared__ float tile[32][33];
+    const int32_t bi = blockIdx.y, bj = blockIdx.x;  // tile rows bi (source), tile columns bj, bj <= bi
+    if (bj > bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // source rows i = bi*32 + .., columns j = bj*32 + ..; destination rows j (must be resident here), columns i
+    const int32_t j_lo = bj * 32, j_hi = j_lo + 32;
+    if (j_hi <= a.row0 || j_lo >= a.row1) return;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int32_t i = bi * 32 + r, j = bj * 32 + tx;
+        float v = INFINITY;
+        if (i < a.n_new && j < a.n_new && j < i) {
+            const int32_t q = i / a.rows_per_rank_new;
+            v = __ldcg(a.dm_new_rank[q] + static_cast<int64_t>(i - q * a.rows_per_rank_new) * a.ld_new + j);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int32_t j = bj * 32 + r, i = bi * 32 + tx;  // write dm[j][i] = dm[i][j]
+        if (i < a.n_new && j < a.n_new && j < i && j >= a.row0 && j < a.row1)
+            a.dm_new[static_cast<int64_t>(j - a.row_base_new) * a.ld_new + i] = tile[tx][r];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap, int32_t key_cap, int32_t* newslot,
+                               int32_t* oldslot, int32_t n_new4, int32_t* n_live_out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(keymap, 0xFF, sizeof(int32_t) * static_cast<size_t>(key_cap), s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(newslot, 0xFF, sizeof(int32_t) * static_cast<size_t>(n_old), s);
+    if (e != cudaSuccess) return e;
+    compact_scatter_kernel<<<static_cast<unsigned>((n_old + 255) / 256), 256, 0, s>>>(ks, n_old, keymap);
+    compact_rank_kernel<<<1, 1024, 0, s>>>(keymap, key_cap, newslot, oldslot, n_new4, n_live_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_state(const CompactArgs& a, cudaStream_t s) {
+    compact_state_kernel<<<static_cast<unsigned>((a.n_new4 + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_rows(const CompactArgs& a, cudaStream_t s) {
+    if (a.row1 <= a.row0) return cudaSuccess;
+    compact_rows_kernel<<<static_cast<unsigned>(a.row1 - a.row0), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mirror_lower(const CompactArgs& a, cudaStream_t s) {
+    if (a.n_new <= 1 || a.row1 <= a.row0) return cudaSuccess;
+    const unsigned nb = static_cast<unsigned>((a.n_new + 31) / 32);
+    mirror_lower_kernel<<<dim3(nb, nb), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace ic

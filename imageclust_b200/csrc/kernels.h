@@ -151,7 +151,7 @@ enum { CTL_N_LIVE = 0, CTL_N_MERGES = 1, CTL_EXHAUSTED = 2, CTL_ERROR = 3, CTL_N
 };
 // CTL_STOP values
 enum { STOP_TARGET = 1, STOP_EXHAUSTED = 2, STOP_MAX_MERGES = 3, STOP_EPOCHS = 4, STOP_ERROR = 5, STOP_HORIZON = 6,
-       STOP_XQ = 7 };
+       STOP_XQ = 7, STOP_ORDER = 8, STOP_COMPACT = 9 };
 constexpr int kLoopThreads = 512;
 // C: rows (slots) per rank, ceil(n / P) rounded up to a multiple of 4
 int64_t merge_loop_rows_per_rank(int64_t n, int n_ranks);
@@ -187,11 +187,17 @@ constexpr int CTL_ITERS = 12;         // ctl[]: iterations of the batched loop
 //                                                    src in iteration slot (iteration mod 3), written by src's block 0
 //   [1280, 1344)    u64 stop[3], head[3]; i32 cnt[3] this rank's own accumulators (local atomics)
 //   [2048, ...)     uint4 cand[src][kBatchXCand][2]  candidate pairs of rank src in the current iteration
+constexpr int kXResCap = 512;
 constexpr int kBatchXCand = 2048;
 constexpr size_t kBatchXSummary = 256, kBatchXAccum = 1280, kBatchXCandBase = 2048;
 constexpr size_t kBatchXBoxBytes = kBatchXCandBase + static_cast<size_t>(kMaxRanks) * kBatchXCand * 32;
 struct BatchState {
-    int32_t n;
+    int32_t n;                             // slots (== items until the first compaction, then the live count at the last one)
+    int32_t key_base;                      // N: the cluster created by merge t carries the key N + t
+    // K4 epochs (compact.cu).  Clusters with key < order_key sit in key order by slot (a row scan of such a cluster only
+    // needs the columns before its own); pairs of two clusters with key < mirror_key are stored in both rows.
+    int32_t order_key, mirror_key;
+    int32_t compact_at;                    // stop (STOP_COMPACT) when the live count is <= this; 0: never
     int32_t n_ranks, rank, rows_per_rank;  // 1, 0, - on one GPU
     uint32_t gen;                          // launch generation (cross-rank barrier sequence numbers)
     float* dm_rank[kMaxRanks];             // sharded: first row of every rank's row block (peer mapped)
@@ -223,10 +229,15 @@ struct BatchState {
     // reference arithmetic (LoopParams::exact): fp32 centroid of every slot's cluster (replicated on every rank), and
     // the queue of the pairs an iteration wrote at or below the horizon {index of the merge in the batch, column slot or
     // 0x80000000 | index of an earlier merge of the batch (cross term)}
-    float* cen;         // [n x ldc], ldc = d rounded up to 4, zero padded
+    float* cen;         // [N x ldc], ldc = d rounded up to 4, zero padded
     int64_t ldc;
-    int4* xq;           // [xq_cap] {merge, column | cross, Lance-Williams value bits, 0}
+    const int32_t* crow; // [n] centroid row of every slot's cluster (slots are renumbered by a compaction, centroids stay)
+    int4* xq;           // [xq_cap] {merge, column | cross, Lance-Williams value bits, position among the merge's queued pairs}
     int32_t xq_cap;
+    // one GPU: the partner list of a new cluster is selected from its re-evaluated pairs (everything else in its row is
+    // above the horizon), so its row needs no scan: xres[merge][position] = {value bits, partner key, partner slot, size}
+    uint4* xres;        // [kMaxBatch][kXResCap]
+    int32_t* xhit;      // [kMaxBatch] pairs queued per merge of the current batch
 };
 size_t merge_batch_smem_bytes(int64_t n);
 int64_t merge_batch_windows(int64_t n);
@@ -234,7 +245,9 @@ cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks);  // *blocks =
 cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);  // n_ranks > 1: sharded
 // ---- reference arithmetic for selected pairs (refine.cu) ---------------------------------------------------------
 // cen[s] = x[s] (zero padded to ldc floats per row): the singleton centroids (clustering.go:19-20)
-cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, cudaStream_t s);
+// and crow[s] = s
+cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, int32_t* crow,
+                                  cudaStream_t s);
 struct RefineArgs {
     float* dm;            // resident rows [r_lo, r_hi) x ld
     int64_t ld;
@@ -243,6 +256,10 @@ struct RefineArgs {
     const int32_t* gkey;  // [n4] keys, padding -1
     const float* cen;
     int64_t ldc;
+    const int32_t* crow;  // centroid row of every slot
+    int32_t mirror_key;   // pairs of two clusters with key < mirror_key are stored in both rows (compact.cu)
+    int32_t rows_per_rank;
+    float* dm_rank[kMaxRanks];  // every rank's row block (mirrored stores); [0] = dm on one GPU
     double lo, hi;        // band: lo < stored value <= hi
     int32_t min_row_key;  // only rows whose cluster key is >= this
     int32_t lower_only;   // keys are still the slot indices: row r only has partners in the columns u < r
@@ -258,6 +275,36 @@ struct RefineArgs {
 cudaError_t launch_refine_collect(const RefineArgs& a, cudaStream_t s);
 // dm[r][u] = WardDistance(centroid r, centroid u) for the first min(*cnt, cap) collected pairs, one warp per pair
 cudaError_t launch_refine_eval(const RefineArgs& a, int num_sms, cudaStream_t s);
+
+// ---- K4 active-cluster compaction (compact.cu) -------------------------------------------------------------------
+struct CompactArgs {
+    int32_t n_old, n_new, n_new4;           // slots before; live clusters == slots after; rounded up to 4
+    const int32_t* oldslot;                 // [n_new4] old slot of every new slot (key order), -1 padding
+    const int32_t* newslot;                 // [n_old]  new slot of every old slot, -1: retired
+    const SlotKS* ks_old;
+    const SlotNN* nn_old;
+    const int32_t* nn_more_old;
+    const int32_t* crow_old;
+    SlotKS* ks_new;
+    int32_t* gkey_new;
+    SlotNN* nn_new;
+    int32_t* nn_more_new;
+    int32_t* crow_new;
+    // matrix: old rows may live on peers (sharded); the new rows [row0, row1) are resident here, first at dm_new
+    const float* dm_old[kMaxRanks];
+    int32_t rows_per_rank_old;
+    int64_t ld_old;
+    float* dm_new;
+    float* dm_new_rank[kMaxRanks];          // every rank's new row block (the mirror pass reads the transposed tiles)
+    int32_t rows_per_rank_new, row_base_new, row0, row1;
+    int64_t ld_new;
+};
+// newslot / oldslot from the live keys (ascending); *n_live_out = live clusters found
+cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap, int32_t key_cap, int32_t* newslot,
+                               int32_t* oldslot, int32_t n_new4, int32_t* n_live_out, cudaStream_t s);
+cudaError_t launch_compact_state(const CompactArgs& a, cudaStream_t s);  // slot tables, partner lists, centroid rows
+cudaError_t launch_compact_rows(const CompactArgs& a, cudaStream_t s);   // lower triangle of the new matrix (+ diagonal, padding)
+cudaError_t launch_mirror_lower(const CompactArgs& a, cudaStream_t s);   // upper triangle <- lower triangle
 
 // device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
 cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);

@@ -120,7 +120,7 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
                     uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXSummary + (static_cast<size_t>(st.rank) * 3 + publish_slot) * 32);
                     __stcg(dst, make_uint4(static_cast<uint32_t>(sstop), static_cast<uint32_t>(sstop >> 32),
                                            static_cast<uint32_t>(shead), static_cast<uint32_t>(shead >> 32)));
-                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(scnt), static_cast<uint32_t>(__ldcg(st.ctl + CTL_XQ_OVERFLOW)), 0u, 0u));
+                    __stcg(dst + 1, make_uint4(static_cast<uint32_t>(scnt), static_cast<uint32_t>((__ldcg(st.ctl + CTL_XQ_OVERFLOW) != 0 ? 1 : 0) | (__ldcg(st.ctl + CTL_ORDER_VIOL) != 0 ? 2 : 0)), 0u, 0u));
                 }
             }
             // block 0's own pushes (the summary) must be performed before the flags; the other blocks fenced theirs
@@ -229,6 +229,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     const uint32_t G = gridDim.x;
     const int32_t n = st.n;
     const int32_t n4 = (n + 3) & ~3;
+    const int32_t kbase = st.key_base;
     const int64_t ld = st.ld;
     const int32_t gtid = static_cast<int32_t>(blockIdx.x) * kBT + tid, GT = static_cast<int32_t>(G) * kBT;
     // work units go to warps block-interleaved: consecutive units run on different SMs
@@ -270,9 +271,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     __shared__ int2 s_pm[kBW];
     __shared__ double s_rcp[kRcpTab];  // 1.0 / size sum, correctly rounded (what lance_williams() computes inline)
     const bool exact = prm.exact != 0;
+    const bool use_xres = exact && !kMulti;
     const int d4 = static_cast<int>(st.ldc);
 
     uint32_t phase = 0;
+    int32_t m_prev = 0;  // merges of the previous iteration
     int32_t n_live = __ldcg(ctl + CTL_N_LIVE);
     int32_t t = __ldcg(ctl + CTL_N_MERGES);
     int32_t launched = 0, stop_reason = 0, iters = 0;
@@ -299,6 +302,58 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         const int sl = static_cast<int>(it % 3u), sl1 = static_cast<int>((it + 1u) % 3u), sl2 = static_cast<int>((it + 2u) % 3u);
         const long long tp0 = timed ? clock64() : 0;
 
+        // ---- partner lists of the clusters the previous iteration created, selected from their re-evaluated pairs ----
+        // (one GPU, reference arithmetic: every pair of the new row at or below the horizon went through the exact phase;
+        // the rest of the row is above the horizon, which therefore bounds the unlisted partners)
+        if (use_xres) {
+            for (int32_t j = gw; j < m_prev; j += GW) {
+                const int32_t c = __ldcg(st.xhit + j);
+                if (lane == 0) st.xhit[j] = 0;
+                if (c <= 0 || c > kXResCap) continue;  // no pair / too many: the row was queued for a scan instead
+                const uint4* src = st.xres + static_cast<int64_t>(j) * kXResCap;
+                constexpr int kPer = kXResCap / 32;
+                uint64_t pk[kPer];
+                uint32_t taken = 0u;
+#pragma unroll
+                for (int x = 0; x < kPer; ++x) {
+                    const int32_t idx = x * 32 + lane;
+                    pk[x] = kPackInf;
+                    if (idx < c) {
+                        const uint4 e = __ldcg(src + idx);
+                        pk[x] = (static_cast<uint64_t>(e.x) << 32) | e.y;
+                    }
+                }
+                const int32_t b = s_b[j];
+                for (int r = 0; r < kNNK; ++r) {
+                    uint64_t best = kPackInf;
+                    int bx = -1;
+#pragma unroll
+                    for (int x = 0; x < kPer; ++x)
+                        if (((taken >> x) & 1u) == 0u && pk[x] < best) {
+                            best = pk[x];
+                            bx = x;
+                        }
+                    const uint64_t wm = warp_min_u64(best);
+                    uint4 out = nn_none();
+                    if (wm != kPackInf) {
+                        const bool win = best == wm;  // packs are unique (distinct partner keys)
+                        const int src_lane = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+                        if (win) taken |= 1u << bx;
+                        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                        if (win) e = __ldcg(src + bx * 32 + lane);
+                        out.x = __shfl_sync(0xffffffffu, e.y, src_lane);  // partner key
+                        out.y = __shfl_sync(0xffffffffu, e.x, src_lane);  // distance bits
+                        out.z = __shfl_sync(0xffffffffu, e.z, src_lane);  // partner slot
+                        out.w = __shfl_sync(0xffffffffu, e.w, src_lane);  // partner size
+                    } else if (r == c) {
+                        out = nn_bound(__float_as_uint(static_cast<float>(prm.horizon)));  // the unlisted partners are above the horizon
+                    }
+                    if (lane == 0) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + r, out);
+                }
+                if (lane == 0) __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit));
+            }
+        }
+
         // One (row, window) unit of a rescan: a warp scans 2048 columns of a queued row; the warp that delivers a row's last
         // window folds the partial lists and writes the row's list.  `during_batch`: the unit runs inside the rows phase of
         // the batch that follows the one the row ran dry in -- clusters of the current batch are excluded through the
@@ -311,7 +366,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 if (during_batch && ((s_bits[r >> 5] >> (r & 31)) & 1u)) return;  // merged in this batch: no list to rebuild
                 const uint32_t ukr = static_cast<uint32_t>(rq.y);
                 const float* rowp = dm + static_cast<int64_t>(r - r_lo) * ld;
-                const int32_t sw0 = min(n4, w * win), sw1 = min(n4, sw0 + win);
+                // a cluster older than the last compaction sits in key order: its lower-key partners are the columns before it
+                const int32_t lim = static_cast<int32_t>(ukr) < st.order_key ? min(n4, (r + 3) & ~3) : n4;
+                const int32_t sw0 = min(lim, w * win), sw1 = min(lim, sw0 + win);
                 ScanCand c;
                 scan_init(c);
                 constexpr int kU = 8;  // 16-byte loads of the row and of the keys in flight per lane
@@ -427,8 +484,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             const int32_t r = rq.x;
             const uint32_t ukr = static_cast<uint32_t>(rq.y);
             const float* rowp = dm + static_cast<int64_t>(r - r_lo) * ld;
-            const int32_t seg = (((n4 + kBW - 1) / kBW) + 127) & ~127;
-            const int32_t sw0 = min(n4, warp * seg), sw1 = min(n4, sw0 + seg);
+            const int32_t lim = static_cast<int32_t>(ukr) < st.order_key ? min(n4, (r + 3) & ~3) : n4;
+            const int32_t seg = (((lim + kBW - 1) / kBW) + 127) & ~127;
+            const int32_t sw0 = min(lim, warp * seg), sw1 = min(lim, sw0 + seg);
             ScanCand c;
             scan_init(c);
             constexpr int kU = 8;
@@ -625,7 +683,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             n_pub = s_xcnt[st.n_ranks];
         } else {
             n_pub = __ldcg(st.counters + sl * 4 + CN_CAND);
-            if (tid == 0) over_local = __ldcg(ctl + CTL_XQ_OVERFLOW);
+            if (tid == 0) over_local = (__ldcg(ctl + CTL_XQ_OVERFLOW) != 0 ? 1 : 0) | (__ldcg(ctl + CTL_ORDER_VIOL) != 0 ? 2 : 0);
             if (tid < static_cast<int>(G)) {
                 const uint4 h0 = __ldcg(st.hdr + tid);
                 tstop = (static_cast<uint64_t>(h0.y) << 32) | h0.x;
@@ -645,7 +703,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         }
         tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
-        const bool xq_over = __syncthreads_or(over_local) != 0;
+        const bool xq_over = __syncthreads_or(over_local & 1) != 0;     // (every rank sees every rank's flags)
+        const bool order_viol = __syncthreads_or(over_local & 2) != 0;
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
         if (n_live <= prm.n_target)
             stop_reason = STOP_TARGET;
@@ -655,6 +714,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             stop_reason = STOP_MAX_MERGES;
         else if (it + 8u >= (1u << 22))
             stop_reason = STOP_EPOCHS;
+        else if (st.compact_at > 0 && n_live <= st.compact_at)
+            stop_reason = STOP_COMPACT;  // half of the slots are retired: the host renumbers the live clusters (compact.cu)
+        else if (exact && order_viol)
+            stop_reason = STOP_ORDER;  // the previous batch was not the reference's sequence: the host starts over with delta_cut
         else if (exact && xq_over)
             stop_reason = STOP_XQ;  // the previous iteration could not queue all its pairs: the host re-evaluates its rows
         else if (exact && static_cast<double>(pack_dist(H)) > prm.safe)
@@ -788,7 +851,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         // ---- bookkeeping (block 0): trace, slot table; counters of the next iterations ----
         if (blockIdx.x == 0) {
             if (tid < m) {
-                const int32_t a = s_a[tid], b = s_b[tid], snew = s_sa[tid] + s_sb[tid], new_key = n + t + tid;
+                const int32_t a = s_a[tid], b = s_b[tid], snew = s_sa[tid] + s_sb[tid], new_key = kbase + t + tid;
                 const float d = __uint_as_float(s_d[tid]), sd = __uint_as_float(s_d[tid + 1]);
                 const float gap = (sd - d) / fmaxf(d, 1e-30f);
                 st.tr_key_hi[t + tid] = s_ka[tid];
@@ -809,13 +872,14 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 for (int x = 1; x < kNNK; ++x) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + x, nn_none());
                 __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit | kDryBit));
                 __stcg(st.nn_more + a, 0);
-                if (b >= r_lo && b < r_hi) st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(b, new_key);
+                // (one GPU with the horizon: the exact phase decides whether the row needs a scan at all)
+                if (!use_xres && b >= r_lo && b < r_hi) st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(b, new_key);
             }
             if (tid == kBT - 1) {
                 st.counters[sl2 * 4 + CN_DRY] = 0;
                 st.counters[sl1 * 4 + CN_CAND] = 0;
                 st.counters[sl2 * 4 + CN_XQ] = 0;   // last read in the exact phase of the previous iteration
-                ctl[CTL_XQ_FIRST_KEY] = n + t;      // the clusters this iteration creates carry the keys n + t ...
+                ctl[CTL_XQ_FIRST_KEY] = kbase + t;  // the clusters this iteration creates carry the keys N + t ...
                 if (kMulti) {  // this rank's exchange-box slot of the next iteration (last read two iterations ago)
                     xb_cnt[sl1] = 0;
                     xb_stop[sl1] = kPackInf;
@@ -876,8 +940,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                         const bool live = keys[e] >= 0 && ((bits >> e) & 1u) == 0u;
                         livem[x] |= live ? (1u << e) : 0u;
                         const float* rc = dm + static_cast<int64_t>(c0 + e - r_lo) * ld;  // row of cluster c: local
-                        db[x][e] = ldcg_if(rc + b, live && keys[e] > kb, rb[e]);
-                        da[x][e] = ldcg_if(rc + a, live && keys[e] > ka, ra[e]);
+                        // (pairs of two clusters older than the last compaction are stored in both rows)
+                        db[x][e] = ldcg_if(rc + b, live && keys[e] > kb && keys[e] >= st.mirror_key, rb[e]);
+                        da[x][e] = ldcg_if(rc + a, live && keys[e] > ka && keys[e] >= st.mirror_key, ra[e]);
                     }
                     livem[x] |= bits << 4;
                 }
@@ -900,8 +965,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                         if (exact && keep && static_cast<double>(lw) <= prm.horizon) hitm |= 1u << (x * 4 + e);
                     }
                 }
-                if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // queue {merge, column, Lance-Williams value}
+                if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // queue {merge, column, Lance-Williams value, position}
                     int32_t idx = warp_reserve(st.counters + sl * 4 + CN_XQ, __popc(hitm), lane);
+                    int32_t pos = use_xres ? warp_reserve(st.xhit + i, __popc(hitm), lane) : 0;
 #pragma unroll
                     for (int x = 0; x < kI; ++x)
 #pragma unroll
@@ -909,10 +975,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                             if ((hitm >> (x * 4 + e)) & 1u) {
                                 if (idx < st.xq_cap)
                                     st.xq[idx] = make_int4(i, c_lo + ch * kUpdCols + x * 128 + lane * 4 + e,
-                                                           static_cast<int32_t>(__float_as_uint(outv[x][e])), 0);
+                                                           static_cast<int32_t>(__float_as_uint(outv[x][e])), pos);
                                 else
                                     ctl[CTL_XQ_OVERFLOW] = 1;
                                 ++idx;
+                                ++pos;
                             }
                 }
 #pragma unroll
@@ -954,9 +1021,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 if (si + saj + sbj <= prm.max_size) val = lance_williams(saj, sbj, si, t1, t2, dj);
                 if (exact && static_cast<double>(val) <= prm.horizon) {  // (lanes diverge here: rare)
                     const int32_t idx = atomicAdd(st.counters + sl * 4 + CN_XQ, 1);
+                    const int32_t pos = use_xres ? atomicAdd(st.xhit + j, 1) : 0;
                     if (idx < st.xq_cap)
                         st.xq[idx] = make_int4(j, static_cast<int32_t>(0x80000000u | static_cast<uint32_t>(i)),
-                                               static_cast<int32_t>(__float_as_uint(val)), 0);
+                                               static_cast<int32_t>(__float_as_uint(val)), pos);
                     else
                         ctl[CTL_XQ_OVERFLOW] = 1;
                 } else {
@@ -999,7 +1067,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     v = nn_bound(last);
                 __stcg(st.nn + static_cast<int64_t>(r) * kNNK + x, v);
             }
-            if (kept == 0 && more) {
+            if (kept < ((prm.debug & 1) ? 2 : 1) && more) {  // (debug bit 0: refill a list that is down to one entry -- larger batches, more scans)
                 __stcg(st.nn_more + r, static_cast<int32_t>(kMoreBit | kDryBit));
                 st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(r, key_r);
             }
@@ -1025,22 +1093,28 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             grid_sync(st.bar, phase, G);  // gpu scope: every queue is local to its rank
             const int32_t nx = min(__ldcg(st.counters + sl * 4 + CN_XQ), st.xq_cap);
             const float d_last = __uint_as_float(s_d[m > 0 ? m - 1 : 0]);
+            if (use_xres && blockIdx.x == 0 && tid < m) {  // new rows without a pair at or below the horizon (or with too many): scan
+                const int32_t c = __ldcg(st.xhit + tid);
+                if (c <= 0 || c > kXResCap || __ldcg(st.counters + sl * 4 + CN_XQ) > st.xq_cap)
+                    st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(s_b[tid], kbase + t - m + tid);
+            }
             int32_t my_exact = 0;
             for (int32_t q = gw; q < nx; q += GW) {
                 const int4 ent = __ldcg(st.xq + q);
                 const int32_t j = ent.x;
                 const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
-                const ExSide A = ex_merged(st.cen + static_cast<int64_t>(aj) * st.ldc, saj, st.cen + static_cast<int64_t>(bj) * st.ldc, sbj);
+                auto cen_of = [&](int32_t slot) { return st.cen + static_cast<int64_t>(__ldcg(st.crow + slot)) * st.ldc; };
+                const ExSide A = ex_merged(cen_of(aj), saj, cen_of(bj), sbj);
                 ExSide B;
                 int32_t size_b, col;
                 if (ent.y < 0) {  // cross term: the other cluster is being created by this batch, too
                     const int32_t i = ent.y & 0x7FFFFFFF;
-                    B = ex_merged(st.cen + static_cast<int64_t>(s_a[i]) * st.ldc, s_sa[i], st.cen + static_cast<int64_t>(s_b[i]) * st.ldc, s_sb[i]);
+                    B = ex_merged(cen_of(s_a[i]), s_sa[i], cen_of(s_b[i]), s_sb[i]);
                     size_b = s_sa[i] + s_sb[i];
                     col = s_b[i];
                 } else {
                     col = ent.y;
-                    B = ex_plain(st.cen + static_cast<int64_t>(col) * st.ldc);
+                    B = ex_plain(cen_of(col));
                     size_b = __ldcg(st.lsize + col);
                 }
                 const float dsq = warp_exact_dsq(A, B, d4, s_ex[warp]);
@@ -1049,6 +1123,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(ent.z)), w, prm.eps_filter, prm.abs_slack);
                     if (j + 1 < m && w < d_last) atomicAdd(ctl + CTL_ORDER_VIOL, 1);  // would have preceded a later pair of the batch
                     __stcg(row_of(bj) + col, w);
+                    if (use_xres && ent.w < kXResCap)
+                        __stcg(st.xres + static_cast<int64_t>(j) * kXResCap + ent.w,
+                               make_uint4(__float_as_uint(w), static_cast<uint32_t>(ent.y < 0 ? kbase + t - m + (ent.y & 0x7FFFFFFF) : __ldcg(st.gkey + col)),
+                                          static_cast<uint32_t>(col), static_cast<uint32_t>(size_b)));
                     if (kMulti && (bj < r_lo || bj >= r_hi)) wrote_remote = true;
                     ++my_exact;
                 }
@@ -1059,13 +1137,14 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             grid_sync_ranks(st, phase, xcount, G, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
         else
             grid_sync(st.bar, phase, G);
+        m_prev = m;
         if (exact) {  // centroids of the new clusters (clustering.go:36-40) replace those of their slots b; every rank keeps a replica
             const int32_t nch = (d4 + 127) / 128;
             for (int32_t u = gw; u < m * nch; u += GW) {
                 const int32_t j = u / nch, e = ((u - j * nch) * 32 + lane) * 4;
                 if (e < d4) {
-                    const float* pa = st.cen + static_cast<int64_t>(s_a[j]) * st.ldc + e;
-                    float* pb = st.cen + static_cast<int64_t>(s_b[j]) * st.ldc + e;
+                    const float* pa = st.cen + static_cast<int64_t>(__ldcg(st.crow + s_a[j])) * st.ldc + e;
+                    float* pb = st.cen + static_cast<int64_t>(__ldcg(st.crow + s_b[j])) * st.ldc + e;
                     const float4 ca = __ldcg(reinterpret_cast<const float4*>(pa)), cb = __ldcg(reinterpret_cast<const float4*>(pb));
                     const float fa = static_cast<float>(s_sa[j]), fb = static_cast<float>(s_sb[j]), fs = static_cast<float>(s_sa[j] + s_sb[j]);
                     __stcg(reinterpret_cast<float4*>(pb), make_float4(ex_merge1(fa, ca.x, fb, cb.x, fs), ex_merge1(fa, ca.y, fb, cb.y, fs),

@@ -22,8 +22,10 @@ namespace {
 constexpr int kColT = 256;
 
 __global__ void __launch_bounds__(256) init_centroids_kernel(const float* __restrict__ x, int64_t n, int64_t d, int64_t ldx,
-                                                             float* __restrict__ cen, int64_t ldc) {
-    const int64_t total = n * ldc;
+                                                             float* __restrict__ cen, int64_t ldc, int32_t* __restrict__ crow) {
+    const int64_t total = cen ? n * ldc : 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        crow[i] = static_cast<int32_t>(i);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = i / ldc, c = i - r * ldc;
@@ -79,8 +81,8 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
     for (int32_t i = gw; i < total; i += GW) {
         const int2 p = a.q[i];
         const int2 kr = a.ks[p.x], ku = a.ks[p.y];
-        const float dsq = warp_exact_dsq(ex_plain(a.cen + static_cast<int64_t>(p.x) * a.ldc),
-                                         ex_plain(a.cen + static_cast<int64_t>(p.y) * a.ldc), d4, s_buf[warp]);
+        const float dsq = warp_exact_dsq(ex_plain(a.cen + static_cast<int64_t>(a.crow[p.x]) * a.ldc),
+                                         ex_plain(a.cen + static_cast<int64_t>(a.crow[p.y]) * a.ldc), d4, s_buf[warp]);
         if (lane == 0) {
             const float w = ward_weight(kr.y, ku.y, dsq);
             float* dst = a.dm + static_cast<int64_t>(p.x - a.r_lo) * a.ld + p.y;
@@ -88,6 +90,10 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
             exact_monitor(a.ctl, stored, w, a.eps_filter, a.abs_slack);
             if (__float_as_uint(stored) != __float_as_uint(w)) {
                 *dst = w;
+                if (kr.x < a.mirror_key) {  // both clusters are older than the last compaction: the pair is stored in both rows
+                    const int32_t q = p.y / a.rows_per_rank;
+                    a.dm_rank[q][static_cast<int64_t>(p.y - q * a.rows_per_rank) * a.ld + p.x] = w;
+                }
                 atomicOr(a.nn_more + p.x, 3);  // kMoreBit | kDryBit: the row's partner list is rebuilt before it is used
             }
             ++n_done;
@@ -97,11 +103,12 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
 }
 }  // namespace
 
-cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, cudaStream_t s) {
+cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, int32_t* crow,
+                                  cudaStream_t s) {
     if (n <= 0 || ldc <= 0) return cudaSuccess;
     const int64_t total = n * ldc;
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 16));
-    init_centroids_kernel<<<blocks, 256, 0, s>>>(x, n, d, ldx, cen, ldc);
+    init_centroids_kernel<<<blocks, 256, 0, s>>>(x, n, d, ldx, cen, ldc, crow);
     return cudaGetLastError();
 }
 

@@ -86,7 +86,10 @@ typedef struct ic_stats {
     float filter_max_err;     /* largest relative error of a stored value seen at re-evaluation */
     double horizon;           /* last horizon */
     float ms_refine;          /* host wall time of the horizon sweeps (inside ms_loop) */
-    float pad0;
+    int32_t n_restarts;       /* 1: an optimistically taken batch failed its order check and the clustering was run again
+                                 with delta_cut_fallback (see "delta_cut") */
+    int32_t n_compactions;    /* K4: times the live clusters were renumbered densely and the matrix moved (compact.cu) */
+    float ms_compact;         /* host wall time of the compactions (inside ms_loop) */
 } ic_stats;
 
 /* ---- context ---------------------------------------------------------- */
