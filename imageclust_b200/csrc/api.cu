@@ -111,16 +111,18 @@ struct ic_ctx {
     int32_t xq_cap = 0;
     uint4* xres = nullptr;
     int32_t* xhit = nullptr;
-    int32_t* crow = nullptr;      // centroid row of every slot
     // K4 compaction (compact.cu): current epoch's geometry, second copies of the per-slot state and of the matrix
     int compact_opt = 1, compact_opt_alloc = -1;  // option "compact"
+    int refill_at = 2;            // option "refill_at" (1 or 2)
+    double compact_ratio = 0.7, compact_ratio_alloc = -1.0;  // option "compact_ratio": compact when live <= ratio * slots
+    int mirror_init = 1;          // option "mirror_init": fill the upper triangle after a lower-triangle-only K1
     int64_t compact_min = 4096;   // no compaction below this many slots
     int64_t n_cur = 0, ld_cur = 0;
     float* dm_cur = nullptr;      // dm (buffer A) or dm_b
     float* dm_b = nullptr;
     size_t dm_b_floats = 0;
     SlotKS* ks_b = nullptr;
-    int32_t *gkey_b = nullptr, *nn_more_b = nullptr, *crow_b = nullptr;
+    int32_t *gkey_b = nullptr, *nn_more_b = nullptr;
     SlotNN* nn_b = nullptr;
     int32_t *keymap = nullptr, *newslot = nullptr, *oldslot = nullptr, *nlive_dev = nullptr;
     int32_t order_key = 0, mirror_key = 0;
@@ -201,12 +203,10 @@ void release_problem(ic_ctx* c) {
     dev_free(c->xq);
     dev_free(c->xres);
     dev_free(c->xhit);
-    dev_free(c->crow);
     dev_free(c->dm_b);
     dev_free(c->ks_b);
     dev_free(c->gkey_b);
     dev_free(c->nn_more_b);
-    dev_free(c->crow_b);
     dev_free(c->nn_b);
     dev_free(c->keymap);
     dev_free(c->newslot);
@@ -329,7 +329,7 @@ int make_operand_map_i8(ic_ctx* ctx, CUtensorMap* map, int8_t* base, int64_t row
 
 int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->x && ctx->dm && ctx->n == n && ctx->d == d && n > 0 && ctx->loop_blocks == ctx->loop_blocks_alloc &&
-        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && (ctx->exact_opt != 0) == (ctx->cen != nullptr) && ctx->compact_opt == ctx->compact_opt_alloc && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
+        ctx->vranks == ctx->vranks_alloc && ctx->no_replica == ctx->no_replica_alloc && (ctx->exact_opt != 0) == (ctx->cen != nullptr) && ctx->compact_opt == ctx->compact_opt_alloc && ctx->compact_ratio == ctx->compact_ratio_alloc && ctx->loop_mode == ctx->loop_mode_alloc && ctx->shard_world == ctx->shard_world_alloc &&
         ctx->shard_rank == ctx->shard_rank_alloc) {
         // same shape as the resident problem: keep the HBM allocations (40 GB at N=100k)
         ctx->loaded = ctx->have_dm = ctx->have_nn = ctx->prepped = ctx->prepped_i8 = false;
@@ -360,7 +360,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const double other = 4.0 * n * d + (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
                          (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20) +
-                         (ctx->exact_opt ? 4.0 * n * round_up(d, 4) + 16.0 * std::max<int64_t>(1 << 20, 16 * n) + 8.0 * (16 << 20) : 0.0);
+                         (ctx->exact_opt ? 8.0 * n * round_up(d, 4) + 16.0 * std::max<int64_t>(1 << 20, 16 * n) + 8.0 * (16 << 20) : 0.0);
     if ((P == 1 || ctx->shard_world > 1) && ctx->loop_mode == 1 && n > 0) {  // batched loop: one GPU, or real shards
         int grid = 0;
         IC_CUDA(merge_batch_grid(ctx->num_sms, n, &grid));
@@ -390,12 +390,12 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->tr_gap, sizeof(float) * nn1 * NL));
     IC_CUDA(cudaMalloc(&ctx->ctl, sizeof(int32_t) * kCtlWords * NL));
     ctx->ldc = round_up(d > 0 ? d : 1, 4);
-    IC_CUDA(cudaMalloc(&ctx->crow, sizeof(int32_t) * (nn1 + 4)));
     ctx->compact_opt_alloc = ctx->compact_opt;
+    ctx->compact_ratio_alloc = ctx->compact_ratio;
     if (ctx->exact_opt) {
         ctx->xq_cap = static_cast<int32_t>(std::max<int64_t>(1 << 20, 16 * static_cast<int64_t>(nn1)));
         ctx->rq_cap = static_cast<int32_t>(std::min<int64_t>(16 << 20, std::max<int64_t>(1024, static_cast<int64_t>(nn1) * static_cast<int64_t>(nn1) / 2)));
-        IC_CUDA(cudaMalloc(&ctx->cen, sizeof(float) * nn1 * static_cast<size_t>(ctx->ldc)));
+        IC_CUDA(cudaMalloc(&ctx->cen, sizeof(float) * 2 * nn1 * static_cast<size_t>(ctx->ldc)));  // by key: N items + up to N merges
         IC_CUDA(cudaMalloc(&ctx->xq, sizeof(int4) * static_cast<size_t>(ctx->xq_cap)));
         IC_CUDA(cudaMalloc(&ctx->xres, sizeof(uint4) * static_cast<size_t>(kMaxBatch) * kXResCap));
         IC_CUDA(cudaMalloc(&ctx->xhit, sizeof(int32_t) * kMaxBatch));
@@ -431,7 +431,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     }
     // K4: second matrix buffer (a quarter of the first) and second copies of the per-slot state; one GPU, batched loop
     if (ctx->compact_opt && ctx->batch_layout && ctx->shard_world <= 1 && P == 1 && n >= ctx->compact_min) {
-        const size_t half = static_cast<size_t>(n / 2 + 32);
+        const size_t half = static_cast<size_t>(static_cast<double>(n) * ctx->compact_ratio + 32);
         const size_t want = half * static_cast<size_t>(round_up(static_cast<int64_t>(half), 32));
         size_t fb = 0, tb = 0;
         IC_CUDA(cudaMemGetInfo(&fb, &tb));
@@ -442,7 +442,6 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
             IC_CUDA(cudaMalloc(&ctx->gkey_b, sizeof(int32_t) * n4));
             IC_CUDA(cudaMalloc(&ctx->nn_b, sizeof(SlotNN) * nn1 * kNNK));
             IC_CUDA(cudaMalloc(&ctx->nn_more_b, sizeof(int32_t) * nn1));
-            IC_CUDA(cudaMalloc(&ctx->crow_b, sizeof(int32_t) * (nn1 + 4)));
             IC_CUDA(cudaMalloc(&ctx->keymap, sizeof(int32_t) * (2 * nn1 + 4)));
             IC_CUDA(cudaMalloc(&ctx->newslot, sizeof(int32_t) * (nn1 + 4)));
             IC_CUDA(cudaMalloc(&ctx->oldslot, sizeof(int32_t) * (nn1 + 4)));
@@ -588,21 +587,29 @@ int do_gram(ic_ctx* ctx, int mode) {
     return IC_OK;
 }
 
+// a fresh matrix: one slot per item, in key order, in buffer A
+void reset_epoch(ic_ctx* ctx) {
+    ctx->n_cur = ctx->n;
+    ctx->ld_cur = ctx->ld;
+    ctx->dm_cur = ctx->dm;
+    ctx->order_key = static_cast<int32_t>(ctx->n);  // singletons: key == slot
+    // a symmetric initial matrix holds every pair of two items in both rows; the lower-triangle-only K1 does not
+    ctx->mirror_key = ctx->dm_lower_only ? 0 : static_cast<int32_t>(ctx->n);
+    ctx->n_compactions = 0;
+    ctx->ms_compact = 0.0;
+}
+
 int init_loop_state(ic_ctx* ctx) {
     const int NL = n_local(ctx);
     const size_t n = static_cast<size_t>(ctx->n), n4 = (n + 3) / 4 * 4;
     IC_CUDA(launch_init_slots(ctx->ks, ctx->gkey, ctx->n, ctx->stream));
     ctx->stats.kernel_launches += 1;
-    // singleton centroids (clustering.go:19-20) when the run keeps them; centroid row of slot s = s
-    IC_CUDA(launch_init_centroids(ctx->x, ctx->n, ctx->d, ctx->d, ctx->exact_on ? ctx->cen : nullptr, ctx->ldc, ctx->crow, ctx->stream));
-    ctx->stats.kernel_launches += 1;
-    ctx->n_cur = ctx->n;
-    ctx->ld_cur = ctx->ld;
-    ctx->dm_cur = ctx->dm;
-    ctx->order_key = static_cast<int32_t>(ctx->n);  // singletons: key == slot
-    ctx->mirror_key = 0;                            // K1 stores a pair in the row of its higher key only
-    ctx->n_compactions = 0;
-    ctx->ms_compact = 0.0;
+    if (ctx->exact_on && ctx->cen) {  // singleton centroids (clustering.go:19-20): rows 0..N-1 of the store (by key)
+        IC_CUDA(launch_init_centroids(ctx->x, ctx->n, ctx->d, ctx->d, ctx->cen, ctx->ldc, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    reset_epoch(ctx);
+    if (ctx->prof) IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
     ctx->horizon = -1.0;
     ctx->abs_slack = ctx->abs_slack_opt >= 0.0 ? ctx->abs_slack_opt : 0.0;
     ctx->hz_factor_cur = ctx->hz_factor;
@@ -645,6 +652,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
     p.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
     p.scan_every = ctx->scan_every;
     p.debug = ctx->loop_debug;
+    p.refill_at = ctx->refill_at;
     p.exact = (ctx->exact_on && use_batch(ctx) && ctx->cen) ? 1 : 0;
     p.eps_filter = static_cast<float>(ctx->eps_filter);
     p.abs_slack = static_cast<float>(ctx->abs_slack);
@@ -666,8 +674,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         bs.key_base = static_cast<int32_t>(ctx->n);
         bs.order_key = ctx->order_key;
         bs.mirror_key = ctx->mirror_key;
-        bs.compact_at = (ctx->dm_b && ctx->n_cur >= ctx->compact_min) ? static_cast<int32_t>(ctx->n_cur / 2) : 0;
-        bs.crow = ctx->crow;
+        bs.compact_at = (ctx->dm_b && ctx->n_cur >= ctx->compact_min) ? static_cast<int32_t>(static_cast<double>(ctx->n_cur) * ctx->compact_ratio) : 0;
         bs.n_ranks = 1;
         bs.rank = 0;
         bs.rows_per_rank = static_cast<int32_t>(rows_per_rank(ctx));
@@ -768,13 +775,12 @@ int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
     a.dm = ctx->dm_cur;
     a.ld = ctx->ld_cur;
     a.n_slots = static_cast<int32_t>(ctx->n_cur);
-    a.crow = ctx->crow;
     a.mirror_key = ctx->mirror_key;
     a.rows_per_rank = ctx->shard_world > 1 ? static_cast<int32_t>(rows_per_rank(ctx)) : 0x40000000;
     for (int q = 0; q < kMaxRanks; ++q)
         a.dm_rank[q] = ctx->shard_world > 1 ? static_cast<float*>(ctx->peer_dm[q]) : ctx->dm_cur;
     a.r_lo = static_cast<int32_t>(row_begin(ctx));
-    a.r_hi = static_cast<int32_t>(row_end(ctx));
+    a.r_hi = static_cast<int32_t>(std::min(row_end(ctx), ctx->n_cur));  // (after a compaction: n_cur dense slots)
     a.ks = ctx->ks;
     a.gkey = ctx->gkey;
     a.cen = ctx->cen;
@@ -875,12 +881,10 @@ int do_compact(ic_ctx* ctx) {
     a.ks_old = ctx->ks;
     a.nn_old = ctx->nn;
     a.nn_more_old = ctx->nn_more;
-    a.crow_old = ctx->crow;
     a.ks_new = ctx->ks_b;
     a.gkey_new = ctx->gkey_b;
     a.nn_new = ctx->nn_b;
     a.nn_more_new = ctx->nn_more_b;
-    a.crow_new = ctx->crow_b;
     for (int q = 0; q < kMaxRanks; ++q) {
         a.dm_old[q] = ctx->dm_cur;
         a.dm_new_rank[q] = target;
@@ -904,7 +908,6 @@ int do_compact(ic_ctx* ctx) {
     std::swap(ctx->gkey, ctx->gkey_b);
     std::swap(ctx->nn, ctx->nn_b);
     std::swap(ctx->nn_more, ctx->nn_more_b);
-    std::swap(ctx->crow, ctx->crow_b);
     ctx->dm_cur = target;
     ctx->n_cur = n_new;
     ctx->ld_cur = ld_new;
@@ -1080,9 +1083,24 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
         IC_CUDA(launch_fill(ctx->dm, (row_end(ctx) - row_begin(ctx)) * ctx->ld, INFINITY, ctx->stream));
         ctx->stats.kernel_launches += 1;
     }
+    if (ctx->mirror_init && ctx->dm_lower_only && ctx->shard_world <= 1 && ctx->n > 1) {
+        CompactArgs a{};
+        a.n_new = static_cast<int32_t>(ctx->n);
+        a.dm_new = ctx->dm;
+        for (int q = 0; q < kMaxRanks; ++q) a.dm_new_rank[q] = ctx->dm;
+        a.rows_per_rank_new = 0x40000000;
+        a.row_base_new = 0;
+        a.row0 = 0;
+        a.row1 = static_cast<int32_t>(ctx->n);
+        a.ld_new = ctx->ld;
+        IC_CUDA(launch_mirror_lower(a, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        ctx->dm_lower_only = false;
+    }
     IC_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     ctx->have_dm = true;
     ctx->have_nn = false;
+    reset_epoch(ctx);
     ctx->gram_mode_used = mode;
     ctx->stats.gram_mode = mode;
     ctx->exact_on = ctx->exact_opt != 0 && ctx->cen != nullptr;
@@ -1283,8 +1301,17 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
     } else if (k == "delta_cut") {
         if (!(value >= 0.0 && value < 0.1)) return fail(ctx, IC_ERR_BAD_ARG, "delta_cut must be in [0, 0.1)");
         ctx->delta_cut = value;
+    } else if (k == "refill_at") {
+        const int v = static_cast<int>(value);
+        if (v < 1 || v > 2) return fail(ctx, IC_ERR_BAD_ARG, "refill_at must be 1 or 2");
+        ctx->refill_at = v;
     } else if (k == "compact") {
         ctx->compact_opt = value != 0.0;
+    } else if (k == "compact_ratio") {
+        if (!(value >= 0.25 && value <= 0.9)) return fail(ctx, IC_ERR_BAD_ARG, "compact_ratio must be in [0.25, 0.9]");
+        ctx->compact_ratio = value;
+    } else if (k == "mirror_init") {
+        ctx->mirror_init = value != 0.0;
     } else if (k == "compact_min") {
         ctx->compact_min = std::max<int64_t>(64, static_cast<int64_t>(value));
     } else if (k == "delta_cut_fallback") {
@@ -1406,6 +1433,7 @@ int ic_set_matrix(ic_ctx* ctx, const float* m_host, int64_t ld) {
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_dm = true;
     ctx->have_nn = false;
+    reset_epoch(ctx);
     // a supplied matrix need not be the distances of the resident X: Lance-Williams values only, unless "exact" = 2
     ctx->exact_on = ctx->exact_opt == 2 && ctx->cen != nullptr;
     ctx->dm_is_reference = false;

@@ -68,16 +68,12 @@ __global__ void __launch_bounds__(256) compact_state_kernel(const CompactArgs a)
     if (o < 0) {
         a.ks_new[s] = make_int2(-1, 0);
         a.gkey_new[s] = -1;
-        if (s < a.n_new) {  // (cannot happen: fewer live keys than the host counted)
-            a.nn_more_new[s] = 0;
-            a.crow_new[s] = 0;
-        }
+        if (s < a.n_new) a.nn_more_new[s] = 0;  // (cannot happen: fewer live keys than the host counted)
         return;
     }
     const int2 k = a.ks_old[o];
     a.ks_new[s] = k;
     a.gkey_new[s] = k.x;
-    a.crow_new[s] = a.crow_old[o];
     int32_t more = a.nn_more_old[o];
 #pragma unroll
     for (int e = 0; e < kNNK; ++e) {
@@ -115,31 +111,49 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const CompactArgs a) 
     }
 }
 
-// upper triangle <- lower triangle, 32 x 32 tiles through shared memory (both sides coalesced)
-__global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a) {
-    __shared__ float tile[32][33];
-    const int32_t bi = blockIdx.y, bj = blockIdx.x;  // tile rows bi (source), tile columns bj, bj <= bi
-    if (bj > bi) return;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    // source rows i = bi*32 + .., columns j = bj*32 + ..; destination rows j (must be resident here), columns i
-    const int32_t j_lo = bj * 32, j_hi = j_lo + 32;
+// upper triangle <- lower triangle, 64 x 64 tiles through shared memory (16-byte accesses on both sides); one block per
+// tile of the lower triangle, tiles enumerated linearly (no empty blocks)
+constexpr int kMT = 64;
+__global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a, int32_t nb) {
+    __shared__ float tile[kMT][kMT + 1];
+    // linear index -> (bi, bj), bj <= bi
+    const int64_t lin = blockIdx.x;
+    int32_t bi = static_cast<int32_t>((sqrt(8.0 * static_cast<double>(lin) + 1.0) - 1.0) * 0.5);
+    while (static_cast<int64_t>(bi) * (bi + 1) / 2 > lin) --bi;
+    while (static_cast<int64_t>(bi + 1) * (bi + 2) / 2 <= lin) ++bi;
+    const int32_t bj = static_cast<int32_t>(lin - static_cast<int64_t>(bi) * (bi + 1) / 2);
+    if (bi >= nb) return;
+    // source rows i in tile bi, columns j in tile bj; destination rows j (must be resident here), columns i
+    const int32_t j_lo = bj * kMT, j_hi = j_lo + kMT;
     if (j_hi <= a.row0 || j_lo >= a.row1) return;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 float4 across, 16 rows per pass
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int32_t i = bi * 32 + r, j = bj * 32 + tx;
-        float v = INFINITY;
-        if (i < a.n_new && j < a.n_new && j < i) {
+    for (int r = ty; r < kMT; r += 16) {
+        const int32_t i = bi * kMT + r, j0 = bj * kMT + tx * 4;
+        float4 v = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        if (i < a.n_new && j0 < a.n_new) {  // ld is a multiple of 32: the 16 bytes are inside the row
             const int32_t q = i / a.rows_per_rank_new;
-            v = __ldcg(a.dm_new_rank[q] + static_cast<int64_t>(i - q * a.rows_per_rank_new) * a.ld_new + j);
+            v = __ldcg(reinterpret_cast<const float4*>(a.dm_new_rank[q] + static_cast<int64_t>(i - q * a.rows_per_rank_new) * a.ld_new + j0));
         }
-        tile[r][tx] = v;
+        tile[r][tx * 4 + 0] = v.x;
+        tile[r][tx * 4 + 1] = v.y;
+        tile[r][tx * 4 + 2] = v.z;
+        tile[r][tx * 4 + 3] = v.w;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int32_t j = bj * 32 + r, i = bi * 32 + tx;  // write dm[j][i] = dm[i][j]
-        if (i < a.n_new && j < a.n_new && j < i && j >= a.row0 && j < a.row1)
-            a.dm_new[static_cast<int64_t>(j - a.row_base_new) * a.ld_new + i] = tile[tx][r];
+    for (int r = ty; r < kMT; r += 16) {
+        const int32_t j = bj * kMT + r, i0 = bi * kMT + tx * 4;  // write dm[j][i0..i0+3] = dm[i0..i0+3][j]
+        if (j >= a.n_new || j < a.row0 || j >= a.row1 || i0 >= a.n_new) continue;
+        float* dst = a.dm_new + static_cast<int64_t>(j - a.row_base_new) * a.ld_new + i0;
+        const float v[4] = {tile[tx * 4 + 0][r], tile[tx * 4 + 1][r], tile[tx * 4 + 2][r], tile[tx * 4 + 3][r]};
+        if (i0 > j && i0 + 3 < a.n_new) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i0 + e > j && i0 + e < a.n_new) dst[e] = v[e];
+        }
     }
 }
 
@@ -169,8 +183,9 @@ cudaError_t launch_compact_rows(const CompactArgs& a, cudaStream_t s) {
 
 cudaError_t launch_mirror_lower(const CompactArgs& a, cudaStream_t s) {
     if (a.n_new <= 1 || a.row1 <= a.row0) return cudaSuccess;
-    const unsigned nb = static_cast<unsigned>((a.n_new + 31) / 32);
-    mirror_lower_kernel<<<dim3(nb, nb), 256, 0, s>>>(a);
+    const int64_t nb = (a.n_new + kMT - 1) / kMT;
+    const int64_t tiles = nb * (nb + 1) / 2;
+    mirror_lower_kernel<<<static_cast<unsigned>(tiles), 256, 0, s>>>(a, static_cast<int32_t>(nb));
     return cudaGetLastError();
 }
 

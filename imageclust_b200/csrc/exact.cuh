@@ -6,8 +6,8 @@
 //                             amd64 with the default GOAMD64=v1)
 //   MergeClusters (:36-40)    centroid[i] = (float32(na)*ca[i] + float32(nb)*cb[i]) / float32(na+nb)
 // The merge loop keeps Lance-Williams values (cheap, off by a few 1e-6) and calls this for the pairs that can decide a
-// merge.  A side is a stored centroid row, or the centroid of a merge of two stored rows formed on
-// the fly (the clusters a batch is creating have no stored centroid yet).
+// merge.  Centroids are stored by cluster KEY (row k < N: item k; row N + t: the cluster made by
+// merge t, written once by the iteration that creates it), so nothing moves when slots are reused or renumbered.
 //
 // The 32 lanes load both rows coalesced and form the squared differences in parallel; the sum itself is the
 // reference's sequential chain (D dependent fp32 adds, ~4 cycles each: 8.4 k cycles at D = 2048) run by lane 0 from
@@ -20,53 +20,26 @@ namespace ic {
 
 constexpr int kExChunk = 256;  // floats staged per step: 1 KB of shared memory per warp
 
-struct ExSide {
-    const float* p0;
-    const float* p1;  // nullptr: stored centroid p0; else merge of p0 (size f0) and p1 (size f1)
-    float f0, f1, fs;
-};
-IC_DEVINL ExSide ex_plain(const float* p) {
-    ExSide s;
-    s.p0 = p;
-    s.p1 = nullptr;
-    s.f0 = s.f1 = s.fs = 1.0f;
-    return s;
-}
-IC_DEVINL ExSide ex_merged(const float* pa, int sa, const float* pb, int sb) {
-    ExSide s;
-    s.p0 = pa;
-    s.p1 = pb;
-    s.f0 = static_cast<float>(sa);  // float32(a.Size), float32(b.Size), float32(newCluster.Size): clustering.go:39
-    s.f1 = static_cast<float>(sb);
-    s.fs = static_cast<float>(sa + sb);
-    return s;
-}
+// centroid[i] = (float32(na)*ca[i] + float32(nb)*cb[i]) / float32(na+nb), clustering.go:39
 IC_DEVINL float ex_merge1(float fa, float a, float fb, float b, float fs) {
     return __fdiv_rn(__fadd_rn(__fmul_rn(fa, a), __fmul_rn(fb, b)), fs);
-}
-IC_DEVINL float4 ex_value(const ExSide& s, float4 r0, float4 r1) {
-    if (s.p1 == nullptr) return r0;
-    return make_float4(ex_merge1(s.f0, r0.x, s.f1, r1.x, s.fs), ex_merge1(s.f0, r0.y, s.f1, r1.y, s.fs),
-                       ex_merge1(s.f0, r0.z, s.f1, r1.z, s.fs), ex_merge1(s.f0, r0.w, s.f1, r1.w, s.fs));
 }
 
 // dsq = DotFloat32(diff, diff), diff = A - B over d4 floats (rows are zero padded to a multiple of 4: +0 terms leave the
 // sum unchanged).  Whole warp; sbuf = this warp's kExChunk floats of shared memory.  Rows are read with ld.global.cg: the
-// centroid store is rewritten by other SMs between phases, L1 must not serve it.
-IC_DEVINL float warp_exact_dsq(const ExSide& A, const ExSide& B, int d4, float* sbuf) {
+// centroid store is written by other SMs in the phase before, L1 must not serve it.
+IC_DEVINL float warp_exact_dsq(const float* __restrict__ pa, const float* __restrict__ pb, int d4, float* sbuf) {
     const int lane = threadIdx.x & 31;
     constexpr int Q = kExChunk / 128;
-    float4 a0[Q], a1[Q], b0[Q], b1[Q];
+    float4 a[Q], b[Q];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     auto issue = [&](int c0) {
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int e = c0 + 4 * (lane + 32 * q);
             const bool ok = e < d4;
-            a0[q] = ok ? __ldcg(reinterpret_cast<const float4*>(A.p0 + e)) : z;
-            a1[q] = (ok && A.p1) ? __ldcg(reinterpret_cast<const float4*>(A.p1 + e)) : z;
-            b0[q] = ok ? __ldcg(reinterpret_cast<const float4*>(B.p0 + e)) : z;
-            b1[q] = (ok && B.p1) ? __ldcg(reinterpret_cast<const float4*>(B.p1 + e)) : z;
+            a[q] = ok ? __ldcg(reinterpret_cast<const float4*>(pa + e)) : z;
+            b[q] = ok ? __ldcg(reinterpret_cast<const float4*>(pb + e)) : z;
         }
     };
     float sum = 0.0f;
@@ -74,8 +47,8 @@ IC_DEVINL float warp_exact_dsq(const ExSide& A, const ExSide& B, int d4, float* 
     for (int c0 = 0; c0 < d4; c0 += kExChunk) {
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const float4 x = ex_value(A, a0[q], a1[q]), y = ex_value(B, b0[q], b1[q]);
-            const float dx = __fsub_rn(x.x, y.x), dy = __fsub_rn(x.y, y.y), dz = __fsub_rn(x.z, y.z), dw = __fsub_rn(x.w, y.w);
+            const float dx = __fsub_rn(a[q].x, b[q].x), dy = __fsub_rn(a[q].y, b[q].y), dz = __fsub_rn(a[q].z, b[q].z),
+                        dw = __fsub_rn(a[q].w, b[q].w);
             reinterpret_cast<float4*>(sbuf)[lane + 32 * q] =
                 make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
         }

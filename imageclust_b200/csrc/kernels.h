@@ -131,6 +131,7 @@ struct LoopParams {
     // within eps_filter.  Merges are only taken among values <= safe = horizon / (1 + 2 eps_filter); when the minimum
     // gets there the kernel stops (STOP_HORIZON) and the host raises the horizon.  Members of a batch after the first
     // must be below T (1 - delta_cut): fp32 centroid distances are reducible only up to rounding.
+    int32_t refill_at;   // a row whose partner list holds fewer valid entries than this (and may have more partners) is rescanned
     int32_t exact;
     float eps_filter;
     float abs_slack;     // absolute error a never re-evaluated tensor-core Gram value may carry (monitor only; safe includes it)
@@ -229,9 +230,8 @@ struct BatchState {
     // reference arithmetic (LoopParams::exact): fp32 centroid of every slot's cluster (replicated on every rank), and
     // the queue of the pairs an iteration wrote at or below the horizon {index of the merge in the batch, column slot or
     // 0x80000000 | index of an earlier merge of the batch (cross term)}
-    float* cen;         // [N x ldc], ldc = d rounded up to 4, zero padded
+    float* cen;         // [2N x ldc] by cluster key (row N + t: the cluster made by merge t), ldc = d rounded up to 4, zero padded
     int64_t ldc;
-    const int32_t* crow; // [n] centroid row of every slot's cluster (slots are renumbered by a compaction, centroids stay)
     int4* xq;           // [xq_cap] {merge, column | cross, Lance-Williams value bits, position among the merge's queued pairs}
     int32_t xq_cap;
     // one GPU: the partner list of a new cluster is selected from its re-evaluated pairs (everything else in its row is
@@ -244,10 +244,9 @@ int64_t merge_batch_windows(int64_t n);
 cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks);  // *blocks = 0: does not fit
 cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);  // n_ranks > 1: sharded
 // ---- reference arithmetic for selected pairs (refine.cu) ---------------------------------------------------------
-// cen[s] = x[s] (zero padded to ldc floats per row): the singleton centroids (clustering.go:19-20)
-// and crow[s] = s
-cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, int32_t* crow,
-                                  cudaStream_t s);
+// cen[k] = x[k] for k < N (zero padded to ldc floats per row): the singleton centroids (clustering.go:19-20); centroids are
+// stored by cluster key
+cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, cudaStream_t s);
 struct RefineArgs {
     float* dm;            // resident rows [r_lo, r_hi) x ld
     int64_t ld;
@@ -256,7 +255,6 @@ struct RefineArgs {
     const int32_t* gkey;  // [n4] keys, padding -1
     const float* cen;
     int64_t ldc;
-    const int32_t* crow;  // centroid row of every slot
     int32_t mirror_key;   // pairs of two clusters with key < mirror_key are stored in both rows (compact.cu)
     int32_t rows_per_rank;
     float* dm_rank[kMaxRanks];  // every rank's row block (mirrored stores); [0] = dm on one GPU
@@ -284,12 +282,10 @@ struct CompactArgs {
     const SlotKS* ks_old;
     const SlotNN* nn_old;
     const int32_t* nn_more_old;
-    const int32_t* crow_old;
     SlotKS* ks_new;
     int32_t* gkey_new;
     SlotNN* nn_new;
     int32_t* nn_more_new;
-    int32_t* crow_new;
     // matrix: old rows may live on peers (sharded); the new rows [row0, row1) are resident here, first at dm_new
     const float* dm_old[kMaxRanks];
     int32_t rows_per_rank_old;

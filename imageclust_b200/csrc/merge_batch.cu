@@ -998,6 +998,23 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 }
             }
         }
+        // ---- centroids of the new clusters (MergeClusters, clustering.go:36-40): row N + t of the centroid store ----
+        // (every rank keeps a replica; read by the exact phase after the next barrier)
+        if (exact) {
+            const int32_t nch = (d4 + 127) / 128;
+            for (int32_t u = gw; u < m * nch; u += GW) {
+                const int32_t j = u / nch, e = ((u - j * nch) * 32 + lane) * 4;
+                if (e < d4) {
+                    const float* pa = st.cen + static_cast<int64_t>(s_ka[j]) * st.ldc + e;  // a: the larger position (clustering.go:237)
+                    const float* pb = st.cen + static_cast<int64_t>(s_kb[j]) * st.ldc + e;
+                    const float4 ca = __ldcg(reinterpret_cast<const float4*>(pa)), cb = __ldcg(reinterpret_cast<const float4*>(pb));
+                    const float fa = static_cast<float>(s_sa[j]), fb = static_cast<float>(s_sb[j]), fs = static_cast<float>(s_sa[j] + s_sb[j]);
+                    __stcg(reinterpret_cast<float4*>(st.cen + static_cast<int64_t>(kbase + t + j) * st.ldc + e),
+                           make_float4(ex_merge1(fa, ca.x, fb, cb.x, fs), ex_merge1(fa, ca.y, fb, cb.y, fs),
+                                       ex_merge1(fa, ca.z, fb, cb.z, fs), ex_merge1(fa, ca.w, fb, cb.w, fs)));
+                }
+            }
+        }
         const long long tq1 = timed ? clock64() : 0;
         // ---- cross terms: d(new_i, new_j), i < j, two chained updates from the four old entries ----
         for (int32_t j = gw; j < m; j += GW) {
@@ -1067,7 +1084,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     v = nn_bound(last);
                 __stcg(st.nn + static_cast<int64_t>(r) * kNNK + x, v);
             }
-            if (kept < ((prm.debug & 1) ? 2 : 1) && more) {  // (debug bit 0: refill a list that is down to one entry -- larger batches, more scans)
+            // a list that is down to one entry is refilled, too: its bound placeholder would be a stopper right above its
+            // head and cut every batch there (measured at config C: 73 merges per iteration instead of 11, 2x the scans)
+            if (kept < prm.refill_at && more) {
                 __stcg(st.nn_more + r, static_cast<int32_t>(kMoreBit | kDryBit));
                 st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(r, key_r);
             }
@@ -1102,22 +1121,21 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             for (int32_t q = gw; q < nx; q += GW) {
                 const int4 ent = __ldcg(st.xq + q);
                 const int32_t j = ent.x;
-                const int32_t aj = s_a[j], bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
-                auto cen_of = [&](int32_t slot) { return st.cen + static_cast<int64_t>(__ldcg(st.crow + slot)) * st.ldc; };
-                const ExSide A = ex_merged(cen_of(aj), saj, cen_of(bj), sbj);
-                ExSide B;
-                int32_t size_b, col;
-                if (ent.y < 0) {  // cross term: the other cluster is being created by this batch, too
+                const int32_t bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
+                // centroids are stored by key; the new clusters' rows were written in the phase before the barrier
+                const float* pa = st.cen + static_cast<int64_t>(kbase + t - m + j) * st.ldc;
+                int32_t size_b, col, key_b;
+                if (ent.y < 0) {  // cross term: the other cluster was created by this batch, too
                     const int32_t i = ent.y & 0x7FFFFFFF;
-                    B = ex_merged(cen_of(s_a[i]), s_sa[i], cen_of(s_b[i]), s_sb[i]);
                     size_b = s_sa[i] + s_sb[i];
                     col = s_b[i];
+                    key_b = kbase + t - m + i;
                 } else {
                     col = ent.y;
-                    B = ex_plain(cen_of(col));
                     size_b = __ldcg(st.lsize + col);
+                    key_b = __ldcg(st.gkey + col);
                 }
-                const float dsq = warp_exact_dsq(A, B, d4, s_ex[warp]);
+                const float dsq = warp_exact_dsq(pa, st.cen + static_cast<int64_t>(key_b) * st.ldc, d4, s_ex[warp]);
                 if (lane == 0) {
                     const float w = ward_weight(saj + sbj, size_b, dsq);
                     exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(ent.z)), w, prm.eps_filter, prm.abs_slack);
@@ -1125,7 +1143,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     __stcg(row_of(bj) + col, w);
                     if (use_xres && ent.w < kXResCap)
                         __stcg(st.xres + static_cast<int64_t>(j) * kXResCap + ent.w,
-                               make_uint4(__float_as_uint(w), static_cast<uint32_t>(ent.y < 0 ? kbase + t - m + (ent.y & 0x7FFFFFFF) : __ldcg(st.gkey + col)),
+                               make_uint4(__float_as_uint(w), static_cast<uint32_t>(key_b),
                                           static_cast<uint32_t>(col), static_cast<uint32_t>(size_b)));
                     if (kMulti && (bj < r_lo || bj >= r_hi)) wrote_remote = true;
                     ++my_exact;
@@ -1138,20 +1156,6 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         else
             grid_sync(st.bar, phase, G);
         m_prev = m;
-        if (exact) {  // centroids of the new clusters (clustering.go:36-40) replace those of their slots b; every rank keeps a replica
-            const int32_t nch = (d4 + 127) / 128;
-            for (int32_t u = gw; u < m * nch; u += GW) {
-                const int32_t j = u / nch, e = ((u - j * nch) * 32 + lane) * 4;
-                if (e < d4) {
-                    const float* pa = st.cen + static_cast<int64_t>(__ldcg(st.crow + s_a[j])) * st.ldc + e;
-                    float* pb = st.cen + static_cast<int64_t>(__ldcg(st.crow + s_b[j])) * st.ldc + e;
-                    const float4 ca = __ldcg(reinterpret_cast<const float4*>(pa)), cb = __ldcg(reinterpret_cast<const float4*>(pb));
-                    const float fa = static_cast<float>(s_sa[j]), fb = static_cast<float>(s_sb[j]), fs = static_cast<float>(s_sa[j] + s_sb[j]);
-                    __stcg(reinterpret_cast<float4*>(pb), make_float4(ex_merge1(fa, ca.x, fb, cb.x, fs), ex_merge1(fa, ca.y, fb, cb.y, fs),
-                                                                     ex_merge1(fa, ca.z, fb, cb.z, fs), ex_merge1(fa, ca.w, fb, cb.w, fs)));
-                }
-            }
-        }
         if (timed) {
             const long long tp4 = clock64();
             c_ph[0] += tp1 - tp0;
@@ -1162,14 +1166,14 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             c_ph[7] += tp4 - tq3;
         }
     }
-    if (timed) {
-        st.prof[0] = c_ph[0];
-        st.prof[1] = c_ph[1];
-        st.prof[2] = c_ph[2];
-        st.prof[3] = c_ph[3];
-        st.prof[5] = launched;
-        st.prof[6] = iters;
-        for (int i = 0; i < 4; ++i) st.prof[10 + i] = c_ph[4 + i];
+    if (timed) {  // accumulated over the launches of one clustering (the host zeroes them when it starts)
+        st.prof[0] += c_ph[0];
+        st.prof[1] += c_ph[1];
+        st.prof[2] += c_ph[2];
+        st.prof[3] += c_ph[3];
+        st.prof[5] += launched;
+        st.prof[6] += iters;
+        for (int i = 0; i < 4; ++i) st.prof[10 + i] += c_ph[4 + i];
     }
     if (blockIdx.x == 0 && tid == 0) {
         ctl[CTL_N_LIVE] = n_live;

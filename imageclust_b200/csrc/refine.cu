@@ -22,10 +22,8 @@ namespace {
 constexpr int kColT = 256;
 
 __global__ void __launch_bounds__(256) init_centroids_kernel(const float* __restrict__ x, int64_t n, int64_t d, int64_t ldx,
-                                                             float* __restrict__ cen, int64_t ldc, int32_t* __restrict__ crow) {
-    const int64_t total = cen ? n * ldc : 0;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-        crow[i] = static_cast<int32_t>(i);
+                                                             float* __restrict__ cen, int64_t ldc) {
+    const int64_t total = n * ldc;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = i / ldc, c = i - r * ldc;
@@ -81,8 +79,8 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
     for (int32_t i = gw; i < total; i += GW) {
         const int2 p = a.q[i];
         const int2 kr = a.ks[p.x], ku = a.ks[p.y];
-        const float dsq = warp_exact_dsq(ex_plain(a.cen + static_cast<int64_t>(a.crow[p.x]) * a.ldc),
-                                         ex_plain(a.cen + static_cast<int64_t>(a.crow[p.y]) * a.ldc), d4, s_buf[warp]);
+        const float dsq = warp_exact_dsq(a.cen + static_cast<int64_t>(kr.x) * a.ldc, a.cen + static_cast<int64_t>(ku.x) * a.ldc, d4,
+                                         s_buf[warp]);  // centroids are stored by key
         if (lane == 0) {
             const float w = ward_weight(kr.y, ku.y, dsq);
             float* dst = a.dm + static_cast<int64_t>(p.x - a.r_lo) * a.ld + p.y;
@@ -103,12 +101,11 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
 }
 }  // namespace
 
-cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, int32_t* crow,
-                                  cudaStream_t s) {
+cudaError_t launch_init_centroids(const float* x, int64_t n, int64_t d, int64_t ldx, float* cen, int64_t ldc, cudaStream_t s) {
     if (n <= 0 || ldc <= 0) return cudaSuccess;
     const int64_t total = n * ldc;
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 16));
-    init_centroids_kernel<<<blocks, 256, 0, s>>>(x, n, d, ldx, cen, ldc, crow);
+    init_centroids_kernel<<<blocks, 256, 0, s>>>(x, n, d, ldx, cen, ldc);
     return cudaGetLastError();
 }
 

@@ -3,8 +3,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         scripts/shard_check.py [big]
 
-Every rank clusters the same matrix as rank r of W shards; rank 0 replays the gathered initial
-matrix through the CPU oracle (Lance-Williams mode) and all ranks must hold that exact trace."""
+Every rank clusters the same matrix as rank r of W shards; rank 0 runs the CPU oracle in REFERENCE arithmetic
+(oracle.fast_cluster(flags=0), bit-identical to the literal restatement of clustering.go) and all ranks must hold
+exactly that trace.  With IC_EXACT=0 the ranks keep Lance-Williams values only and the oracle's Lance-Williams mode
+replays the gathered initial matrix instead."""
 import hashlib
 import os
 import sys
@@ -25,6 +27,8 @@ big = len(sys.argv) > 1 and sys.argv[1] == "big"
 
 eng = clustering.Engine(local)
 eng.set_option("loop_mode", int(os.environ.get("IC_LOOP_MODE", "1")))  # 1: batched loop across the ranks, 0: one merge per iteration
+exact_mode = int(os.environ.get("IC_EXACT", "1")) != 0 and int(os.environ.get("IC_LOOP_MODE", "1")) == 1
+eng.set_option("exact", 1 if exact_mode else 0)
 sh = sharding.ShardedEngine(eng, rank, world)
 ok = True
 cases = [(600, 48, 3, 10, _lib.GRAM_EXACT_FP32), (3001, 64, 4, 12, _lib.GRAM_TCGEN05_3XTF32),
@@ -46,14 +50,18 @@ for n, d, mn, mx, mode in cases:
     same = len(set(digests)) == 1
     if rank == 0:
         from oracle import oracle as O
-        m = np.tril(m_own.cpu().numpy(), -1)
-        m = m + m.T
-        o = O.fast_cluster(x, mn, mx, flags=O.FAST_EAGER | O.FAST_LW, init_matrix=m)
+        if exact_mode:
+            o = O.fast_cluster(x, mn, mx, flags=0)
+        else:
+            m = np.tril(m_own.cpu().numpy(), -1)
+            m = m + m.T
+            o = O.fast_cluster(x, mn, mx, flags=O.FAST_EAGER | O.FAST_LW, init_matrix=m)
         exact = (len(tr.key_hi) == o.n_merges and np.array_equal(tr.key_hi, o.key_hi) and np.array_equal(tr.key_lo, o.key_lo)
                  and np.array_equal(tr.dist.view(np.uint32), o.dist.view(np.uint32))
                  and len(cl) == len(o.clusters) and all(np.array_equal(a, b) for a, b in zip(cl, o.clusters)))
         st = eng.stats()
-        print(f"shard_check W={world} N={n} D={d} {mn}/{mx}: merges={st['n_merges']} ranks_agree={same} oracle_exact={exact} "
+        exact = exact and st["exact"] == (1 if exact_mode else 0) and st["n_filter_viol"] == 0 and st["n_order_viol"] == 0
+        print(f"shard_check W={world} N={n} D={d} {mn}/{mx}: merges={st['n_merges']} ranks_agree={same} oracle_exact={exact} reference_arithmetic={exact_mode} "
               f"loop {st['ms_loop']:.2f} ms rescans={st['n_rescans']} iterations={st['n_iterations']} loop_mode={st['loop_mode']}", flush=True)
         ok = ok and same and exact
 eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
@@ -72,7 +80,7 @@ if big:
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             tr = eng.merge_trace()
-            digest = hashlib.sha256(tr.key_hi.tobytes() + tr.key_lo.tobytes() + tr.dist.tobytes()).hexdigest()
+            digest = hashlib.sha256(tr.key_hi.tobytes() + tr.key_lo.tobytes() + tr.dist.tobytes() + tr.size.tobytes()).hexdigest()
             digests = [None] * world
             dist.all_gather_object(digests, digest)
             s = r.stats
@@ -81,7 +89,8 @@ if big:
                 mg = max(p["merges"], 1)
                 print(f"config {cfg} W={world}: {dt:.3f} s  merges={s['n_merges']} out={s['n_out']} ranks_agree={len(set(digests)) == 1} "
                       f"prep {s['ms_prep']:.2f} gram {s['ms_gram']:.2f} nn {s['ms_nn_init']:.2f} loop {s['ms_loop']:.2f} ms "
-                      f"rescans={s['n_rescans']} iterations={s['n_iterations']} loop_mode={s['loop_mode']} trace_sha={digest[:12]} | cycles/merge "
+                      f"rescans={s['n_rescans']} iterations={s['n_iterations']} loop_mode={s['loop_mode']} trace_sha={digest[:12]} exact={s['exact']} "
+                      f"n_exact={s['n_exact']} filter_viol={s['n_filter_viol']} order_viol={s['n_order_viol']} refine {s['ms_refine']:.1f} ms | cycles/merge "
                       + " ".join(f"{k}={v / mg:.0f}" for k, v in p.items() if k in ("publish", "exchange", "update", "scan", "fold", "pub_fence", "pub_stores", "exch_poll", "exch_rank"))
                       + f" bubbles={p['bubbles']}", flush=True)
                 ok = ok and len(set(digests)) == 1
