@@ -36,9 +36,16 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# dram__bytes_read.sum + dram__bytes_write.sum of the merge-loop launch (ncu --set full, profiles/r01_summary.md), GB
-LOOP_TRAFFIC_GB = {("C", False): 971.4, ("C", True): 1016.2}
 sys.path.insert(0, ROOT)
+
+
+def loop_traffic_gb(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the merge-loop launches of one clustering (GB), from the committed
+    ncu --set full capture of this round's kernel (profiles/r02_loop_traffic.json); None if not captured for the config."""
+    p = os.path.join(ROOT, "profiles", "r02_loop_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(config)
+    return None
 
 from imageclust_b200 import synth  # noqa: E402
 
@@ -159,7 +166,7 @@ def run_reference(args, rank):
               f"N={n_sample} x {d}, min/max {mn_s}/{mx_s}, {merges} merges per step; the full N={n} workload "
               f"scales ~ (N/{n_sample})^3 => ~{v * (n / n_sample) ** 3:.3g} s")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config {args.config}: N={n} x {d} min/max {mn}/{mx}; reference arm sample N={n_sample}"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
@@ -167,8 +174,13 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(d, budget_n=2000):
+def cpu_baseline_leg(d, eng, budget_n=2000):
+    """CPU numbers beside the GPU line, and the oracle used AS THE CHECKER of the same samples run through the GPU path
+    (``like_for_like``: BASELINE config 1; ``parity_sample``: N = 6000, the size at which Lance-Williams values alone
+    diverge from the reference's arithmetic)."""
+    import torch
     from oracle import oracle as O
+    out = {}
     dt, merges = cpu_literal_sample(budget_n, d, 5, 20)
     # strongest CPU comparator: same semantics, NN cache, all cores
     cores = os.cpu_count() or 1
@@ -177,11 +189,108 @@ def cpu_baseline_leg(d, budget_n=2000):
     t0 = time.perf_counter()
     r = O.fast_cluster(x, 10, 50, n_threads=cores)
     dtf = time.perf_counter() - t0
-    return {"value": dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"literal C restatement of clustering.go (not Go), 1 thread, N={budget_n} x {d}, 5/20, {merges} merges",
-            "fast_oracle": {"value": dtf, "unit": UNIT, "cores": cores,
-                            "sample": f"oracle_fast (same results, NN cache, OpenMP) N={nf} x {d}, 10/50, {r.n_merges} merges"},
-            "host_cores": cores}
+    out["cpu_baseline"] = {"value": dt, "unit": UNIT, "cores": 1, "kind": "port",
+                           "sample": f"literal C restatement of clustering.go (not Go), 1 thread, N={budget_n} x {d}, 5/20, {merges} merges",
+                           "fast_oracle": {"value": dtf, "unit": UNIT, "cores": cores,
+                                           "sample": f"oracle_fast (same results, NN cache, OpenMP) N={nf} x {d}, 10/50, {r.n_merges} merges"},
+                           "host_cores": cores}
+    # the GPU path (default tensor-core Gram) on the same N = 6000 sample, checked against that reference-arithmetic run
+    xs = eng.pinned_empty((nf, d))
+    xs[:] = x
+    res = eng.cluster(xs, 10, 50)
+    tr = eng.merge_trace()
+    same = (len(tr.key_hi) == r.n_merges and np.array_equal(tr.key_hi, r.key_hi) and np.array_equal(tr.key_lo, r.key_lo))
+    first = -1
+    if not same:
+        m = min(len(tr.key_hi), r.n_merges)
+        neq = np.flatnonzero((tr.key_hi[:m] != r.key_hi[:m]) | (tr.key_lo[:m] != r.key_lo[:m]))
+        first = int(neq[0]) if len(neq) else m
+    from sklearn.metrics import adjusted_rand_score
+    lab_a = np.full(nf, -1)
+    lab_b = np.full(nf, -1)
+    for cid, c in enumerate(res.clusters):
+        lab_a[c] = cid
+    for cid, c in enumerate(r.clusters):
+        lab_b[c] = cid
+    out["parity_sample"] = {"workload": f"N={nf} x {d}, min/max 10/50, default Gram, vs oracle in reference arithmetic (flags=0)",
+                            "ari_vs_reference": float(adjusted_rand_score(lab_a, lab_b)), "trace_identical": bool(same),
+                            "dist_bits_identical": bool(same and np.array_equal(tr.dist.view(np.uint32), r.dist.view(np.uint32))),
+                            "first_divergence": first, "n_filter_viol": res.stats["n_filter_viol"],
+                            "n_order_viol": res.stats["n_order_viol"]}
+    # BASELINE config 1 (N = 1000 x 2048, 5/20) on both arms: the literal CPU restatement (1 thread) and the GPU path end to
+    # end from host memory through ic_cluster_with_constraints
+    n1, d1, mn1, mx1 = synth.CONFIGS["A"]
+    x1 = synth.gaussian_mixture(n1, d1, mn1, mx1, seed=20240)
+    t0 = time.perf_counter()
+    lit = O.literal_cluster(x1, mn1, mx1)
+    t_cpu = time.perf_counter() - t0
+    xp = eng.pinned_empty((n1, d1))
+    xp[:] = x1
+    eng.cluster(xp, mn1, mx1)
+    reps = 10
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r1 = eng.cluster(xp, mn1, mx1)
+    torch.cuda.synchronize()
+    t_gpu = (time.perf_counter() - t0) / reps
+    tr1 = eng.merge_trace()
+    out["like_for_like"] = {"workload": f"BASELINE config 1: N={n1} x {d1}, min/max {mn1}/{mx1}, {lit.n_merges} merges, same matrix on both arms",
+                            "gpu_e2e_s": t_gpu, "cpu_literal_s": t_cpu, "cpu_cores": 1, "ratio": t_cpu / t_gpu,
+                            "same_result": bool(len(tr1.key_hi) == lit.n_merges and np.array_equal(tr1.key_hi, lit.key_hi)
+                                                and np.array_equal(tr1.key_lo, lit.key_lo)
+                                                and np.array_equal(tr1.dist.view(np.uint32), lit.dist.view(np.uint32))
+                                                and len(r1.clusters) == len(lit.clusters)
+                                                and all(np.array_equal(a, b) for a, b in zip(r1.clusters, lit.clusters)))}
+    return out
+
+
+def measure_tensor_peaks():
+    """TF32 and int8 dense matmul throughput of this GPU, measured the way MEASURED_PEAKS.json's bf16 figure was
+    (torch.matmul / torch._int_mm 8192^3, best of 10): the denominators of K1's roofline lines."""
+    import torch
+    out = {}
+    n = 8192
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        best = 1e9
+        for _ in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out["tf32_tflops"] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+    except Exception as e:  # noqa: BLE001
+        out["tf32_error"] = str(e)[:80]
+    try:
+        a = torch.randint(-64, 64, (n, n), device="cuda", dtype=torch.int8)
+        b = torch.randint(-64, 64, (n, n), device="cuda", dtype=torch.int8)
+        best = 1e9
+        for _ in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out["int8_tops"] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    except Exception as e:  # noqa: BLE001
+        out["int8_error"] = str(e)[:80]
+    torch.cuda.empty_cache()
+    return out
+
+
+def trace_sha(tr):
+    import hashlib
+    return hashlib.sha256(tr.key_hi.tobytes() + tr.key_lo.tobytes() + tr.dist.tobytes() + tr.size.tobytes()).hexdigest()
 
 
 # ------------------------------------------------------------------------------------------
@@ -249,6 +358,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- cold call: the first clustering of this process (allocations, first launches) through the e2e entry point ----
+    barrier()
+    t0 = time.perf_counter()
+    runner.cluster(x_host, mn, mx)
+    barrier()
+    cold_s = max_over_ranks(time.perf_counter() - t0)
+
     # ---- resident leg: X in HBM before the timed region --------------------------------
     runner.load(x_host)
     stats = []
@@ -266,6 +382,12 @@ def main():
     dt = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     sec_per_step = dt / args.steps
+    sha = trace_sha(eng.merge_trace())  # every rank records the same trace; N = 1, 2, 4, 8 must print the same digest
+    ranks_agree = True
+    if world > 1:
+        shas = [None] * world
+        dist.all_gather_object(shas, sha)
+        ranks_agree = len(set(shas)) == 1
 
     # ---- e2e leg: host buffers through the reference-facing call ---------------------------
     for _ in range(1):
@@ -282,8 +404,10 @@ def main():
 
     # ---- kernel microbenchmarks for the roofline legs (rank 0) ----------------------------
     kern = {}
+    tpeaks = {}
     if rank == 0 and not sharded:
-        eng.load(x_host)
+        eng.load(x_host)  # (releases nothing: same shape) -- the 40 GB matrix stays; the 8192^3 probes need < 1 GB
+        tpeaks = measure_tensor_peaks()
         kern["gram_ms"] = eng.time_kernel({0: "gram", 1: "gram_exact", 2: "gram_i8"}[args.gram_mode],
                                           1 if args.gram_mode == 1 else 3)
         kern["nn_sweep_ms"] = eng.time_kernel("nn_sweep", 5)
@@ -308,7 +432,10 @@ def main():
         hbm = peaks["hbm_gbs"]
         # K1: 2*D flops per unordered pair; peak = TF32 dense = half the measured bf16 figure
         gram_flops = 2.0 * d * pairs
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        # the time_kernel figure is an isolated launch: burst denominators.  Measured TF32 / int8 matmul peaks of this GPU
+        # (torch 8192^3, this run) where available, else bf16 / 2 and bf16 x 2 of MEASURED_PEAKS
+        tf32_peak = tpeaks.get("tf32_tflops") or peaks["bf16_tflops"] / 2.0
+        int8_peak = tpeaks.get("int8_tops") or peaks["bf16_tflops"] * 2.0
         gram_tf = gram_flops / (kern["gram_ms"] * 1e-3) / 1e12 if kern.get("gram_ms") else 0.0
         sweep_gbs = 4.0 * pairs / (kern["nn_sweep_ms"] * 1e-3) / 1e9 if kern.get("nn_sweep_ms") else 0.0
         phases = {k: avg(k) for k in ("ms_prep", "ms_gram", "ms_nn_init", "ms_loop", "ms_d2h", "ms_host", "ms_total")}
@@ -316,19 +443,25 @@ def main():
         line = {
             "metric": METRIC, "value": sec_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": False,
-            "scaling": "strong" if sharded else "weak",
+            # one clustering of fixed size, on 1 GPU or row-block sharded over N: total work does not grow with N
+            "scaling": "weak" if (world > 1 and args.replicas) else "strong",
+            "trace_sha": sha, "ranks_agree": ranks_agree, "cold_first_call_s": cold_s,
             "vs_baseline": None, "dtype": {0: "tf32+f32", 1: "f32", 2: "i8/i32 (22-bit fixed point) + f32"}[args.gram_mode], "data": "synthetic",
             "config": {"workload": f"config {args.config}: N={n} x {d} Gaussian-mixture fp32 embeddings, "
                                    f"minSize={mn}, maxSize={mx} -> {stats[-1]['n_target']} clusters, {merges} merges",
                        "parallelism": "1 GPU" if world == 1 else (
                            f"one clustering row-block sharded over {world} GPUs (peer-mapped rows; the ranks' persistent kernels "
-                           f"exchange their candidate pairs once per iteration of ~10 merges over NVLink)" if sharded else f"{world} independent clustering jobs (one per GPU)"),
+                           f"exchange their candidate pairs once per iteration over NVLink)" if sharded else f"{world} independent clustering jobs (one per GPU)"),
                        "l2": "inputs larger than L2 (X %.0f MB, distance matrix %.1f GB)" % (4e-6 * n * d, stats[-1]["matrix_bytes"] / 1e9),
                        "gram": {0: "tcgen05 kind::tf32, exact fixed-point slice + residual (4 products)", 1: "exact fp32 SIMT", 2: "tcgen05 kind::i8, three int8 digits of a 22-bit fixed-point row, exact int32 accumulation (6 products)"}[args.gram_mode]},
             "merges_per_s": merges / (ms_loop * 1e-3) if ms_loop > 0 else None,
             "dist_matrix_gbs": 4.0 * pairs / (ms_gram * 1e-3) / 1e9 if ms_gram > 0 else None,
             "phases_ms": phases,
             "n_near_ties": stats[-1]["n_near_ties"], "n_rescans": stats[-1]["n_rescans"],
+            # reference arithmetic: pairs re-evaluated as WardDistance of two fp32 centroids, and the
+            # two guarantees that make the merge sequence the reference's (both must be 0)
+            "reference_arithmetic": {k: stats[-1][k] for k in ("exact", "n_exact", "n_horizon_raises", "n_filter_viol", "n_order_viol",
+                                                               "n_restarts", "n_compactions", "filter_max_err", "ms_refine", "ms_compact")},
             "exhausted": stats[-1]["exhausted"], "n_out": stats[-1]["n_out"],
             "e2e": {"value": e2e_sec, "unit": UNIT,
                     "h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"], "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"],
@@ -343,17 +476,18 @@ def main():
                          "peak": hbm, "unit": "GB/s", "frac": loop_gbs / hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full at this exact
                          # workload (profiles/); GB per launch like `achieved`'s numerator (60 GB at config C)
-                         "traffic": LOOP_TRAFFIC_GB.get((args.config, batched)) if (world == 1 and not args.n) else None,
-                         "traffic_unit": "GB per launch (ncu, profiles/r01_summary.md)",
+                         "traffic": loop_traffic_gb(args.config) if (world == 1 and not args.n and batched) else None,
+                         "traffic_unit": "GB per clustering, all launches of the loop kernel (ncu --set full, profiles/r02_summary.md)",
                          # what the launch actually moves over its measured time, against the same peak (information:
                          # the gap to `frac` is re-read rows, retired columns, partner lists, sector-granular gathers)
-                         "traffic_frac": (LOOP_TRAFFIC_GB[(args.config, batched)] / (ms_loop * 1e-3) / hbm
-                                          if (world == 1 and not args.n and (args.config, batched) in LOOP_TRAFFIC_GB and ms_loop > 0)
+                         "traffic_frac": (loop_traffic_gb(args.config) / (ms_loop * 1e-3) / hbm
+                                          if (world == 1 and not args.n and batched and loop_traffic_gb(args.config) and ms_loop > 0)
                                           else None),
                          "peak_source": peaks["source"] + " copy bandwidth",
-                         "note": ("algorithmic bytes 12*n per merge; the batched loop takes ~10 provably consecutive merges per "
-                                  "iteration, each iteration is three grid-wide phases of dependent DRAM round trips: bound by "
-                                  "latency and by per-SM request throughput of the scattered column gathers, not by bandwidth"
+                         "note": ("algorithmic bytes 12*n per merge over the time between the CUDA events around the whole loop "
+                                  "(all launches of the kernel, the horizon sweeps of refine.cu and the compactions in between); "
+                                  "an iteration takes every provably consecutive merge (dozens) in four grid-wide phases: "
+                                  "row scans, heads, Lance-Williams rows, exact re-evaluation"
                                   if batched else
                                   "algorithmic bytes 12*n per merge; the loop is a chain of dependent merges bound by one "
                                   "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth"),
@@ -364,11 +498,17 @@ def main():
                     "frac": gram_tf / tf32_peak, "ms": kern.get("gram_ms"),
                     # what the pipe itself executes: 6 int8 products (4 TF32 products) per algorithmic product, against
                     # the int8 (TF32) dense peak = measured sustained bf16 x 2 (/ 2)
-                    "pipe_frac": (gram_tf * 6.0 / (peaks["bf16_tflops_sustained"] * 2.0) if args.gram_mode == 2 else
+                    "pipe_frac": (gram_tf * 6.0 / int8_peak if args.gram_mode == 2 else
                                   gram_tf * 4.0 / tf32_peak if args.gram_mode == 0 else None),
-                    "note": "algorithmic flops 2*D per unordered pair over the fp32-accurate (TF32-equivalent) peak = measured "
-                            "sustained bf16 / 2; the int8 path issues 6 kind::i8 MMAs per k-step (6x the algorithmic "
-                            "flops, on a pipe 4x as fast), the tf32 path 4 kind::tf32 MMAs"},
+                    "peak_source": ("torch.matmul TF32 8192^3 best of 12, this run" if tpeaks.get("tf32_tflops") else "MEASURED_PEAKS bf16 burst / 2"),
+                    "pipe_peak": int8_peak if args.gram_mode == 2 else tf32_peak,
+                    "pipe_peak_source": ("torch._int_mm int8 8192^3 best of 12, this run" if (args.gram_mode == 2 and tpeaks.get("int8_tops")) else
+                                         "MEASURED_PEAKS bf16 burst x 2" if args.gram_mode == 2 else "as peak"),
+                    "measured_peaks": tpeaks,
+                    "note": "isolated launch (ic_time_kernel); frac = algorithmic flops (2*D per unordered pair) over the measured TF32 "
+                            "matmul peak -- the fp32-accurate rate a plain GEMM would get; pipe_frac = what the tensor pipe executes "
+                            "(6 kind::i8 MMAs per k-step = 6x the algorithmic flops; the tf32 path 4 kind::tf32 MMAs) over the measured "
+                            "int8 (TF32) matmul peak"},
                 "nn_sweep": {"bound": "hbm", "achieved": sweep_gbs, "peak": hbm, "unit": "GB/s", "frac": sweep_gbs / hbm,
                              "ms": kern.get("nn_sweep_ms"), "note": "algorithmic bytes 4 per pair (lower triangle read once)"},
             },
@@ -389,7 +529,7 @@ def main():
             line["reference_sample"] = {"workload": f"N={n_s} x {d}, min/max {mn_s}/{mx_s} (one step of --impl reference)",
                                         "value": (time.perf_counter() - t0) / reps, "unit": UNIT, "merges": rs.stats["n_merges"]}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_leg(d)
+            line.update(cpu_baseline_leg(d, eng))
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
