@@ -120,6 +120,24 @@ func PerformClusteringWithConstraints(embeddings [][]float32, productReferenceID
 		return nil, false
 	}
 
+	// what workflow.go:89-97 cannot see in the map (SURVEY 8f-2): kept for Report()
+	rep := RunReport{Items: n, Clusters: int(k), Merges: int(st.n_merges), NearTies: int(st.n_near_ties),
+		NearTieTol: float64(st.near_tie_tol), Exhausted: st.exhausted != 0, ReferenceArithmetic: st.exact != 0,
+		PairsReevaluated: int64(st.n_exact), FilterViolations: int(st.n_filter_viol), OrderViolations: int(st.n_order_viol),
+		Restarts: int(st.n_restarts)}
+	seen := make([]bool, n)
+	for i := 0; i < int(offsets[int(k)]); i++ {
+		seen[int(members[i])] = true
+	}
+	for i := 0; i < n; i++ {
+		if !seen[i] {
+			rep.DroppedItems = append(rep.DroppedItems, productReferenceIDs[i])
+		}
+	}
+	reportMu.Lock()
+	lastReport = rep
+	reportMu.Unlock()
+
 	clusterMap := make(map[int][]string, int(k))
 	for id := 0; id < int(k); id++ {
 		lo, hi := int(offsets[id]), int(offsets[id+1])
@@ -138,6 +156,34 @@ func PerformClusteringWithConstraints(embeddings [][]float32, productReferenceID
 	}
 	log.Printf("Clustering successful. Formed %d valid clusters.", len(clusterMap))
 	return clusterMap, true
+}
+
+// RunReport is what PerformClusteringWithConstraints' (map, bool) cannot carry (SURVEY 8f-2, workflow.go:89-97):
+// the items that are in no cluster because theirs stayed below minSize (clustering.go:268-271), the near-tie count, and
+// the checks behind "same merge sequence as the reference's arithmetic" (both violation counts must be 0).
+type RunReport struct {
+	Items, Clusters, Merges int
+	DroppedItems            []string
+	NearTies                int
+	NearTieTol              float64
+	Exhausted               bool // the loop ended with no admissible pair (clustering.go:222-225)
+	ReferenceArithmetic     bool // pairs that could decide a merge were evaluated as WardDistance of two fp32 centroids
+	PairsReevaluated        int64
+	FilterViolations        int
+	OrderViolations         int
+	Restarts                int
+}
+
+var (
+	reportMu   sync.Mutex
+	lastReport RunReport
+)
+
+// Report returns the report of the LAST successful PerformClusteringWithConstraints call of this process.
+func Report() RunReport {
+	reportMu.Lock()
+	defer reportMu.Unlock()
+	return lastReport
 }
 
 // Linkage returns the merge trace of the LAST clustering as a dendrogram in the layout of

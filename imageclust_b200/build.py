@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static"], check=True)
+    subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl"], check=True)
     return LIB
 
 

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/imageclust_b200.h"
 #include "kernels.h"
 
@@ -85,6 +87,7 @@ struct ic_ctx {
     int32_t *tr_key_hi = nullptr, *tr_key_lo = nullptr, *tr_size = nullptr;
     float *tr_dist = nullptr, *tr_gap = nullptr;
     uint8_t *records = nullptr, *partials = nullptr, *rankbox = nullptr;  // mailboxes, zeroed once at allocation
+    BatchState* vstates = nullptr;  // the virtual ranks' states of the batched loop (test hook)
     long long* prof = nullptr;
     int32_t* ctl = nullptr;
     int loop_grid = 0;  // blocks per rank
@@ -142,6 +145,12 @@ struct ic_ctx {
 
 namespace {
 
+// NVTX range of one phase of the path (visible in nsys / ncu --nvtx): upload, K0, K1, K2, loop, refine, compact, readback
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+};
+
 int fail(ic_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
@@ -198,6 +207,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->records);
     dev_free(c->partials);
     dev_free(c->rankbox);
+    dev_free(c->vstates);
     dev_free(c->batch_scratch);
     dev_free(c->cen);
     dev_free(c->xq);
@@ -361,7 +371,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     const double other = 4.0 * n * d + (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
                          (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20) +
                          (ctx->exact_opt ? 8.0 * n * round_up(d, 4) + 16.0 * std::max<int64_t>(1 << 20, 16 * n) + 8.0 * (16 << 20) : 0.0);
-    if ((P == 1 || ctx->shard_world > 1) && ctx->loop_mode == 1 && n > 0) {  // batched loop: one GPU, or real shards
+    if (ctx->loop_mode == 1 && n > 0) {  // batched loop: one GPU, real shards, or virtual ranks (test hook)
         int grid = 0;
         IC_CUDA(merge_batch_grid(ctx->num_sms, n, &grid));
         if (grid > 0) {
@@ -378,8 +388,10 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->x, sizeof(float) * nn1 * static_cast<size_t>(d > 0 ? d : 1)));
     IC_CUDA(cudaMalloc(&ctx->dm, sizeof(float) * static_cast<size_t>(rows > 0 ? rows : 1) *
                                      static_cast<size_t>(ctx->ld > 0 ? ctx->ld : 1)));
-    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * (nn1 * NL + 4)));  // + padding up to a multiple of 4 slots: key -1
-    IC_CUDA(cudaMemsetAsync(ctx->ks + nn1 * NL, 0xFF, sizeof(SlotKS) * 4, ctx->stream));
+    // (virtual) rank v keeps its replica at ks + v * n (one-merge-per-iteration loop) or ks + v * (n4 + 4) (batched loop, which
+    // reads the table four slots at a time: padding key -1)
+    IC_CUDA(cudaMalloc(&ctx->ks, sizeof(SlotKS) * (n4 + 4) * NL));
+    IC_CUDA(cudaMemsetAsync(ctx->ks, 0xFF, sizeof(SlotKS) * (n4 + 4) * NL, ctx->stream));
     IC_CUDA(cudaMalloc(&ctx->gkey, sizeof(int32_t) * n4 * NL));
     IC_CUDA(cudaMalloc(&ctx->nn, sizeof(SlotNN) * nn1 * kNNK));
     IC_CUDA(cudaMalloc(&ctx->nn_more, sizeof(int32_t) * nn1));
@@ -396,7 +408,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
         ctx->xq_cap = static_cast<int32_t>(std::max<int64_t>(1 << 20, 16 * static_cast<int64_t>(nn1)));
         ctx->rq_cap = static_cast<int32_t>(std::min<int64_t>(16 << 20, std::max<int64_t>(1024, static_cast<int64_t>(nn1) * static_cast<int64_t>(nn1) / 2)));
         IC_CUDA(cudaMalloc(&ctx->cen, sizeof(float) * 2 * nn1 * static_cast<size_t>(ctx->ldc)));  // by key: N items + up to N merges
-        IC_CUDA(cudaMalloc(&ctx->xq, sizeof(int4) * static_cast<size_t>(ctx->xq_cap)));
+        IC_CUDA(cudaMalloc(&ctx->xq, sizeof(int4) * static_cast<size_t>(ctx->xq_cap) * NL));
         IC_CUDA(cudaMalloc(&ctx->xres, sizeof(uint4) * static_cast<size_t>(kMaxBatch) * kXResCap));
         IC_CUDA(cudaMalloc(&ctx->xhit, sizeof(int32_t) * kMaxBatch));
         IC_CUDA(cudaMalloc(&ctx->rq, sizeof(int2) * static_cast<size_t>(ctx->rq_cap)));
@@ -411,23 +423,24 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMalloc(&ctx->records, rb * NL));
     IC_CUDA(cudaMalloc(&ctx->partials, pb * NL));
     // (+ the exchange box of the sharded batched loop, behind the rank mailboxes: one IPC handle covers both)
-    IC_CUDA(cudaMalloc(&ctx->rankbox, xb * NL + kBatchXBoxBytes));
+    IC_CUDA(cudaMalloc(&ctx->rankbox, xb * NL + kBatchXBoxBytes * NL));
+    IC_CUDA(cudaMalloc(&ctx->vstates, sizeof(BatchState) * kMaxRanks));
     IC_CUDA(cudaMemsetAsync(ctx->records, 0, rb * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->partials, 0, pb * NL, ctx->stream));
-    IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL + kBatchXBoxBytes, ctx->stream));
+    IC_CUDA(cudaMemsetAsync(ctx->rankbox, 0, xb * NL + kBatchXBoxBytes * NL, ctx->stream));
     IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
     if (ctx->batch_layout) {  // batched loop: scratch
         const size_t sizes[11] = {static_cast<size_t>(kBatchMaxBlocks) * 32, 32 * nn1,
                                   3 * 4 * 4, 8 * nn1, static_cast<size_t>(kBatchMaxDry) * kBatchMaxWin * 128,
-                                  static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), 0, 0, 0};
+                                  static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), static_cast<size_t>(kBatchMaxBlocks) * 32, 0, 0};
         size_t off = 0;
         for (int i = 0; i < 11; ++i) {
             ctx->batch_off[i] = off;
             off += (sizes[i] + 255) / 256 * 256;
         }
         ctx->batch_scratch_bytes = off;
-        IC_CUDA(cudaMalloc(&ctx->batch_scratch, off));
-        IC_CUDA(cudaMemsetAsync(ctx->batch_scratch, 0, off, ctx->stream));
+        IC_CUDA(cudaMalloc(&ctx->batch_scratch, off * NL));
+        IC_CUDA(cudaMemsetAsync(ctx->batch_scratch, 0, off * NL, ctx->stream));
     }
     // K4: second matrix buffer (a quarter of the first) and second copies of the per-slot state; one GPU, batched loop
     if (ctx->compact_opt && ctx->batch_layout && ctx->shard_world <= 1 && P == 1 && n >= ctx->compact_min) {
@@ -502,6 +515,7 @@ int loop_state(ic_ctx* c, LoopState* out) {
 
 int do_prep_i8(ic_ctx* ctx) {
     if (ctx->prepped_i8) return IC_OK;
+    Nvtx range("ic K0 prep (centre, int8 digits, norms)");
     const size_t pad_elems = static_cast<size_t>(ctx->n_pad) * static_cast<size_t>(ctx->d_pad8);
     if (!ctx->i8h) IC_CUDA(cudaMalloc(&ctx->i8h, pad_elems ? pad_elems : 1));
     if (!ctx->i8m) IC_CUDA(cudaMalloc(&ctx->i8m, pad_elems ? pad_elems : 1));
@@ -527,6 +541,7 @@ int do_prep_i8(ic_ctx* ctx) {
 
 int do_prep(ic_ctx* ctx) {
     if (ctx->prepped) return IC_OK;
+    Nvtx range("ic K0 prep (centre, tf32 split, norms)");
     ctx->prepped_i8 = false;  // norms will belong to the tf32 representation
     const size_t pad_elems = static_cast<size_t>(ctx->n_pad) * static_cast<size_t>(ctx->d_pad);
     if (!ctx->hi) IC_CUDA(cudaMalloc(&ctx->hi, sizeof(float) * pad_elems));
@@ -552,6 +567,7 @@ int do_prep(ic_ctx* ctx) {
 bool use_batch(const ic_ctx* c);
 
 int do_gram(ic_ctx* ctx, int mode) {
+    Nvtx range("ic K1 initial distances");
     ctx->dm_lower_only = false;
     if (mode == IC_GRAM_EXACT_FP32) {
         IC_CUDA(launch_gram_exact(ctx->x, ctx->n, ctx->d, ctx->d, ctx->dm, ctx->ld, row_begin(ctx), row_end(ctx), ctx->stream));
@@ -625,7 +641,8 @@ int init_loop_state(ic_ctx* ctx) {
     ctx->h_ctl[CTL_N_LIVE] = ctx->n_live;
     for (int v = 0; v < NL; ++v) {
         if (v > 0 && n > 0) {  // every (virtual) rank keeps its own replica of the slot table
-            IC_CUDA(cudaMemcpyAsync(ctx->ks + v * n, ctx->ks, sizeof(SlotKS) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+            const size_t ks_stride = use_batch(ctx) ? n4 + 4 : n;
+            IC_CUDA(cudaMemcpyAsync(ctx->ks + v * ks_stride, ctx->ks, sizeof(SlotKS) * n, cudaMemcpyDeviceToDevice, ctx->stream));
             IC_CUDA(cudaMemcpyAsync(ctx->gkey + v * n4, ctx->gkey, sizeof(int32_t) * n4, cudaMemcpyDeviceToDevice,
                                     ctx->stream));
         }
@@ -636,7 +653,7 @@ int init_loop_state(ic_ctx* ctx) {
 
 // the batched loop runs on an unsharded context whose slice state fits (it always does below ~1e6 items)
 bool use_batch(const ic_ctx* c) {
-    return c->loop_mode == 1 && c->batch_layout && (n_ranks(c) == 1 || c->shard_world > 1) && c->batch_grid > 0 && c->n > 0;
+    return c->loop_mode == 1 && c->batch_layout && c->batch_grid > 0 && c->n > 0;
 }
 
 // One launch of the persistent loop (enqueued; sync_loop_result waits and relaunches if the kernel ran out of
@@ -668,75 +685,102 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         ctx->loop_mode_used = mode;
     }
     if (use_batch(ctx)) {
-        BatchState bs{};
-        uint8_t* sc = ctx->batch_scratch;
-        bs.n = static_cast<int32_t>(ctx->n_cur);
-        bs.key_base = static_cast<int32_t>(ctx->n);
-        bs.order_key = ctx->order_key;
-        bs.mirror_key = ctx->mirror_key;
-        bs.compact_at = (ctx->dm_b && ctx->n_cur >= ctx->compact_min) ? static_cast<int32_t>(static_cast<double>(ctx->n_cur) * ctx->compact_ratio) : 0;
-        bs.n_ranks = 1;
-        bs.rank = 0;
-        bs.rows_per_rank = static_cast<int32_t>(rows_per_rank(ctx));
-        if (ctx->shard_world > 1) {  // real shards: peer-mapped row blocks and exchange boxes
-            if (!ctx->peers_open) return fail(ctx, IC_ERR_STATE, "sharded context: ic_shard_connect has not run");
-            bs.n_ranks = ctx->shard_world;
-            bs.rank = ctx->shard_rank;
-            for (int q = 0; q < ctx->shard_world; ++q) {
-                bs.dm_rank[q] = static_cast<float*>(ctx->peer_dm[q]);
-                bs.xbox[q] = static_cast<uint8_t*>(ctx->peer_box[q]) + merge_loop_rankbox_bytes();
+        const int VR = ctx->shard_world > 1 ? 1 : ctx->vranks;  // virtual ranks of this launch (test hook), else 1
+        const size_t n4s = (static_cast<size_t>(ctx->n) + 3) / 4 * 4;
+        if (ctx->shard_world > 1 && !ctx->peers_open) return fail(ctx, IC_ERR_STATE, "sharded context: ic_shard_connect has not run");
+        if (VR > 1 || ctx->shard_world > 1) ++ctx->barrier_seq;
+        std::vector<BatchState> states(static_cast<size_t>(VR));
+        for (int v = 0; v < VR; ++v) {
+            BatchState& bs = states[static_cast<size_t>(v)];
+            bs = BatchState{};
+            uint8_t* sc = ctx->batch_scratch + static_cast<size_t>(v) * ctx->batch_scratch_bytes;
+            bs.n = static_cast<int32_t>(ctx->n_cur);
+            bs.key_base = static_cast<int32_t>(ctx->n);
+            bs.order_key = ctx->order_key;
+            bs.mirror_key = ctx->mirror_key;
+            bs.compact_at = (ctx->dm_b && ctx->n_cur >= ctx->compact_min) ? static_cast<int32_t>(static_cast<double>(ctx->n_cur) * ctx->compact_ratio) : 0;
+            bs.n_ranks = 1;
+            bs.rank = 0;
+            bs.rows_per_rank = static_cast<int32_t>(rows_per_rank(ctx));
+            bs.ld = ctx->ld_cur;
+            bs.dm = ctx->dm_cur;
+            if (ctx->shard_world > 1) {  // real shards: peer-mapped row blocks and exchange boxes
+                bs.n_ranks = ctx->shard_world;
+                bs.rank = ctx->shard_rank;
+                for (int q = 0; q < ctx->shard_world; ++q) {
+                    bs.dm_rank[q] = static_cast<float*>(ctx->peer_dm[q]);
+                    bs.xbox[q] = static_cast<uint8_t*>(ctx->peer_box[q]) + merge_loop_rankbox_bytes();
+                }
+                bs.gen = static_cast<uint32_t>(ctx->barrier_seq);
+            } else if (VR > 1) {  // virtual ranks: the peers' row blocks and boxes are addresses of this device
+                bs.n_ranks = VR;
+                bs.rank = v;
+                for (int q = 0; q < VR; ++q) {
+                    bs.dm_rank[q] = ctx->dm + static_cast<int64_t>(q) * bs.rows_per_rank * ctx->ld;
+                    bs.xbox[q] = ctx->rankbox + merge_loop_rankbox_bytes() * VR + static_cast<size_t>(q) * kBatchXBoxBytes;
+                }
+                bs.dm = bs.dm_rank[v];
+                bs.gen = static_cast<uint32_t>(ctx->barrier_seq);
             }
+            // per (virtual) rank: replica of the slot table and keys, its own trace, control words, scratch and queue
+            bs.ks = ctx->ks + static_cast<size_t>(v) * (n4s + 4);
+            bs.gkey = ctx->gkey + static_cast<size_t>(v) * n4s;
+            bs.nn = ctx->nn;
+            bs.nn_more = ctx->nn_more;
+            const size_t tro = static_cast<size_t>(v) * static_cast<size_t>(ctx->n > 0 ? ctx->n : 1);
+            bs.tr_key_hi = ctx->tr_key_hi + tro;
+            bs.tr_key_lo = ctx->tr_key_lo + tro;
+            bs.tr_dist = ctx->tr_dist + tro;
+            bs.tr_size = ctx->tr_size + tro;
+            bs.tr_gap = ctx->tr_gap + tro;
+            bs.ctl = ctx->ctl + kCtlWords * v;
+            bs.prof = (ctx->profile_loop && v == 0) ? ctx->prof : nullptr;
+            bs.hdr = reinterpret_cast<uint4*>(sc + ctx->batch_off[0]);
+            bs.cand = reinterpret_cast<uint4*>(sc + ctx->batch_off[1]);
+            bs.counters = reinterpret_cast<int32_t*>(sc + ctx->batch_off[2]);
+            bs.dryq = reinterpret_cast<int2*>(sc + ctx->batch_off[3]);
+            bs.partials = reinterpret_cast<uint4*>(sc + ctx->batch_off[4]);
+            bs.part_cnt = reinterpret_cast<int32_t*>(sc + ctx->batch_off[5]);
+            bs.bar = reinterpret_cast<uint32_t*>(sc + ctx->batch_off[6]);
+            bs.lsize = reinterpret_cast<int32_t*>(sc + ctx->batch_off[7]);
+            bs.blockmin = reinterpret_cast<uint4*>(sc + ctx->batch_off[8]);
+            bs.cen = ctx->cen;  // (virtual ranks share one centroid store: every rank writes the same values)
+            bs.ldc = ctx->ldc;
+            bs.xq = ctx->xq ? ctx->xq + static_cast<size_t>(v) * static_cast<size_t>(ctx->xq_cap) : nullptr;
+            bs.xq_cap = ctx->xq_cap;
+            bs.xres = ctx->xres;
+            bs.xhit = ctx->xhit;
+            // scratch of a launch: counters and the barrier at zero
+            IC_CUDA(cudaMemsetAsync(bs.counters, 0, 3 * 4 * 4, ctx->stream));
+            IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
+            IC_CUDA(cudaMemsetAsync(bs.bar, 0, 256, ctx->stream));
+            IC_CUDA(cudaMemsetAsync(bs.ctl + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
+            if (bs.n_ranks > 1) {
+                // this rank's exchange-box slots: no candidates, no minima (the flags keep counting up across launches)
+                uint8_t* xb = bs.xbox[bs.rank];
+                if (ctx->shard_world > 1) xb = ctx->rankbox + merge_loop_rankbox_bytes();  // (own box through the local mapping)
+                IC_CUDA(cudaMemsetAsync(xb + kBatchXAccum, 0xFF, 48, ctx->stream));
+                IC_CUDA(cudaMemsetAsync(xb + kBatchXAccum + 48, 0, 16, ctx->stream));
+            }
+            merge_batch_fill_windows(&bs);
         }
-        bs.ld = ctx->ld_cur;
-        bs.dm = ctx->dm_cur;
-        bs.ks = ctx->ks;
-        bs.gkey = ctx->gkey;
-        bs.nn = ctx->nn;
-        bs.nn_more = ctx->nn_more;
-        bs.tr_key_hi = ctx->tr_key_hi;
-        bs.tr_key_lo = ctx->tr_key_lo;
-        bs.tr_dist = ctx->tr_dist;
-        bs.tr_size = ctx->tr_size;
-        bs.tr_gap = ctx->tr_gap;
-        bs.ctl = ctx->ctl;
-        bs.prof = ctx->profile_loop ? ctx->prof : nullptr;
-        bs.hdr = reinterpret_cast<uint4*>(sc + ctx->batch_off[0]);
-        bs.cand = reinterpret_cast<uint4*>(sc + ctx->batch_off[1]);
-        bs.counters = reinterpret_cast<int32_t*>(sc + ctx->batch_off[2]);
-        bs.dryq = reinterpret_cast<int2*>(sc + ctx->batch_off[3]);
-        bs.partials = reinterpret_cast<uint4*>(sc + ctx->batch_off[4]);
-        bs.part_cnt = reinterpret_cast<int32_t*>(sc + ctx->batch_off[5]);
-        bs.bar = reinterpret_cast<uint32_t*>(sc + ctx->batch_off[6]);
-        bs.lsize = reinterpret_cast<int32_t*>(sc + ctx->batch_off[7]);
-        bs.cen = ctx->cen;
-        bs.ldc = ctx->ldc;
-        bs.xq = ctx->xq;
-        bs.xq_cap = ctx->xq_cap;
-        bs.xres = ctx->xres;
-        bs.xhit = ctx->xhit;
         if (ctx->xhit) IC_CUDA(cudaMemsetAsync(ctx->xhit, 0, sizeof(int32_t) * kMaxBatch, ctx->stream));
-        // scratch of a launch: counters and the barrier at zero
-        IC_CUDA(cudaMemsetAsync(bs.counters, 0, 3 * 4 * 4, ctx->stream));
-        IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
-        IC_CUDA(cudaMemsetAsync(bs.bar, 0, 256, ctx->stream));
-        IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_DONE, 0, sizeof(int32_t), ctx->stream));
-        if (ctx->shard_world > 1) {
-            // this rank's exchange-box slots: no candidates, no minima (the flags keep counting up across launches);
-            // then all ranks line up: nobody starts before every box is reset
-            uint8_t* xb = ctx->rankbox + merge_loop_rankbox_bytes();
-            IC_CUDA(cudaMemsetAsync(xb + kBatchXAccum, 0xFF, 48, ctx->stream));
-            IC_CUDA(cudaMemsetAsync(xb + kBatchXAccum + 48, 0, 16, ctx->stream));
-            ++ctx->barrier_seq;
-            bs.gen = static_cast<uint32_t>(ctx->barrier_seq);
+        if (ctx->shard_world > 1) {  // all ranks line up: nobody starts before every box is reset
             IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
             ctx->stats.kernel_launches += 1;
         }
-        IC_CUDA(launch_merge_batch(bs, p, ctx->batch_grid, ctx->stream));
+        if (VR > 1) {
+            IC_CUDA(cudaMemcpyAsync(ctx->vstates, states.data(), sizeof(BatchState) * static_cast<size_t>(VR), cudaMemcpyHostToDevice, ctx->stream));
+            IC_CUDA(cudaStreamSynchronize(ctx->stream));  // (the host vector goes out of scope; test hook)
+            IC_CUDA(launch_merge_batch_virtual(ctx->vstates, VR, ctx->n_cur, p, std::max(1, std::min(ctx->batch_grid, ctx->num_sms / VR)), ctx->stream));
+        } else {
+            IC_CUDA(launch_merge_batch(states[0], p, ctx->batch_grid, ctx->stream));
+        }
         ++ctx->loop_launches;
         ctx->stats.kernel_launches += 1;
         IC_CUDA(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(ctx->h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
-        if (bs.prof)
-            IC_CUDA(cudaMemcpyAsync(ctx->h_prof, bs.prof, sizeof(ctx->h_prof), cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->profile_loop)
+            IC_CUDA(cudaMemcpyAsync(ctx->h_prof, ctx->prof, sizeof(ctx->h_prof), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->trace_on_host = false;
         return IC_OK;
     }
@@ -770,6 +814,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
 // Pairs of the resident rows whose stored value lies in (lo, hi] get the reference's own value (refine.cu).  Rows are
 // swept in one go; if the queue overflows, in row chunks sized from the count.
 int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
+    Nvtx range("ic refine (horizon sweep, reference arithmetic)");
     const double t0 = now_ms();
     RefineArgs a{};
     a.dm = ctx->dm_cur;
@@ -863,6 +908,7 @@ int raise_horizon(ic_ctx* ctx) {
 // K4 (compact.cu): renumber the live clusters densely in key order, move the matrix into the other buffer (both
 // triangles), permute the per-slot state.  Host-driven: the loop kernel stopped with STOP_COMPACT.
 int do_compact(ic_ctx* ctx) {
+    Nvtx range("ic K4 compaction");
     const double t0 = now_ms();
     const int32_t n_old = static_cast<int32_t>(ctx->n_cur), n_new = ctx->n_live, n_new4 = (n_new + 3) & ~3;
     const int64_t ld_new = round_up(n_new, 32);
@@ -928,6 +974,7 @@ int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges
 }
 
 int sync_loop_result(ic_ctx* ctx) {
+    Nvtx range("ic K3b merge loop (sync, horizon raises, compactions, relaunches)");
     for (;;) {
         IC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
@@ -943,7 +990,8 @@ int sync_loop_result(ic_ctx* ctx) {
         } else if (stop == STOP_XQ) {  // the exact-evaluation queue of the last iteration overflowed: redo its rows
             int rc = refine_band(ctx, -1.0, ctx->horizon, ctx->h_ctl[CTL_XQ_FIRST_KEY]);
             if (rc != IC_OK) return rc;
-            IC_CUDA(cudaMemsetAsync(ctx->ctl + CTL_XQ_OVERFLOW, 0, sizeof(int32_t), ctx->stream));
+            for (int v = 0; v < n_local(ctx); ++v)
+                IC_CUDA(cudaMemsetAsync(ctx->ctl + kCtlWords * v + CTL_XQ_OVERFLOW, 0, sizeof(int32_t), ctx->stream));
         } else if (stop == STOP_COMPACT) {
             const int rc = do_compact(ctx);
             if (rc != IC_OK) return rc;
@@ -961,6 +1009,7 @@ int sync_loop_result(ic_ctx* ctx) {
 
 int fetch_trace(ic_ctx* ctx) {
     if (ctx->trace_on_host) return IC_OK;
+    Nvtx range("ic merge trace D2H");
     const size_t m = static_cast<size_t>(ctx->n_merges);
     ctx->h_key_hi.resize(m);
     ctx->h_key_lo.resize(m);
@@ -984,6 +1033,7 @@ int fetch_trace(ic_ctx* ctx) {
 // cluster are members(hi) ++ members(lo) (clustering.go:31,237); clusters below minSize are
 // skipped without consuming an id (:268-271).
 int assemble(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offsets, int32_t* members, int32_t* n_out) {
+    Nvtx range("ic output assembly (host)");
     const int64_t n = ctx->n, m = ctx->n_merges;
     std::vector<uint8_t> consumed(static_cast<size_t>(n + m), 0);
     for (int64_t t = 0; t < m; ++t) {
@@ -1036,6 +1086,7 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 }
 
 int load_common(ic_ctx* ctx, const float* x, int64_t n, int64_t d, int64_t ldx, cudaMemcpyKind kind) {
+    Nvtx range("ic upload X");
     int rc = validate_sizes(ctx, n, d, ldx);
     if (rc != IC_OK) return rc;
     if (n > 0 && d > 0 && !x) return fail(ctx, IC_ERR_BAD_ARG, "x is NULL");
@@ -1083,7 +1134,7 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
         IC_CUDA(launch_fill(ctx->dm, (row_end(ctx) - row_begin(ctx)) * ctx->ld, INFINITY, ctx->stream));
         ctx->stats.kernel_launches += 1;
     }
-    if (ctx->mirror_init && ctx->dm_lower_only && ctx->shard_world <= 1 && ctx->n > 1) {
+    if (ctx->mirror_init && ctx->dm_lower_only && n_ranks(ctx) == 1 && ctx->n > 1) {
         CompactArgs a{};
         a.n_new = static_cast<int32_t>(ctx->n);
         a.dm_new = ctx->dm;
@@ -1109,6 +1160,7 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
 }
 
 int nn_init(ic_ctx* ctx) {
+    Nvtx range("ic K2 first nearest-neighbour sweep");
     if (!ctx->have_dm) return fail(ctx, IC_ERR_STATE, "no distance matrix");
     int rc = init_loop_state(ctx);
     if (rc != IC_OK) return rc;
@@ -1366,6 +1418,9 @@ int ic_load_combined(ic_ctx* ctx, const float* img_host, int64_t n, int64_t d_im
         if (label_offsets[i] < 0 || label_offsets[i] > label_offsets[i + 1])
             return fail(ctx, IC_ERR_BAD_ARG, "label_offsets must be non-decreasing");
     if (nnz > 0 && !label_ids) return fail(ctx, IC_ERR_BAD_ARG, "label_ids is NULL");
+    for (int64_t q = 0; q < nnz; ++q)  // -1: a label that is not in the set (ignored, embeddings.go:169); anything else must index the set
+        if (label_ids[q] < -1 || label_ids[q] >= n_labels)
+            return fail(ctx, IC_ERR_BAD_ARG, "label id " + std::to_string(label_ids[q]) + " outside [-1, n_labels)");
     IC_CUDA(cudaSetDevice(ctx->device));
     rc = alloc_problem(ctx, n, d);
     if (rc != IC_OK) return rc;
@@ -1374,7 +1429,13 @@ int ic_load_combined(ic_ctx* ctx, const float* img_host, int64_t n, int64_t d_im
     ctx->stats.dim = d;
     ctx->stats.near_tie_tol = static_cast<float>(ctx->near_tie_tol);
     ctx->stats.matrix_bytes = static_cast<int64_t>(sizeof(float)) * (row_end(ctx) - row_begin(ctx)) * ctx->ld;
-    int32_t *d_off = nullptr, *d_ids = nullptr;
+    struct Temp {  // freed on every path out of this function
+        int32_t* p = nullptr;
+        ~Temp() {
+            if (p) cudaFree(p);
+        }
+    } t_off, t_ids;
+    int32_t *&d_off = t_off.p, *&d_ids = t_ids.p;
     IC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (n > 0) {
         if (d_img > 0)  // copy(combined, embedding): the image block of every row (embeddings.go:180)
@@ -1391,8 +1452,6 @@ int ic_load_combined(ic_ctx* ctx, const float* img_host, int64_t n, int64_t d_im
     }
     IC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));  // the host arrays and the two temporaries are done with
-    if (d_off) cudaFree(d_off);
-    if (d_ids) cudaFree(d_ids);
     ctx->loaded = true;
     return IC_OK;
 }
@@ -1456,10 +1515,23 @@ int ic_find_closest(ic_ctx* ctx, int32_t* key_hi, int32_t* key_lo, float* dist) 
     if (!ctx || !key_hi || !key_lo || !dist) return IC_ERR_BAD_ARG;
     if (!ctx->have_nn) return fail(ctx, IC_ERR_STATE, "ic_nn_init has not run");
     IC_CUDA(cudaSetDevice(ctx->device));
-    int rc = run_loop(ctx, 0, 0x3FFFFFFF, 0);  // zero merges: fold the NN cache only
-    if (rc != IC_OK) return rc;
-    rc = sync_loop_result(ctx);
-    if (rc != IC_OK) return rc;
+    ctx->delta_cut_cur = ctx->delta_cut;
+    int rc = IC_OK;
+    for (int tries = 0; tries < 16; ++tries) {
+        rc = run_loop(ctx, 0, 0x3FFFFFFF, 0);  // zero merges: fold the NN cache only
+        if (rc != IC_OK) return rc;
+        rc = sync_loop_result(ctx);
+        if (rc != IC_OK) return rc < 0 ? rc : fail(ctx, IC_ERR_INTERNAL, "batch order check failed");
+        // with the horizon, the minimum is the reference's own value only once it lies at or below the safe bound
+        if (!(ctx->exact_on && use_batch(ctx) && ctx->cen) || ctx->h_ctl[CTL_NEXT_HI] < 0) break;
+        float h = 0.0f;
+        const uint32_t hb = static_cast<uint32_t>(ctx->h_ctl[CTL_NEXT_DIST]);
+        std::memcpy(&h, &hb, 4);
+        const double safe = ctx->horizon < 0.0 ? -1.0 : (ctx->horizon - ctx->abs_slack) / (1.0 + 2.0 * ctx->eps_filter);
+        if (static_cast<double>(h) <= safe) break;
+        rc = raise_horizon(ctx);
+        if (rc != IC_OK) return rc;
+    }
     *key_hi = ctx->h_ctl[CTL_NEXT_HI];
     *key_lo = ctx->h_ctl[CTL_NEXT_LO];
     const uint32_t bits = static_cast<uint32_t>(ctx->h_ctl[CTL_NEXT_DIST]);

@@ -191,7 +191,10 @@ constexpr int CTL_ITERS = 12;         // ctl[]: iterations of the batched loop
 constexpr int kXResCap = 512;
 constexpr int kBatchXCand = 2048;
 constexpr size_t kBatchXSummary = 256, kBatchXAccum = 1280, kBatchXCandBase = 2048;
-constexpr size_t kBatchXBoxBytes = kBatchXCandBase + static_cast<size_t>(kMaxRanks) * kBatchXCand * 32;
+//   [.., +768)      uint4 rankmin[src][slot][2]      behind the candidates: the smallest head of a rank whose candidates did
+//                                                    not fit its region (then only the global minimum is merged)
+constexpr size_t kBatchXRankMin = kBatchXCandBase + static_cast<size_t>(kMaxRanks) * kBatchXCand * 32;
+constexpr size_t kBatchXBoxBytes = kBatchXRankMin + 1024;
 struct BatchState {
     int32_t n;                             // slots (== items until the first compaction, then the live count at the last one)
     int32_t key_base;                      // N: the cluster created by merge t carries the key N + t
@@ -220,6 +223,7 @@ struct BatchState {
     long long* prof;    // [16] or NULL
     // scratch (zeroed before every launch)
     uint4* hdr;         // [kBatchMaxBlocks] per block: {stopper minimum lo, hi, head minimum lo, hi}
+    uint4* blockmin;    // [kBatchMaxBlocks][2] sharded: every block's smallest head as a candidate record
     uint4* cand;        // [n][2] candidate pairs {head lo, head hi, row slot, partner slot} {size, size, partner key, 0}
     int32_t* counters;  // [3][4] dry rows, candidate pairs; per iteration mod 3
     int2* dryq;         // [n]   rows to rescan {slot, key}
@@ -243,6 +247,10 @@ size_t merge_batch_smem_bytes(int64_t n);
 int64_t merge_batch_windows(int64_t n);
 cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks);  // *blocks = 0: does not fit
 cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int blocks, cudaStream_t s);  // n_ranks > 1: sharded
+// test hook: P virtual ranks of the sharded kernel on one GPU (one cooperative launch, P * blocks_per_rank blocks)
+void merge_batch_fill_windows(BatchState* st);
+cudaError_t launch_merge_batch_virtual(const BatchState* d_states, int n_ranks, int64_t n, const LoopParams& p, int blocks_per_rank,
+                                       cudaStream_t s);
 // ---- reference arithmetic for selected pairs (refine.cu) ---------------------------------------------------------
 // cen[k] = x[k] for k < N (zero padded to ldc floats per row): the singleton centroids (clustering.go:19-20); centroids are
 // stored by cluster key

@@ -96,7 +96,7 @@ IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* 
 // `remote_stores`: the blocks wrote to peer memory in this phase (their stores must be performed at system scope before
 // the rank reports; stores to the rank's own memory only need the gpu-scope release of the arrival -- block 0's system
 // fence after it has acquired all arrivals is cumulative).
-IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& xcount, uint32_t G, bool remote_stores,
+IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& xcount, uint32_t G, uint32_t bid, bool remote_stores,
                                int publish_slot, long long* wait_acc = nullptr) {
     __syncthreads();
     ++phase;
@@ -106,7 +106,7 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
         if (remote_stores) asm volatile("fence.acq_rel.sys;" ::: "memory");
         red_release_add_u32(st.bar, 1u);
         uint32_t spins = 0;
-        if (blockIdx.x == 0) {
+        if (bid == 0) {
             const uint32_t target = phase * G;
             while (ld_acquire_u32(st.bar) < target)
                 if (++spins > kBarSpin) __trap();
@@ -116,6 +116,26 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
                 const unsigned long long sstop = __ldcg(reinterpret_cast<const unsigned long long*>(acc) + publish_slot);
                 const unsigned long long shead = __ldcg(reinterpret_cast<const unsigned long long*>(acc) + 3 + publish_slot);
                 const int32_t scnt = __ldcg(reinterpret_cast<const int32_t*>(acc + 48) + publish_slot);
+                if (scnt > kBatchXCand) {
+                    // more candidates than this rank's region holds (which ones were dropped depends on the atomics'
+                    // order): publish the rank's smallest head as well -- every rank then merges the global minimum only
+                    uint64_t best = kPackInf;
+                    uint32_t bb = 0;
+                    for (uint32_t g = 0; g < G; ++g) {
+                        const uint4 r0 = __ldcg(st.blockmin + 2 * g);
+                        const uint64_t hp = (static_cast<uint64_t>(r0.y) << 32) | r0.x;
+                        if (hp < best) {
+                            best = hp;
+                            bb = g;
+                        }
+                    }
+                    const uint4 m0 = __ldcg(st.blockmin + 2 * bb), m1 = __ldcg(st.blockmin + 2 * bb + 1);
+                    for (int q = 0; q < st.n_ranks; ++q) {
+                        uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXRankMin + (static_cast<size_t>(st.rank) * 3 + publish_slot) * 32);
+                        __stcg(dst, m0);
+                        __stcg(dst + 1, m1);
+                    }
+                }
                 for (int q = 0; q < st.n_ranks; ++q) {
                     uint4* dst = reinterpret_cast<uint4*>(st.xbox[q] + kBatchXSummary + (static_cast<size_t>(st.rank) * 3 + publish_slot) * 32);
                     __stcg(dst, make_uint4(static_cast<uint32_t>(sstop), static_cast<uint32_t>(sstop >> 32),
@@ -137,8 +157,10 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
                     if (spins > kBarSpin) __trap();  // a missing peer must not hang the GPU box
                 }
             }
-            // acquire at gpu scope: what the peers pushed landed in THIS GPU's L2, and everything read after the barrier
-            // is read with ld.global.cg (never from a stale L1 line); a system-scope fence here cost ~3 400 cycles
+            // acquire at system scope (the flags were polled with relaxed loads), then release the rank's blocks at gpu scope:
+            // cumulativity makes what the peers pushed before their flags visible to every block of this rank.  ~3 400
+            // cycles per barrier (profiles/r01_nvlink_pingpong.txt); with dozens of merges per iteration that is noise
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(st.bar + 32), "r"(phase) : "memory");
         } else {
             while (ld_acquire_u32(st.bar + 32) < phase)
@@ -222,18 +244,31 @@ int64_t merge_batch_windows(int64_t n) {
     return std::max<int64_t>(1, (n4 + win - 1) / win);
 }
 
-template <bool kMulti>
+// kVirt (test hook, option "virtual_ranks"): the ranks of a sharded run are emulated on ONE GPU by one cooperative launch --
+// blocks [v * G, (v + 1) * G) are rank v and take their BatchState from vstates[v]; the peers' rows and exchange boxes are
+// simply other addresses of the same device.  Same code path as one process per GPU (kMulti), so pytest -m gpu covers it.
+template <bool kMulti, bool kVirt>
 __global__ void __launch_bounds__(kBT, 1)
-merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant__ LoopParams prm) {
+merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_constant__ LoopParams prm,
+                   const BatchState* __restrict__ vstates, int32_t blocks_per_rank) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t G = gridDim.x;
+    __shared__ BatchState s_vst;
+    if (kVirt) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(vstates + blockIdx.x / blocks_per_rank);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_vst);
+        for (int i = tid; i < static_cast<int>(sizeof(BatchState) / 4); i += kBT) dst[i] = src[i];
+        __syncthreads();
+    }
+    const BatchState& st = kVirt ? s_vst : st_param;
+    const uint32_t bid = kVirt ? blockIdx.x % static_cast<uint32_t>(blocks_per_rank) : blockIdx.x;
+    const uint32_t G = kVirt ? static_cast<uint32_t>(blocks_per_rank) : gridDim.x;
     const int32_t n = st.n;
     const int32_t n4 = (n + 3) & ~3;
     const int32_t kbase = st.key_base;
     const int64_t ld = st.ld;
-    const int32_t gtid = static_cast<int32_t>(blockIdx.x) * kBT + tid, GT = static_cast<int32_t>(G) * kBT;
+    const int32_t gtid = static_cast<int32_t>(bid) * kBT + tid, GT = static_cast<int32_t>(G) * kBT;
     // work units go to warps block-interleaved: consecutive units run on different SMs
-    const int32_t gw = warp * static_cast<int32_t>(G) + static_cast<int32_t>(blockIdx.x), GW = static_cast<int32_t>(G) * kBW;
+    const int32_t gw = warp * static_cast<int32_t>(G) + static_cast<int32_t>(bid), GW = static_cast<int32_t>(G) * kBW;
     const int32_t win = st.win_cols, nwin = st.n_win;
     float* const dm = st.dm;  // first row of this rank's row block (row 0 on one GPU)
     int32_t* const ctl = st.ctl;
@@ -251,6 +286,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     int32_t* const xb_cnt = reinterpret_cast<int32_t*>(xb_head + 3);
     uint32_t xcount = 0;
     __shared__ int32_t s_xcnt[kMaxRanks + 1];  // candidate pairs per rank (prefix sums)
+    __shared__ int32_t s_xover[kMaxRanks];     // rank dropped candidates (its region of the exchange box was full)
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     float (*const s_ex)[kExChunk] = reinterpret_cast<float (*)[kExChunk]>(dyn_smem);  // exact phase: one chunk of squared differences per warp
@@ -280,7 +316,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
     int32_t t = __ldcg(ctl + CTL_N_MERGES);
     int32_t launched = 0, stop_reason = 0, iters = 0;
     long long n_rescans = 0;
-    const bool timed = st.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool timed = st.prof != nullptr && bid == 0 && tid == 0;
     const bool small_sizes = prm.max_size < kRcpTab;  // every admissible size sum has its reciprocal in the table
     __shared__ long long c_ph[8];  // cycles of block 0 per phase (profile_loop)
     if (tid < 8) c_ph[tid] = 0;
@@ -479,7 +515,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         // chain.  Long rows must be spread over many SMs: one SM streams a 400 KB row (+ its keys) in ~50 k cycles
         // (measured at config C; the window mode below takes 32 k per iteration for ~28 rows).
         const bool row_per_block = Q <= 2 * static_cast<int32_t>(G) && n4 <= 32768;
-        for (int32_t q = blockIdx.x; row_per_block && q < Q; q += static_cast<int32_t>(G)) {
+        for (int32_t q = static_cast<int32_t>(bid); row_per_block && q < Q; q += static_cast<int32_t>(G)) {
             const int2 rq = __ldcg(st.dryq + q);
             const int32_t r = rq.x;
             const uint32_t ukr = static_cast<uint32_t>(rq.y);
@@ -575,6 +611,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         int p2_remote = 0;  // this block pushed candidates into the peers' boxes
         {
             uint64_t bstop = kPackInf, bhead = kPackInf, dropped = kPackInf;
+            uint64_t my_head = kPackInf;  // sharded: this thread's smallest head as a candidate record
+            uint4 my_w0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u), my_w1 = make_uint4(0u, 0u, 0u, 0u);
             bool pushed = false;
             int32_t* const cnt_cand = kMulti ? xb_cnt + sl : st.counters + sl * 4 + CN_CAND;
             uint4* const cand_out = st.cand;
@@ -606,6 +644,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
 #pragma unroll
                 for (int x = 0; x < kP2R; ++x) {
                     bhead = umin64(bhead, h[x].head);
+                    if (kMulti && h[x].head < my_head) {
+                        my_head = h[x].head;
+                        my_w0 = make_uint4(static_cast<uint32_t>(h[x].head), static_cast<uint32_t>(h[x].head >> 32),
+                                           static_cast<uint32_t>(rr[x]), h[x].partner_slot);
+                        my_w1 = make_uint4(static_cast<uint32_t>(sr[x]), static_cast<uint32_t>(h[x].partner_size), h[x].partner_key, 0u);
+                    }
                     if (h[x].head < bstop) {
                         const int32_t k = atomicAdd(cnt_cand, 1);
                         if (!kMulti || k < kBatchXCand) {
@@ -633,6 +677,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 }
             }
             bhead = block_min_u64(bhead, s_red);
+            if (kMulti) {  // the block's smallest head (packs are unique: one owner), or "none"
+                if (bhead == kPackInf ? tid == 0 : my_head == bhead) {
+                    __stcg(st.blockmin + 2 * bid, my_w0);
+                    __stcg(st.blockmin + 2 * bid + 1, my_w1);
+                }
+            }
             if (kMulti) p2_remote = __syncthreads_or(pushed ? 1 : 0);
             if (kMulti) {  // rank-wide minima in the exchange box
                 dropped = block_min_u64(dropped, s_red);
@@ -642,12 +692,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                     if (bhead != kPackInf) atomicMin(xb_head + sl, static_cast<unsigned long long>(bhead));
                 }
             } else if (tid == 0) {
-                __stcg(st.hdr + blockIdx.x, make_uint4(static_cast<uint32_t>(bstop), static_cast<uint32_t>(bstop >> 32),
+                __stcg(st.hdr + bid, make_uint4(static_cast<uint32_t>(bstop), static_cast<uint32_t>(bstop >> 32),
                                                        static_cast<uint32_t>(bhead), static_cast<uint32_t>(bhead >> 32)));
             }
         }
         if (kMulti)
-            grid_sync_ranks(st, phase, xcount, G, p2_remote != 0, sl, timed ? &c_ph[6] : nullptr);
+            grid_sync_ranks(st, phase, xcount, G, bid, p2_remote != 0, sl, timed ? &c_ph[6] : nullptr);
         else
             grid_sync(st.bar, phase, G, timed ? &c_ph[6] : nullptr);
         const long long tp2 = timed ? clock64() : 0;
@@ -672,7 +722,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                 tstop = (static_cast<uint64_t>(s0.y) << 32) | s0.x;
                 H = (static_cast<uint64_t>(s0.w) << 32) | s0.z;
                 s_xcnt[tid + 1] = min(static_cast<int32_t>(s1.x), kBatchXCand);
-                over_local = static_cast<int>(s1.y);
+                s_xover[tid] = static_cast<int32_t>(s1.x) > kBatchXCand ? 1 : 0;
+                over_local = static_cast<int>(s1.y) | (s_xover[tid] ? 4 : 0);
             }
             __syncthreads();
             if (tid == 0) {
@@ -704,6 +755,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
         const bool xq_over = __syncthreads_or(over_local & 1) != 0;     // (every rank sees every rank's flags)
+        const bool cand_over = kMulti && __syncthreads_or(over_local & 4) != 0;  // some rank's candidates did not fit its region
         const bool order_viol = __syncthreads_or(over_local & 2) != 0;
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
         if (n_live <= prm.n_target)
@@ -723,7 +775,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         else if (exact && static_cast<double>(pack_dist(H)) > prm.safe)
             stop_reason = STOP_HORIZON;  // the minimum reached the horizon: the host raises it (refine.cu)
         if (stop_reason != 0) {
-            if (blockIdx.x == 0) {  // what FindClosestClusters would return now
+            if (bid == 0) {  // what FindClosestClusters would return now
                 if (!pack_selectable(H)) {
                     if (tid == 0) {
                         ctl[CTL_NEXT_HI] = -1;
@@ -731,13 +783,14 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
                         ctl[CTL_NEXT_DIST] = static_cast<int32_t>(kInfBits);
                     }
                 } else {
+                    if (tid == 0) {  // distance and row key are the pack itself; the partner comes from the pair's record
+                        ctl[CTL_NEXT_HI] = static_cast<int32_t>(pack_key(H));
+                        ctl[CTL_NEXT_DIST] = static_cast<int32_t>(H >> 32);
+                    }
                     for (int32_t i = tid; i < n_pub; i += kBT) {
                         const uint4 p = __ldcg(cand_ptr(i));
-                        if (((static_cast<uint64_t>(p.y) << 32) | p.x) == H) {
-                            ctl[CTL_NEXT_HI] = static_cast<int32_t>(p.x);
+                        if (((static_cast<uint64_t>(p.y) << 32) | p.x) == H)
                             ctl[CTL_NEXT_LO] = static_cast<int32_t>(__ldcg(cand_ptr(i) + 1).z);
-                            ctl[CTL_NEXT_DIST] = static_cast<int32_t>(p.y);
-                        }
                     }
                 }
             }
@@ -750,7 +803,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         // candidate pairs below theta are examined; theta = the stopper minimum unless more than kMaxBatch pairs are
         // below it (any prefix of a valid batch is a valid batch): bisection on the packed value, packs are unique
         uint64_t theta = tstop;
-        if (n_pub > kMaxBatch) {
+        if (cand_over) theta = H + 1ull;  // only the global minimum (always valid); its record comes from the rank minima
+        if (!cand_over && n_pub > kMaxBatch) {
             auto count_lt = [&](uint64_t th) {
                 int c = 0;
                 for (int32_t i = tid; i < n_pub; i += kBT) {
@@ -789,6 +843,26 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             }
         }
         __syncthreads();
+        if (cand_over && tid == 0) {  // the smallest head of every rank that dropped candidates (if it is not listed already)
+            for (int q = 0; q < st.n_ranks; ++q) {
+                if (!s_xover[q]) continue;
+                const uint4* rec = reinterpret_cast<const uint4*>(xb + kBatchXRankMin + (static_cast<size_t>(q) * 3 + sl) * 32);
+                const uint4 p = __ldcg(rec), p1 = __ldcg(rec + 1);
+                const uint64_t hp = (static_cast<uint64_t>(p.y) << 32) | p.x;
+                bool have = !(hp < theta);
+                for (int k = 0; k < s_m && !have; ++k) have = s_hp[k] == hp;
+                if (!have && s_m < kMaxBatch) {
+                    const int k = s_m++;
+                    s_hp[k] = hp;
+                    s_ca[k] = static_cast<int32_t>(p.z);
+                    s_cb[k] = static_cast<int32_t>(p.w);
+                    s_csa[k] = static_cast<int32_t>(p1.x);
+                    s_csb[k] = static_cast<int32_t>(p1.y);
+                    s_ckb[k] = static_cast<int32_t>(p1.z);
+                }
+            }
+        }
+        if (cand_over) __syncthreads();
         const int32_t n_cand = s_m;  // <= kMaxBatch
         // slot conflicts: a pair that shares a cluster with an earlier pair is a stopper
         uint64_t mine = kPackInf, conf = kPackInf;
@@ -826,7 +900,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         const int rank = take ? n_less : -1;  // everything below an accepted pair is accepted
         const int32_t m_all = block_sum_i32(rank >= 0 ? 1 : 0, s_redi);  // >= 1: the global minimum head is always among them
         const int32_t m = min(m_all, limit);                              // merges of this iteration
-        if (exact && blockIdx.x == 0 && __syncthreads_or(was_cut) != 0 && tid == 0) atomicAdd(ctl + CTL_N_CUT, 1);
+        if (exact && bid == 0 && __syncthreads_or(was_cut) != 0 && tid == 0) atomicAdd(ctl + CTL_N_CUT, 1);
         if (rank >= 0) {
             s_d[rank] = static_cast<uint32_t>(mine >> 32);
             if (rank < m) {
@@ -849,7 +923,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         const long long tp3 = timed ? clock64() : 0;
 
         // ---- bookkeeping (block 0): trace, slot table; counters of the next iterations ----
-        if (blockIdx.x == 0) {
+        if (bid == 0) {
             if (tid < m) {
                 const int32_t a = s_a[tid], b = s_b[tid], snew = s_sa[tid] + s_sb[tid], new_key = kbase + t + tid;
                 const float d = __uint_as_float(s_d[tid]), sd = __uint_as_float(s_d[tid + 1]);
@@ -1112,7 +1186,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             grid_sync(st.bar, phase, G);  // gpu scope: every queue is local to its rank
             const int32_t nx = min(__ldcg(st.counters + sl * 4 + CN_XQ), st.xq_cap);
             const float d_last = __uint_as_float(s_d[m > 0 ? m - 1 : 0]);
-            if (use_xres && blockIdx.x == 0 && tid < m) {  // new rows without a pair at or below the horizon (or with too many): scan
+            if (use_xres && bid == 0 && tid < m) {  // new rows without a pair at or below the horizon (or with too many): scan
                 const int32_t c = __ldcg(st.xhit + tid);
                 if (c <= 0 || c > kXResCap || __ldcg(st.counters + sl * 4 + CN_XQ) > st.xq_cap)
                     st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(s_b[tid], kbase + t - m + tid);
@@ -1152,7 +1226,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
             if (lane == 0 && my_exact > 0) atomicAdd(ctl + CTL_N_EXACT, my_exact);
         }
         if (kMulti)
-            grid_sync_ranks(st, phase, xcount, G, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
+            grid_sync_ranks(st, phase, xcount, G, bid, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
         else
             grid_sync(st.bar, phase, G);
         m_prev = m;
@@ -1175,7 +1249,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
         st.prof[6] += iters;
         for (int i = 0; i < 4; ++i) st.prof[10 + i] += c_ph[4 + i];
     }
-    if (blockIdx.x == 0 && tid == 0) {
+    if (bid == 0 && tid == 0) {
         ctl[CTL_N_LIVE] = n_live;
         ctl[CTL_N_MERGES] = t;
         ctl[CTL_EXHAUSTED] = stop_reason == STOP_EXHAUSTED ? 1 : 0;
@@ -1190,15 +1264,17 @@ merge_batch_kernel(const __grid_constant__ BatchState st, const __grid_constant_
 cudaError_t merge_batch_grid(int num_sms, int64_t n, int* blocks) {
     *blocks = 0;
     const size_t smem = merge_batch_smem_bytes(n);
-    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(merge_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        e = cudaFuncSetAttribute(merge_batch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(merge_batch_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return cudaSuccess;  // does not fit: *blocks stays 0
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_batch_kernel<true>, kBT, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_batch_kernel<true, true>, kBT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaSuccess;
     // small problems: fewer blocks make the grid barriers cheaper
@@ -1213,14 +1289,36 @@ cudaError_t launch_merge_batch(const BatchState& st, const LoopParams& p, int bl
     st_copy.win_cols = static_cast<int32_t>(batch_window_cols(st.n));
     st_copy.n_win = static_cast<int32_t>(merge_batch_windows(st.n));
     LoopParams p_copy = p;
-    void* args[] = {&st_copy, &p_copy};
+    const BatchState* none = nullptr;
+    int32_t bpr = blocks;
+    void* args[] = {&st_copy, &p_copy, &none, &bpr};
     const size_t smem = merge_batch_smem_bytes(st.n);
     const bool multi = st.n_ranks > 1;
-    void* fn = multi ? reinterpret_cast<void*>(merge_batch_kernel<true>) : reinterpret_cast<void*>(merge_batch_kernel<false>);
-    cudaError_t e = multi ? cudaFuncSetAttribute(merge_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                          : cudaFuncSetAttribute(merge_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    void* fn = multi ? reinterpret_cast<void*>(merge_batch_kernel<true, false>) : reinterpret_cast<void*>(merge_batch_kernel<false, false>);
+    cudaError_t e = multi ? cudaFuncSetAttribute(merge_batch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                          : cudaFuncSetAttribute(merge_batch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kBT), args, smem, s);
+}
+
+// P virtual ranks in one cooperative launch of P * blocks_per_rank blocks; d_states = the ranks' BatchStates in device memory
+// (win_cols / n_win filled in by the caller through merge_batch_fill_windows)
+void merge_batch_fill_windows(BatchState* st) {
+    st->win_cols = static_cast<int32_t>(batch_window_cols(st->n));
+    st->n_win = static_cast<int32_t>(merge_batch_windows(st->n));
+}
+cudaError_t launch_merge_batch_virtual(const BatchState* d_states, int n_ranks, int64_t n, const LoopParams& p, int blocks_per_rank,
+                                       cudaStream_t s) {
+    if (blocks_per_rank <= 0 || n_ranks < 2) return cudaErrorInvalidConfiguration;
+    BatchState dummy{};
+    LoopParams p_copy = p;
+    int32_t bpr = blocks_per_rank;
+    void* args[] = {&dummy, &p_copy, &d_states, &bpr};
+    const size_t smem = merge_batch_smem_bytes(n);
+    cudaError_t e = cudaFuncSetAttribute(merge_batch_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(merge_batch_kernel<true, true>), dim3(blocks_per_rank * n_ranks), dim3(kBT),
+                                       args, smem, s);
 }
 
 }  // namespace ic

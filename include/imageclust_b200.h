@@ -42,7 +42,7 @@ extern "C" {
 /* ic_initial_distances modes */
 #define IC_GRAM_TCGEN05_3XTF32 0 /* K1 (first version): TMA + tcgen05 kind::tf32, exact fixed-point slice + residual, fp32 TMEM */
 #define IC_GRAM_EXACT_FP32 1     /* SIMT kernel with the reference's own sequential fp32 arithmetic (audit path) */
-#define IC_GRAM_TCGEN05_I8 2     /* K1 (default): TMA + tcgen05 kind::i8, three int8 digits of a 21-bit fixed-point row, exact int32
+#define IC_GRAM_TCGEN05_I8 2     /* K1 (default): TMA + tcgen05 kind::i8, three int8 digits of a 22-bit fixed-point row, exact int32
                                     accumulation in TMEM (6 products per k-step at 4x the TF32 rate) */
 
 typedef struct ic_ctx ic_ctx;
@@ -133,8 +133,8 @@ int ic_load_device(ic_ctx *ctx, const float *x_dev, int64_t n, int64_t d, int64_
  * internal/workflow/workflow.go:167-168.  Row i of X = image embedding i (d_img floats) ++ a vector over the label
  * set (n_labels floats) holding 1.0 at the index of every label of item i that is in the set, 0.0 elsewhere.
  * label_ids[label_offsets[i] .. label_offsets[i+1]) are item i's labels as indices into the label set (the shim does
- * the map[string]int lookup of embeddings.go:169); an index outside [0, n_labels) stands for a label that is not in
- * the set and is ignored, as the reference ignores it.  Only the image block crosses PCIe. */
+ * the map[string]int lookup of embeddings.go:169); -1 stands for a label that is not in the set and is ignored, as the
+ * reference ignores it; any other index outside [0, n_labels) is IC_ERR_BAD_ARG.  Only the image block crosses PCIe. */
 int ic_load_combined(ic_ctx *ctx, const float *img_host, int64_t n, int64_t d_img, int64_t ld_img,
                      const int32_t *label_offsets, const int32_t *label_ids, int64_t n_labels);
 /* the resident X [n x d] back on the host (row stride ld >= d) -- inspection / tests */
@@ -170,8 +170,8 @@ int ic_build_clusters(ic_ctx *ctx, int64_t min_size, int32_t *cluster_offsets, i
  *   ic_shard_export(ctx, blob)                  CUDA-IPC handles of my row block + rank mailbox
  *   <host all-gathers the world blobs, rank order>   (torch.distributed / MPI / Go net: plumbing)
  *   ic_shard_connect(ctx, blobs)                peer-maps the other ranks' row blocks over NVLink
- *   ic_run_resident(...) / ic_merge_loop(...)   as on one GPU; the ranks' persistent kernels exchange
- *                                               one 128-byte record per merge through peer memory
+ *   ic_run_resident(...) / ic_merge_loop(...)   as on one GPU; the ranks' persistent kernels exchange their candidate
+ *                                               pairs once per iteration (dozens of merges) through peer memory
  * ic_read_matrix / ic_set_matrix touch only the rows [row_begin,row_end) of ic_shard_rows. */
 #define IC_SHARD_HANDLE_BYTES 192
 int ic_shard_init(ic_ctx *ctx, int rank, int world);

@@ -32,9 +32,17 @@ eng.set_option("exact", 1 if exact_mode else 0)
 sh = sharding.ShardedEngine(eng, rank, world)
 ok = True
 cases = [(600, 48, 3, 10, _lib.GRAM_EXACT_FP32), (3001, 64, 4, 12, _lib.GRAM_TCGEN05_3XTF32),
-         (5000, 256, 6, 8, _lib.GRAM_TCGEN05_I8)]
+         (5000, 256, 6, 8, _lib.GRAM_TCGEN05_I8),
+         # 6000 exact duplicate pairs: every pair is a head at distance 0 and none conflicts, so each rank has ~3000
+         # candidates below the stopper -- more than its region of the exchange box holds (kBatchXCand = 2048)
+         (12000, 8, 1, 4, _lib.GRAM_EXACT_FP32)]
 for n, d, mn, mx, mode in cases:
-    x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=n + d)
+    if d == 8:
+        rng = np.random.default_rng(11)
+        base = (rng.standard_normal((n // 2, d)) * 50).astype(np.float32)
+        x = np.concatenate([base, base])[rng.permutation(n)]
+    else:
+        x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=n + d)
     eng.set_option("gram_mode", mode)
     sh.load(x)
     eng.initial_distances(mode, mx)

@@ -33,9 +33,10 @@ def test_stats_struct_layout_matches_header():
     body = re.search(r"typedef struct ic_stats \{(.*?)\} ic_stats;", hdr, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
-    for ctype, name in re.findall(r"\b(int64_t|int32_t|float)\s+([a-z_0-9]+);", body):
+    for ctype, name in re.findall(r"\b(int64_t|int32_t|float|double)\s+([a-z_0-9]+);", body):
         fields.append((name, ctype))
-    got = [(n, {"c_long": "int64_t", "c_int": "int32_t", "c_float": "float"}[t.__name__]) for n, t in _lib.Stats._fields_]
+    got = [(n, {"c_long": "int64_t", "c_int": "int32_t", "c_float": "float", "c_double": "double"}[t.__name__])
+           for n, t in _lib.Stats._fields_]
     assert fields == got
 
 

@@ -300,8 +300,9 @@ def test_members_follow_the_reference_order(eng, oracle):
 
 
 # ---- row-block sharding on ONE GPU: P virtual ranks in one cooperative launch -------------
-# The same kernel path as the multi-GPU build (two-level exchange, per-rank replicas of the slot
-# table, peer row pointers); only the peers' memory happens to be on the same device.
+# The same kernel path as the multi-GPU build -- merge_batch_kernel<multi> (the kernel bench.py --gpus N runs: exchange
+# boxes, cross-rank barriers, peer row pointers, per-rank replicas of the slot table) with loop_mode 1, merge_loop_kernel
+# with loop_mode 0 -- only the peers' memory happens to be on the same device.
 
 @pytest.fixture
 def knobs(eng):
@@ -315,12 +316,12 @@ def knobs(eng):
 
 
 @pytest.mark.parametrize("name", SMALL_GOLDENS)
-@pytest.mark.parametrize("ranks", [2, 3, 8])
-def test_virtual_shards_goldens_bit_exact(eng, oracle, knobs, name, ranks):
+@pytest.mark.parametrize("ranks,loop_mode", [(2, 1), (3, 1), (8, 1), (2, 0), (8, 0)])
+def test_virtual_shards_goldens_bit_exact(eng, oracle, knobs, name, ranks, loop_mode):
     g = load_golden(name)
     mn, mx = int(g["min_size"]), int(g["max_size"])
     o = oracle.fast_cluster(g["x"], mn, mx, flags=LW_EAGER, init_matrix=g["init_matrix"])
-    knobs(virtual_ranks=ranks)
+    knobs(virtual_ranks=ranks, loop_mode=loop_mode)
     eng.load(g["x"])
     eng.set_matrix(g["init_matrix"])
     eng.nn_init()
@@ -329,14 +330,15 @@ def test_virtual_shards_goldens_bit_exact(eng, oracle, knobs, name, ranks):
     assert same_clusters(eng.build_clusters(mn), o.clusters)
 
 
+@pytest.mark.parametrize("loop_mode", [1, 0])
 @pytest.mark.parametrize("n,d,mn,mx,ranks,blocks,no_replica", [
     (3000, 64, 4, 12, 2, 0, 0), (3000, 64, 4, 12, 4, 8, 0), (3001, 64, 4, 12, 8, 3, 1), (5000, 32, 6, 8, 3, 16, 0),
     (2500, 100, 1, 2500, 2, 5, 1), (3000, 64, 4, 12, 1, 7, 1), (4000, 24, 2, 6, 1, 148, 0)])
-def test_sharded_loop_replays_bit_exact(eng, oracle, knobs, n, d, mn, mx, ranks, blocks, no_replica):
-    """Tensor-core initial matrix -> sharded device loop (virtual ranks, forced block counts, keys streamed
+def test_sharded_loop_replays_bit_exact(eng, oracle, knobs, n, d, mn, mx, ranks, blocks, no_replica, loop_mode):
+    """Tensor-core initial matrix -> sharded device loop (virtual ranks, forced block counts; loop_mode 0: keys streamed
     from L2 instead of the shared-memory replica); the oracle replays the SAME matrix."""
     x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=n + d)
-    knobs(virtual_ranks=ranks, loop_blocks=blocks, no_replica=no_replica)
+    knobs(virtual_ranks=ranks, loop_blocks=blocks, no_replica=no_replica, loop_mode=loop_mode)
     with lw_only(eng):
         eng.load(x)
         eng.initial_distances(_lib.GRAM_TCGEN05_I8 if ranks % 2 else _lib.GRAM_TCGEN05_3XTF32, mx)
@@ -350,15 +352,17 @@ def test_sharded_loop_replays_bit_exact(eng, oracle, knobs, n, d, mn, mx, ranks,
     assert int((key >= 0).sum()) == o.n_final and int(size[key >= 0].sum()) == n
 
 
-def test_sharded_duplicates_many_dry_rows(eng, oracle, knobs):
-    """Dozens of rows lose all their cached partners at once (exact duplicates): their rescans are served
-    a few per iteration while lower bounds hold the merge back (bubbles), on 4 virtual ranks."""
+@pytest.mark.parametrize("loop_mode", [1, 0])
+def test_sharded_duplicates_many_dry_rows(eng, oracle, knobs, loop_mode):
+    """Dozens of rows lose all their cached partners at once (exact duplicates), on 4 virtual ranks: the batched sharded
+    kernel with the horizon reproduces the reference arithmetic, the one-merge-per-iteration kernel (rescans served a few
+    per iteration while lower bounds hold the merge back) the Lance-Williams oracle."""
     rng = np.random.default_rng(5)
     x = rng.standard_normal((400, 8)).astype(np.float32)
     x[50:120] = x[7]
     x[200:230] = x[9]
-    o = oracle.fast_cluster(x, 1, 6, flags=LW_EAGER)
-    knobs(virtual_ranks=4, loop_blocks=2)
+    o = oracle.fast_cluster(x, 1, 6, flags=0 if loop_mode == 1 else LW_EAGER)
+    knobs(virtual_ranks=4, loop_blocks=2, loop_mode=loop_mode)
     eng.set_option("gram_mode", _lib.GRAM_EXACT_FP32)
     try:
         res = eng.cluster(x, 1, 6)
@@ -368,10 +372,11 @@ def test_sharded_duplicates_many_dry_rows(eng, oracle, knobs):
     assert same_clusters(res.clusters, o.clusters)
 
 
-def test_sharded_staged_resume(eng, oracle, knobs):
+@pytest.mark.parametrize("loop_mode", [1, 0])
+def test_sharded_staged_resume(eng, oracle, knobs, loop_mode):
     x = synth.gaussian_mixture(700, 48, 3, 10, seed=34)
-    o = oracle.fast_cluster(x, 3, 10, flags=LW_EAGER)
-    knobs(virtual_ranks=2, loop_blocks=3)
+    o = oracle.fast_cluster(x, 3, 10, flags=0 if loop_mode == 1 else LW_EAGER)
+    knobs(virtual_ranks=2, loop_blocks=3, loop_mode=loop_mode)
     eng.load(x)
     eng.initial_distances(_lib.GRAM_EXACT_FP32, 10)
     eng.nn_init()
@@ -384,6 +389,41 @@ def test_sharded_staged_resume(eng, oracle, knobs):
     eng.merge_loop(3, 10)
     _same_trace(eng.merge_trace(), o)
     assert same_clusters(eng.build_clusters(3), o.clusters)
+
+
+@pytest.mark.parametrize("ranks,n,d,mn,mx,gram", [(2, 3000, 64, 4, 12, _lib.GRAM_TCGEN05_I8), (4, 2000, 2048, 10, 50, _lib.GRAM_TCGEN05_I8),
+                                                  (8, 2500, 100, 1, 2500, _lib.GRAM_EXACT_FP32), (3, 5000, 32, 6, 8, _lib.GRAM_TCGEN05_3XTF32)])
+def test_virtual_shards_equal_reference_arithmetic(eng, oracle, knobs, ranks, n, d, mn, mx, gram):
+    """The sharded batched kernel (what bench.py --gpus N runs), P virtual ranks, whole path with the horizon: the merge
+    trace is the reference-arithmetic one; every rank's queue, exact phase and exchange of the overflow / order flags ran."""
+    x = synth.gaussian_mixture(n, d, mn, min(mx, 40), seed=ranks + n)
+    o = oracle.fast_cluster(x, mn, mx, flags=0)
+    knobs(virtual_ranks=ranks)
+    eng.set_option("gram_mode", gram)
+    try:
+        res = eng.cluster(x, mn, mx)
+    finally:
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(res.clusters, o.clusters)
+    _assert_reference_run(res.stats)
+
+
+def test_virtual_shards_more_candidates_than_the_exchange_box_holds(eng, oracle, knobs):
+    """6 000 exact duplicate pairs on 2 virtual ranks: ~3 000 heads per rank sit below the stopper, more than a rank's
+    region of the exchange box holds (kBatchXCand = 2 048).  Which candidates are dropped depends on the order of the
+    atomics; the ranks then publish their minimum and merge the global minimum only -- the result must not depend on it."""
+    rng = np.random.default_rng(11)
+    base = (rng.standard_normal((6000, 8)) * 50).astype(np.float32)
+    x = np.concatenate([base, base])[rng.permutation(12000)]
+    o = oracle.fast_cluster(x, 1, 4, flags=0)
+    knobs(virtual_ranks=2, gram_mode=_lib.GRAM_EXACT_FP32)
+    try:
+        res = eng.cluster(x, 1, 4)
+    finally:
+        eng.set_option("gram_mode", _lib.GRAM_TCGEN05_I8)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(res.clusters, o.clusters)
 
 
 # ---- BASELINE.json's full sizes --------------------------------------------------------------------
