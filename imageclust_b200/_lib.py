@@ -37,7 +37,7 @@ SYMBOLS = [
     "ic_shard_init", "ic_shard_export", "ic_shard_connect", "ic_shard_rows",
     "ic_load_combined", "ic_read_x", "ic_get_loop_block_waits", "ic_get_linkage",
 ]
-SHARD_HANDLE_BYTES = 192
+SHARD_HANDLE_BYTES = 256
 
 
 class Stats(C.Structure):

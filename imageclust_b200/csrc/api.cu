@@ -63,6 +63,7 @@ struct ic_ctx {
     int shard_rank_alloc = -1, shard_world_alloc = -1;
     bool peers_open = false;
     void* peer_dm[kMaxRanks] = {nullptr};   // every rank's row block (own + cudaIpc mapped)
+    void* peer_dm_b[kMaxRanks] = {nullptr}; // every rank's second matrix buffer (compaction target), if allocated
     void* peer_box[kMaxRanks] = {nullptr};  // every rank's inter-rank mailbox
     uint64_t barrier_seq = 0;
     // resident problem
@@ -114,6 +115,7 @@ struct ic_ctx {
     int32_t xq_cap = 0;
     uint4* xres = nullptr;
     int32_t* xhit = nullptr;
+    int2* xqm = nullptr;
     // K4 compaction (compact.cu): current epoch's geometry, second copies of the per-slot state and of the matrix
     int compact_opt = 1, compact_opt_alloc = -1;  // option "compact"
     int refill_at = 2;            // option "refill_at" (1 or 2)
@@ -174,9 +176,10 @@ void close_peers(ic_ctx* c) {
     for (int q = 0; q < kMaxRanks; ++q) {
         if (c->peers_open && q != c->shard_rank_alloc) {
             if (c->peer_dm[q]) cudaIpcCloseMemHandle(c->peer_dm[q]);
+            if (c->peer_dm_b[q]) cudaIpcCloseMemHandle(c->peer_dm_b[q]);
             if (c->peer_box[q]) cudaIpcCloseMemHandle(c->peer_box[q]);
         }
-        c->peer_dm[q] = c->peer_box[q] = nullptr;
+        c->peer_dm[q] = c->peer_dm_b[q] = c->peer_box[q] = nullptr;
     }
     c->peers_open = false;
 }
@@ -213,6 +216,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->xq);
     dev_free(c->xres);
     dev_free(c->xhit);
+    dev_free(c->xqm);
     dev_free(c->dm_b);
     dev_free(c->ks_b);
     dev_free(c->gkey_b);
@@ -305,8 +309,20 @@ int64_t row_end(const ic_ctx* c) {
     return c->shard_world > 1 ? std::min(c->n, row_begin(c) + rows_per_rank(c)) : c->n;
 }
 
+// geometry of the CURRENT epoch (after compactions the matrix has n_cur dense slots, re-blocked over the ranks)
+int64_t rows_per_rank_cur(const ic_ctx* c) { return merge_loop_rows_per_rank(c->n_cur, n_ranks(c)); }
+int64_t row_begin_cur(const ic_ctx* c) { return c->shard_world > 1 ? std::min(c->n_cur, c->shard_rank * rows_per_rank_cur(c)) : 0; }
+int64_t row_end_cur(const ic_ctx* c) {
+    return c->shard_world > 1 ? std::min(c->n_cur, row_begin_cur(c) + rows_per_rank_cur(c)) : c->n_cur;
+}
+// first row of rank q's block in the current matrix buffer (own memory, a peer mapping, or -- virtual ranks -- this device)
+float* rank_block(const ic_ctx* c, int q) {
+    if (c->shard_world > 1) return static_cast<float*>(c->dm_cur == c->dm ? c->peer_dm[q] : c->peer_dm_b[q]);
+    return c->dm_cur + static_cast<int64_t>(q) * rows_per_rank_cur(c) * c->ld_cur;
+}
+
 // 128 x 128 tiles of the int8 kernel, lower triangle, in 2048 x 2048 super-tiles (operand panels stay in L2)
-std::vector<int2> build_tile_list_i8(int64_t n, int64_t row_begin, int64_t row_end) {
+std::vector<int2> build_tile_list_i8(int64_t n, int64_t row_begin, int64_t row_end, bool lower_only) {
     std::vector<int2> tiles;
     const int nb = static_cast<int>((n + kI8Tile - 1) / kI8Tile);
     const int S = 16;
@@ -316,7 +332,9 @@ std::vector<int2> build_tile_list_i8(int64_t n, int64_t row_begin, int64_t row_e
                 for (int cb = sc * S; cb < (sc + 1) * S && cb <= rb; ++cb) {
                     const int64_t r0 = static_cast<int64_t>(rb) * kI8Tile, c0 = static_cast<int64_t>(cb) * kI8Tile;
                     const bool rows_in = !(r0 + kI8Tile <= row_begin || r0 >= row_end);
-                    const bool cols_in = !(c0 + kI8Tile <= row_begin || c0 >= row_end);
+                    // (a tile whose columns only touch the row block serves the mirrored stores: not needed when K1 stores the
+                    // lower triangle only -- the batched loop -- and the upper one is filled by the mirror pass)
+                    const bool cols_in = !lower_only && !(c0 + kI8Tile <= row_begin || c0 >= row_end);
                     if (!rows_in && !cols_in) continue;
                     tiles.push_back(make_int2(rb, cb));
                 }
@@ -410,7 +428,8 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
         IC_CUDA(cudaMalloc(&ctx->cen, sizeof(float) * 2 * nn1 * static_cast<size_t>(ctx->ldc)));  // by key: N items + up to N merges
         IC_CUDA(cudaMalloc(&ctx->xq, sizeof(int4) * static_cast<size_t>(ctx->xq_cap) * NL));
         IC_CUDA(cudaMalloc(&ctx->xres, sizeof(uint4) * static_cast<size_t>(kMaxBatch) * kXResCap));
-        IC_CUDA(cudaMalloc(&ctx->xhit, sizeof(int32_t) * kMaxBatch));
+        IC_CUDA(cudaMalloc(&ctx->xhit, sizeof(int32_t) * kMaxBatch * NL));
+        IC_CUDA(cudaMalloc(&ctx->xqm, sizeof(int2) * static_cast<size_t>(kMaxBatch) * kXResCap * NL));
         IC_CUDA(cudaMalloc(&ctx->rq, sizeof(int2) * static_cast<size_t>(ctx->rq_cap)));
         IC_CUDA(cudaMalloc(&ctx->rq_cnt, sizeof(int32_t) * 4));
     }
@@ -443,16 +462,19 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
         IC_CUDA(cudaMemsetAsync(ctx->batch_scratch, 0, off * NL, ctx->stream));
     }
     // K4: second matrix buffer (a quarter of the first) and second copies of the per-slot state; one GPU, batched loop
-    if (ctx->compact_opt && ctx->batch_layout && ctx->shard_world <= 1 && P == 1 && n >= ctx->compact_min) {
+    if (ctx->compact_opt && ctx->batch_layout && n >= ctx->compact_min) {
         const size_t half = static_cast<size_t>(static_cast<double>(n) * ctx->compact_ratio + 32);
-        const size_t want = half * static_cast<size_t>(round_up(static_cast<int64_t>(half), 32));
+        // a sharded context holds its row block of the compacted matrix only
+        const size_t half_rows = ctx->shard_world > 1 ? static_cast<size_t>(merge_loop_rows_per_rank(static_cast<int64_t>(half), P)) : half;
+        const size_t want = half_rows * static_cast<size_t>(round_up(static_cast<int64_t>(half), 32));
         size_t fb = 0, tb = 0;
         IC_CUDA(cudaMemGetInfo(&fb, &tb));
         if (static_cast<double>(want) * 4.0 + 64.0 * nn1 + (256 << 20) < static_cast<double>(fb)) {
             ctx->dm_b_floats = want;
             IC_CUDA(cudaMalloc(&ctx->dm_b, sizeof(float) * want));
-            IC_CUDA(cudaMalloc(&ctx->ks_b, sizeof(SlotKS) * (nn1 + 4)));
-            IC_CUDA(cudaMalloc(&ctx->gkey_b, sizeof(int32_t) * n4));
+            IC_CUDA(cudaMalloc(&ctx->ks_b, sizeof(SlotKS) * (n4 + 4) * NL));
+            IC_CUDA(cudaMemsetAsync(ctx->ks_b, 0xFF, sizeof(SlotKS) * (n4 + 4) * NL, ctx->stream));
+            IC_CUDA(cudaMalloc(&ctx->gkey_b, sizeof(int32_t) * n4 * NL));
             IC_CUDA(cudaMalloc(&ctx->nn_b, sizeof(SlotNN) * nn1 * kNNK));
             IC_CUDA(cudaMalloc(&ctx->nn_more_b, sizeof(int32_t) * nn1));
             IC_CUDA(cudaMalloc(&ctx->keymap, sizeof(int32_t) * (2 * nn1 + 4)));
@@ -513,6 +535,8 @@ int loop_state(ic_ctx* c, LoopState* out) {
     return IC_OK;
 }
 
+bool use_batch(const ic_ctx* c);
+
 int do_prep_i8(ic_ctx* ctx) {
     if (ctx->prepped_i8) return IC_OK;
     Nvtx range("ic K0 prep (centre, int8 digits, norms)");
@@ -528,7 +552,7 @@ int do_prep_i8(ic_ctx* ctx) {
                             ctx->quanta, ctx->norms, ctx->n_pad, ctx->d_pad8, ctx->stream));
     ctx->stats.kernel_launches += 2;
     if (!ctx->tiles8) {
-        const std::vector<int2> tiles = build_tile_list_i8(ctx->n, row_begin(ctx), row_end(ctx));
+        const std::vector<int2> tiles = build_tile_list_i8(ctx->n, row_begin(ctx), row_end(ctx), use_batch(ctx));
         ctx->n_tiles8 = static_cast<int>(tiles.size());
         IC_CUDA(cudaMalloc(&ctx->tiles8, sizeof(int2) * (tiles.size() ? tiles.size() : 1)));
         IC_CUDA(cudaMemcpyAsync(ctx->tiles8, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -701,14 +725,14 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             bs.compact_at = (ctx->dm_b && ctx->n_cur >= ctx->compact_min) ? static_cast<int32_t>(static_cast<double>(ctx->n_cur) * ctx->compact_ratio) : 0;
             bs.n_ranks = 1;
             bs.rank = 0;
-            bs.rows_per_rank = static_cast<int32_t>(rows_per_rank(ctx));
+            bs.rows_per_rank = static_cast<int32_t>(rows_per_rank_cur(ctx));
             bs.ld = ctx->ld_cur;
             bs.dm = ctx->dm_cur;
             if (ctx->shard_world > 1) {  // real shards: peer-mapped row blocks and exchange boxes
                 bs.n_ranks = ctx->shard_world;
                 bs.rank = ctx->shard_rank;
                 for (int q = 0; q < ctx->shard_world; ++q) {
-                    bs.dm_rank[q] = static_cast<float*>(ctx->peer_dm[q]);
+                    bs.dm_rank[q] = rank_block(ctx, q);
                     bs.xbox[q] = static_cast<uint8_t*>(ctx->peer_box[q]) + merge_loop_rankbox_bytes();
                 }
                 bs.gen = static_cast<uint32_t>(ctx->barrier_seq);
@@ -716,7 +740,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
                 bs.n_ranks = VR;
                 bs.rank = v;
                 for (int q = 0; q < VR; ++q) {
-                    bs.dm_rank[q] = ctx->dm + static_cast<int64_t>(q) * bs.rows_per_rank * ctx->ld;
+                    bs.dm_rank[q] = rank_block(ctx, q);
                     bs.xbox[q] = ctx->rankbox + merge_loop_rankbox_bytes() * VR + static_cast<size_t>(q) * kBatchXBoxBytes;
                 }
                 bs.dm = bs.dm_rank[v];
@@ -749,7 +773,8 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             bs.xq = ctx->xq ? ctx->xq + static_cast<size_t>(v) * static_cast<size_t>(ctx->xq_cap) : nullptr;
             bs.xq_cap = ctx->xq_cap;
             bs.xres = ctx->xres;
-            bs.xhit = ctx->xhit;
+            bs.xhit = ctx->xhit ? ctx->xhit + static_cast<size_t>(v) * kMaxBatch : nullptr;
+            bs.xqm = ctx->xqm ? ctx->xqm + static_cast<size_t>(v) * kMaxBatch * kXResCap : nullptr;
             // scratch of a launch: counters and the barrier at zero
             IC_CUDA(cudaMemsetAsync(bs.counters, 0, 3 * 4 * 4, ctx->stream));
             IC_CUDA(cudaMemsetAsync(bs.part_cnt, 0, static_cast<size_t>(kBatchMaxDry) * 4, ctx->stream));
@@ -764,7 +789,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             }
             merge_batch_fill_windows(&bs);
         }
-        if (ctx->xhit) IC_CUDA(cudaMemsetAsync(ctx->xhit, 0, sizeof(int32_t) * kMaxBatch, ctx->stream));
+        if (ctx->xhit) IC_CUDA(cudaMemsetAsync(ctx->xhit, 0, sizeof(int32_t) * kMaxBatch * VR, ctx->stream));
         if (ctx->shard_world > 1) {  // all ranks line up: nobody starts before every box is reset
             IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
             ctx->stats.kernel_launches += 1;
@@ -821,11 +846,11 @@ int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
     a.ld = ctx->ld_cur;
     a.n_slots = static_cast<int32_t>(ctx->n_cur);
     a.mirror_key = ctx->mirror_key;
-    a.rows_per_rank = ctx->shard_world > 1 ? static_cast<int32_t>(rows_per_rank(ctx)) : 0x40000000;
+    a.rows_per_rank = ctx->shard_world > 1 ? static_cast<int32_t>(rows_per_rank_cur(ctx)) : 0x40000000;
     for (int q = 0; q < kMaxRanks; ++q)
-        a.dm_rank[q] = ctx->shard_world > 1 ? static_cast<float*>(ctx->peer_dm[q]) : ctx->dm_cur;
-    a.r_lo = static_cast<int32_t>(row_begin(ctx));
-    a.r_hi = static_cast<int32_t>(std::min(row_end(ctx), ctx->n_cur));  // (after a compaction: n_cur dense slots)
+        a.dm_rank[q] = (ctx->shard_world > 1 && q < ctx->shard_world) ? rank_block(ctx, q) : ctx->dm_cur;
+    a.r_lo = static_cast<int32_t>(row_begin_cur(ctx));
+    a.r_hi = static_cast<int32_t>(row_end_cur(ctx));  // (after a compaction: n_cur dense slots)
     a.ks = ctx->ks;
     a.gkey = ctx->gkey;
     a.cen = ctx->cen;
@@ -910,42 +935,63 @@ int raise_horizon(ic_ctx* ctx) {
 int do_compact(ic_ctx* ctx) {
     Nvtx range("ic K4 compaction");
     const double t0 = now_ms();
+    const int P = n_ranks(ctx), NL = n_local(ctx);
+    const bool real = ctx->shard_world > 1;
     const int32_t n_old = static_cast<int32_t>(ctx->n_cur), n_new = ctx->n_live, n_new4 = (n_new + 3) & ~3;
     const int64_t ld_new = round_up(n_new, 32);
-    float* target = ctx->dm_cur == ctx->dm ? ctx->dm_b : ctx->dm;
-    const size_t cap = ctx->dm_cur == ctx->dm ? ctx->dm_b_floats : static_cast<size_t>(ctx->n) * static_cast<size_t>(ctx->ld);
-    if (static_cast<size_t>(n_new4) * static_cast<size_t>(ld_new) > cap)
-        return fail(ctx, IC_ERR_INTERNAL, "compaction target buffer too small");
+    const int32_t c_old = static_cast<int32_t>(rows_per_rank_cur(ctx));
+    const int32_t c_new = static_cast<int32_t>(merge_loop_rows_per_rank(n_new, P));
+    const bool to_b = ctx->dm_cur == ctx->dm;
+    float* target = to_b ? ctx->dm_b : ctx->dm;
+    const size_t cap = to_b ? ctx->dm_b_floats
+                            : static_cast<size_t>(real ? rows_per_rank(ctx) : ctx->n) * static_cast<size_t>(ctx->ld);
+    const size_t rows_here = real ? static_cast<size_t>(c_new) : static_cast<size_t>(n_new4);
+    if (rows_here * static_cast<size_t>(ld_new) > cap) return fail(ctx, IC_ERR_INTERNAL, "compaction target buffer too small");
+    if (real && !ctx->peers_open) return fail(ctx, IC_ERR_STATE, "sharded context: ic_shard_connect has not run");
     IC_CUDA(launch_compact_map(ctx->ks, n_old, ctx->keymap, static_cast<int32_t>(ctx->n + ctx->n_merges), ctx->newslot,
                                ctx->oldslot, n_new4, ctx->nlive_dev, ctx->stream));
+    const size_t n4s = (static_cast<size_t>(ctx->n) + 3) / 4 * 4;
     CompactArgs a{};
     a.n_old = n_old;
     a.n_new = n_new;
     a.n_new4 = n_new4;
     a.oldslot = ctx->oldslot;
     a.newslot = ctx->newslot;
-    a.ks_old = ctx->ks;
     a.nn_old = ctx->nn;
     a.nn_more_old = ctx->nn_more;
-    a.ks_new = ctx->ks_b;
-    a.gkey_new = ctx->gkey_b;
     a.nn_new = ctx->nn_b;
     a.nn_more_new = ctx->nn_more_b;
+    a.my_rank = real ? ctx->shard_rank : -1;  // real shards: the partner list of a row that changes owner is rebuilt
     for (int q = 0; q < kMaxRanks; ++q) {
-        a.dm_old[q] = ctx->dm_cur;
-        a.dm_new_rank[q] = target;
+        a.dm_old[q] = q < P ? rank_block(ctx, q) : nullptr;
+        a.dm_new_rank[q] = q >= P ? nullptr
+                           : real ? static_cast<float*>(to_b ? ctx->peer_dm_b[q] : ctx->peer_dm[q])
+                                  : target + static_cast<int64_t>(q) * c_new * ld_new;
     }
-    a.rows_per_rank_old = a.rows_per_rank_new = 0x40000000;
+    a.rows_per_rank_old = c_old;
+    a.rows_per_rank_new = c_new;
     a.ld_old = ctx->ld_cur;
     a.dm_new = target;
-    a.row_base_new = 0;
-    a.row0 = 0;
-    a.row1 = n_new;
+    a.row_base_new = real ? std::min(n_new, ctx->shard_rank * c_new) : 0;
+    a.row0 = a.row_base_new;
+    a.row1 = real ? std::min(n_new, a.row_base_new + c_new) : n_new;
     a.ld_new = ld_new;
-    IC_CUDA(launch_compact_state(a, ctx->stream));
+    for (int v = 0; v < NL; ++v) {  // every (virtual) rank's replica of the slot table; the partner lists once
+        a.ks_old = ctx->ks + static_cast<size_t>(v) * (n4s + 4);
+        a.ks_new = ctx->ks_b + static_cast<size_t>(v) * (n4s + 4);
+        a.gkey_new = ctx->gkey_b + static_cast<size_t>(v) * n4s;
+        CompactArgs av = a;
+        if (v > 0) av.nn_new = nullptr;
+        IC_CUDA(launch_compact_state(av, ctx->stream));
+    }
+    a.ks_old = ctx->ks;
     IC_CUDA(launch_compact_rows(a, ctx->stream));
+    if (real) {  // every rank's lower triangle is complete before anyone mirrors it
+        ++ctx->barrier_seq;
+        IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
+    }
     IC_CUDA(launch_mirror_lower(a, ctx->stream));
-    ctx->stats.kernel_launches += 5;
+    ctx->stats.kernel_launches += 4 + NL;
     int32_t found = 0;
     IC_CUDA(cudaMemcpyAsync(&found, ctx->nlive_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1134,16 +1180,23 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
         IC_CUDA(launch_fill(ctx->dm, (row_end(ctx) - row_begin(ctx)) * ctx->ld, INFINITY, ctx->stream));
         ctx->stats.kernel_launches += 1;
     }
-    if (ctx->mirror_init && ctx->dm_lower_only && n_ranks(ctx) == 1 && ctx->n > 1) {
+    if (ctx->mirror_init && ctx->dm_lower_only && ctx->n > 1 && max_size >= 2 && (ctx->shard_world <= 1 || ctx->peers_open)) {
+        // fill the upper triangle: every row then holds all its partners (fewer gathers in the loop's first epoch).  Sharded:
+        // the transposed tiles are read from their owners, once every rank's K1 is complete
+        const bool real = ctx->shard_world > 1;
         CompactArgs a{};
         a.n_new = static_cast<int32_t>(ctx->n);
         a.dm_new = ctx->dm;
-        for (int q = 0; q < kMaxRanks; ++q) a.dm_new_rank[q] = ctx->dm;
-        a.rows_per_rank_new = 0x40000000;
-        a.row_base_new = 0;
-        a.row0 = 0;
-        a.row1 = static_cast<int32_t>(ctx->n);
+        a.rows_per_rank_new = real ? static_cast<int32_t>(rows_per_rank(ctx)) : 0x40000000;
+        for (int q = 0; q < kMaxRanks; ++q) a.dm_new_rank[q] = real ? static_cast<float*>(ctx->peer_dm[q]) : ctx->dm;
+        a.row_base_new = static_cast<int32_t>(row_begin(ctx));
+        a.row0 = a.row_base_new;
+        a.row1 = static_cast<int32_t>(row_end(ctx));
         a.ld_new = ctx->ld;
+        if (real) {
+            ++ctx->barrier_seq;
+            IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
+        }
         IC_CUDA(launch_mirror_lower(a, ctx->stream));
         ctx->stats.kernel_launches += 1;
         ctx->dm_lower_only = false;
@@ -1605,7 +1658,8 @@ struct ShardHandle {  // what ic_shard_export writes (IC_SHARD_HANDLE_BYTES)
     int32_t rank, world;
     int32_t pad;
     int64_t n, ld, rows;
-    cudaIpcMemHandle_t dm, box;
+    cudaIpcMemHandle_t dm, box, dm_b;
+    int32_t has_b, pad2;
 };
 static_assert(sizeof(ShardHandle) <= IC_SHARD_HANDLE_BYTES, "handle blob too small");
 constexpr uint32_t kShardMagic = 0x49435348u;
@@ -1634,6 +1688,8 @@ int ic_shard_export(ic_ctx* ctx, void* handle) {
     h.rows = rows_per_rank(ctx);
     IC_CUDA(cudaIpcGetMemHandle(&h.dm, ctx->dm));
     IC_CUDA(cudaIpcGetMemHandle(&h.box, ctx->rankbox));
+    h.has_b = ctx->dm_b ? 1 : 0;
+    if (ctx->dm_b) IC_CUDA(cudaIpcGetMemHandle(&h.dm_b, ctx->dm_b));
     std::memset(handle, 0, IC_SHARD_HANDLE_BYTES);
     std::memcpy(handle, &h, sizeof(h));
     return IC_OK;
@@ -1654,9 +1710,13 @@ int ic_shard_connect(ic_ctx* ctx, const void* handles) {
         if (q == ctx->shard_rank) {
             ctx->peer_dm[q] = ctx->dm;
             ctx->peer_box[q] = ctx->rankbox;
+            ctx->peer_dm_b[q] = ctx->dm_b;
         } else {
             IC_CUDA(cudaIpcOpenMemHandle(&ctx->peer_dm[q], h.dm, cudaIpcMemLazyEnablePeerAccess));
             IC_CUDA(cudaIpcOpenMemHandle(&ctx->peer_box[q], h.box, cudaIpcMemLazyEnablePeerAccess));
+            if ((h.has_b != 0) != (ctx->dm_b != nullptr))
+                return fail(ctx, IC_ERR_BAD_ARG, "rank " + std::to_string(q) + " and this rank disagree about the compaction buffer");
+            if (h.has_b) IC_CUDA(cudaIpcOpenMemHandle(&ctx->peer_dm_b[q], h.dm_b, cudaIpcMemLazyEnablePeerAccess));
         }
     }
     ctx->peers_open = true;

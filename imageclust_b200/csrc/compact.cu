@@ -74,6 +74,17 @@ __global__ void __launch_bounds__(256) compact_state_kernel(const CompactArgs a)
     const int2 k = a.ks_old[o];
     a.ks_new[s] = k;
     a.gkey_new[s] = k.x;
+    if (a.nn_new == nullptr) return;  // (a further replica of the slot table: the lists were permuted with the first)
+    if (a.my_rank >= 0) {  // real shards: only the owner of a row holds its list
+        if (s / a.rows_per_rank_new != a.my_rank) return;
+        if (o / a.rows_per_rank_old != a.my_rank) {  // the row moves here: its list is rebuilt by a scan before it is used
+            a.nn_new[static_cast<int64_t>(s) * kNNK] = make_uint4(kNoPartner, 0u, kNoPartner, 0u);
+#pragma unroll
+            for (int e = 1; e < kNNK; ++e) a.nn_new[static_cast<int64_t>(s) * kNNK + e] = make_uint4(kNoPartner, kNoPartner, kNoPartner, 0u);
+            a.nn_more_new[s] = 3;
+            return;
+        }
+    }
     int32_t more = a.nn_more_old[o];
 #pragma unroll
     for (int e = 0; e < kNNK; ++e) {

@@ -67,6 +67,64 @@ IC_DEVINL float warp_exact_dsq(const float* __restrict__ pa, const float* __rest
     return __shfl_sync(0xffffffffu, sum, 0);
 }
 
+// Up to kExGroup pairs that share their first cluster, one warp: the squared differences of every pair are staged side by
+// side and lanes 0 .. np-1 run the np sequential chains in lockstep -- the chain latency (the floor of one evaluation) is
+// paid once per group, and row A is read once.  `pb` is lane k's second row (lanes >= np: ignored); returns pair k's dsq
+// on lane k.  sbuf = kExGroup * kExStride floats of this warp (the stride keeps the lanes' 16-byte reads on distinct banks).
+constexpr int kExGroup = 4;
+constexpr int kExStride = kExChunk + 4;
+IC_DEVINL float warp_exact_dsq_group(const float* __restrict__ pa, const float* pb, int np, int d4, float* sbuf) {
+    const int lane = threadIdx.x & 31;
+    constexpr int Q = kExChunk / 128;
+    const float* pbk[kExGroup];
+#pragma unroll
+    for (int k = 0; k < kExGroup; ++k) {
+        const unsigned long long v = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(pb), k);
+        pbk[k] = reinterpret_cast<const float*>(v);
+    }
+    float4 a[Q], b[kExGroup][Q];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto issue = [&](int c0) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int e = c0 + 4 * (lane + 32 * q);
+            const bool ok = e < d4;
+            a[q] = ok ? __ldcg(reinterpret_cast<const float4*>(pa + e)) : z;
+#pragma unroll
+            for (int k = 0; k < kExGroup; ++k) b[k][q] = (ok && k < np) ? __ldcg(reinterpret_cast<const float4*>(pbk[k] + e)) : z;
+        }
+    };
+    float sum = 0.0f;
+    issue(0);
+    for (int c0 = 0; c0 < d4; c0 += kExChunk) {
+#pragma unroll
+        for (int k = 0; k < kExGroup; ++k) {
+            if (k < np) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float dx = __fsub_rn(a[q].x, b[k][q].x), dy = __fsub_rn(a[q].y, b[k][q].y), dz = __fsub_rn(a[q].z, b[k][q].z),
+                                dw = __fsub_rn(a[q].w, b[k][q].w);
+                    reinterpret_cast<float4*>(sbuf + k * kExStride)[lane + 32 * q] =
+                        make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
+                }
+            }
+        }
+        __syncwarp();
+        if (c0 + kExChunk < d4) issue(c0 + kExChunk);  // in flight while the chains run
+        if (lane < np) {
+            const int n4 = (min(kExChunk, d4 - c0)) >> 2;
+            const float4* src = reinterpret_cast<const float4*>(sbuf + lane * kExStride);
+#pragma unroll 4
+            for (int i = 0; i < n4; ++i) {
+                const float4 v = src[i];
+                sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
+            }
+        }
+        __syncwarp();
+    }
+    return sum;
+}
+
 // (float32(na * nb) / float32(na + nb)) * dsq: integer product first (clustering.go:142-144)
 IC_DEVINL float ward_weight(int na, int nb, float dsq) {
     const float num = __ll2float_rn(static_cast<long long>(na) * static_cast<long long>(nb));

@@ -236,7 +236,8 @@ struct BatchState {
     // 0x80000000 | index of an earlier merge of the batch (cross term)}
     float* cen;         // [2N x ldc] by cluster key (row N + t: the cluster made by merge t), ldc = d rounded up to 4, zero padded
     int64_t ldc;
-    int4* xq;           // [xq_cap] {merge, column | cross, Lance-Williams value bits, position among the merge's queued pairs}
+    int2* xqm;          // [kMaxBatch][kXResCap] per merge of the batch: {column | cross, Lance-Williams value bits}
+    int4* xq;           // [xq_cap] overflow of the merges' queues: {merge, column | cross, value bits, position}
     int32_t xq_cap;
     // one GPU: the partner list of a new cluster is selected from its re-evaluated pairs (everything else in its row is
     // above the horizon), so its row needs no scan: xres[merge][position] = {value bits, partner key, partner slot, size}
@@ -302,6 +303,7 @@ struct CompactArgs {
     float* dm_new_rank[kMaxRanks];          // every rank's new row block (the mirror pass reads the transposed tiles)
     int32_t rows_per_rank_new, row_base_new, row0, row1;
     int64_t ld_new;
+    int32_t my_rank;                        // real shards: partner lists live with their row's owner; -1 otherwise
 };
 // newslot / oldslot from the live keys (ascending); *n_live_out = live clusters found
 cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap, int32_t key_cap, int32_t* newslot,

@@ -233,7 +233,7 @@ IC_DEVINL RowHead row_head(uint4 e0, uint4 e1, uint32_t more_bits, uint32_t key_
 size_t merge_batch_smem_bytes(int64_t n) {
     const size_t n4 = static_cast<size_t>((n + 3) / 4 * 4);
     const size_t bitmap = ((n4 + 31) / 32 + 3) / 4 * 4 * sizeof(uint32_t);
-    return bitmap + sizeof(float) * kBW * kExChunk;  // + the warps' chunk buffers of the exact phase
+    return bitmap + sizeof(float) * kBW * kExGroup * kExStride;  // + the warps' staging buffers of the exact phase
 }
 static int64_t batch_window_cols(int64_t n) {  // at most kBatchMaxWin windows per row: <= 4 partial lists per lane in the fold
     const int64_t n4 = (n + 3) / 4 * 4;
@@ -287,10 +287,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
     uint32_t xcount = 0;
     __shared__ int32_t s_xcnt[kMaxRanks + 1];  // candidate pairs per rank (prefix sums)
     __shared__ int32_t s_xover[kMaxRanks];     // rank dropped candidates (its region of the exchange box was full)
+    __shared__ int32_t s_xcntm[kMaxBatch], s_upre[kMaxBatch + 1], s_wsum[kBW];  // exact phase: queued pairs / groups per merge
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    float (*const s_ex)[kExChunk] = reinterpret_cast<float (*)[kExChunk]>(dyn_smem);  // exact phase: one chunk of squared differences per warp
-    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kBW * kExChunk);  // merged-slot bitmap of the current batch
+    // exact phase: squared differences of one chunk of up to kExGroup pairs per warp
+    float (*const s_ex)[kExGroup * kExStride] = reinterpret_cast<float (*)[kExGroup * kExStride]>(dyn_smem);
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kBW * kExGroup * kExStride);  // merged-slot bitmap of the current batch
     const int32_t n_words = (n4 + 31) >> 5;
 
     __shared__ uint64_t s_red[kBW];
@@ -341,6 +343,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         // ---- partner lists of the clusters the previous iteration created, selected from their re-evaluated pairs ----
         // (one GPU, reference arithmetic: every pair of the new row at or below the horizon went through the exact phase;
         // the rest of the row is above the horizon, which therefore bounds the unlisted partners)
+        if (exact && !use_xres)
+            for (int32_t j = gtid; j < m_prev; j += GT) st.xhit[j] = 0;  // (read by every block in the exact phase before the barrier)
         if (use_xres) {
             for (int32_t j = gw; j < m_prev; j += GW) {
                 const int32_t c = __ldcg(st.xhit + j);
@@ -1039,20 +1043,24 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                         if (exact && keep && static_cast<double>(lw) <= prm.horizon) hitm |= 1u << (x * 4 + e);
                     }
                 }
-                if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // queue {merge, column, Lance-Williams value, position}
-                    int32_t idx = warp_reserve(st.counters + sl * 4 + CN_XQ, __popc(hitm), lane);
-                    int32_t pos = use_xres ? warp_reserve(st.xhit + i, __popc(hitm), lane) : 0;
+                if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // the merge's queue: {column, Lance-Williams value}
+                    int32_t pos = warp_reserve(st.xhit + i, __popc(hitm), lane);
 #pragma unroll
                     for (int x = 0; x < kI; ++x)
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             if ((hitm >> (x * 4 + e)) & 1u) {
-                                if (idx < st.xq_cap)
-                                    st.xq[idx] = make_int4(i, c_lo + ch * kUpdCols + x * 128 + lane * 4 + e,
-                                                           static_cast<int32_t>(__float_as_uint(outv[x][e])), pos);
-                                else
-                                    ctl[CTL_XQ_OVERFLOW] = 1;
-                                ++idx;
+                                const int32_t col = c_lo + ch * kUpdCols + x * 128 + lane * 4 + e;
+                                const int32_t lwb = static_cast<int32_t>(__float_as_uint(outv[x][e]));
+                                if (pos < kXResCap) {
+                                    st.xqm[static_cast<int64_t>(i) * kXResCap + pos] = make_int2(col, lwb);
+                                } else {  // more pairs than a merge's queue holds: the shared overflow queue
+                                    const int32_t idx = atomicAdd(st.counters + sl * 4 + CN_XQ, 1);
+                                    if (idx < st.xq_cap)
+                                        st.xq[idx] = make_int4(i, col, lwb, pos);
+                                    else
+                                        ctl[CTL_XQ_OVERFLOW] = 1;
+                                }
                                 ++pos;
                             }
                 }
@@ -1111,13 +1119,18 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 float val = __uint_as_float(kInfBits);
                 if (si + saj + sbj <= prm.max_size) val = lance_williams(saj, sbj, si, t1, t2, dj);
                 if (exact && static_cast<double>(val) <= prm.horizon) {  // (lanes diverge here: rare)
-                    const int32_t idx = atomicAdd(st.counters + sl * 4 + CN_XQ, 1);
-                    const int32_t pos = use_xres ? atomicAdd(st.xhit + j, 1) : 0;
-                    if (idx < st.xq_cap)
-                        st.xq[idx] = make_int4(j, static_cast<int32_t>(0x80000000u | static_cast<uint32_t>(i)),
-                                               static_cast<int32_t>(__float_as_uint(val)), pos);
-                    else
-                        ctl[CTL_XQ_OVERFLOW] = 1;
+                    const int32_t pos = atomicAdd(st.xhit + j, 1);
+                    const int32_t colx = static_cast<int32_t>(0x80000000u | static_cast<uint32_t>(i));
+                    const int32_t lwb = static_cast<int32_t>(__float_as_uint(val));
+                    if (pos < kXResCap) {
+                        st.xqm[static_cast<int64_t>(j) * kXResCap + pos] = make_int2(colx, lwb);
+                    } else {
+                        const int32_t idx = atomicAdd(st.counters + sl * 4 + CN_XQ, 1);
+                        if (idx < st.xq_cap)
+                            st.xq[idx] = make_int4(j, colx, lwb, pos);
+                        else
+                            ctl[CTL_XQ_OVERFLOW] = 1;
+                    }
                 } else {
                     __stcg(row_of(bj) + bi, val);  // new_j carries the higher key
                 }
@@ -1192,34 +1205,83 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(s_b[tid], kbase + t - m + tid);
             }
             int32_t my_exact = 0;
-            for (int32_t q = gw; q < nx; q += GW) {
-                const int4 ent = __ldcg(st.xq + q);
-                const int32_t j = ent.x;
-                const int32_t bj = s_b[j], saj = s_sa[j], sbj = s_sb[j];
-                // centroids are stored by key; the new clusters' rows were written in the phase before the barrier
-                const float* pa = st.cen + static_cast<int64_t>(kbase + t - m + j) * st.ldc;
-                int32_t size_b, col, key_b;
-                if (ent.y < 0) {  // cross term: the other cluster was created by this batch, too
-                    const int32_t i = ent.y & 0x7FFFFFFF;
+            // what one lane does with the reference's value of its pair: monitors, the matrix entry, the new row's list
+            auto finish = [&](int32_t j, int32_t col, int32_t key_b, int32_t size_b, int32_t lwb, int32_t pos, float dsq) {
+                const int32_t bj = s_b[j];
+                const float w = ward_weight(s_sa[j] + s_sb[j], size_b, dsq);
+                exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(lwb)), w, prm.eps_filter, prm.abs_slack);
+                if (j + 1 < m && w < d_last) atomicAdd(ctl + CTL_ORDER_VIOL, 1);  // would have preceded a later pair of the batch
+                __stcg(row_of(bj) + col, w);
+                if (use_xres && pos < kXResCap)
+                    __stcg(st.xres + static_cast<int64_t>(j) * kXResCap + pos,
+                           make_uint4(__float_as_uint(w), static_cast<uint32_t>(key_b), static_cast<uint32_t>(col), static_cast<uint32_t>(size_b)));
+                if (kMulti && (bj < r_lo || bj >= r_hi)) wrote_remote = true;
+            };
+            auto decode = [&](int32_t colx, int32_t& col, int32_t& key_b, int32_t& size_b) {
+                if (colx < 0) {  // cross term: the other cluster was created by this batch, too
+                    const int32_t i = colx & 0x7FFFFFFF;
                     size_b = s_sa[i] + s_sb[i];
                     col = s_b[i];
                     key_b = kbase + t - m + i;
                 } else {
-                    col = ent.y;
+                    col = colx;
                     size_b = __ldcg(st.lsize + col);
                     key_b = __ldcg(st.gkey + col);
                 }
+            };
+            // groups of up to kExGroup queued pairs of one merge: they share the new cluster's centroid and the chain latency
+            {
+                int32_t cj = 0;
+                if (tid < m) cj = min(__ldcg(st.xhit + tid), kXResCap);
+                if (tid < kMaxBatch) s_xcntm[tid] = cj;
+                int32_t g = (cj + kExGroup - 1) / kExGroup, inc = g;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                int32_t woff = 0;
+                for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
+                if (tid < kMaxBatch) s_upre[tid + 1] = woff + inc;
+                if (tid == 0) s_upre[0] = 0;
+                __syncthreads();
+            }
+            const int32_t n_groups = s_upre[min(m, kMaxBatch)];
+            for (int32_t u = gw; u < n_groups; u += GW) {
+                int32_t lo_j = 0, hi_j = m;  // largest j with s_upre[j] <= u
+                while (hi_j - lo_j > 1) {
+                    const int32_t mid = (lo_j + hi_j) >> 1;
+                    if (s_upre[mid] <= u)
+                        lo_j = mid;
+                    else
+                        hi_j = mid;
+                }
+                const int32_t j = lo_j, p0 = (u - s_upre[j]) * kExGroup, np = min(kExGroup, s_xcntm[j] - p0);
+                const float* pa = st.cen + static_cast<int64_t>(kbase + t - m + j) * st.ldc;  // written in the phase before the barrier
+                int32_t col = 0, key_b = 0, size_b = 0, lwb = 0;
+                const float* pb = nullptr;
+                if (lane < np) {
+                    const int2 ent = __ldcg(st.xqm + static_cast<int64_t>(j) * kXResCap + p0 + lane);
+                    lwb = ent.y;
+                    decode(ent.x, col, key_b, size_b);
+                    pb = st.cen + static_cast<int64_t>(key_b) * st.ldc;
+                }
+                const float dsq = warp_exact_dsq_group(pa, pb, np, d4, s_ex[warp]);
+                if (lane < np) finish(j, col, key_b, size_b, lwb, p0 + lane, dsq);
+                if (lane == 0) my_exact += np;
+            }
+            // pairs beyond a merge's queue (rare): one at a time
+            for (int32_t q = gw; q < nx; q += GW) {
+                const int4 ent = __ldcg(st.xq + q);
+                const int32_t j = ent.x;
+                const float* pa = st.cen + static_cast<int64_t>(kbase + t - m + j) * st.ldc;
+                int32_t size_b, col, key_b;
+                decode(ent.y, col, key_b, size_b);
                 const float dsq = warp_exact_dsq(pa, st.cen + static_cast<int64_t>(key_b) * st.ldc, d4, s_ex[warp]);
                 if (lane == 0) {
-                    const float w = ward_weight(saj + sbj, size_b, dsq);
-                    exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(ent.z)), w, prm.eps_filter, prm.abs_slack);
-                    if (j + 1 < m && w < d_last) atomicAdd(ctl + CTL_ORDER_VIOL, 1);  // would have preceded a later pair of the batch
-                    __stcg(row_of(bj) + col, w);
-                    if (use_xres && ent.w < kXResCap)
-                        __stcg(st.xres + static_cast<int64_t>(j) * kXResCap + ent.w,
-                               make_uint4(__float_as_uint(w), static_cast<uint32_t>(key_b),
-                                          static_cast<uint32_t>(col), static_cast<uint32_t>(size_b)));
-                    if (kMulti && (bj < r_lo || bj >= r_hi)) wrote_remote = true;
+                    finish(j, col, key_b, size_b, ent.z, ent.w, dsq);
                     ++my_exact;
                 }
             }

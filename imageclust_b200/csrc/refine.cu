@@ -70,31 +70,48 @@ __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_cons
 }
 
 __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant__ RefineArgs a) {
-    __shared__ __align__(16) float s_buf[8][kExChunk];
+    __shared__ __align__(16) float s_buf[8][kExGroup * kExStride];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t total = min(__ldg(a.cnt), a.cap);
     const int32_t gw = static_cast<int32_t>(blockIdx.x) * 8 + warp, GW = static_cast<int32_t>(gridDim.x) * 8;
     const int d4 = static_cast<int>(a.ldc);
     int32_t n_done = 0;
-    for (int32_t i = gw; i < total; i += GW) {
-        const int2 p = a.q[i];
-        const int2 kr = a.ks[p.x], ku = a.ks[p.y];
-        const float dsq = warp_exact_dsq(a.cen + static_cast<int64_t>(kr.x) * a.ldc, a.cen + static_cast<int64_t>(ku.x) * a.ldc, d4,
-                                         s_buf[warp]);  // centroids are stored by key
-        if (lane == 0) {
-            const float w = ward_weight(kr.y, ku.y, dsq);
-            float* dst = a.dm + static_cast<int64_t>(p.x - a.r_lo) * a.ld + p.y;
-            const float stored = *dst;
-            exact_monitor(a.ctl, stored, w, a.eps_filter, a.abs_slack);
-            if (__float_as_uint(stored) != __float_as_uint(w)) {
-                *dst = w;
-                if (kr.x < a.mirror_key) {  // both clusters are older than the last compaction: the pair is stored in both rows
-                    const int32_t q = p.y / a.rows_per_rank;
-                    a.dm_rank[q][static_cast<int64_t>(p.y - q * a.rows_per_rank) * a.ld + p.x] = w;
-                }
-                atomicOr(a.nn_more + p.x, 3);  // kMoreBit | kDryBit: the row's partner list is rebuilt before it is used
+    // the collect kernel appends a row's pairs in runs: consecutive entries mostly share their row, whose centroid (and the
+    // latency of the summation chain) is then shared by up to kExGroup evaluations
+    for (int32_t base = gw * kExGroup; base < total; base += GW * kExGroup) {
+        const int32_t cnt = min(kExGroup, total - base);
+        int2 p = make_int2(-1, -1);
+        if (lane < cnt) p = a.q[base + lane];
+        int32_t done = 0;
+        while (done < cnt) {
+            const int32_t r0 = __shfl_sync(0xffffffffu, p.x, done);
+            const uint32_t same = __ballot_sync(0xffffffffu, lane >= done && lane < cnt && p.x == r0) >> done;
+            const int32_t run = __ffs(~same) - 1;  // entries done .. done + run - 1 share the row
+            const int32_t u = __shfl_sync(0xffffffffu, p.y, min(done + lane, 31));
+            const int2 kr = a.ks[r0];
+            int2 ku = make_int2(0, 0);
+            const float* pb = nullptr;
+            if (lane < run) {
+                ku = a.ks[u];
+                pb = a.cen + static_cast<int64_t>(ku.x) * a.ldc;  // centroids are stored by key
             }
-            ++n_done;
+            const float dsq = warp_exact_dsq_group(a.cen + static_cast<int64_t>(kr.x) * a.ldc, pb, run, d4, s_buf[warp]);
+            if (lane < run) {
+                const float w = ward_weight(kr.y, ku.y, dsq);
+                float* dst = a.dm + static_cast<int64_t>(r0 - a.r_lo) * a.ld + u;
+                const float stored = *dst;
+                exact_monitor(a.ctl, stored, w, a.eps_filter, a.abs_slack);
+                if (__float_as_uint(stored) != __float_as_uint(w)) {
+                    *dst = w;
+                    if (kr.x < a.mirror_key) {  // both clusters are older than the last compaction: the pair is stored in both rows
+                        const int32_t q = u / a.rows_per_rank;
+                        a.dm_rank[q][static_cast<int64_t>(u - q * a.rows_per_rank) * a.ld + r0] = w;
+                    }
+                    atomicOr(a.nn_more + r0, 3);  // kMoreBit | kDryBit: the row's partner list is rebuilt before it is used
+                }
+            }
+            if (lane == 0) n_done += run;
+            done += run;
         }
     }
     if (lane == 0 && n_done > 0) atomicAdd(a.ctl + CTL_N_EXACT, n_done);

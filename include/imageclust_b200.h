@@ -173,7 +173,7 @@ int ic_build_clusters(ic_ctx *ctx, int64_t min_size, int32_t *cluster_offsets, i
  *   ic_run_resident(...) / ic_merge_loop(...)   as on one GPU; the ranks' persistent kernels exchange their candidate
  *                                               pairs once per iteration (dozens of merges) through peer memory
  * ic_read_matrix / ic_set_matrix touch only the rows [row_begin,row_end) of ic_shard_rows. */
-#define IC_SHARD_HANDLE_BYTES 192
+#define IC_SHARD_HANDLE_BYTES 256
 int ic_shard_init(ic_ctx *ctx, int rank, int world);
 int ic_shard_export(ic_ctx *ctx, void *handle);
 int ic_shard_connect(ic_ctx *ctx, const void *handles);
