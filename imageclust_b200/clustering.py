@@ -286,6 +286,10 @@ class Engine:
         """Cycles block 0 spent per phase of the last merge-loop launch (option profile_loop=1)."""
         out = (C.c_int64 * 16)()
         self._check(self._L.ic_get_loop_profile(self._h, out))
+        # batched loop (merge_batch.cu): publish = phase 1 (new rows' lists + rescans), exchange = phase 2 (heads), update = batch
+        # selection, scan = phase 3 + 4 (rows .. end of iteration); pub_argmin = Lance-Williams rows + centroids, pub_reduce /
+        # pub_fence = barrier waits after phase 1 / 2, pub_stores = end of validation .. end of iteration, of which exch_poll =
+        # wait for the slowest block's rows phase and exch_rank = this block's share of the exact phase
         return dict(zip(("publish", "exchange", "update", "scan", "fold", "merges", "iterations", "rescans",
                          "reserved", "bubbles", "pub_argmin", "pub_reduce", "pub_fence", "pub_stores", "exch_poll",
                          "exch_rank"), list(out)))

@@ -320,8 +320,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
     long long n_rescans = 0;
     const bool timed = st.prof != nullptr && bid == 0 && tid == 0;
     const bool small_sizes = prm.max_size < kRcpTab;  // every admissible size sum has its reciprocal in the table
-    __shared__ long long c_ph[8];  // cycles of block 0 per phase (profile_loop)
-    if (tid < 8) c_ph[tid] = 0;
+    __shared__ long long c_ph[10];  // cycles of block 0 per phase (profile_loop)
+    if (tid < 10) c_ph[tid] = 0;
 
     for (int i = tid; i < kRcpTab; i += kBT) s_rcp[i] = 1.0 / static_cast<double>(i > 0 ? i : 1);
     __syncthreads();
@@ -974,7 +974,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         {
             // sharded: a rank updates the columns of its own row block -- rows a and b are coalesced (possibly remote) reads,
             // the gathers from the rows of newer clusters c are local, its part of the new row is a coalesced remote store
-            const int32_t c_lo = r_lo, c_hi = kMulti ? min(n4, r_lo + C) : n4;
+            // (multiples of 4: a rank whose block starts beyond the last slot has r_lo == n, which need not be one)
+            const int32_t c_lo = kMulti ? min(n4, st.rank * C) : 0, c_hi = kMulti ? min(n4, c_lo + C) : n4;
             const int32_t n_chunks = (c_hi - c_lo + kUpdCols - 1) / kUpdCols;
             const int64_t units = static_cast<int64_t>(m) * n_chunks;
             for (int64_t u = gw; u < units; u += GW) {
@@ -1197,6 +1198,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         // formed on the fly from the two stored ones, which are only overwritten after the barrier that ends this phase.
         if (exact) {
             grid_sync(st.bar, phase, G);  // gpu scope: every queue is local to its rank
+            const long long te0 = timed ? clock64() : 0;
             const int32_t nx = min(__ldcg(st.counters + sl * 4 + CN_XQ), st.xq_cap);
             const float d_last = __uint_as_float(s_d[m > 0 ? m - 1 : 0]);
             if (use_xres && bid == 0 && tid < m) {  // new rows without a pair at or below the horizon (or with too many): scan
@@ -1286,6 +1288,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 }
             }
             if (lane == 0 && my_exact > 0) atomicAdd(ctl + CTL_N_EXACT, my_exact);
+            if (timed) {
+                c_ph[8] += te0 - tq3;        // waiting for the slowest block's rows phase
+                c_ph[9] += clock64() - te0;  // this block's share of the exact phase
+            }
         }
         if (kMulti)
             grid_sync_ranks(st, phase, xcount, G, bid, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
@@ -1309,7 +1315,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         st.prof[3] += c_ph[3];
         st.prof[5] += launched;
         st.prof[6] += iters;
-        for (int i = 0; i < 4; ++i) st.prof[10 + i] += c_ph[4 + i];
+        for (int i = 0; i < 6; ++i) st.prof[10 + i] += c_ph[4 + i];
     }
     if (bid == 0 && tid == 0) {
         ctl[CTL_N_LIVE] = n_live;

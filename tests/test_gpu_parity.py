@@ -311,8 +311,8 @@ def knobs(eng):
         for k, v in kw.items():
             eng.set_option(k, v)
     yield set_
-    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode", "exact"):
-        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode", "exact") else 0)
+    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode", "exact", "mirror_init", "compact"):
+        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode", "exact", "mirror_init", "compact") else 0)
 
 
 @pytest.mark.parametrize("name", SMALL_GOLDENS)
@@ -598,6 +598,26 @@ def test_batched_and_sequential_loops_agree(eng, knobs, n, d, mn, mx):
     assert digests[0] == digests[1]
 
 
+@pytest.mark.parametrize("ratio,mirror", [(0.5, 1), (0.7, 0), (0.9, 1)])
+def test_compaction_does_not_change_the_trace(eng, knobs, ratio, mirror):
+    """K4: renumbering the live clusters and moving the matrix (any ratio, with or without the initial mirror pass) leaves
+    the merge trace bit-identical -- in Lance-Williams arithmetic (every stored value matters) and with the horizon."""
+    x = synth.gaussian_mixture(9000, 96, 4, 12, seed=19)
+    for exact in (0, 1):
+        digests, ncomp = [], []
+        for compact in (0, 1):
+            knobs(exact=exact, compact=compact, mirror_init=mirror)
+            eng.set_option("compact_ratio", ratio)
+            try:
+                res = eng.cluster(x, 4, 12)
+            finally:
+                eng.set_option("compact_ratio", 0.7)
+            digests.append(_trace_digest(eng.merge_trace()))
+            ncomp.append(res.stats["n_compactions"])
+        assert digests[0] == digests[1]
+        assert ncomp[0] == 0 and ncomp[1] >= 1
+
+
 def test_batched_more_disjoint_pairs_than_the_batch_capacity(eng, oracle, knobs):
     """1 500 exact duplicate pairs: every pair is a head at distance 0 and none conflicts, so far more than
     kMaxBatch (512) pairs sit below the stopper; the batch is cut to a prefix by bisection on the packed value."""
@@ -630,10 +650,10 @@ def test_batched_loop_exhaustion_and_tight_max(eng, oracle, knobs):
 
 
 def test_batched_loop_stats_and_mode_guard(eng, knobs):
-    """ic_stats reports the loop that ran and its iterations; the loop mode cannot change once the batched path's
-    lower-triangle-only initial matrix exists (the one-merge-per-iteration loop needs the mirrored entries)."""
+    """ic_stats reports the loop that ran and its iterations; the loop mode cannot change while the matrix holds the lower
+    triangle only (K1 of the batched path without the mirror pass: the one-merge-per-iteration loop needs both)."""
     x = synth.gaussian_mixture(1500, 64, 4, 12, seed=77)
-    eng.set_option("exact", 0)  # (restored by the knobs fixture) the two loops share Lance-Williams arithmetic only
+    knobs(exact=0, mirror_init=0)  # the two loops share Lance-Williams arithmetic only
     res = eng.cluster(x, 4, 12)
     assert res.stats["loop_mode"] == 1
     assert 0 < res.stats["n_iterations"] < res.stats["n_merges"]
