@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimageclust_b200.so")
-SOURCES = ["api.cu", "prep.cu", "gram_exact.cu", "gram_tcgen05.cu", "gram_i8.cu", "nn_sweep.cu", "refine.cu", "compact.cu", "merge_loop.cu", "merge_batch.cu"]
+SOURCES = ["api.cu", "prep.cu", "gram_exact.cu", "gram_tcgen05.cu", "gram_i8.cu", "nn_sweep.cu", "refine.cu", "compact.cu", "near.cu", "merge_loop.cu", "merge_batch.cu"]
 HEADERS = ["common.cuh", "kernels.h", "loop_common.cuh", "exact.cuh", os.path.join("..", "..", "include", "imageclust_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -116,6 +116,14 @@ struct ic_ctx {
     uint4* xres = nullptr;
     int32_t* xhit = nullptr;
     int2* xqm = nullptr;
+    int32_t* xfar = nullptr;
+    // near lists (near.cu)
+    int2 *near_meta = nullptr, *near_meta_b = nullptr;
+    uint2* near_pool = nullptr;
+    int32_t near_pool_cap = 0;
+    int32_t *near_cursor = nullptr, *slot_of_key = nullptr;
+    int near_opt = 1;  // option "near_lists"
+    double ms_near = 0.0;
     // K4 compaction (compact.cu): current epoch's geometry, second copies of the per-slot state and of the matrix
     int compact_opt = 1, compact_opt_alloc = -1;  // option "compact"
     int refill_at = 2;            // option "refill_at" (1 or 2)
@@ -217,6 +225,12 @@ void release_problem(ic_ctx* c) {
     dev_free(c->xres);
     dev_free(c->xhit);
     dev_free(c->xqm);
+    dev_free(c->xfar);
+    dev_free(c->near_meta);
+    dev_free(c->near_meta_b);
+    dev_free(c->near_pool);
+    dev_free(c->near_cursor);
+    dev_free(c->slot_of_key);
     dev_free(c->dm_b);
     dev_free(c->ks_b);
     dev_free(c->gkey_b);
@@ -388,7 +402,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     IC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const double other = 4.0 * n * d + (ctx->gram_mode == IC_GRAM_TCGEN05_3XTF32 ? 8.0 * ctx->n_pad * ctx->d_pad : 0.0) +
                          (ctx->gram_mode == IC_GRAM_TCGEN05_I8 ? 3.0 * ctx->n_pad * ctx->d_pad8 : 0.0) + 260.0 * n + (160 << 20) +
-                         (ctx->exact_opt ? 8.0 * n * round_up(d, 4) + 16.0 * std::max<int64_t>(1 << 20, 16 * n) + 8.0 * (16 << 20) : 0.0);
+                         (ctx->exact_opt ? 8.0 * 192 * n + 8.0 * n * round_up(d, 4) + 16.0 * std::max<int64_t>(1 << 20, 16 * n) + 8.0 * (16 << 20) : 0.0);
     if (ctx->loop_mode == 1 && n > 0) {  // batched loop: one GPU, real shards, or virtual ranks (test hook)
         int grid = 0;
         IC_CUDA(merge_batch_grid(ctx->num_sms, n, &grid));
@@ -430,6 +444,14 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
         IC_CUDA(cudaMalloc(&ctx->xres, sizeof(uint4) * static_cast<size_t>(kMaxBatch) * kXResCap));
         IC_CUDA(cudaMalloc(&ctx->xhit, sizeof(int32_t) * kMaxBatch * NL));
         IC_CUDA(cudaMalloc(&ctx->xqm, sizeof(int2) * static_cast<size_t>(kMaxBatch) * kXResCap * NL));
+        IC_CUDA(cudaMalloc(&ctx->xfar, sizeof(int32_t) * kMaxBatch * NL));
+        // near lists: ~150 pairs per item are at or below the horizon on the benchmark mixtures (initial + created)
+        ctx->near_pool_cap = static_cast<int32_t>(std::min<int64_t>(0x7FFFFFF0, std::max<int64_t>(1 << 20, 192 * static_cast<int64_t>(nn1))));
+        IC_CUDA(cudaMalloc(&ctx->near_meta, sizeof(int2) * (nn1 + 4)));
+        IC_CUDA(cudaMalloc(&ctx->near_meta_b, sizeof(int2) * (nn1 + 4)));
+        IC_CUDA(cudaMalloc(&ctx->near_pool, sizeof(uint2) * static_cast<size_t>(ctx->near_pool_cap)));
+        IC_CUDA(cudaMalloc(&ctx->near_cursor, sizeof(int32_t) * 4));
+        IC_CUDA(cudaMalloc(&ctx->slot_of_key, sizeof(int32_t) * (2 * nn1 + 4)));
         IC_CUDA(cudaMalloc(&ctx->rq, sizeof(int2) * static_cast<size_t>(ctx->rq_cap)));
         IC_CUDA(cudaMalloc(&ctx->rq_cnt, sizeof(int32_t) * 4));
     }
@@ -451,7 +473,7 @@ int alloc_problem(ic_ctx* ctx, int64_t n, int64_t d) {
     if (ctx->batch_layout) {  // batched loop: scratch
         const size_t sizes[11] = {static_cast<size_t>(kBatchMaxBlocks) * 32, 32 * nn1,
                                   3 * 4 * 4, 8 * nn1, static_cast<size_t>(kBatchMaxDry) * kBatchMaxWin * 128,
-                                  static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), static_cast<size_t>(kBatchMaxBlocks) * 32, 0, 0};
+                                  static_cast<size_t>(kBatchMaxDry) * 4, 256, 4 * (nn1 + 4), static_cast<size_t>(kBatchMaxBlocks) * 32, 8 * nn1, 0};
         size_t off = 0;
         for (int i = 0; i < 11; ++i) {
             ctx->batch_off[i] = off;
@@ -649,6 +671,13 @@ int init_loop_state(ic_ctx* ctx) {
         ctx->stats.kernel_launches += 1;
     }
     reset_epoch(ctx);
+    if (ctx->slot_of_key) {
+        IC_CUDA(launch_slot_of_key_init(ctx->slot_of_key, static_cast<int32_t>(ctx->n), static_cast<int32_t>(2 * ctx->n), ctx->stream));
+        IC_CUDA(cudaMemsetAsync(ctx->near_meta, 0xFF, sizeof(int2) * (n + 4), ctx->stream));  // no near lists yet
+        IC_CUDA(cudaMemsetAsync(ctx->near_cursor, 0, sizeof(int32_t) * 4, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    ctx->ms_near = 0.0;
     if (ctx->prof) IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
     ctx->horizon = -1.0;
     ctx->abs_slack = ctx->abs_slack_opt >= 0.0 ? ctx->abs_slack_opt : 0.0;
@@ -768,6 +797,14 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             bs.bar = reinterpret_cast<uint32_t*>(sc + ctx->batch_off[6]);
             bs.lsize = reinterpret_cast<int32_t*>(sc + ctx->batch_off[7]);
             bs.blockmin = reinterpret_cast<uint4*>(sc + ctx->batch_off[8]);
+            bs.nearq = reinterpret_cast<int2*>(sc + ctx->batch_off[9]);
+            const bool near_on = p.exact != 0 && ctx->near_opt != 0 && ctx->near_meta != nullptr && ctx->horizon >= 0.0;
+            bs.near_meta = near_on ? ctx->near_meta : nullptr;
+            bs.near_pool = ctx->near_pool;
+            bs.near_pool_cap = ctx->near_pool_cap;
+            bs.near_cursor = ctx->near_cursor;
+            bs.slot_of_key = ctx->slot_of_key;
+            bs.xfar = ctx->xfar ? ctx->xfar + static_cast<size_t>(v) * kMaxBatch : nullptr;
             bs.cen = ctx->cen;  // (virtual ranks share one centroid store: every rank writes the same values)
             bs.ldc = ctx->ldc;
             bs.xq = ctx->xq ? ctx->xq + static_cast<size_t>(v) * static_cast<size_t>(ctx->xq_cap) : nullptr;
@@ -790,6 +827,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             merge_batch_fill_windows(&bs);
         }
         if (ctx->xhit) IC_CUDA(cudaMemsetAsync(ctx->xhit, 0, sizeof(int32_t) * kMaxBatch * VR, ctx->stream));
+        if (ctx->xfar) IC_CUDA(cudaMemsetAsync(ctx->xfar, 0, sizeof(int32_t) * kMaxBatch * VR, ctx->stream));
         if (ctx->shard_world > 1) {  // all ranks line up: nobody starts before every box is reset
             IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
             ctx->stats.kernel_launches += 1;
@@ -892,6 +930,35 @@ int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
     return IC_OK;
 }
 
+// Near lists of the resident rows for the current horizon (near.cu): two sweeps of the live matrix.
+int build_near(ic_ctx* ctx, bool mark_dry) {
+    if (!ctx->near_meta || !ctx->near_opt) return IC_OK;
+    Nvtx range("ic near lists (two sweeps)");
+    const double t0 = now_ms();
+    NearArgs a{};
+    a.dm = ctx->dm_cur;
+    a.ld = ctx->ld_cur;
+    a.n_slots = static_cast<int32_t>(ctx->n_cur);
+    a.r_lo = static_cast<int32_t>(row_begin_cur(ctx));
+    a.r_hi = static_cast<int32_t>(row_end_cur(ctx));
+    a.gkey = ctx->gkey;
+    a.order_key = ctx->order_key;
+    a.horizon = ctx->horizon;
+    a.meta = ctx->near_meta;
+    a.pool = ctx->near_pool;
+    a.pool_cap = ctx->near_pool_cap;
+    a.cursor = ctx->near_cursor;
+    IC_CUDA(launch_near_build(a, ctx->stream));
+    ctx->stats.kernel_launches += 3;
+    if (mark_dry) {  // bounds at the old horizon are stale: every live row re-selects its list (cheap: from its near list)
+        IC_CUDA(launch_mark_rows_dry(ctx->gkey, ctx->nn_more, a.r_lo, a.r_hi, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+    }
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ms_near += now_ms() - t0;
+    return IC_OK;
+}
+
 // STOP_HORIZON: the smallest candidate H is above the range in which stored values are guaranteed to be the reference's.
 // New horizon = factor * (H (1 + 2 eps) + 2 slack); the band between the old and the new one is re-evaluated.  The factor
 // escalates while a horizon buys fewer than 64 merges (isolated tiny distances below the bulk).
@@ -925,9 +992,10 @@ int raise_horizon(ic_ctx* ctx) {
         }
     }
     ctx->horizon = hi;
+    const bool initial = ctx->n_merges == 0;  // the first sweep kernel has just rebuilt every list from the whole rows
     ctx->merges_at_raise = ctx->n_merges;
     ++ctx->n_raises;
-    return IC_OK;
+    return build_near(ctx, !initial);
 }
 
 // K4 (compact.cu): renumber the live clusters densely in key order, move the matrix into the other buffer (both
@@ -962,6 +1030,10 @@ int do_compact(ic_ctx* ctx) {
     a.nn_new = ctx->nn_b;
     a.nn_more_new = ctx->nn_more_b;
     a.my_rank = real ? ctx->shard_rank : -1;  // real shards: the partner list of a row that changes owner is rebuilt
+    a.order_key_old = ctx->order_key;
+    a.near_meta_old = ctx->near_meta;
+    a.near_meta_new = ctx->near_meta_b;
+    a.slot_of_key = ctx->slot_of_key;
     for (int q = 0; q < kMaxRanks; ++q) {
         a.dm_old[q] = q < P ? rank_block(ctx, q) : nullptr;
         a.dm_new_rank[q] = q >= P ? nullptr
@@ -1000,6 +1072,7 @@ int do_compact(ic_ctx* ctx) {
     std::swap(ctx->gkey, ctx->gkey_b);
     std::swap(ctx->nn, ctx->nn_b);
     std::swap(ctx->nn_more, ctx->nn_more_b);
+    std::swap(ctx->near_meta, ctx->near_meta_b);
     ctx->dm_cur = target;
     ctx->n_cur = n_new;
     ctx->ld_cur = ld_new;
@@ -1244,7 +1317,7 @@ void fill_stats(ic_ctx* ctx) {
         std::memcpy(&s.filter_max_err, &eb, 4);
     }
     s.horizon = ctx->horizon;
-    s.ms_refine = static_cast<float>(ctx->ms_refine);
+    s.ms_refine = static_cast<float>(ctx->ms_refine + ctx->ms_near);  // horizon sweeps: re-evaluation + near lists
     s.n_restarts = ctx->n_restarts;
     s.n_compactions = ctx->n_compactions;
     s.ms_compact = static_cast<float>(ctx->ms_compact);
@@ -1412,6 +1485,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         ctx->refill_at = v;
     } else if (k == "compact") {
         ctx->compact_opt = value != 0.0;
+    } else if (k == "near_lists") {
+        ctx->near_opt = value != 0.0;
     } else if (k == "compact_ratio") {
         if (!(value >= 0.25 && value <= 0.9)) return fail(ctx, IC_ERR_BAD_ARG, "compact_ratio must be in [0.25, 0.9]");
         ctx->compact_ratio = value;

@@ -75,9 +75,12 @@ __global__ void __launch_bounds__(256) compact_state_kernel(const CompactArgs a)
     a.ks_new[s] = k;
     a.gkey_new[s] = k.x;
     if (a.nn_new == nullptr) return;  // (a further replica of the slot table: the lists were permuted with the first)
+    if (a.slot_of_key != nullptr) a.slot_of_key[k.x] = s;
+    if (a.near_meta_new != nullptr) a.near_meta_new[s] = a.near_meta_old[o];  // near lists carry keys: the pool stays
     if (a.my_rank >= 0) {  // real shards: only the owner of a row holds its list
         if (s / a.rows_per_rank_new != a.my_rank) return;
         if (o / a.rows_per_rank_old != a.my_rank) {  // the row moves here: its list is rebuilt by a scan before it is used
+            if (a.near_meta_new != nullptr) a.near_meta_new[s] = make_int2(0, -1);  // (its near list stayed with the old owner)
             a.nn_new[static_cast<int64_t>(s) * kNNK] = make_uint4(kNoPartner, 0u, kNoPartner, 0u);
 #pragma unroll
             for (int e = 1; e < kNNK; ++e) a.nn_new[static_cast<int64_t>(s) * kNNK + e] = make_uint4(kNoPartner, kNoPartner, kNoPartner, 0u);
@@ -105,6 +108,10 @@ __global__ void __launch_bounds__(256) compact_state_kernel(const CompactArgs a)
 
 // new row s' <- the live lower-key partners of its cluster, from the cluster's old row (a pair lives in the row of its
 // higher-key cluster; lower key == lower new slot).  One block per new row.
+//   local source row:  gather the wanted columns (oldslot[u] for u < s'): every other sector of the old row is touched once;
+//   remote source row (another rank's memory, NVLink): 4-byte gathers are request-bound there, so the old row is STREAMED with
+//   coalesced 16-byte loads -- the columns before the cluster's own old slot if it is older than the last compaction (its
+//   partners all sit there), the whole row otherwise -- and the live lower-key columns are scattered into the (local) new row.
 __global__ void __launch_bounds__(256) compact_rows_kernel(const CompactArgs a) {
     const int32_t s = a.row0 + static_cast<int32_t>(blockIdx.x);
     if (s >= a.row1) return;
@@ -112,13 +119,28 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const CompactArgs a) 
     const int32_t q = o / a.rows_per_rank_old;
     const float* src = a.dm_old[q] + static_cast<int64_t>(o - q * a.rows_per_rank_old) * a.ld_old;
     float* dst = a.dm_new + static_cast<int64_t>(s - a.row_base_new) * a.ld_new;
-    for (int32_t u = threadIdx.x; u < a.n_new4; u += 256) {
-        float v = INFINITY;
-        if (u < s)
-            v = __ldg(src + a.oldslot[u]);
-        else if (u == s)
-            v = 0.0f;
-        dst[u] = v;
+    if (a.my_rank < 0 || q == a.my_rank) {
+        for (int32_t u = threadIdx.x; u < a.n_new4; u += 256) {
+            float v = INFINITY;
+            if (u < s)
+                v = __ldg(src + a.oldslot[u]);
+            else if (u == s)
+                v = 0.0f;
+            dst[u] = v;
+        }
+        return;
+    }
+    for (int32_t u = s + threadIdx.x; u < a.n_new4; u += 256) dst[u] = u == s ? 0.0f : INFINITY;  // diagonal, upper part, padding
+    const int32_t key_o = a.ks_old[o].x;
+    const int32_t n_old4 = (a.n_old + 3) & ~3;
+    const int32_t end = key_o < a.order_key_old ? min(n_old4, (o + 3) & ~3) : n_old4;
+    for (int32_t c0 = threadIdx.x * 4; c0 < end; c0 += 256 * 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + c0));
+        const int4 ns = *reinterpret_cast<const int4*>(a.newslot + c0);  // (newslot is padded to a multiple of 4 with -1)
+        if (ns.x >= 0 && ns.x < s) dst[ns.x] = v.x;
+        if (ns.y >= 0 && ns.y < s) dst[ns.y] = v.y;
+        if (ns.z >= 0 && ns.z < s) dst[ns.z] = v.z;
+        if (ns.w >= 0 && ns.w < s) dst[ns.w] = v.w;
     }
 }
 
@@ -174,7 +196,7 @@ cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap,
                                int32_t* oldslot, int32_t n_new4, int32_t* n_live_out, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(keymap, 0xFF, sizeof(int32_t) * static_cast<size_t>(key_cap), s);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(newslot, 0xFF, sizeof(int32_t) * static_cast<size_t>(n_old), s);
+    e = cudaMemsetAsync(newslot, 0xFF, sizeof(int32_t) * static_cast<size_t>((n_old + 3) / 4 * 4), s);
     if (e != cudaSuccess) return e;
     compact_scatter_kernel<<<static_cast<unsigned>((n_old + 255) / 256), 256, 0, s>>>(ks, n_old, keymap);
     compact_rank_kernel<<<1, 1024, 0, s>>>(keymap, key_cap, newslot, oldslot, n_new4, n_live_out);

@@ -243,6 +243,14 @@ struct BatchState {
     // above the horizon), so its row needs no scan: xres[merge][position] = {value bits, partner key, partner slot, size}
     uint4* xres;        // [kMaxBatch][kXResCap]
     int32_t* xhit;      // [kMaxBatch] pairs queued per merge of the current batch
+    int32_t* xfar;      // [kMaxBatch] the merge's new row has finite values above the horizon
+    // near lists (near.cu); near_meta == nullptr: not in use (Lance-Williams only runs)
+    int2* near_meta;    // [n] by slot
+    uint2* near_pool;
+    int32_t near_pool_cap;
+    int32_t* near_cursor;  // [0]: next free pool entry
+    int32_t* slot_of_key;  // [2N] slot of every live cluster's key, -1: not alive
+    int2* nearq;        // [n] rows whose partner list is re-selected from their near list {slot, key}
 };
 size_t merge_batch_smem_bytes(int64_t n);
 int64_t merge_batch_windows(int64_t n);
@@ -304,6 +312,10 @@ struct CompactArgs {
     int32_t rows_per_rank_new, row_base_new, row0, row1;
     int64_t ld_new;
     int32_t my_rank;                        // real shards: partner lists live with their row's owner; -1 otherwise
+    int32_t order_key_old;                  // clusters with a key below this sat in key order by slot in the old layout
+    const int2* near_meta_old;              // near lists follow their rows (nullptr: not in use)
+    int2* near_meta_new;
+    int32_t* slot_of_key;                   // rewritten for the live clusters' new slots
 };
 // newslot / oldslot from the live keys (ascending); *n_live_out = live clusters found
 cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap, int32_t key_cap, int32_t* newslot,
@@ -311,6 +323,26 @@ cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap,
 cudaError_t launch_compact_state(const CompactArgs& a, cudaStream_t s);  // slot tables, partner lists, centroid rows
 cudaError_t launch_compact_rows(const CompactArgs& a, cudaStream_t s);   // lower triangle of the new matrix (+ diagonal, padding)
 cudaError_t launch_mirror_lower(const CompactArgs& a, cudaStream_t s);   // upper triangle <- lower triangle
+
+// ---- near lists (near.cu): every lower-key partner of a row whose stored value is <= horizon ----------------------
+// meta[slot] = {offset into the pool, count | kNearFarBit if partners beyond the horizon may exist}; .y == -1: the row has no
+// near list (the loop scans the whole row instead)
+constexpr int32_t kNearFarBit = 0x40000000, kNearCntMask = 0x3FFFFFFF;
+struct NearArgs {
+    const float* dm;      // resident rows [r_lo, r_hi) x ld
+    int64_t ld;
+    int32_t n_slots, r_lo, r_hi;
+    const int32_t* gkey;
+    int32_t order_key;    // rows of clusters with a key below this only have partners in the columns before their own
+    double horizon;
+    int2* meta;           // [n_slots]
+    uint2* pool;          // {value bits, partner key}
+    int32_t pool_cap;
+    int32_t* cursor;      // [0]: entries in use after the build, [1]: 1 if the pool held them all
+};
+cudaError_t launch_slot_of_key_init(int32_t* sok, int32_t n, int32_t cap, cudaStream_t s);  // sok[k] = k for items, -1 above
+cudaError_t launch_near_build(const NearArgs& a, cudaStream_t s);  // count sweep, scan, fill sweep
+cudaError_t launch_mark_rows_dry(const int32_t* gkey, int32_t* nn_more, int32_t r_lo, int32_t r_hi, cudaStream_t s);
 
 // device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
 cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);

@@ -57,7 +57,7 @@ constexpr int kRcpTab = 1024;
 constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead of the update pass
 
 // counters[slot][*]
-enum { CN_DRY = 0, CN_CAND = 1, CN_XQ = 2 };
+enum { CN_DRY = 0, CN_CAND = 1, CN_XQ = 2, CN_NEAR = 3 };
 
 // Every lane reserves `cnt` consecutive entries of a global queue with one atomic per warp; returns the lane's first index.
 IC_DEVINL int32_t warp_reserve(int32_t* counter, int cnt, int lane) {
@@ -208,15 +208,19 @@ IC_DEVINL float ldcg_if(const float* p, bool pred, float other) {
 struct RowHead {
     uint64_t head;  // (dist bits << 32 | row key), kPackInf: none
     uint64_t stop;  // smallest pack a second pair of this row may have, +1 (see P2); kPackInf: none
+    uint64_t bound; // the row has no listed partner but may have partners at or above this pack (beyond the horizon)
     uint32_t partner_slot, partner_key;
     int32_t partner_size;
 };
 IC_DEVINL RowHead row_head(uint4 e0, uint4 e1, uint32_t more_bits, uint32_t key_r) {
     RowHead h;
-    h.head = h.stop = kPackInf;
+    h.head = h.stop = h.bound = kPackInf;
     h.partner_slot = h.partner_key = kNoPartner;
     h.partner_size = 0;
-    if (e0.z == kNoPartner) return h;  // no partner (a bound cannot be here: dry rows were rescanned in P1)
+    if (e0.z == kNoPartner) {  // no listed partner; a bound here comes from a near list whose entries all died (near.cu):
+        if (e0.y != kNoPartner) h.bound = (static_cast<uint64_t>(e0.y) << 32) | key_r;  // the row's pairs are beyond the horizon
+        return h;
+    }
     h.head = (static_cast<uint64_t>(e0.y) << 32) | key_r;
     h.partner_slot = e0.z;
     h.partner_key = e0.x;
@@ -326,9 +330,16 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
     for (int i = tid; i < kRcpTab; i += kBT) s_rcp[i] = 1.0 / static_cast<double>(i > 0 ? i : 1);
     __syncthreads();
     // rows that were dry when the previous launch stopped (or rows the other loop left dry): queue slot 0
+    // a row whose partner list has to be rebuilt: re-selected from its near list if it has one, else scanned
+    auto queue_row = [&](int32_t r, int32_t key, int slot3) {
+        if (st.near_meta != nullptr && __ldcg(&st.near_meta[r].y) >= 0)
+            st.nearq[atomicAdd(st.counters + slot3 * 4 + CN_NEAR, 1)] = make_int2(r, key);
+        else
+            st.dryq[atomicAdd(st.counters + slot3 * 4 + CN_DRY, 1)] = make_int2(r, key);
+    };
     for (int32_t r = r_lo + gtid; r < r_hi; r += GT)
         if ((static_cast<uint32_t>(__ldcg(st.nn_more + r)) & kDryBit) != 0u && __ldcg(st.ks + r).x >= 0)
-            st.dryq[atomicAdd(st.counters + 0 * 4 + CN_DRY, 1)] = make_int2(r, __ldcg(st.ks + r).x);
+            queue_row(r, __ldcg(st.ks + r).x, 0);
     // live size of every slot (0: retired / padding): what the update pass streams beside the two rows
     for (int32_t r = gtid; r < n4; r += GT) {
         const int2 k = __ldcg(st.ks + r);
@@ -348,9 +359,25 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         if (use_xres) {
             for (int32_t j = gw; j < m_prev; j += GW) {
                 const int32_t c = __ldcg(st.xhit + j);
-                if (lane == 0) st.xhit[j] = 0;
-                if (c <= 0 || c > kXResCap) continue;  // no pair / too many: the row was queued for a scan instead
+                const bool far = __ldcg(st.xfar + j) != 0;  // the row has finite values above the horizon
+                if (lane == 0) {
+                    st.xhit[j] = 0;
+                    st.xfar[j] = 0;
+                }
+                // too many pairs, or a queue overflowed (the host re-evaluates the rows): the row was queued for a scan
+                if (c > kXResCap || __ldcg(ctl + CTL_XQ_OVERFLOW) != 0) continue;
                 const uint4* src = st.xres + static_cast<int64_t>(j) * kXResCap;
+                {   // the re-evaluated pairs ARE the row's near list (near.cu): everything else in the row is above the horizon
+                    int32_t base = 0;
+                    if (lane == 0 && c > 0) base = atomicAdd(st.near_cursor, c);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const bool fits = base + c <= st.near_pool_cap;
+                    for (int32_t i = lane; i < c && fits; i += 32) {
+                        const uint4 e = __ldcg(src + i);
+                        st.near_pool[static_cast<int64_t>(base) + i] = make_uint2(e.x, e.y);
+                    }
+                    if (lane == 0) st.near_meta[s_b[j]] = fits ? make_int2(base, c | (far ? kNearFarBit : 0)) : make_int2(0, -1);
+                }
                 constexpr int kPer = kXResCap / 32;
                 uint64_t pk[kPer];
                 uint32_t taken = 0u;
@@ -385,12 +412,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                         out.y = __shfl_sync(0xffffffffu, e.x, src_lane);  // distance bits
                         out.z = __shfl_sync(0xffffffffu, e.z, src_lane);  // partner slot
                         out.w = __shfl_sync(0xffffffffu, e.w, src_lane);  // partner size
-                    } else if (r == c) {
+                    } else if (r == c && far) {
                         out = nn_bound(__float_as_uint(static_cast<float>(prm.horizon)));  // the unlisted partners are above the horizon
                     }
                     if (lane == 0) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + r, out);
                 }
-                if (lane == 0) __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit));
+                if (lane == 0) __stcg(st.nn_more + b, (c > kNNK || far) ? static_cast<int32_t>(kMoreBit) : 0);
             }
         }
 
@@ -512,8 +539,53 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 }
         };
         // ================= P1: row rescans =================
+        // rows with a near list: one warp re-selects the 4 smallest LIVE entries (liveness: slot_of_key); the unlisted
+        // partners are the remaining near entries and, if the row has any, everything beyond the horizon
+        const int32_t Qn = __ldcg(st.counters + sl * 4 + CN_NEAR);
+        for (int32_t q = gw; q < Qn; q += GW) {
+            const int32_t r = __ldcg(st.nearq + q).x;
+            const int2 meta = __ldcg(st.near_meta + r);
+            const int32_t cnt = meta.y & kNearCntMask;
+            const bool far = (meta.y & kNearFarBit) != 0;
+            const uint2* seg = st.near_pool + meta.x;
+            uint64_t t0 = kPackInf, t1 = kPackInf, t2 = kPackInf, t3 = kPackInf;  // this lane's smallest live entries, ascending
+            int32_t alive = 0;
+            for (int32_t i = lane; i < cnt; i += 32) {
+                const uint2 e = __ldcg(seg + i);
+                if (__ldcg(st.slot_of_key + e.y) < 0) continue;
+                ++alive;
+                uint64_t p = (static_cast<uint64_t>(e.x) << 32) | e.y;
+                if (p < t0) { const uint64_t x = t0; t0 = p; p = x; }
+                if (p < t1) { const uint64_t x = t1; t1 = p; p = x; }
+                if (p < t2) { const uint64_t x = t2; t2 = p; p = x; }
+                if (p < t3) t3 = p;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) alive += __shfl_xor_sync(0xffffffffu, alive, o);
+            int n_out = 0;
+            for (int k = 0; k < kNNK; ++k) {
+                const uint64_t wm = warp_min_u64(t0);
+                uint4 out = nn_none();
+                if (wm != kPackInf) {
+                    if (t0 == wm) {  // packs are unique (distinct partner keys): one lane
+                        t0 = t1;
+                        t1 = t2;
+                        t2 = t3;
+                        t3 = kPackInf;
+                    }
+                    const uint32_t pkey = pack_key(wm);
+                    const int32_t ps = __ldcg(st.slot_of_key + pkey);
+                    out = make_uint4(pkey, static_cast<uint32_t>(wm >> 32), static_cast<uint32_t>(ps), static_cast<uint32_t>(__ldcg(st.lsize + ps)));
+                    n_out = k + 1;
+                } else if (k == n_out && far) {
+                    out = nn_bound(__float_as_uint(static_cast<float>(prm.horizon)));
+                }
+                if (lane == 0) __stcg(st.nn + static_cast<int64_t>(r) * kNNK + k, out);
+            }
+            if (lane == 0) __stcg(st.nn_more + r, (alive > kNNK || far) ? static_cast<int32_t>(kMoreBit) : 0);
+        }
         const int32_t Q = __ldcg(st.counters + sl * 4 + CN_DRY);
-        n_rescans += Q;
+        n_rescans += Q + Qn;
         // Short rows, a few dozen of them: ONE BLOCK PER ROW.  Its sixteen warps scan a sixteenth of the row each and the
         // partial lists are folded in shared memory -- no partial records in global memory, no fence / atomic / re-read
         // chain.  Long rows must be spread over many SMs: one SM streams a 400 KB row (+ its keys) in ~50 k cycles
@@ -628,7 +700,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 for (int x = 0; x < kP2R; ++x) {
                     const int32_t r = r0 + x * GT + gtid;
                     rr[x] = r;
-                    h[x].head = h[x].stop = kPackInf;
+                    h[x].head = h[x].stop = h[x].bound = kPackInf;
                     h[x].partner_slot = h[x].partner_key = kNoPartner;
                     h[x].partner_size = 0;
                     sr[x] = 0;
@@ -647,7 +719,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 bstop = umin64(bstop, block_min_u64(tstop_min, s_red));  // running minimum: any value >= T is a valid filter
 #pragma unroll
                 for (int x = 0; x < kP2R; ++x) {
-                    bhead = umin64(bhead, h[x].head);
+                    bhead = umin64(bhead, umin64(h[x].head, h[x].bound));  // (a bound only ever stops the loop at the horizon)
                     if (kMulti && h[x].head < my_head) {
                         my_head = h[x].head;
                         my_w0 = make_uint4(static_cast<uint32_t>(h[x].head), static_cast<uint32_t>(h[x].head >> 32),
@@ -903,6 +975,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         }
         const int rank = take ? n_less : -1;  // everything below an accepted pair is accepted
         const int32_t m_all = block_sum_i32(rank >= 0 ? 1 : 0, s_redi);  // >= 1: the global minimum head is always among them
+        if (m_all <= 0) {  // cannot happen (the global minimum is a candidate below every stopper): never spin on it
+            stop_reason = STOP_ERROR;
+            break;
+        }
         const int32_t m = min(m_all, limit);                              // merges of this iteration
         if (exact && bid == 0 && __syncthreads_or(was_cut) != 0 && tid == 0) atomicAdd(ctl + CTL_N_CUT, 1);
         if (rank >= 0) {
@@ -950,11 +1026,18 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 for (int x = 1; x < kNNK; ++x) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + x, nn_none());
                 __stcg(st.nn_more + b, static_cast<int32_t>(kMoreBit | kDryBit));
                 __stcg(st.nn_more + a, 0);
+                if (st.near_meta != nullptr) {
+                    st.slot_of_key[s_ka[tid]] = -1;
+                    st.slot_of_key[s_kb[tid]] = -1;
+                    st.slot_of_key[new_key] = b;
+                    st.near_meta[b] = make_int2(0, -1);  // (one GPU: replaced by the row's re-evaluated pairs after the exact phase)
+                }
                 // (one GPU with the horizon: the exact phase decides whether the row needs a scan at all)
                 if (!use_xres && b >= r_lo && b < r_hi) st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(b, new_key);
             }
             if (tid == kBT - 1) {
                 st.counters[sl2 * 4 + CN_DRY] = 0;
+                st.counters[sl2 * 4 + CN_NEAR] = 0;
                 st.counters[sl1 * 4 + CN_CAND] = 0;
                 st.counters[sl2 * 4 + CN_XQ] = 0;   // last read in the exact phase of the previous iteration
                 ctl[CTL_XQ_FIRST_KEY] = kbase + t;  // the clusters this iteration creates carry the keys N + t ...
@@ -1027,6 +1110,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 }
                 float outv[kI][4];
                 uint32_t hitm = 0u;  // elements written at or below the horizon: the exact phase owns them
+                bool farm = false;   // the new row has selectable values beyond the horizon (its list then ends in a bound)
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
                     const int32_t sizes[4] = {k01[x].y, k01[x].w, k23[x].y, k23[x].w};
@@ -1042,8 +1126,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                         const bool keep = ((livem[x] >> e) & 1u) != 0u && den <= prm.max_size;
                         outv[x][e] = keep ? lw : __uint_as_float(kInfBits);
                         if (exact && keep && static_cast<double>(lw) <= prm.horizon) hitm |= 1u << (x * 4 + e);
+                        if (use_xres && keep && static_cast<double>(lw) > prm.horizon && __float_as_uint(lw) < kMaxFloatBits) farm = true;
                     }
                 }
+                if (use_xres && __any_sync(0xffffffffu, farm) && lane == 0) st.xfar[i] = 1;
                 if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // the merge's queue: {column, Lance-Williams value}
                     int32_t pos = warp_reserve(st.xhit + i, __popc(hitm), lane);
 #pragma unroll
@@ -1134,6 +1220,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     }
                 } else {
                     __stcg(row_of(bj) + bi, val);  // new_j carries the higher key
+                    if (use_xres && __float_as_uint(val) < kMaxFloatBits) st.xfar[j] = 1;
                 }
             }
         }
@@ -1176,7 +1263,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             // head and cut every batch there (measured at config C: 73 merges per iteration instead of 11, 2x the scans)
             if (kept < prm.refill_at && more) {
                 __stcg(st.nn_more + r, static_cast<int32_t>(kMoreBit | kDryBit));
-                st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(r, key_r);
+                queue_row(r, key_r, sl1);
             }
         };
 #pragma unroll
@@ -1202,8 +1289,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             const int32_t nx = min(__ldcg(st.counters + sl * 4 + CN_XQ), st.xq_cap);
             const float d_last = __uint_as_float(s_d[m > 0 ? m - 1 : 0]);
             if (use_xres && bid == 0 && tid < m) {  // new rows without a pair at or below the horizon (or with too many): scan
-                const int32_t c = __ldcg(st.xhit + tid);
-                if (c <= 0 || c > kXResCap || __ldcg(st.counters + sl * 4 + CN_XQ) > st.xq_cap)
+                const int32_t c = __ldcg(st.xhit + tid);  // (a row without any pair at or below the horizon needs no scan: its list is a bound)
+                if (c > kXResCap || __ldcg(st.counters + sl * 4 + CN_XQ) > st.xq_cap)
                     st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(s_b[tid], kbase + t - m + tid);
             }
             int32_t my_exact = 0;

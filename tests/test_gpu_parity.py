@@ -311,8 +311,8 @@ def knobs(eng):
         for k, v in kw.items():
             eng.set_option(k, v)
     yield set_
-    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode", "exact", "mirror_init", "compact"):
-        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode", "exact", "mirror_init", "compact") else 0)
+    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode", "exact", "mirror_init", "compact", "near_lists"):
+        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode", "exact", "mirror_init", "compact", "near_lists") else 0)
 
 
 @pytest.mark.parametrize("name", SMALL_GOLDENS)
@@ -502,6 +502,9 @@ def test_config_c_full_size_properties_and_sharded_identity(eng, knobs):
     tr = eng.merge_trace()
     st = res.stats
     _assert_reference_run(st)
+    # sha256 of the merge trace (keys, distance bits, sizes) of the CPU oracle in REFERENCE arithmetic at this exact size:
+    # oracle.fast_cluster(flags=0), 820 s on 16 host cores (scripts/replay_full.py C -> profiles/r02_replay_configC.txt)
+    assert _trace_digest(tr) == "51f51453df136d2fe592f68de112c13745137c724d21f478d1281f8f7d9d7ce4"
     assert st["n_target"] == 2750 and st["n_merges"] == n - 2750 and not st["exhausted"]
     sizes = np.array([len(c) for c in res.clusters])
     assert sizes.min() >= mn and sizes.max() <= mx
@@ -616,6 +619,20 @@ def test_compaction_does_not_change_the_trace(eng, knobs, ratio, mirror):
             ncomp.append(res.stats["n_compactions"])
         assert digests[0] == digests[1]
         assert ncomp[0] == 0 and ncomp[1] >= 1
+
+
+@pytest.mark.parametrize("n,d,mn,mx,ranks", [(9000, 96, 4, 12, 1), (6000, 2048, 10, 50, 1), (5000, 32, 6, 8, 1), (6000, 64, 4, 12, 3)])
+def test_near_lists_do_not_change_the_trace(eng, knobs, n, d, mn, mx, ranks):
+    """Partner lists re-selected from the rows' near lists (every pair at or below the horizon, near.cu) instead of full row
+    scans: same trace, far fewer bytes; also across horizon raises, compactions, exhaustion and on virtual ranks."""
+    x = synth.gaussian_mixture(n, d, mn, mx, seed=23 + n)
+    digests = []
+    for near in (0, 1):
+        knobs(near_lists=near, virtual_ranks=ranks)
+        res = eng.cluster(x, mn, mx)
+        digests.append(_trace_digest(eng.merge_trace()))
+        _assert_reference_run(res.stats)
+    assert digests[0] == digests[1]
 
 
 def test_batched_more_disjoint_pairs_than_the_batch_capacity(eng, oracle, knobs):
