@@ -932,7 +932,14 @@ int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
 
 // Near lists of the resident rows for the current horizon (near.cu): two sweeps of the live matrix.
 int build_near(ic_ctx* ctx, bool mark_dry) {
-    if (!ctx->near_meta || !ctx->near_opt) return IC_OK;
+    if (!ctx->near_meta || !ctx->near_opt) {  // no near lists: stale bounds are replaced by full row scans
+        if (mark_dry) {
+            IC_CUDA(launch_mark_rows_dry(ctx->gkey, ctx->nn_more, static_cast<int32_t>(row_begin_cur(ctx)),
+                                         static_cast<int32_t>(row_end_cur(ctx)), ctx->stream));
+            ctx->stats.kernel_launches += 1;
+        }
+        return IC_OK;
+    }
     Nvtx range("ic near lists (two sweeps)");
     const double t0 = now_ms();
     NearArgs a{};

@@ -314,6 +314,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
     __shared__ double s_rcp[kRcpTab];  // 1.0 / size sum, correctly rounded (what lance_williams() computes inline)
     const bool exact = prm.exact != 0;
     const bool use_xres = exact && !kMulti;
+    // what a list says about partners that are not in a near list / not re-evaluated: they are ABOVE the horizon, i.e. at
+    // least the next float (a bound AT the horizon could equal the safe bound when the horizon is 0: duplicates)
+    const uint32_t hz_bound = prm.horizon >= 0.0 ? __float_as_uint(static_cast<float>(prm.horizon)) + 1u : 0u;
     const int d4 = static_cast<int>(st.ldc);
 
     uint32_t phase = 0;
@@ -359,24 +362,25 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         if (use_xres) {
             for (int32_t j = gw; j < m_prev; j += GW) {
                 const int32_t c = __ldcg(st.xhit + j);
-                const bool far = __ldcg(st.xfar + j) != 0;  // the row has finite values above the horizon
-                if (lane == 0) {
-                    st.xhit[j] = 0;
-                    st.xfar[j] = 0;
-                }
+                // the rest of the row is above the horizon (assumed to hold selectable values: if it does not -- everything else
+                // masked by maxSize -- the spurious bound costs one more horizon raise at the very end, whose sweep clears it)
+                const bool far = true;
+                if (lane == 0) st.xhit[j] = 0;
                 // too many pairs, or a queue overflowed (the host re-evaluates the rows): the row was queued for a scan
                 if (c > kXResCap || __ldcg(ctl + CTL_XQ_OVERFLOW) != 0) continue;
                 const uint4* src = st.xres + static_cast<int64_t>(j) * kXResCap;
                 {   // the re-evaluated pairs ARE the row's near list (near.cu): everything else in the row is above the horizon
                     int32_t base = 0;
-                    if (lane == 0 && c > 0) base = atomicAdd(st.near_cursor, c);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const bool fits = base + c <= st.near_pool_cap;
-                    for (int32_t i = lane; i < c && fits; i += 32) {
-                        const uint4 e = __ldcg(src + i);
-                        st.near_pool[static_cast<int64_t>(base) + i] = make_uint2(e.x, e.y);
+                    if (st.near_meta != nullptr) {
+                        if (lane == 0 && c > 0) base = atomicAdd(st.near_cursor, c);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const bool fits = base + c <= st.near_pool_cap;
+                        for (int32_t i = lane; i < c && fits; i += 32) {
+                            const uint4 e = __ldcg(src + i);
+                            st.near_pool[static_cast<int64_t>(base) + i] = make_uint2(e.x, e.y);
+                        }
+                        if (lane == 0) st.near_meta[s_b[j]] = fits ? make_int2(base, c | (far ? kNearFarBit : 0)) : make_int2(0, -1);
                     }
-                    if (lane == 0) st.near_meta[s_b[j]] = fits ? make_int2(base, c | (far ? kNearFarBit : 0)) : make_int2(0, -1);
                 }
                 constexpr int kPer = kXResCap / 32;
                 uint64_t pk[kPer];
@@ -413,7 +417,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                         out.z = __shfl_sync(0xffffffffu, e.z, src_lane);  // partner slot
                         out.w = __shfl_sync(0xffffffffu, e.w, src_lane);  // partner size
                     } else if (r == c && far) {
-                        out = nn_bound(__float_as_uint(static_cast<float>(prm.horizon)));  // the unlisted partners are above the horizon
+                        out = nn_bound(hz_bound);  // the unlisted partners are above the horizon
                     }
                     if (lane == 0) __stcg(st.nn + static_cast<int64_t>(b) * kNNK + r, out);
                 }
@@ -578,7 +582,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     out = make_uint4(pkey, static_cast<uint32_t>(wm >> 32), static_cast<uint32_t>(ps), static_cast<uint32_t>(__ldcg(st.lsize + ps)));
                     n_out = k + 1;
                 } else if (k == n_out && far) {
-                    out = nn_bound(__float_as_uint(static_cast<float>(prm.horizon)));
+                    out = nn_bound(hz_bound);
                 }
                 if (lane == 0) __stcg(st.nn + static_cast<int64_t>(r) * kNNK + k, out);
             }
@@ -753,8 +757,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 }
             }
             bhead = block_min_u64(bhead, s_red);
-            if (kMulti) {  // the block's smallest head (packs are unique: one owner), or "none"
-                if (bhead == kPackInf ? tid == 0 : my_head == bhead) {
+            if (kMulti) {  // the block's smallest REAL head (packs are unique: one owner), or "none" (bhead may be a bound)
+                const uint64_t breal = block_min_u64(my_head, s_red);
+                if (breal == kPackInf ? tid == 0 : my_head == breal) {
+                    if (breal == kPackInf) my_w0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
                     __stcg(st.blockmin + 2 * bid, my_w0);
                     __stcg(st.blockmin + 2 * bid + 1, my_w1);
                 }
@@ -1110,7 +1116,6 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 }
                 float outv[kI][4];
                 uint32_t hitm = 0u;  // elements written at or below the horizon: the exact phase owns them
-                bool farm = false;   // the new row has selectable values beyond the horizon (its list then ends in a bound)
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
                     const int32_t sizes[4] = {k01[x].y, k01[x].w, k23[x].y, k23[x].w};
@@ -1126,10 +1131,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                         const bool keep = ((livem[x] >> e) & 1u) != 0u && den <= prm.max_size;
                         outv[x][e] = keep ? lw : __uint_as_float(kInfBits);
                         if (exact && keep && static_cast<double>(lw) <= prm.horizon) hitm |= 1u << (x * 4 + e);
-                        if (use_xres && keep && static_cast<double>(lw) > prm.horizon && __float_as_uint(lw) < kMaxFloatBits) farm = true;
                     }
                 }
-                if (use_xres && __any_sync(0xffffffffu, farm) && lane == 0) st.xfar[i] = 1;
                 if (exact && __any_sync(0xffffffffu, hitm != 0u)) {  // the merge's queue: {column, Lance-Williams value}
                     int32_t pos = warp_reserve(st.xhit + i, __popc(hitm), lane);
 #pragma unroll
@@ -1220,7 +1223,6 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     }
                 } else {
                     __stcg(row_of(bj) + bi, val);  // new_j carries the higher key
-                    if (use_xres && __float_as_uint(val) < kMaxFloatBits) st.xfar[j] = 1;
                 }
             }
         }
@@ -1411,6 +1413,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         ctl[CTL_ITERS] = ctl[CTL_ITERS] + iters;
         ctl[CTL_RESCANS] = ctl[CTL_RESCANS] + static_cast<int32_t>(n_rescans);
         ctl[CTL_STOP] = stop_reason;
+        if (stop_reason == STOP_ERROR) ctl[CTL_ERROR] = 3;  // no candidate below the stopper: a protocol bug, reported by the host
         __threadfence();
         ctl[CTL_DONE] = 1;
     }
