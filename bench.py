@@ -426,9 +426,12 @@ def main():
         ms_gram = avg("ms_gram")
         ms_prep = avg("ms_prep")
         ms_nn = avg("ms_nn_init")
-        # algorithmic bytes of the merge loop: 12*n per merge (read row a, read row b, write the new row)
+        # algorithmic bytes of the merge loop: 12*n per merge (read row a, read row b, write the new row), over the device time of
+        # the loop kernel's launches (CUDA events around every launch, summed: ic_stats.ms_loop_kernel); ms_loop additionally
+        # holds the horizon sweeps (refine.cu, near.cu), the compactions and the host round trips between the launches
         loop_bytes = 12.0 * sum(range(n_final + 1, n + 1)) if merges else 0.0
-        loop_gbs = loop_bytes / (ms_loop * 1e-3) / 1e9 if ms_loop > 0 else 0.0
+        ms_loop_kernel = avg("ms_loop_kernel") if stats[-1].get("ms_loop_kernel", 0) > 0 else ms_loop
+        loop_gbs = loop_bytes / (ms_loop_kernel * 1e-3) / 1e9 if ms_loop_kernel > 0 else 0.0
         hbm = peaks["hbm_gbs"]
         # K1: 2*D flops per unordered pair; peak = TF32 dense = half the measured bf16 figure
         gram_flops = 2.0 * d * pairs
@@ -474,20 +477,22 @@ def main():
             "roofline": {"kernel": "merge_batch_kernel (K3b, persistent, batched)" if batched else "merge_loop_kernel (K3, persistent)",
                          "bound": "hbm", "achieved": loop_gbs,
                          "peak": hbm, "unit": "GB/s", "frac": loop_gbs / hbm,
+                         "launches_per_step": stats[-1].get("loop_launches"), "ms_kernel_per_step": ms_loop_kernel,
+                         "ms_loop_per_step": ms_loop,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full at this exact
                          # workload (profiles/); GB per launch like `achieved`'s numerator (60 GB at config C)
                          "traffic": loop_traffic_gb(args.config) if (world == 1 and not args.n and batched) else None,
                          "traffic_unit": "GB per clustering, all launches of the loop kernel (ncu --set full, profiles/r02_summary.md)",
                          # what the launch actually moves over its measured time, against the same peak (information:
                          # the gap to `frac` is re-read rows, retired columns, partner lists, sector-granular gathers)
-                         "traffic_frac": (loop_traffic_gb(args.config) / (ms_loop * 1e-3) / hbm
-                                          if (world == 1 and not args.n and batched and loop_traffic_gb(args.config) and ms_loop > 0)
+                         "traffic_frac": (loop_traffic_gb(args.config) / (ms_loop_kernel * 1e-3) / hbm
+                                          if (world == 1 and not args.n and batched and loop_traffic_gb(args.config) and ms_loop_kernel > 0)
                                           else None),
                          "peak_source": peaks["source"] + " copy bandwidth",
-                         "note": ("algorithmic bytes 12*n per merge over the time between the CUDA events around the whole loop "
-                                  "(all launches of the kernel, the horizon sweeps of refine.cu and the compactions in between); "
-                                  "an iteration takes every provably consecutive merge (dozens) in four grid-wide phases: "
-                                  "row scans, heads, Lance-Williams rows, exact re-evaluation"
+                         "note": ("algorithmic bytes 12*n per merge over the summed device time of the kernel's launches (one per "
+                                  "segment between horizon raises and compactions); an iteration takes every provably consecutive "
+                                  "merge (dozens) in four grid-wide phases: partner lists, heads, Lance-Williams rows, exact "
+                                  "re-evaluation; traffic = DRAM bytes of all launches of one clustering"
                                   if batched else
                                   "algorithmic bytes 12*n per merge; the loop is a chain of dependent merges bound by one "
                                   "mailbox exchange + one DRAM round trip per merge (merges_per_s), not by bandwidth"),

@@ -53,7 +53,7 @@ class Stats(C.Structure):
         ("matrix_bytes", C.c_int64), ("n_iterations", C.c_int32), ("loop_mode", C.c_int32),
         ("exact", C.c_int32), ("n_horizon_raises", C.c_int32), ("n_exact", C.c_int64),
         ("n_filter_viol", C.c_int32), ("n_order_viol", C.c_int32), ("n_cut", C.c_int32), ("filter_max_err", C.c_float),
-        ("horizon", C.c_double), ("ms_refine", C.c_float), ("n_restarts", C.c_int32), ("n_compactions", C.c_int32), ("ms_compact", C.c_float),
+        ("horizon", C.c_double), ("ms_refine", C.c_float), ("n_restarts", C.c_int32), ("n_compactions", C.c_int32), ("ms_compact", C.c_float), ("ms_loop_kernel", C.c_float), ("loop_launches", C.c_int32),
     ]
 
     def as_dict(self):

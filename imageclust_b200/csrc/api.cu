@@ -56,6 +56,7 @@ struct ic_ctx {
     bool loop_replica = false;
     uint32_t loop_gen = 0;    // generation of the last merge-loop launch (mailbox tags)
     int64_t loop_launches = 0;
+    int32_t loop_launches_run = 0;  // launches of the loop kernel in the current clustering
     int64_t loop_n_target = 0, loop_max_size = 0, loop_max_merges = -1;
     int32_t loop_merges_at_start = 0;
     // real shards: one process / GPU / rank (ic_shard_*)
@@ -150,7 +151,9 @@ struct ic_ctx {
     std::vector<float> h_dist, h_gap;
     bool trace_on_host = false;
     ic_stats stats{};
-    cudaEvent_t ev[10] = {nullptr};
+    cudaEvent_t ev[12] = {nullptr};  // [10], [11]: around every launch of the loop kernel
+    double ms_loop_kernel = 0.0;     // device time of the loop kernel's launches alone (no sweeps, no compactions)
+    bool loop_launch_pending = false;
 };
 
 namespace {
@@ -678,6 +681,8 @@ int init_loop_state(ic_ctx* ctx) {
         ctx->stats.kernel_launches += 1;
     }
     ctx->ms_near = 0.0;
+    ctx->ms_loop_kernel = 0.0;
+    ctx->loop_launches_run = 0;
     if (ctx->prof) IC_CUDA(cudaMemsetAsync(ctx->prof, 0, sizeof(long long) * 256, ctx->stream));
     ctx->horizon = -1.0;
     ctx->abs_slack = ctx->abs_slack_opt >= 0.0 ? ctx->abs_slack_opt : 0.0;
@@ -832,6 +837,7 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
             IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
             ctx->stats.kernel_launches += 1;
         }
+        IC_CUDA(cudaEventRecord(ctx->ev[10], ctx->stream));
         if (VR > 1) {
             IC_CUDA(cudaMemcpyAsync(ctx->vstates, states.data(), sizeof(BatchState) * static_cast<size_t>(VR), cudaMemcpyHostToDevice, ctx->stream));
             IC_CUDA(cudaStreamSynchronize(ctx->stream));  // (the host vector goes out of scope; test hook)
@@ -839,7 +845,10 @@ int enqueue_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_me
         } else {
             IC_CUDA(launch_merge_batch(states[0], p, ctx->batch_grid, ctx->stream));
         }
+        IC_CUDA(cudaEventRecord(ctx->ev[11], ctx->stream));
+        ctx->loop_launch_pending = true;
         ++ctx->loop_launches;
+        ++ctx->loop_launches_run;
         ctx->stats.kernel_launches += 1;
         IC_CUDA(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl, sizeof(ctx->h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->profile_loop)
@@ -1099,10 +1108,16 @@ int run_loop(ic_ctx* ctx, int64_t n_target, int64_t max_size, int64_t max_merges
     return enqueue_loop(ctx, n_target, max_size, max_merges);
 }
 
+float ev_ms(cudaEvent_t a, cudaEvent_t b);
+
 int sync_loop_result(ic_ctx* ctx) {
     Nvtx range("ic K3b merge loop (sync, horizon raises, compactions, relaunches)");
     for (;;) {
         IC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->loop_launch_pending) {
+            ctx->ms_loop_kernel += ev_ms(ctx->ev[10], ctx->ev[11]);
+            ctx->loop_launch_pending = false;
+        }
         if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
         if (ctx->h_ctl[CTL_ERROR] != 0)
             return fail(ctx, IC_ERR_INTERNAL, "merge loop protocol error " + std::to_string(ctx->h_ctl[CTL_ERROR]));
@@ -1326,6 +1341,8 @@ void fill_stats(ic_ctx* ctx) {
     s.horizon = ctx->horizon;
     s.ms_refine = static_cast<float>(ctx->ms_refine + ctx->ms_near);  // horizon sweeps: re-evaluation + near lists
     s.n_restarts = ctx->n_restarts;
+    s.ms_loop_kernel = static_cast<float>(ctx->ms_loop_kernel);
+    s.loop_launches = static_cast<int32_t>(ctx->loop_launches_run);
     s.n_compactions = ctx->n_compactions;
     s.ms_compact = static_cast<float>(ctx->ms_compact);
     s.n_iterations = s.loop_mode ? ctx->h_ctl[CTL_ITERS] : ctx->n_merges + ctx->h_ctl[CTL_BUBBLES];

@@ -90,6 +90,8 @@ typedef struct ic_stats {
                                  with delta_cut_fallback (see "delta_cut") */
     int32_t n_compactions;    /* K4: times the live clusters were renumbered densely and the matrix moved (compact.cu) */
     float ms_compact;         /* host wall time of the compactions (inside ms_loop) */
+    float ms_loop_kernel;     /* device time of the loop kernel's launches alone (CUDA events around each launch) */
+    int32_t loop_launches;    /* launches of the loop kernel (one per segment between horizon raises / compactions) */
 } ic_stats;
 
 /* ---- context ---------------------------------------------------------- */

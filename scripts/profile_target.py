@@ -38,8 +38,11 @@ with clustering.Engine(0) as eng:
     if mode == 1:  # batched loop: cycles of block 0 per phase
         it = max(p["iterations"], 1)
         print(f"batched loop: iterations={p['iterations']} merges/iteration={p['merges'] / it:.1f} cycles per iteration: "
-              f"rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} select={p['update'] / it:.0f} apply={p['scan'] / it:.0f} "
-              f"(rows={p['pub_argmin'] / it:.0f}) | block 0 waits at the barriers: after rescans={p['pub_reduce'] / it:.0f} after heads={p['pub_fence'] / it:.0f} after apply={p['pub_stores'] / it:.0f}")
+              f"lists+rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} select={p['update'] / it:.0f} apply={p['scan'] / it:.0f} "
+              f"(rows+centroids={p['pub_argmin'] / it:.0f}, wait for the slowest block={p['exch_poll'] / it:.0f}, exact phase={p['exch_rank'] / it:.0f}) | "
+              f"block 0 waits at the barriers: after rescans={p['pub_reduce'] / it:.0f} after heads={p['pub_fence'] / it:.0f}; "
+              f"exact={s['exact']} n_exact={s['n_exact']} raises={s['n_horizon_raises']} compactions={s['n_compactions']} "
+              f"refine+near {s['ms_refine']:.1f} ms compact {s['ms_compact']:.1f} ms filter_viol={s['n_filter_viol']} order_viol={s['n_order_viol']}")
         sys.exit(0)
     print("loop cycles per merge (block 0): " + " ".join(f"{k}={v / m:.0f}" for k, v in p.items() if k not in ("merges", "iterations", "rescans", "reserved", "bubbles"))
           + f" | iterations={p["iterations"]} rescans={p["rescans"]} bubbles={p["bubbles"]}")
