@@ -119,18 +119,13 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const CompactArgs a) 
     const int32_t q = o / a.rows_per_rank_old;
     const float* src = a.dm_old[q] + static_cast<int64_t>(o - q * a.rows_per_rank_old) * a.ld_old;
     float* dst = a.dm_new + static_cast<int64_t>(s - a.row_base_new) * a.ld_new;
+    // (the mirror pass that follows writes every entry above the diagonal; only the padding columns need a value here)
+    for (int32_t u = a.n_new + threadIdx.x; u < a.n_new4; u += 256) dst[u] = INFINITY;
+    if (threadIdx.x == 0) dst[s] = 0.0f;
     if (a.my_rank < 0 || q == a.my_rank) {
-        for (int32_t u = threadIdx.x; u < a.n_new4; u += 256) {
-            float v = INFINITY;
-            if (u < s)
-                v = __ldg(src + a.oldslot[u]);
-            else if (u == s)
-                v = 0.0f;
-            dst[u] = v;
-        }
+        for (int32_t u = threadIdx.x; u < s; u += 256) dst[u] = __ldg(src + a.oldslot[u]);
         return;
     }
-    for (int32_t u = s + threadIdx.x; u < a.n_new4; u += 256) dst[u] = u == s ? 0.0f : INFINITY;  // diagonal, upper part, padding
     const int32_t key_o = a.ks_old[o].x;
     const int32_t n_old4 = (a.n_old + 3) & ~3;
     const int32_t end = key_o < a.order_key_old ? min(n_old4, (o + 3) & ~3) : n_old4;

@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(256) init_centroids_kernel(const float* __rest
     }
 }
 
-// one block per row; 16-byte loads of the row and of the keys; matching pairs are appended with one atomic per warp
+// one block per row; 16-byte loads of the row and of the keys.  Two passes over the row (the second one hits L2): count the
+// pairs in the band, reserve ONE contiguous range of the queue for the row, fill it -- consecutive queue entries then share
+// their row, so the evaluation kernel runs four summation chains per warp and reads the row's centroid once per four pairs.
 __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_constant__ RefineArgs a) {
     const int32_t r = a.row0 + static_cast<int32_t>(blockIdx.x);
     if (r >= a.row1) return;
@@ -43,28 +45,44 @@ __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_cons
     const int lane = threadIdx.x & 31;
     const float lo = static_cast<float>(a.lo), hi = static_cast<float>(a.hi);
     const bool lo_open = a.lo < 0.0;  // band starts below every value
-    for (int32_t u0 = threadIdx.x * 4; u0 < ((u_end + kColT * 4 - 1) / (kColT * 4)) * (kColT * 4); u0 += kColT * 4) {
-        float4 v = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-        int4 k = make_int4(-1, -1, -1, -1);
-        if (u0 < u_end) {
-            v = ld_stream_f4(reinterpret_cast<const float4*>(row + u0));
-            k = __ldg(reinterpret_cast<const int4*>(a.gkey + u0));
-        }
-        const float vs[4] = {v.x, v.y, v.z, v.w};
-        const int32_t ks4[4] = {k.x, k.y, k.z, k.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool hit = ks4[e] >= 0 && ks4[e] < key_r && (lo_open || vs[e] > lo) && vs[e] <= hi;
-            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            if (mask == 0u) continue;
-            int32_t base = 0;
-            const int leader = __ffs(mask) - 1;
-            if (lane == leader) base = atomicAdd(a.cnt, __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (hit) {
-                const int32_t idx = base + __popc(mask & ((1u << lane) - 1u));
-                if (idx < a.cap) a.q[idx] = make_int2(r, u0 + e);
+    __shared__ int32_t s_cnt, s_base, s_total;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int32_t u_pad = ((u_end + kColT * 4 - 1) / (kColT * 4)) * (kColT * 4);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int32_t u0 = threadIdx.x * 4; u0 < u_pad; u0 += kColT * 4) {
+            float4 v = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+            int4 k = make_int4(-1, -1, -1, -1);
+            if (u0 < u_end) {
+                v = pass == 0 ? ld_stream_f4(reinterpret_cast<const float4*>(row + u0)) : __ldcg(reinterpret_cast<const float4*>(row + u0));
+                k = __ldg(reinterpret_cast<const int4*>(a.gkey + u0));
             }
+            const float vs[4] = {v.x, v.y, v.z, v.w};
+            const int32_t ks4[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool hit = ks4[e] >= 0 && ks4[e] < key_r && (lo_open || vs[e] > lo) && vs[e] <= hi;
+                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                if (mask == 0u) continue;
+                int32_t pos = 0;
+                const int leader = __ffs(mask) - 1;
+                if (lane == leader) pos = atomicAdd(&s_cnt, __popc(mask));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (pass == 1 && hit) {
+                    const int32_t idx = s_base + pos + __popc(mask & ((1u << lane) - 1u));
+                    if (idx < a.cap) a.q[idx] = make_int2(r, u0 + e);
+                }
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (threadIdx.x == 0) {
+                s_total = s_cnt;
+                s_base = s_cnt > 0 ? atomicAdd(a.cnt, s_cnt) : 0;
+                s_cnt = 0;
+            }
+            __syncthreads();
+            if (s_total == 0) return;  // (uniform) nothing of this row lies in the band
         }
     }
 }
