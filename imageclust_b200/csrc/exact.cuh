@@ -18,7 +18,7 @@
 
 namespace ic {
 
-constexpr int kExChunk = 256;  // floats staged per step: 1 KB of shared memory per warp
+constexpr int kExChunk = 256;  // floats of every row staged per step (merge loop; refine.cu: 128)
 
 // centroid[i] = (float32(na)*ca[i] + float32(nb)*cb[i]) / float32(na+nb), clustering.go:39
 IC_DEVINL float ex_merge1(float fa, float a, float fb, float b, float fs) {
@@ -67,22 +67,25 @@ IC_DEVINL float warp_exact_dsq(const float* __restrict__ pa, const float* __rest
     return __shfl_sync(0xffffffffu, sum, 0);
 }
 
-// Up to kExGroup pairs that share their first cluster, one warp: the squared differences of every pair are staged side by
-// side and lanes 0 .. np-1 run the np sequential chains in lockstep -- the chain latency (the floor of one evaluation) is
-// paid once per group, and row A is read once.  `pb` is lane k's second row (lanes >= np: ignored); returns pair k's dsq
-// on lane k.  sbuf = kExGroup * kExStride floats of this warp (the stride keeps the lanes' 16-byte reads on distinct banks).
-constexpr int kExGroup = 4;
-constexpr int kExStride = kExChunk + 4;
+// Up to G pairs that share their first cluster, one warp: the squared differences of every pair are staged side by side
+// (CH floats per step) and lanes 0 .. np-1 run the np sequential chains in lockstep -- the chain latency (the floor of one
+// evaluation) is paid once per group, row A is read once, and the fp32 add pipe (one warp instruction per 2 cycles and
+// scheduler whatever the number of active lanes) issues 1/np of the instructions.  `pb` is lane k's second row (lanes >= np:
+// ignored); returns pair k's dsq on lane k.  sbuf = G * (CH + 4) floats of this warp (the stride keeps the lanes' 16-byte
+// reads on distinct banks).  The merge loop's exact phase has ~10 groups per SM and iteration: G = 4, CH = 256 (more, shorter
+// groups); refine.cu has millions: G = 8, CH = 128.
+template <int G, int CH>
 IC_DEVINL float warp_exact_dsq_group(const float* __restrict__ pa, const float* pb, int np, int d4, float* sbuf) {
     const int lane = threadIdx.x & 31;
-    constexpr int Q = kExChunk / 128;
-    const float* pbk[kExGroup];
+    constexpr int Q = CH / 128;
+    constexpr int kStride = CH + 4;
+    const float* pbk[G];
 #pragma unroll
-    for (int k = 0; k < kExGroup; ++k) {
+    for (int k = 0; k < G; ++k) {
         const unsigned long long v = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(pb), k);
         pbk[k] = reinterpret_cast<const float*>(v);
     }
-    float4 a[Q], b[kExGroup][Q];
+    float4 a[Q], b[G][Q];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     auto issue = [&](int c0) {
 #pragma unroll
@@ -91,29 +94,29 @@ IC_DEVINL float warp_exact_dsq_group(const float* __restrict__ pa, const float* 
             const bool ok = e < d4;
             a[q] = ok ? __ldcg(reinterpret_cast<const float4*>(pa + e)) : z;
 #pragma unroll
-            for (int k = 0; k < kExGroup; ++k) b[k][q] = (ok && k < np) ? __ldcg(reinterpret_cast<const float4*>(pbk[k] + e)) : z;
+            for (int k = 0; k < G; ++k) b[k][q] = (ok && k < np) ? __ldcg(reinterpret_cast<const float4*>(pbk[k] + e)) : z;
         }
     };
     float sum = 0.0f;
     issue(0);
-    for (int c0 = 0; c0 < d4; c0 += kExChunk) {
+    for (int c0 = 0; c0 < d4; c0 += CH) {
 #pragma unroll
-        for (int k = 0; k < kExGroup; ++k) {
+        for (int k = 0; k < G; ++k) {
             if (k < np) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const float dx = __fsub_rn(a[q].x, b[k][q].x), dy = __fsub_rn(a[q].y, b[k][q].y), dz = __fsub_rn(a[q].z, b[k][q].z),
                                 dw = __fsub_rn(a[q].w, b[k][q].w);
-                    reinterpret_cast<float4*>(sbuf + k * kExStride)[lane + 32 * q] =
+                    reinterpret_cast<float4*>(sbuf + k * kStride)[lane + 32 * q] =
                         make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
                 }
             }
         }
         __syncwarp();
-        if (c0 + kExChunk < d4) issue(c0 + kExChunk);  // in flight while the chains run
+        if (c0 + CH < d4) issue(c0 + CH);  // in flight while the chains run
         if (lane < np) {
-            const int n4 = (min(kExChunk, d4 - c0)) >> 2;
-            const float4* src = reinterpret_cast<const float4*>(sbuf + lane * kExStride);
+            const int n4 = (min(CH, d4 - c0)) >> 2;
+            const float4* src = reinterpret_cast<const float4*>(sbuf + lane * kStride);
 #pragma unroll 4
             for (int i = 0; i < n4; ++i) {
                 const float4 v = src[i];
@@ -124,6 +127,10 @@ IC_DEVINL float warp_exact_dsq_group(const float* __restrict__ pa, const float* 
     }
     return sum;
 }
+constexpr int kExGroup = 4;                    // merge loop
+constexpr int kExStride = kExChunk + 4;
+constexpr int kExGroupR = 8, kExChunkR = 128;  // refine.cu
+constexpr int kExStrideR = kExChunkR + 4;
 
 // (float32(na * nb) / float32(na + nb)) * dsq: integer product first (clustering.go:142-144)
 IC_DEVINL float ward_weight(int na, int nb, float dsq) {
@@ -132,13 +139,20 @@ IC_DEVINL float ward_weight(int na, int nb, float dsq) {
     return __fmul_rn(__fdiv_rn(num, den), dsq);
 }
 
-// bookkeeping of one re-evaluation: how far off was the stored value?  (lane 0 only)
-IC_DEVINL void exact_monitor(int32_t* ctl, float stored, float w, float eps_filter, float abs_slack) {
-    if (!(stored < __uint_as_float(kMaxFloatBits))) return;
-    const float excess = fmaxf(fabsf(stored - w) - abs_slack, 0.0f);  // beyond what a tensor-core Gram value may be off by
+// bookkeeping of one re-evaluation: how far off was the stored value?  Returns the relative error (beyond what a tensor-core
+// Gram value may be off by); a violation of the filter tolerance is counted right away (rare), the running maximum is kept by
+// the caller and published once (exact_monitor_flush): one atomic per evaluation on one address serialises the whole phase.
+IC_DEVINL float exact_monitor(int32_t* ctl, float stored, float w, float eps_filter, float abs_slack) {
+    if (!(stored < __uint_as_float(kMaxFloatBits))) return 0.0f;
+    const float excess = fmaxf(fabsf(stored - w) - abs_slack, 0.0f);
     const float err = excess / fmaxf(w, 1e-30f);
     if (err > eps_filter) atomicAdd(ctl + CTL_FILTER_VIOL, 1);
-    if (err > 0.0f && err == err) atomicMax(ctl + CTL_FILTER_MAXERR, static_cast<int32_t>(__float_as_uint(fminf(err, 1e30f))));
+    return (err == err) ? fminf(err, 1e30f) : 1e30f;
+}
+IC_DEVINL void exact_monitor_flush(int32_t* ctl, float max_err) {  // whole warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_err = fmaxf(max_err, __shfl_xor_sync(0xffffffffu, max_err, o));
+    if ((threadIdx.x & 31) == 0 && max_err > 0.0f) atomicMax(ctl + CTL_FILTER_MAXERR, static_cast<int32_t>(__float_as_uint(max_err)));
 }
 
 }  // namespace ic

@@ -1296,11 +1296,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     st.dryq[atomicAdd(st.counters + sl1 * 4 + CN_DRY, 1)] = make_int2(s_b[tid], kbase + t - m + tid);
             }
             int32_t my_exact = 0;
+            float my_maxerr = 0.0f;
             // what one lane does with the reference's value of its pair: monitors, the matrix entry, the new row's list
             auto finish = [&](int32_t j, int32_t col, int32_t key_b, int32_t size_b, int32_t lwb, int32_t pos, float dsq) {
                 const int32_t bj = s_b[j];
                 const float w = ward_weight(s_sa[j] + s_sb[j], size_b, dsq);
-                exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(lwb)), w, prm.eps_filter, prm.abs_slack);
+                my_maxerr = fmaxf(my_maxerr, exact_monitor(ctl, __uint_as_float(static_cast<uint32_t>(lwb)), w, prm.eps_filter, prm.abs_slack));
                 if (j + 1 < m && w < d_last) atomicAdd(ctl + CTL_ORDER_VIOL, 1);  // would have preceded a later pair of the batch
                 __stcg(row_of(bj) + col, w);
                 if (use_xres && pos < kXResCap)
@@ -1359,7 +1360,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     decode(ent.x, col, key_b, size_b);
                     pb = st.cen + static_cast<int64_t>(key_b) * st.ldc;
                 }
-                const float dsq = warp_exact_dsq_group(pa, pb, np, d4, s_ex[warp]);
+                const float dsq = warp_exact_dsq_group<kExGroup, kExChunk>(pa, pb, np, d4, s_ex[warp]);
                 if (lane < np) finish(j, col, key_b, size_b, lwb, p0 + lane, dsq);
                 if (lane == 0) my_exact += np;
             }
@@ -1377,6 +1378,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 }
             }
             if (lane == 0 && my_exact > 0) atomicAdd(ctl + CTL_N_EXACT, my_exact);
+            exact_monitor_flush(ctl, my_maxerr);
             if (timed) {
                 c_ph[8] += te0 - tq3;        // waiting for the slowest block's rows phase
                 c_ph[9] += clock64() - te0;  // this block's share of the exact phase

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) init_centroids_kernel(const float* __rest
 
 // one block per row; 16-byte loads of the row and of the keys.  Two passes over the row (the second one hits L2): count the
 // pairs in the band, reserve ONE contiguous range of the queue for the row, fill it -- consecutive queue entries then share
-// their row, so the evaluation kernel runs four summation chains per warp and reads the row's centroid once per four pairs.
+// their row, so the evaluation kernel runs eight summation chains per warp and reads the row's centroid once per eight pairs.
 __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_constant__ RefineArgs a) {
     const int32_t r = a.row0 + static_cast<int32_t>(blockIdx.x);
     if (r >= a.row1) return;
@@ -88,16 +88,17 @@ __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_cons
 }
 
 __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant__ RefineArgs a) {
-    __shared__ __align__(16) float s_buf[8][kExGroup * kExStride];
+    __shared__ __align__(16) float s_buf[8][kExGroupR * kExStrideR];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t total = min(__ldg(a.cnt), a.cap);
     const int32_t gw = static_cast<int32_t>(blockIdx.x) * 8 + warp, GW = static_cast<int32_t>(gridDim.x) * 8;
     const int d4 = static_cast<int>(a.ldc);
     int32_t n_done = 0;
+    float max_err = 0.0f;
     // the collect kernel appends a row's pairs in runs: consecutive entries mostly share their row, whose centroid (and the
-    // latency of the summation chain) is then shared by up to kExGroup evaluations
-    for (int32_t base = gw * kExGroup; base < total; base += GW * kExGroup) {
-        const int32_t cnt = min(kExGroup, total - base);
+    // latency of the summation chain) is then shared by up to kExGroupR evaluations
+    for (int32_t base = gw * kExGroupR; base < total; base += GW * kExGroupR) {
+        const int32_t cnt = min(kExGroupR, total - base);
         int2 p = make_int2(-1, -1);
         if (lane < cnt) p = a.q[base + lane];
         int32_t done = 0;
@@ -113,12 +114,12 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
                 ku = a.ks[u];
                 pb = a.cen + static_cast<int64_t>(ku.x) * a.ldc;  // centroids are stored by key
             }
-            const float dsq = warp_exact_dsq_group(a.cen + static_cast<int64_t>(kr.x) * a.ldc, pb, run, d4, s_buf[warp]);
+            const float dsq = warp_exact_dsq_group<kExGroupR, kExChunkR>(a.cen + static_cast<int64_t>(kr.x) * a.ldc, pb, run, d4, s_buf[warp]);
             if (lane < run) {
                 const float w = ward_weight(kr.y, ku.y, dsq);
                 float* dst = a.dm + static_cast<int64_t>(r0 - a.r_lo) * a.ld + u;
                 const float stored = *dst;
-                exact_monitor(a.ctl, stored, w, a.eps_filter, a.abs_slack);
+                max_err = fmaxf(max_err, exact_monitor(a.ctl, stored, w, a.eps_filter, a.abs_slack));
                 if (__float_as_uint(stored) != __float_as_uint(w)) {
                     *dst = w;
                     if (kr.x < a.mirror_key) {  // both clusters are older than the last compaction: the pair is stored in both rows
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) refine_eval_kernel(const __grid_constant_
         }
     }
     if (lane == 0 && n_done > 0) atomicAdd(a.ctl + CTL_N_EXACT, n_done);
+    exact_monitor_flush(a.ctl, max_err);
 }
 }  // namespace
 
