@@ -1002,16 +1002,20 @@ int raise_horizon(ic_ctx* ctx) {
     if (!(first && ctx->dm_is_reference)) {
         const int rc = refine_band(ctx, first ? -1.0 : ctx->horizon, hi, 0);
         if (rc != IC_OK) return rc;
-        if (ctx->n_merges == 0) {  // keys are still the slot indices: the first sweep kernel rebuilds every partner list
+        // the partner lists of the rows whose values changed are stale.  With near lists every live row simply re-selects its
+        // list from them (below: build_near marks all rows); without, the first sweep kernel rebuilds every list from the
+        // whole rows while keys are still the slot indices (later: the rows marked by refine.cu are scanned by the loop)
+        if (ctx->n_merges == 0 && !(ctx->near_meta && ctx->near_opt)) {
             IC_CUDA(launch_nn_sweep(ctx->dm, row_begin(ctx), row_end(ctx), ctx->ld, ctx->nn, ctx->nn_more, ctx->stream));
             ctx->stats.kernel_launches += 1;
         }
     }
     ctx->horizon = hi;
-    const bool initial = ctx->n_merges == 0;  // the first sweep kernel has just rebuilt every list from the whole rows
+    // (first horizon over an initial matrix that already holds the reference's values: the lists of the first sweep stand)
+    const bool lists_stand = ctx->n_merges == 0 && (!(ctx->near_meta && ctx->near_opt) || (first && ctx->dm_is_reference));
     ctx->merges_at_raise = ctx->n_merges;
     ++ctx->n_raises;
-    return build_near(ctx, !initial);
+    return build_near(ctx, !lists_stand);
 }
 
 // K4 (compact.cu): renumber the live clusters densely in key order, move the matrix into the other buffer (both
