@@ -23,10 +23,14 @@ def digest(key_hi, key_lo, dist, size):
 def main():
     eng = clustering.Engine(0)
     for spec in sys.argv[1:]:
-        cfg, _, mn_override = spec.partition(":")
+        parts = spec.split(":")  # config[:minSize[:oracle flags]]
+        cfg = parts[0]
         n, d, mn, mx = synth.CONFIGS[cfg]
-        if mn_override:
-            mn = int(mn_override)
+        if len(parts) > 1 and parts[1]:
+            mn = int(parts[1])
+        # flags 1 = FAST_EAGER: inadmissible pairs masked when written instead of rejected lazily -- same merge sequence
+        # (tests/test_oracle_fast.py), without the reference's one-rescan-per-rejection cost (millions at min 6 / max 8)
+        oflags = int(parts[2]) if len(parts) > 2 else 0
         seed = 20240 + "ABCDE".index(cfg)
         x = synth.combined_features(n, 2048, d - 2048, 2, 8, seed=seed) if cfg == "E" else synth.gaussian_mixture(n, d, mn, mx, seed=seed)
         t0 = time.time()
@@ -35,7 +39,7 @@ def main():
         tr = eng.merge_trace()
         st = res.stats
         t0 = time.time()
-        o = O.fast_cluster(x, mn, mx, flags=0)
+        o = O.fast_cluster(x, mn, mx, flags=oflags)
         t_cpu = time.time() - t0
         m = min(len(tr.key_hi), o.n_merges)
         neq = np.flatnonzero((tr.key_hi[:m] != o.key_hi[:m]) | (tr.key_lo[:m] != o.key_lo[:m]))
@@ -47,7 +51,7 @@ def main():
         for cid, c in enumerate(o.clusters):
             lb[c] = cid
         print(json.dumps(dict(
-            config=cfg, n=n, d=d, min_size=mn, max_size=mx, merges_gpu=len(tr.key_hi), merges_oracle=o.n_merges,
+            config=cfg, n=n, d=d, min_size=mn, max_size=mx, oracle_flags=oflags, merges_gpu=len(tr.key_hi), merges_oracle=o.n_merges,
             exhausted_gpu=bool(st["exhausted"]), exhausted_oracle=o.exhausted,
             digest_gpu=digest(tr.key_hi, tr.key_lo, tr.dist, tr.size), digest_oracle=digest(o.key_hi, o.key_lo, o.dist, o.size),
             first_divergence=int(neq[0]) if len(neq) else -1, dist_bits_identical=bool(len(neq) == 0 and len(tr.key_hi) == o.n_merges and np.array_equal(tr.dist.view(np.uint32), o.dist.view(np.uint32))),
