@@ -531,6 +531,23 @@ def test_config_c_full_size_properties_and_sharded_identity(eng, knobs):
         assert _trace_digest(eng.merge_trace()) == want
 
 
+@pytest.mark.parametrize("mn,want,exhausted", [
+    (2, "12a460c80c3263b8a5acf911620e40e897f3cea84349fdc877bc9d94bd3cb334", False),
+    (6, "24327edbc359afde85a919e226988cc5228c3a65c7b52b12859aae6fd98a866e", True)])
+def test_config_e_full_size_equals_the_recorded_oracle_digest(eng, mn, want, exhausted):
+    """BASELINE config 5 (N=50,000 x 2148: 2048-d image block + 100-d label one-hot, maxSize=8) at full size, minSize 2 and 6
+    (the latter ends by exhaustion): the sha256 of the merge trace equals the one of the CPU oracle in reference arithmetic
+    at this exact size (171 s / 222 s on 16 host cores: scripts/replay_full.py E:2 E:6:1 -> profiles/r02_replay_configE.txt)."""
+    n, d, _, mx = synth.CONFIGS["E"]
+    x = synth.combined_features(n, 2048, d - 2048, 2, 8, seed=20244)
+    res = eng.cluster(x, mn, mx)
+    assert _trace_digest(eng.merge_trace()) == want
+    assert bool(res.stats["exhausted"]) == exhausted
+    _assert_reference_run(res.stats)
+    sizes = np.array([len(c) for c in res.clusters])
+    assert sizes.min() >= mn and sizes.max() <= mx
+
+
 # ---- K1, int8 path: exact integer tensor-core Gram (gram_i8.cu) -------------------------------------------------
 
 def _gram_case_mode(eng, oracle, x, mode):
