@@ -105,10 +105,10 @@ struct ic_ctx {
     bool dm_is_reference = false; // the initial matrix already holds the reference's values (gram_mode 1)
     // delta_cut = 0: batches are taken optimistically and CHECKED (every pair a batch creates is compared with the batch's
     // later members, CTL_ORDER_VIOL); a failed check restarts the clustering with delta_cut_fallback
-    double hz_factor = 1.25, eps_filter = 3e-5, delta_cut = 0.0, delta_cut_fallback = 1e-5, abs_slack_opt = -1.0;
+    double hz_factor = 1.18, eps_filter = 3e-5, delta_cut = 0.0, delta_cut_fallback = 1e-5, abs_slack_opt = -1.0;
     double delta_cut_cur = 0.0;
     int32_t n_restarts = 0;
-    double horizon = -1.0, abs_slack = 0.0, hz_factor_cur = 1.25;
+    double horizon = -1.0, abs_slack = 0.0, hz_factor_cur = 1.18;
     int32_t merges_at_raise = 0;
     float* cen = nullptr;
     int64_t ldc = 0;
