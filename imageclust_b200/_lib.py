@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libimageclust_b200.so")
+# IMAGECLUST_B200_LIB: another build of the same library (A/B runs of kernel variants: scripts/build_variants.sh)
+LIB_PATH = os.environ.get("IMAGECLUST_B200_LIB") or os.path.join(HERE, "libimageclust_b200.so")
 
 IC_OK = 0
 IC_ERR_TOO_FEW = -1

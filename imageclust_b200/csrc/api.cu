@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -1911,8 +1912,10 @@ int ic_get_loop_block_waits(ic_ctx* ctx, int64_t* out, int64_t capacity, int64_t
 int ic_get_loop_profile(ic_ctx* ctx, int64_t* out16) {
     if (!ctx || !out16) return IC_ERR_BAD_ARG;
     for (int i = 0; i < 16; ++i) out16[i] = ctx->h_prof[i];
-    out16[9] = ctx->h_ctl[CTL_BUBBLES];
-    out16[7] = ctx->h_ctl[CTL_RESCANS];
+    if (ctx->loop_mode_used != 1) {  // (the batched loop keeps cycle counters of its selection phase in these two)
+        out16[9] = ctx->h_ctl[CTL_BUBBLES];
+        out16[7] = ctx->h_ctl[CTL_RESCANS];
+    }
     return IC_OK;
 }
 

@@ -129,6 +129,74 @@ IC_DEVINL float warp_exact_dsq_group(const float* __restrict__ pa, const float* 
 }
 constexpr int kExGroup = 4;                    // merge loop
 constexpr int kExStride = kExChunk + 4;
+
+// The same evaluation with the rows staged by cp.async (merge loop): a ring of S stages of CH floats of the G + 1 rows per
+// warp, S - 1 chunks in flight while the chains of the current chunk run.  With register staging (above) one chunk is in
+// flight, and a warp that has a single group per iteration -- the merge loop's case -- waits a full memory latency per chunk:
+// round 2 measured 42 k cycles per iteration for a chain of 8.4 k.  Every lane copies, squares (in place, over the second
+// rows) and publishes its own 16 bytes of every row; lanes 0 .. np-1 then run the chains.  sbuf = kExAsyncFloats floats.
+constexpr int kExAsyncCH = 128, kExAsyncStages = 3;
+constexpr int kExAsyncRow = kExAsyncCH + 4;                         // floats (the pad keeps the chains' 16-byte reads on distinct banks)
+constexpr int kExAsyncStage = (kExGroup + 1) * kExAsyncRow;         // floats
+constexpr int kExAsyncFloats = kExAsyncStages * kExAsyncStage;      // 1 980 floats = 7 920 bytes per warp
+IC_DEVINL float warp_exact_dsq_group_async(const float* __restrict__ pa, const float* pb, int np, int d4, float* sbuf) {
+    constexpr int G = kExGroup, CH = kExAsyncCH, S = kExAsyncStages;
+    static_assert(CH == 128, "one 16-byte copy per lane, row and chunk");
+    const int lane = threadIdx.x & 31;
+    const float* pbk[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const unsigned long long v = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(pb), k);
+        pbk[k] = reinterpret_cast<const float*>(v);
+    }
+    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sbuf)) + static_cast<uint32_t>(lane) * 16u;
+    const int nch = (d4 + CH - 1) / CH;
+    auto issue = [&](int c) {  // chunk c into stage c % S; always commits one group
+        const int e = c * CH + 4 * lane;
+        if (c < nch && e < d4) {
+            const uint32_t dst = sbase + static_cast<uint32_t>((c % S) * kExAsyncStage * 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pa + e) : "memory");
+#pragma unroll
+            for (int k = 0; k < G; ++k)
+                if (k < np)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + static_cast<uint32_t>((k + 1) * kExAsyncRow * 4)), "l"(pbk[k] + e) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int c = 0; c < S - 1; ++c) issue(c);
+    float sum = 0.0f;
+    for (int c = 0; c < nch; ++c) {
+        issue(c + S - 1);  // into the stage of chunk c - 1, whose chains finished before the __syncwarp that ended the last trip
+        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");  // this lane's copies of chunk c have landed
+        float* stg = sbuf + (c % S) * kExAsyncStage;
+        if (c * CH + 4 * lane < d4) {
+            const float4 a = reinterpret_cast<const float4*>(stg)[lane];
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                if (k < np) {
+                    float4* q = reinterpret_cast<float4*>(stg + (k + 1) * kExAsyncRow) + lane;
+                    const float4 b = *q;
+                    const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z), dw = __fsub_rn(a.w, b.w);
+                    *q = make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < np) {
+            const int n4 = (min(CH, d4 - c * CH)) >> 2;
+            const float4* src = reinterpret_cast<const float4*>(stg + (lane + 1) * kExAsyncRow);
+#pragma unroll 4
+            for (int i = 0; i < n4; ++i) {
+                const float4 v = src[i];
+                sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return sum;
+}
 constexpr int kExGroupR = 8, kExChunkR = 128;  // refine.cu
 constexpr int kExStrideR = kExChunkR + 4;
 

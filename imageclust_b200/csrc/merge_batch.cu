@@ -54,6 +54,13 @@ constexpr uint32_t kBarSpin = 1u << 24;
 #endif
 constexpr int kUpdCols = IC_UPD_COLS;  // columns of one update unit (one warp: 4 x 32 lanes x 4, all loads in flight at once)
 constexpr int kRcpTab = 1024;
+// exact phase: 1 = register-staged chunks (one in flight; A/B against the cp.async ring of exact.cuh)
+#ifndef IC_EXACT_SYNC
+#define IC_EXACT_SYNC 0
+#endif
+// floats of shared memory per warp: the exact phase's cp.async ring (or one register-staged chunk)
+constexpr int kWarpStage = kExAsyncFloats > kExChunk ? kExAsyncFloats : kExChunk;
+static_assert(kWarpStage % 4 == 0 && kWarpStage >= kExGroup * kExStride, "per-warp staging memory");
 constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead of the update pass
 
 // counters[slot][*]
@@ -237,7 +244,7 @@ IC_DEVINL RowHead row_head(uint4 e0, uint4 e1, uint32_t more_bits, uint32_t key_
 size_t merge_batch_smem_bytes(int64_t n) {
     const size_t n4 = static_cast<size_t>((n + 3) / 4 * 4);
     const size_t bitmap = ((n4 + 31) / 32 + 3) / 4 * 4 * sizeof(uint32_t);
-    return bitmap + sizeof(float) * kBW * kExGroup * kExStride;  // + the warps' staging buffers of the exact phase
+    return bitmap + sizeof(float) * kBW * kWarpStage;  // + the warps' staging buffers (exact phase; ring of the rows phase)
 }
 static int64_t batch_window_cols(int64_t n) {  // at most kBatchMaxWin windows per row: <= 4 partial lists per lane in the fold
     const int64_t n4 = (n + 3) / 4 * 4;
@@ -295,8 +302,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     // exact phase: squared differences of one chunk of up to kExGroup pairs per warp
-    float (*const s_ex)[kExGroup * kExStride] = reinterpret_cast<float (*)[kExGroup * kExStride]>(dyn_smem);
-    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kBW * kExGroup * kExStride);  // merged-slot bitmap of the current batch
+    float (*const s_ex)[kWarpStage] = reinterpret_cast<float (*)[kWarpStage]>(dyn_smem);
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kBW * kWarpStage);  // merged-slot bitmap of the current batch
     const int32_t n_words = (n4 + 31) >> 5;
 
     __shared__ uint64_t s_red[kBW];
@@ -329,6 +336,8 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
     const bool small_sizes = prm.max_size < kRcpTab;  // every admissible size sum has its reciprocal in the table
     __shared__ long long c_ph[10];  // cycles of block 0 per phase (profile_loop)
     if (tid < 10) c_ph[tid] = 0;
+    __shared__ long long c_sel[4];  // selection phase: candidates loaded + minima, theta, filter, (rest: conflicts + ranks); bookkeeping
+    if (tid < 4) c_sel[tid] = 0;
 
     for (int i = tid; i < kRcpTab; i += kBT) s_rcp[i] = 1.0 / static_cast<double>(i > 0 ? i : 1);
     __syncthreads();
@@ -794,6 +803,13 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             for (int y = 0; y < kNNK; ++y)
                 ve[x][y] = r < r_hi ? __ldcg(st.nn + static_cast<int64_t>(r) * kNNK + y) : nn_none();
         }
+        // (one GPU: this thread's first candidate record, requested before the count is known -- the list holds a record per
+        // row -- which takes a dependent round trip off the phase)
+        uint4 spec0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u), spec1 = make_uint4(0u, 0u, 0u, 0u);
+        if (!kMulti && tid < n) {
+            spec0 = __ldcg(st.cand + 2 * static_cast<int64_t>(tid));
+            spec1 = __ldcg(st.cand + 2 * static_cast<int64_t>(tid) + 1);
+        }
         uint64_t tstop = kPackInf, H = kPackInf;
         int32_t n_pub;  // heads below their block's stopper minimum, all ranks
         int over_local = 0;  // some rank's exact-evaluation queue overflowed in the previous iteration
@@ -829,16 +845,24 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             while (i >= s_xcnt[q + 1]) ++q;
             return reinterpret_cast<const uint4*>(xb + kBatchXCandBase) + 2 * (static_cast<int64_t>(q) * kBatchXCand + (i - s_xcnt[q]));
         };
-        uint4 c0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < n_pub) {
-            c0 = __ldcg(cand_ptr(tid));
-            c1 = __ldcg(cand_ptr(tid) + 1);
+        // this thread's candidates tid, tid + kBT, ...: first halves {pack, slots} kept in registers for the count and the filter
+        // pass (a few thousand heads are published for a batch of dozens)
+        constexpr int kCandReg = 4;
+        uint4 cq[kCandReg];
+        uint4 c1 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int x = 0; x < kCandReg; ++x) {
+            cq[x] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+            const int32_t i = tid + x * kBT;
+            if (i < n_pub) cq[x] = (!kMulti && x == 0) ? spec0 : __ldcg(cand_ptr(i));
         }
+        if (tid < n_pub) c1 = kMulti ? __ldcg(cand_ptr(tid) + 1) : spec1;
         tstop = block_min_u64(tstop, s_red);
         H = block_min_u64(H, s_red);
         const bool xq_over = __syncthreads_or(over_local & 1) != 0;     // (every rank sees every rank's flags)
         const bool cand_over = kMulti && __syncthreads_or(over_local & 4) != 0;  // some rank's candidates did not fit its region
         const bool order_viol = __syncthreads_or(over_local & 2) != 0;
+        const long long ts1 = timed ? clock64() : 0;
         // termination (clustering.go:220 loop condition, :222-225 exhaustion)
         if (n_live <= prm.n_target)
             stop_reason = STOP_TARGET;
@@ -889,7 +913,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         if (!cand_over && n_pub > kMaxBatch) {
             auto count_lt = [&](uint64_t th) {
                 int c = 0;
-                for (int32_t i = tid; i < n_pub; i += kBT) {
+#pragma unroll
+                for (int x = 0; x < kCandReg; ++x) c += ((static_cast<uint64_t>(cq[x].y) << 32) | cq[x].x) < th ? 1 : 0;  // (none: all ones)
+                for (int32_t i = tid + kCandReg * kBT; i < n_pub; i += kBT) {
                     const uint4 p = __ldcg(cand_ptr(i));
                     c += ((static_cast<uint64_t>(p.y) << 32) | p.x) < th ? 1 : 0;
                 }
@@ -907,14 +933,14 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 theta = lo_t;
             }
         }
+        const long long ts2 = timed ? clock64() : 0;
         if (tid == 0) s_m = 0;
         for (int32_t w = tid; w < n_words; w += kBT) s_bits[w] = 0u;
         __syncthreads();
-        for (int32_t i = tid; i < n_pub; i += kBT) {
-            const uint4 p = i == tid ? c0 : __ldcg(cand_ptr(i));
+        auto take_cand = [&](int32_t i, const uint4& p, bool have_p1) {
             const uint64_t hp = (static_cast<uint64_t>(p.y) << 32) | p.x;
-            if (hp < theta) {
-                const uint4 p1 = i == tid ? c1 : __ldcg(cand_ptr(i) + 1);
+            if (hp < theta) {  // (theta <= all ones: an empty register slot never passes)
+                const uint4 p1 = have_p1 ? c1 : __ldcg(cand_ptr(i) + 1);
                 const int k = atomicAdd(&s_m, 1);
                 s_hp[k] = hp;
                 s_ca[k] = static_cast<int32_t>(p.z);
@@ -923,7 +949,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 s_csb[k] = static_cast<int32_t>(p1.y);
                 s_ckb[k] = static_cast<int32_t>(p1.z);
             }
-        }
+        };
+#pragma unroll
+        for (int x = 0; x < kCandReg; ++x) take_cand(tid + x * kBT, cq[x], x == 0);
+        for (int32_t i = tid + kCandReg * kBT; i < n_pub; i += kBT) take_cand(i, __ldcg(cand_ptr(i)), false);
         __syncthreads();
         if (cand_over && tid == 0) {  // the smallest head of every rank that dropped candidates (if it is not listed already)
             for (int q = 0; q < st.n_ranks; ++q) {
@@ -946,20 +975,25 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         }
         if (cand_over) __syncthreads();
         const int32_t n_cand = s_m;  // <= kMaxBatch
+        const int32_t n_cand_prof = n_cand + (n_pub << 10) * 0;
+        const long long ts3 = timed ? clock64() : 0;
         // slot conflicts: a pair that shares a cluster with an earlier pair is a stopper
         uint64_t mine = kPackInf, conf = kPackInf;
         int n_less = 0;
         if (tid < n_cand) {
             mine = s_hp[tid];
             const int32_t a = s_ca[tid], b = s_cb[tid];
-            bool hit = false;
+            // branch-free and unrolled: with a short-circuit || every trip waited for its own shared-memory loads (~80 cycles
+            // per candidate, 13 k cycles per iteration at config C)
+            int hit = 0;
+#pragma unroll 8
             for (int j = 0; j < n_cand; ++j) {
                 const int32_t aj = s_ca[j], bj = s_cb[j];
-                const bool less = s_hp[j] < mine;
-                n_less += less ? 1 : 0;
-                hit = hit || (less && (aj == a || aj == b || bj == a || bj == b));
+                const int less = s_hp[j] < mine ? 1 : 0;
+                n_less += less;
+                hit |= less & ((aj == a ? 1 : 0) | (aj == b ? 1 : 0) | (bj == a ? 1 : 0) | (bj == b ? 1 : 0));
             }
-            if (hit) conf = mine;
+            if (hit != 0) conf = mine;
         }
         const uint64_t T = umin64(theta, block_min_u64(conf, s_red));
         bool take = tid < n_cand && mine < T;
@@ -1146,10 +1180,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                                     st.xqm[static_cast<int64_t>(i) * kXResCap + pos] = make_int2(col, lwb);
                                 } else {  // more pairs than a merge's queue holds: the shared overflow queue
                                     const int32_t idx = atomicAdd(st.counters + sl * 4 + CN_XQ, 1);
-                                    if (idx < st.xq_cap)
+                                    if (idx < st.xq_cap) {
                                         st.xq[idx] = make_int4(i, col, lwb, pos);
-                                    else
-                                        ctl[CTL_XQ_OVERFLOW] = 1;
+                                    } else {  // nowhere to queue it: the Lance-Williams value is stored, and the host's sweep
+                                        ctl[CTL_XQ_OVERFLOW] = 1;  // of the band (STOP_XQ) finds and replaces it
+                                        hitm &= ~(1u << (x * 4 + e));
+                                    }
                                 }
                                 ++pos;
                             }
@@ -1360,7 +1396,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     decode(ent.x, col, key_b, size_b);
                     pb = st.cen + static_cast<int64_t>(key_b) * st.ldc;
                 }
+#if IC_EXACT_SYNC  // (A/B: register-staged chunks, one in flight)
                 const float dsq = warp_exact_dsq_group<kExGroup, kExChunk>(pa, pb, np, d4, s_ex[warp]);
+#else
+                const float dsq = warp_exact_dsq_group_async(pa, pb, np, d4, s_ex[warp]);
+#endif
                 if (lane < np) finish(j, col, key_b, size_b, lwb, p0 + lane, dsq);
                 if (lane == 0) my_exact += np;
             }
@@ -1397,6 +1437,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             c_ph[3] += tp4 - tp3;
             c_ph[4] += tq1 - tp3;
             c_ph[7] += tp4 - tq3;
+            c_sel[0] += ts1 - tp2;
+            c_sel[1] += ts2 - ts1;
+            c_sel[2] += ts3 - ts2;
+            c_sel[3] += n_cand_prof;
         }
     }
     if (timed) {  // accumulated over the launches of one clustering (the host zeroes them when it starts)
@@ -1407,6 +1451,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         st.prof[5] += launched;
         st.prof[6] += iters;
         for (int i = 0; i < 6; ++i) st.prof[10 + i] += c_ph[4 + i];
+        st.prof[4] += c_sel[0];
+        st.prof[7] += c_sel[1];
+        st.prof[8] += c_sel[2];
+        st.prof[9] += c_sel[3];
     }
     if (bid == 0 && tid == 0) {
         ctl[CTL_N_LIVE] = n_live;

@@ -41,6 +41,7 @@ with clustering.Engine(0) as eng:
               f"lists+rescans={p['publish'] / it:.0f} heads={p['exchange'] / it:.0f} select={p['update'] / it:.0f} apply={p['scan'] / it:.0f} "
               f"(rows+centroids={p['pub_argmin'] / it:.0f}, wait for the slowest block={p['exch_poll'] / it:.0f}, exact phase={p['exch_rank'] / it:.0f}) | "
               f"block 0 waits at the barriers: after rescans={p['pub_reduce'] / it:.0f} after heads={p['pub_fence'] / it:.0f}; "
+              f"select = load+minima {p['fold'] / it:.0f} + theta {p['rescans'] / it:.0f} + filter {p['reserved'] / it:.0f} + conflicts/ranks; candidates below theta {p['bubbles'] / it:.1f}; "
               f"exact={s['exact']} n_exact={s['n_exact']} raises={s['n_horizon_raises']} compactions={s['n_compactions']} "
               f"refine+near {s['ms_refine']:.1f} ms compact {s['ms_compact']:.1f} ms filter_viol={s['n_filter_viol']} order_viol={s['n_order_viol']}")
         sys.exit(0)
