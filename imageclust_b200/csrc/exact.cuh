@@ -25,6 +25,35 @@ IC_DEVINL float ex_merge1(float fa, float a, float fb, float b, float fs) {
     return __fdiv_rn(__fadd_rn(__fmul_rn(fa, a), __fmul_rn(fb, b)), fs);
 }
 
+// The reference's sequential sum (clustering.go:152-155) over n4 float4 of shared memory: sum = fl(sum + p_i), i ascending.
+// The adds are one dependent chain (4 cycles each); the shared-memory loads are not, so four float4 are requested a batch
+// ahead -- issued just in time, every float4 added ~30 cycles of load latency to 16 cycles of adds (round 2's capture:
+// the chain's FADDs waited on the short scoreboard, ~1.8 k cycles per 128-float chunk instead of ~0.55 k).
+IC_DEVINL float ex_chain_sum(const float4* __restrict__ src, int n4, float sum) {
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
+    if (n4 > 0) c0 = src[0];
+    if (n4 > 1) c1 = src[1];
+    if (n4 > 2) c2 = src[2];
+    if (n4 > 3) c3 = src[3];
+    int i = 0;
+    for (; i + 4 <= n4; i += 4) {
+        float4 d0 = c0, d1 = c1, d2 = c2, d3 = c3;
+        if (i + 4 < n4) c0 = src[i + 4];
+        if (i + 5 < n4) c1 = src[i + 5];
+        if (i + 6 < n4) c2 = src[i + 6];
+        if (i + 7 < n4) c3 = src[i + 7];
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d0.x), d0.y), d0.z), d0.w);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d1.x), d1.y), d1.z), d1.w);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d2.x), d2.y), d2.z), d2.w);
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d3.x), d3.y), d3.z), d3.w);
+    }
+    // tail (n4 % 4 float4, already loaded): +0 terms must NOT be added for real data, so only the valid ones
+    if (i < n4) sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, c0.x), c0.y), c0.z), c0.w);
+    if (i + 1 < n4) sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, c1.x), c1.y), c1.z), c1.w);
+    if (i + 2 < n4) sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, c2.x), c2.y), c2.z), c2.w);
+    return sum;
+}
+
 // dsq = DotFloat32(diff, diff), diff = A - B over d4 floats (rows are zero padded to a multiple of 4: +0 terms leave the
 // sum unchanged).  Whole warp; sbuf = this warp's kExChunk floats of shared memory.  Rows are read with ld.global.cg: the
 // centroid store is written by other SMs in the phase before, L1 must not serve it.
@@ -54,14 +83,7 @@ IC_DEVINL float warp_exact_dsq(const float* __restrict__ pa, const float* __rest
         }
         __syncwarp();
         if (c0 + kExChunk < d4) issue(c0 + kExChunk);  // in flight while lane 0 runs the chain
-        if (lane == 0) {
-            const int n4 = (min(kExChunk, d4 - c0)) >> 2;
-#pragma unroll 4
-            for (int i = 0; i < n4; ++i) {
-                const float4 v = reinterpret_cast<const float4*>(sbuf)[i];
-                sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
-            }
-        }
+        if (lane == 0) sum = ex_chain_sum(reinterpret_cast<const float4*>(sbuf), (min(kExChunk, d4 - c0)) >> 2, sum);
         __syncwarp();
     }
     return __shfl_sync(0xffffffffu, sum, 0);
@@ -114,15 +136,7 @@ IC_DEVINL float warp_exact_dsq_group(const float* __restrict__ pa, const float* 
         }
         __syncwarp();
         if (c0 + CH < d4) issue(c0 + CH);  // in flight while the chains run
-        if (lane < np) {
-            const int n4 = (min(CH, d4 - c0)) >> 2;
-            const float4* src = reinterpret_cast<const float4*>(sbuf + lane * kStride);
-#pragma unroll 4
-            for (int i = 0; i < n4; ++i) {
-                const float4 v = src[i];
-                sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
-            }
-        }
+        if (lane < np) sum = ex_chain_sum(reinterpret_cast<const float4*>(sbuf + lane * kStride), (min(CH, d4 - c0)) >> 2, sum);
         __syncwarp();
     }
     return sum;
@@ -134,13 +148,13 @@ constexpr int kExStride = kExChunk + 4;
 // warp, S - 1 chunks in flight while the chains of the current chunk run.  With register staging (above) one chunk is in
 // flight, and a warp that has a single group per iteration -- the merge loop's case -- waits a full memory latency per chunk:
 // round 2 measured 42 k cycles per iteration for a chain of 8.4 k.  Every lane copies, squares (in place, over the second
-// rows) and publishes its own 16 bytes of every row; lanes 0 .. np-1 then run the chains.  sbuf = kExAsyncFloats floats.
-constexpr int kExAsyncCH = 128, kExAsyncStages = 3;
+// rows) and publishes its own 16 bytes of every row; lanes 0 .. np-1 then run the chains.
+constexpr int kExAsyncCH = 128;
 constexpr int kExAsyncRow = kExAsyncCH + 4;                         // floats (the pad keeps the chains' 16-byte reads on distinct banks)
 constexpr int kExAsyncStage = (kExGroup + 1) * kExAsyncRow;         // floats
-constexpr int kExAsyncFloats = kExAsyncStages * kExAsyncStage;      // 1 980 floats = 7 920 bytes per warp
+template <int S>  // stages of the ring: S * kExAsyncStage floats (2 640 bytes each)
 IC_DEVINL float warp_exact_dsq_group_async(const float* __restrict__ pa, const float* pb, int np, int d4, float* sbuf) {
-    constexpr int G = kExGroup, CH = kExAsyncCH, S = kExAsyncStages;
+    constexpr int G = kExGroup, CH = kExAsyncCH;
     static_assert(CH == 128, "one 16-byte copy per lane, row and chunk");
     const int lane = threadIdx.x & 31;
     const float* pbk[G];
@@ -183,15 +197,7 @@ IC_DEVINL float warp_exact_dsq_group_async(const float* __restrict__ pa, const f
             }
         }
         __syncwarp();
-        if (lane < np) {
-            const int n4 = (min(CH, d4 - c * CH)) >> 2;
-            const float4* src = reinterpret_cast<const float4*>(stg + (lane + 1) * kExAsyncRow);
-#pragma unroll 4
-            for (int i = 0; i < n4; ++i) {
-                const float4 v = src[i];
-                sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
-            }
-        }
+        if (lane < np) sum = ex_chain_sum(reinterpret_cast<const float4*>(stg + (lane + 1) * kExAsyncRow), (min(CH, d4 - c * CH)) >> 2, sum);
         __syncwarp();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -58,9 +58,22 @@ constexpr int kRcpTab = 1024;
 #ifndef IC_EXACT_SYNC
 #define IC_EXACT_SYNC 0
 #endif
-// floats of shared memory per warp: the exact phase's cp.async ring (or one register-staged chunk)
-constexpr int kWarpStage = kExAsyncFloats > kExChunk ? kExAsyncFloats : kExChunk;
-static_assert(kWarpStage % 4 == 0 && kWarpStage >= kExGroup * kExStride, "per-warp staging memory");
+// Exact phase: an iteration has about one group of four pairs per 2.5 warps (config C), and what bounds the phase is how
+// many bytes of centroid rows are in flight -- so the first kExWarps warps of a block take the groups, each with a ring of
+// kExStages chunks (2 640 bytes each) in flight, instead of all sixteen with a shallow one.
+#ifndef IC_PROF_EXACT  // debug: the selection phase's profile slots carry block 0 / warp 0's exact-phase group timing instead
+#define IC_PROF_EXACT 0
+#endif
+#ifndef IC_EX_STAGES
+#define IC_EX_STAGES 6
+#endif
+#ifndef IC_EX_WARPS
+#define IC_EX_WARPS 8
+#endif
+constexpr int kExStages = IC_EX_STAGES, kExWarps = IC_EX_WARPS;
+constexpr int kExRing = kExStages * kExAsyncStage > kExGroup * kExStride ? kExStages * kExAsyncStage : kExGroup * kExStride;  // floats per ring
+constexpr int kExSmemFloats = kExWarps * kExRing + kBW * kExChunk;  // + one register-staged chunk per warp (single pairs)
+static_assert(kExRing % 4 == 0 && kExWarps >= 1 && kExWarps <= kBW, "exact phase staging memory");
 constexpr int kVR = 1;         // rows per thread whose lists are loaded ahead of the update pass
 
 // counters[slot][*]
@@ -244,7 +257,7 @@ IC_DEVINL RowHead row_head(uint4 e0, uint4 e1, uint32_t more_bits, uint32_t key_
 size_t merge_batch_smem_bytes(int64_t n) {
     const size_t n4 = static_cast<size_t>((n + 3) / 4 * 4);
     const size_t bitmap = ((n4 + 31) / 32 + 3) / 4 * 4 * sizeof(uint32_t);
-    return bitmap + sizeof(float) * kBW * kWarpStage;  // + the warps' staging buffers (exact phase; ring of the rows phase)
+    return bitmap + sizeof(float) * kExSmemFloats;  // + the exact phase's rings and staging buffers
 }
 static int64_t batch_window_cols(int64_t n) {  // at most kBatchMaxWin windows per row: <= 4 partial lists per lane in the fold
     const int64_t n4 = (n + 3) / 4 * 4;
@@ -302,8 +315,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
 
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     // exact phase: squared differences of one chunk of up to kExGroup pairs per warp
-    float (*const s_ex)[kWarpStage] = reinterpret_cast<float (*)[kWarpStage]>(dyn_smem);
-    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kBW * kWarpStage);  // merged-slot bitmap of the current batch
+    float (*const s_ex)[kExRing] = reinterpret_cast<float (*)[kExRing]>(dyn_smem);  // rings of the first kExWarps warps
+    float (*const s_one)[kExChunk] = reinterpret_cast<float (*)[kExChunk]>(dyn_smem + sizeof(float) * kExWarps * kExRing);
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(float) * kExSmemFloats);  // merged-slot bitmap of the current batch
     const int32_t n_words = (n4 + 31) >> 5;
 
     __shared__ uint64_t s_red[kBW];
@@ -1377,7 +1391,10 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 __syncthreads();
             }
             const int32_t n_groups = s_upre[min(m, kMaxBatch)];
-            for (int32_t u = gw; u < n_groups; u += GW) {
+            for (int32_t u = gw; warp < kExWarps && u < n_groups; u += static_cast<int32_t>(G) * kExWarps) {
+#if IC_PROF_EXACT
+                const long long tx0 = timed ? clock64() : 0;
+#endif
                 int32_t lo_j = 0, hi_j = m;  // largest j with s_upre[j] <= u
                 while (hi_j - lo_j > 1) {
                     const int32_t mid = (lo_j + hi_j) >> 1;
@@ -1396,13 +1413,26 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                     decode(ent.x, col, key_b, size_b);
                     pb = st.cen + static_cast<int64_t>(key_b) * st.ldc;
                 }
+#if IC_PROF_EXACT
+                const long long tx1 = timed ? clock64() : 0;
+#endif
 #if IC_EXACT_SYNC  // (A/B: register-staged chunks, one in flight)
                 const float dsq = warp_exact_dsq_group<kExGroup, kExChunk>(pa, pb, np, d4, s_ex[warp]);
 #else
-                const float dsq = warp_exact_dsq_group_async(pa, pb, np, d4, s_ex[warp]);
+                const float dsq = warp_exact_dsq_group_async<kExStages>(pa, pb, np, d4, s_ex[warp]);
+#endif
+#if IC_PROF_EXACT
+                const long long tx2 = timed ? clock64() : 0;
 #endif
                 if (lane < np) finish(j, col, key_b, size_b, lwb, p0 + lane, dsq);
                 if (lane == 0) my_exact += np;
+#if IC_PROF_EXACT
+                if (timed) {
+                    c_sel[1] += tx1 - tx0;
+                    c_sel[2] += tx2 - tx1;
+                    c_sel[3] += 1;
+                }
+#endif
             }
             // pairs beyond a merge's queue (rare): one at a time
             for (int32_t q = gw; q < nx; q += GW) {
@@ -1411,7 +1441,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 const float* pa = st.cen + static_cast<int64_t>(kbase + t - m + j) * st.ldc;
                 int32_t size_b, col, key_b;
                 decode(ent.y, col, key_b, size_b);
-                const float dsq = warp_exact_dsq(pa, st.cen + static_cast<int64_t>(key_b) * st.ldc, d4, s_ex[warp]);
+                const float dsq = warp_exact_dsq(pa, st.cen + static_cast<int64_t>(key_b) * st.ldc, d4, s_one[warp]);
                 if (lane == 0) {
                     finish(j, col, key_b, size_b, ent.z, ent.w, dsq);
                     ++my_exact;
@@ -1438,9 +1468,11 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             c_ph[4] += tq1 - tp3;
             c_ph[7] += tp4 - tq3;
             c_sel[0] += ts1 - tp2;
+#if !IC_PROF_EXACT
             c_sel[1] += ts2 - ts1;
             c_sel[2] += ts3 - ts2;
             c_sel[3] += n_cand_prof;
+#endif
         }
     }
     if (timed) {  // accumulated over the launches of one clustering (the host zeroes them when it starts)
