@@ -131,6 +131,7 @@ struct ic_ctx {
     double compact_ratio = 0.7, compact_ratio_alloc = -1.0;  // option "compact_ratio": compact when live <= ratio * slots
     int mirror_init = 1;          // option "mirror_init": fill the upper triangle after a lower-triangle-only K1
     int64_t compact_min = 4096;   // no compaction below this many slots
+    int compact_tiles = 1;        // option "compact_tiles": one-pass tile kernel (one process); 0: compact_rows + mirror_lower
     int64_t n_cur = 0, ld_cur = 0;
     float* dm_cur = nullptr;      // dm (buffer A) or dm_b
     float* dm_b = nullptr;
@@ -1077,12 +1078,16 @@ int do_compact(ic_ctx* ctx) {
         IC_CUDA(launch_compact_state(av, ctx->stream));
     }
     a.ks_old = ctx->ks;
-    IC_CUDA(launch_compact_rows(a, ctx->stream));
-    if (real) {  // every rank's lower triangle is complete before anyone mirrors it
-        ++ctx->barrier_seq;
-        IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
+    if (!real && ctx->compact_tiles) {  // one process: old and new matrix are contiguous -- both triangles in one pass
+        IC_CUDA(launch_compact_tiles(a, ctx->stream));
+    } else {
+        IC_CUDA(launch_compact_rows(a, ctx->stream));
+        if (real) {  // every rank's lower triangle is complete before anyone mirrors it
+            ++ctx->barrier_seq;
+            IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
+        }
+        IC_CUDA(launch_mirror_lower(a, ctx->stream));
     }
-    IC_CUDA(launch_mirror_lower(a, ctx->stream));
     ctx->stats.kernel_launches += 4 + NL;
     int32_t found = 0;
     IC_CUDA(cudaMemcpyAsync(&found, ctx->nlive_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1122,9 +1127,9 @@ int sync_loop_result(ic_ctx* ctx) {
             ctx->ms_loop_kernel += ev_ms(ctx->ev[10], ctx->ev[11]);
             ctx->loop_launch_pending = false;
         }
-        if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
-        if (ctx->h_ctl[CTL_ERROR] != 0)
+        if (ctx->h_ctl[CTL_ERROR] != 0)  // (4: a grid / cross-rank barrier was given up -- the kernel left without hanging)
             return fail(ctx, IC_ERR_INTERNAL, "merge loop protocol error " + std::to_string(ctx->h_ctl[CTL_ERROR]));
+        if (ctx->h_ctl[CTL_DONE] != 1) return fail(ctx, IC_ERR_INTERNAL, "merge loop did not complete");
         ctx->n_live = ctx->h_ctl[CTL_N_LIVE];
         ctx->n_merges = ctx->h_ctl[CTL_N_MERGES];
         ctx->exhausted = ctx->h_ctl[CTL_EXHAUSTED];
@@ -1520,6 +1525,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
         ctx->compact_ratio = value;
     } else if (k == "mirror_init") {
         ctx->mirror_init = value != 0.0;
+    } else if (k == "compact_tiles") {
+        ctx->compact_tiles = value != 0.0;
     } else if (k == "compact_min") {
         ctx->compact_min = std::max<int64_t>(64, static_cast<int64_t>(value));
     } else if (k == "delta_cut_fallback") {

@@ -323,6 +323,8 @@ cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap,
 cudaError_t launch_compact_state(const CompactArgs& a, cudaStream_t s);  // slot tables, partner lists, centroid rows
 cudaError_t launch_compact_rows(const CompactArgs& a, cudaStream_t s);   // lower triangle of the new matrix (+ diagonal, padding)
 cudaError_t launch_mirror_lower(const CompactArgs& a, cudaStream_t s);   // upper triangle <- lower triangle
+// one process (contiguous matrices): both triangles of the new matrix in one pass, 64 x 64 tiles
+cudaError_t launch_compact_tiles(const CompactArgs& a, cudaStream_t s);
 
 // ---- near lists (near.cu): every lower-key partner of a row whose stored value is <= horizon ----------------------
 // meta[slot] = {offset into the pool, count | kNearFarBit if partners beyond the horizon may exist}; .y == -1: the row has no

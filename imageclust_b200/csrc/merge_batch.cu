@@ -94,20 +94,44 @@ IC_DEVINL int32_t warp_reserve(int32_t* counter, int cnt, int lane) {
     return base + inc - cnt;
 }
 
+// A barrier that is not completed after kBarSpin polls (seconds: a protocol bug, or a peer that died) must neither hang
+// the GPU nor poison the CUDA context (__trap() does: every later call of the process fails).  The block that gives up
+// raises an abort word next to the barrier counter and reports CTL_ERROR = 4; every poll loop looks at the word now and
+// then; a block that sees it leaves the kernel (all its threads, right after the barrier's __syncthreads).  The host finds
+// CTL_ERROR / no CTL_DONE and returns IC_ERR_INTERNAL; the context stays usable.
+constexpr int kBarAbortWord = 40;  // (the barrier scratch is 64 words, zeroed by the host before every launch)
+IC_DEVINL bool bar_give_up(uint32_t* bar, int32_t* ctl, uint32_t spins) {
+    if ((spins & 0x3FFu) != 0u) return false;
+    if (spins <= kBarSpin && ld_acquire_u32(bar + kBarAbortWord) == 0u) return false;
+    atomicExch(bar + kBarAbortWord, 1u);
+    atomicExch(ctl + CTL_ERROR, 4);
+    return true;
+}
+#define IC_BAR_EXIT_IF(flag)                  \
+    do {                                      \
+        if (flag) asm volatile("exit;");      \
+    } while (0)
+
 // grid-wide barrier on one monotone counter: arrive with a release reduction, poll with acquire loads
-IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* wait_acc = nullptr) {
+IC_DEVINL void grid_sync(uint32_t* bar, int32_t* ctl, uint32_t& phase, uint32_t G, long long* wait_acc = nullptr) {
+    __shared__ int s_abort;
     __syncthreads();
     ++phase;
     if (threadIdx.x == 0) {
         const long long t_arrive = wait_acc ? clock64() : 0;
+        s_abort = 0;
         red_release_add_u32(bar, 1u);
         const uint32_t target = phase * G;
         uint32_t spins = 0;
         while (ld_acquire_u32(bar) < target)
-            if (++spins > kBarSpin) __trap();  // a protocol bug must not hang the GPU box
+            if (bar_give_up(bar, ctl, ++spins)) {
+                s_abort = 1;
+                break;
+            }
         if (wait_acc) *wait_acc += clock64() - t_arrive;
     }
     __syncthreads();
+    IC_BAR_EXIT_IF(s_abort);
 }
 
 // Barrier of all blocks of ALL ranks (sharded runs): every block fences its stores to peer memory at system scope and
@@ -118,18 +142,23 @@ IC_DEVINL void grid_sync(uint32_t* bar, uint32_t& phase, uint32_t G, long long* 
 // fence after it has acquired all arrivals is cumulative).
 IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& xcount, uint32_t G, uint32_t bid, bool remote_stores,
                                int publish_slot, long long* wait_acc = nullptr) {
+    __shared__ int s_abort_r;
     __syncthreads();
     ++phase;
     ++xcount;
     if (threadIdx.x == 0) {
         const long long t_arrive = wait_acc ? clock64() : 0;
+        s_abort_r = 0;
         if (remote_stores) asm volatile("fence.acq_rel.sys;" ::: "memory");
         red_release_add_u32(st.bar, 1u);
         uint32_t spins = 0;
         if (bid == 0) {
             const uint32_t target = phase * G;
             while (ld_acquire_u32(st.bar) < target)
-                if (++spins > kBarSpin) __trap();
+                if (bar_give_up(st.bar, st.ctl, ++spins)) {
+                    s_abort_r = 1;
+                    break;
+                }
             const unsigned long long seq = (static_cast<unsigned long long>(st.gen) << 32) | xcount;
             if (publish_slot >= 0) {  // this rank's minima and candidate count of the iteration go into every rank's box
                 const uint8_t* acc = st.xbox[st.rank] + kBatchXAccum;
@@ -171,10 +200,10 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
             for (int q = 0; q < st.n_ranks; ++q) {
                 if (q == st.rank) continue;
                 unsigned long long seen = 0;
-                for (spins = 0;; ++spins) {
+                for (spins = 1; s_abort_r == 0; ++spins) {
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(reinterpret_cast<unsigned long long*>(st.xbox[st.rank]) + q) : "memory");
                     if (seen >= seq) break;
-                    if (spins > kBarSpin) __trap();  // a missing peer must not hang the GPU box
+                    if (bar_give_up(st.bar, st.ctl, spins)) s_abort_r = 1;  // a missing peer must not hang the GPU box
                 }
             }
             // acquire at system scope (the flags were polled with relaxed loads), then release the rank's blocks at gpu scope:
@@ -184,11 +213,15 @@ IC_DEVINL void grid_sync_ranks(const BatchState& st, uint32_t& phase, uint32_t& 
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(st.bar + 32), "r"(phase) : "memory");
         } else {
             while (ld_acquire_u32(st.bar + 32) < phase)
-                if (++spins > kBarSpin) __trap();
+                if (bar_give_up(st.bar, st.ctl, ++spins)) {
+                    s_abort_r = 1;
+                    break;
+                }
         }
         if (wait_acc) *wait_acc += clock64() - t_arrive;
     }
     __syncthreads();
+    IC_BAR_EXIT_IF(s_abort_r);
 }
 
 IC_DEVINL uint64_t block_min_u64(uint64_t v, uint64_t* s_red) {
@@ -371,7 +404,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         const int2 k = __ldcg(st.ks + r);
         st.lsize[r] = (r < n && k.x >= 0) ? k.y : 0;
     }
-    grid_sync(st.bar, phase, G);
+    grid_sync(st.bar, st.ctl, phase, G);
 
     for (uint32_t it = 0;; ++it) {
         const int sl = static_cast<int>(it % 3u), sl1 = static_cast<int>((it + 1u) % 3u), sl2 = static_cast<int>((it + 2u) % 3u);
@@ -705,9 +738,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             const int32_t rows = min(Q - base, kBatchMaxDry);
             const int64_t units = static_cast<int64_t>(rows) * nwin;
             for (int64_t u = gw; u < units; u += GW) scan_window_unit(base, rows, u, false);
-            if (base + kBatchMaxDry < Q) grid_sync(st.bar, phase, G);  // the partial buffers are reused
+            if (base + kBatchMaxDry < Q) grid_sync(st.bar, st.ctl, phase, G);  // the partial buffers are reused
         }
-        grid_sync(st.bar, phase, G, timed ? &c_ph[5] : nullptr);
+        grid_sync(st.bar, st.ctl, phase, G, timed ? &c_ph[5] : nullptr);
         const long long tp1 = timed ? clock64() : 0;
 
         // ================= P2: heads and stoppers; candidates go to one global list =================
@@ -804,7 +837,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         if (kMulti)
             grid_sync_ranks(st, phase, xcount, G, bid, p2_remote != 0, sl, timed ? &c_ph[6] : nullptr);
         else
-            grid_sync(st.bar, phase, G, timed ? &c_ph[6] : nullptr);
+            grid_sync(st.bar, st.ctl, phase, G, timed ? &c_ph[6] : nullptr);
         const long long tp2 = timed ? clock64() : 0;
 
         // ================= P3: the batch =================
@@ -1336,7 +1369,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         // WardDistance(centroid k, centroid of the new cluster), clustering.go:83-86; the new centroid (clustering.go:39) is
         // formed on the fly from the two stored ones, which are only overwritten after the barrier that ends this phase.
         if (exact) {
-            grid_sync(st.bar, phase, G);  // gpu scope: every queue is local to its rank
+            grid_sync(st.bar, st.ctl, phase, G);  // gpu scope: every queue is local to its rank
             const long long te0 = timed ? clock64() : 0;
             const int32_t nx = min(__ldcg(st.counters + sl * 4 + CN_XQ), st.xq_cap);
             const float d_last = __uint_as_float(s_d[m > 0 ? m - 1 : 0]);
@@ -1457,7 +1490,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         if (kMulti)
             grid_sync_ranks(st, phase, xcount, G, bid, __syncthreads_or(wrote_remote ? 1 : 0) != 0, -1);
         else
-            grid_sync(st.bar, phase, G);
+            grid_sync(st.bar, st.ctl, phase, G);
         m_prev = m;
         if (timed) {
             const long long tp4 = clock64();

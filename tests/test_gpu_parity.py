@@ -625,17 +625,20 @@ def test_compaction_does_not_change_the_trace(eng, knobs, ratio, mirror):
     x = synth.gaussian_mixture(9000, 96, 4, 12, seed=19)
     for exact in (0, 1):
         digests, ncomp = [], []
-        for compact in (0, 1):
+        # no compaction; the one-pass tile kernel; compact_rows + mirror_lower (what a sharded run uses)
+        for compact, tiles in ((0, 1), (1, 1), (1, 0)):
             knobs(exact=exact, compact=compact, mirror_init=mirror)
             eng.set_option("compact_ratio", ratio)
+            eng.set_option("compact_tiles", tiles)
             try:
                 res = eng.cluster(x, 4, 12)
             finally:
                 eng.set_option("compact_ratio", 0.7)
+                eng.set_option("compact_tiles", 1)
             digests.append(_trace_digest(eng.merge_trace()))
             ncomp.append(res.stats["n_compactions"])
-        assert digests[0] == digests[1]
-        assert ncomp[0] == 0 and ncomp[1] >= 1
+        assert digests[0] == digests[1] == digests[2]
+        assert ncomp[0] == 0 and ncomp[1] >= 1 and ncomp[2] == ncomp[1]
 
 
 @pytest.mark.parametrize("n,d,mn,mx,ranks", [(9000, 96, 4, 12, 1), (6000, 2048, 10, 50, 1), (5000, 32, 6, 8, 1), (6000, 64, 4, 12, 3)])
