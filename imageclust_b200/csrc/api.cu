@@ -105,6 +105,7 @@ struct ic_ctx {
     bool dm_is_reference = false; // the initial matrix already holds the reference's values (gram_mode 1)
     // delta_cut = 0: batches are taken optimistically and CHECKED (every pair a batch creates is compared with the batch's
     // later members, CTL_ORDER_VIOL); a failed check restarts the clustering with delta_cut_fallback
+    double hz_factor_first = 0.0;  // option "horizon_factor_first": factor of the first horizon (0: the same as later ones)
     double hz_factor = 1.18, eps_filter = 3e-5, delta_cut = 0.0, delta_cut_fallback = 1e-5, abs_slack_opt = -1.0;
     double delta_cut_cur = 0.0;
     int32_t n_restarts = 0;
@@ -997,7 +998,7 @@ int raise_horizon(ic_ctx* ctx) {
     if (!first && ctx->n_merges - ctx->merges_at_raise < 64)
         ctx->hz_factor_cur = std::min(ctx->hz_factor_cur * ctx->hz_factor_cur, 1e6);
     else
-        ctx->hz_factor_cur = ctx->hz_factor;
+        ctx->hz_factor_cur = (first && ctx->hz_factor_first > 1.0) ? ctx->hz_factor_first : ctx->hz_factor;
     const double base = std::max(static_cast<double>(h), ctx->horizon);
     const double hi = ctx->hz_factor_cur * (base * (1.0 + 2.0 * ctx->eps_filter) + 2.0 * ctx->abs_slack);
     if (!(first && ctx->dm_is_reference)) {
@@ -1506,6 +1507,9 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
     } else if (k == "horizon_factor") {
         if (!(value > 1.0)) return fail(ctx, IC_ERR_BAD_ARG, "horizon_factor must be > 1");
         ctx->hz_factor = value;
+    } else if (k == "horizon_factor_first") {
+        if (!(value == 0.0 || value > 1.0)) return fail(ctx, IC_ERR_BAD_ARG, "horizon_factor_first must be 0 or > 1");
+        ctx->hz_factor_first = value;
     } else if (k == "eps_filter") {
         if (!(value >= 0.0 && value < 0.1)) return fail(ctx, IC_ERR_BAD_ARG, "eps_filter must be in [0, 0.1)");
         ctx->eps_filter = value;
