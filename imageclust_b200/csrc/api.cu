@@ -941,7 +941,7 @@ int refine_band(ic_ctx* ctx, double lo, double hi, int32_t min_row_key) {
     return IC_OK;
 }
 
-// Near lists of the resident rows for the current horizon (near.cu): two sweeps of the live matrix.
+// Near lists of the resident rows for the current horizon (near.cu): one sweep of the live matrix.
 int build_near(ic_ctx* ctx, bool mark_dry) {
     if (!ctx->near_meta || !ctx->near_opt) {  // no near lists: stale bounds are replaced by full row scans
         if (mark_dry) {
@@ -951,7 +951,7 @@ int build_near(ic_ctx* ctx, bool mark_dry) {
         }
         return IC_OK;
     }
-    Nvtx range("ic near lists (two sweeps)");
+    Nvtx range("ic near lists (one sweep)");
     const double t0 = now_ms();
     NearArgs a{};
     a.dm = ctx->dm_cur;
@@ -967,7 +967,7 @@ int build_near(ic_ctx* ctx, bool mark_dry) {
     a.pool_cap = ctx->near_pool_cap;
     a.cursor = ctx->near_cursor;
     IC_CUDA(launch_near_build(a, ctx->stream));
-    ctx->stats.kernel_launches += 3;
+    ctx->stats.kernel_launches += 1;
     if (mark_dry) {  // bounds at the old horizon are stale: every live row re-selects its list (cheap: from its near list)
         IC_CUDA(launch_mark_rows_dry(ctx->gkey, ctx->nn_more, a.r_lo, a.r_hi, ctx->stream));
         ctx->stats.kernel_launches += 1;

@@ -31,9 +31,12 @@ __global__ void __launch_bounds__(256) init_centroids_kernel(const float* __rest
     }
 }
 
-// one block per row; 16-byte loads of the row and of the keys.  Two passes over the row (the second one hits L2): count the
-// pairs in the band, reserve ONE contiguous range of the queue for the row, fill it -- consecutive queue entries then share
-// their row, so the evaluation kernel runs eight summation chains per warp and reads the row's centroid once per eight pairs.
+// one block per row; 16-byte loads of the row and of the keys.  The columns of the row's pairs in the band are stashed in
+// shared memory, then ONE contiguous range of the queue is reserved for the row and filled from the stash -- consecutive
+// queue entries share their row, so the evaluation kernel runs eight summation chains per warp and reads the row's centroid
+// once per eight pairs.  A row with more than kStash pairs in the band is swept a second time (rare; the second sweep of
+// every row, which this replaces, did not stay in L2: 57 GB of DRAM reads for the three sweeps of config C).
+constexpr int kStash = 2048;
 __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_constant__ RefineArgs a) {
     const int32_t r = a.row0 + static_cast<int32_t>(blockIdx.x);
     if (r >= a.row1) return;
@@ -46,6 +49,7 @@ __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_cons
     const float lo = static_cast<float>(a.lo), hi = static_cast<float>(a.hi);
     const bool lo_open = a.lo < 0.0;  // band starts below every value
     __shared__ int32_t s_cnt, s_base, s_total;
+    __shared__ int32_t s_stash[kStash];
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int32_t u_pad = ((u_end + kColT * 4 - 1) / (kColT * 4)) * (kColT * 4);
@@ -67,22 +71,29 @@ __global__ void __launch_bounds__(kColT) refine_collect_kernel(const __grid_cons
                 int32_t pos = 0;
                 const int leader = __ffs(mask) - 1;
                 if (lane == leader) pos = atomicAdd(&s_cnt, __popc(mask));
-                pos = __shfl_sync(0xffffffffu, pos, leader);
-                if (pass == 1 && hit) {
-                    const int32_t idx = s_base + pos + __popc(mask & ((1u << lane) - 1u));
-                    if (idx < a.cap) a.q[idx] = make_int2(r, u0 + e);
+                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(mask & ((1u << lane) - 1u));
+                if (hit) {
+                    if (pass == 0) {
+                        if (pos < kStash) s_stash[pos] = u0 + e;
+                    } else if (s_base + pos < a.cap) {
+                        a.q[s_base + pos] = make_int2(r, u0 + e);
+                    }
                 }
             }
         }
+        if (pass == 1) return;
         __syncthreads();
-        if (pass == 0) {
-            if (threadIdx.x == 0) {
-                s_total = s_cnt;
-                s_base = s_cnt > 0 ? atomicAdd(a.cnt, s_cnt) : 0;
-                s_cnt = 0;
-            }
-            __syncthreads();
-            if (s_total == 0) return;  // (uniform) nothing of this row lies in the band
+        if (threadIdx.x == 0) {
+            s_total = s_cnt;
+            s_base = s_cnt > 0 ? atomicAdd(a.cnt, s_cnt) : 0;
+            s_cnt = 0;
+        }
+        __syncthreads();
+        if (s_total == 0) return;  // (uniform) nothing of this row lies in the band
+        if (s_total <= kStash) {
+            for (int32_t i = threadIdx.x; i < s_total; i += kColT)
+                if (s_base + i < a.cap) a.q[s_base + i] = make_int2(r, s_stash[i]);
+            return;
         }
     }
 }

@@ -110,7 +110,15 @@ void ic_pinned_free(void *p);
  * batched loop -- every iteration takes all merges that are provably the next ones of the reference's sequence, on one
  * GPU or across the ranks of a sharded context; 0: one merge per iteration, also what "virtual_ranks" runs; set it
  * before ic_load, it cannot change once ic_initial_distances has run), "no_replica",
- * "profile_loop", "verbose" */
+ * "profile_loop", "verbose".
+ * Reference arithmetic (none of these may change the result, only the time):
+ * "exact" (0/1, default 1: every stored value at or below the horizon is the reference's own WardDistance),
+ * "horizon_factor" (> 1, default 1.18) / "horizon_factor_first" (0 = the same), "eps_filter" (3e-5), "delta_cut" (0 =
+ * optimistic batches with the order check) / "delta_cut_fallback" (1e-5, used after a failed check), "refill_at" (1/2),
+ * "near_lists" (0/1), "abs_slack".
+ * K4: "compact" (0/1), "compact_ratio" (0.25..0.9, default 0.7), "compact_min" (no compaction below this many slots,
+ * default 4096), "compact_tiles" (1: one-pass tile kernel on an unsharded context; 0: the two-pass path sharded runs use),
+ * "mirror_init" (mirror pass after K1). */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 
 /* ---- CalculateOptimalClusters, clustering.go:168-186 (host, exact) ---- */
