@@ -52,6 +52,10 @@ constexpr uint32_t kBarSpin = 1u << 24;
 #ifndef IC_UPD_COLS
 #define IC_UPD_COLS 256
 #endif
+#ifndef IC_UPD_GROUP
+#define IC_UPD_GROUP 1
+#endif
+constexpr int kUpdGroup = IC_UPD_GROUP;  // merges of one update unit (they share the unit's slot-table chunk)
 constexpr int kUpdCols = IC_UPD_COLS;  // columns of one update unit (one warp: 4 x 32 lanes x 4, all loads in flight at once)
 constexpr int kRcpTab = 1024;
 // exact phase: 1 = register-staged chunks (one in flight; A/B against the cp.async ring of exact.cuh)
@@ -1147,9 +1151,24 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
             // (multiples of 4: a rank whose block starts beyond the last slot has r_lo == n, which need not be one)
             const int32_t c_lo = kMulti ? min(n4, st.rank * C) : 0, c_hi = kMulti ? min(n4, c_lo + C) : n4;
             const int32_t n_chunks = (c_hi - c_lo + kUpdCols - 1) / kUpdCols;
-            const int64_t units = static_cast<int64_t>(m) * n_chunks;
-            for (int64_t u = gw; u < units; u += GW) {
-                const int32_t ch = static_cast<int32_t>(u / m), i = static_cast<int32_t>(u - static_cast<int64_t>(ch) * m);
+            // a unit = kUpdGroup consecutive merges of the batch x kUpdCols columns: the slot-table chunk ({key, size} of the
+            // columns: a third of the phase's L2 sectors when every merge fetched its own) is loaded once per unit
+            const int32_t mg = (m + kUpdGroup - 1) / kUpdGroup;
+            const int32_t units = mg * n_chunks;
+            for (int32_t u = gw; u < units; u += GW) {
+              const int32_t ch = u / mg, i_first = (u - ch * mg) * kUpdGroup;
+              constexpr int kI = kUpdCols / 128;
+              int4 k01[kI], k23[kI];
+#pragma unroll
+              for (int x = 0; x < kI; ++x) {
+                  const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
+                  k01[x] = k23[x] = make_int4(-1, 0, -1, 0);
+                  if (c0 < c_hi) {
+                      k01[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0));
+                      k23[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0 + 2));
+                  }
+              }
+              for (int32_t i = i_first; i < min(m, i_first + kUpdGroup); ++i) {
                 const int32_t a = s_a[i], b = s_b[i], sa = s_sa[i], sb = s_sb[i], snew = sa + sb;
                 const int32_t ka = s_ka[i], kb = s_kb[i];
                 if (kMulti && (b < r_lo || b >= r_hi)) wrote_remote = true;  // this unit's slice of the new row goes to a peer
@@ -1157,17 +1176,12 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                 const double sad = static_cast<double>(sa), sbd = static_cast<double>(sb), dabd = static_cast<double>(dab);
                 const float* row_a = row_of(a);
                 float* row_b = row_of(b);
-                constexpr int kI = kUpdCols / 128;
-                int4 k01[kI], k23[kI];
                 float4 va[kI], vb[kI];
 #pragma unroll
                 for (int x = 0; x < kI; ++x) {
                     const int32_t c0 = c_lo + ch * kUpdCols + x * 128 + lane * 4;
-                    k01[x] = k23[x] = make_int4(-1, 0, -1, 0);
                     va[x] = vb[x] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (c0 < c_hi) {
-                        k01[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0));
-                        k23[x] = __ldcg(reinterpret_cast<const int4*>(st.ks + c0 + 2));
                         va[x] = __ldcg(reinterpret_cast<const float4*>(row_a + c0));
                         vb[x] = __ldcg(reinterpret_cast<const float4*>(row_b + c0));
                     }
@@ -1251,6 +1265,7 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
                             if (((bits >> e) & 1u) == 0u) __stcg(row_b + c0 + e, outv[x][e]);
                     }
                 }
+              }
             }
         }
         // ---- centroids of the new clusters (MergeClusters, clustering.go:36-40): row N + t of the centroid store ----
