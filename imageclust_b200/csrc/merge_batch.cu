@@ -747,6 +747,9 @@ merge_batch_kernel(const __grid_constant__ BatchState st_param, const __grid_con
         grid_sync(st.bar, st.ctl, phase, G, timed ? &c_ph[5] : nullptr);
         const long long tp1 = timed ? clock64() : 0;
 
+        // (test hook, option loop_debug = 77: block 1 leaves in its third iteration -- the others must give the barrier up
+        // and report it, not hang: tests/test_gpu_parity.py::test_barrier_timeout_is_reported_and_the_context_survives)
+        if (prm.debug == 77 && it == 2u && bid == 1u && G > 1u) asm volatile("exit;");
         // ================= P2: heads and stoppers; candidates go to one global list =================
         int p2_remote = 0;  // this block pushed candidates into the peers' boxes
         {

@@ -655,6 +655,24 @@ def test_near_lists_do_not_change_the_trace(eng, knobs, n, d, mn, mx, ranks):
     assert digests[0] == digests[1]
 
 
+def test_barrier_timeout_is_reported_and_the_context_survives(eng, oracle):
+    """A block that never arrives at a grid barrier (test hook loop_debug = 77) must not hang the GPU or poison the CUDA
+    context: the other blocks give the barrier up after 2^24 polls, the call fails with the library's internal-error code,
+    and the same engine clusters correctly afterwards."""
+    x = synth.gaussian_mixture(3000, 64, 4, 12, seed=5)
+    o = oracle.fast_cluster(x, 4, 12, flags=0)
+    eng.set_option("loop_debug", 77)
+    try:
+        with pytest.raises(clustering.EngineError) as ei:
+            eng.cluster(x, 4, 12)
+        assert ei.value.code == _lib.IC_ERR_INTERNAL
+    finally:
+        eng.set_option("loop_debug", 0)
+    res = eng.cluster(x, 4, 12)
+    _same_trace(eng.merge_trace(), o)
+    assert same_clusters(res.clusters, o.clusters)
+
+
 def test_batched_more_disjoint_pairs_than_the_batch_capacity(eng, oracle, knobs):
     """1 500 exact duplicate pairs: every pair is a head at distance 0 and none conflicts, so far more than
     kMaxBatch (512) pairs sit below the stopper; the batch is cut to a prefix by bisection on the packed value."""
