@@ -1089,7 +1089,8 @@ int do_compact(ic_ctx* ctx) {
         }
         IC_CUDA(launch_mirror_lower(a, ctx->stream));
     }
-    ctx->stats.kernel_launches += 4 + NL;
+    // scatter + rank, one state kernel per (virtual) rank, then tiles | rows (+ rank barrier) + mirror
+    ctx->stats.kernel_launches += 2 + NL + ((!real && ctx->compact_tiles) ? 1 : (real ? 3 : 2));
     int32_t found = 0;
     IC_CUDA(cudaMemcpyAsync(&found, ctx->nlive_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     IC_CUDA(cudaStreamSynchronize(ctx->stream));
