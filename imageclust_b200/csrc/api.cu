@@ -131,6 +131,11 @@ struct ic_ctx {
     int refill_at = 2;            // option "refill_at" (1 or 2)
     double compact_ratio = 0.7, compact_ratio_alloc = -1.0;  // option "compact_ratio": compact when live <= ratio * slots
     int mirror_init = 1;          // option "mirror_init": fill the upper triangle after a lower-triangle-only K1
+    // option "fast_start": with the horizon and near lists on, the first sweep (K2) is not needed -- its only product that
+    // survives the first horizon is the global minimum, which the mirror pass after K1 collects on the way
+    int fast_start = 1;
+    uint32_t* gmin_dev = nullptr;  // [1] bits of the smallest selectable initial distance (mirror pass)
+    bool gmin_valid = false;
     int64_t compact_min = 4096;   // no compaction below this many slots
     int compact_tiles = 1;        // option "compact_tiles": one-pass tile kernel (one process); 0: compact_rows + mirror_lower
     int64_t n_cur = 0, ld_cur = 0;
@@ -237,6 +242,7 @@ void release_problem(ic_ctx* c) {
     dev_free(c->near_cursor);
     dev_free(c->slot_of_key);
     dev_free(c->dm_b);
+    dev_free(c->gmin_dev);
     dev_free(c->ks_b);
     dev_free(c->gkey_b);
     dev_free(c->nn_more_b);
@@ -710,6 +716,9 @@ int init_loop_state(ic_ctx* ctx) {
     }
     return IC_OK;
 }
+
+int raise_horizon(ic_ctx* ctx);
+int nn_init(ic_ctx* ctx);
 
 // the batched loop runs on an unsharded context whose slice state fits (it always does below ~1e6 items)
 bool use_batch(const ic_ctx* c) {
@@ -1277,6 +1286,7 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
         if (rc != IC_OK) return rc;
     }
     IC_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->gmin_valid = false;
     if (max_size >= 2) {
         const int rc = do_gram(ctx, mode);
         if (rc != IC_OK) return rc;
@@ -1303,9 +1313,15 @@ int initial_distances(ic_ctx* ctx, int mode, int64_t max_size) {
             ++ctx->barrier_seq;
             IC_CUDA(launch_rank_barrier(ctx->peer_box, ctx->shard_world, ctx->shard_rank, ctx->barrier_seq, ctx->stream));
         }
+        if (!real) {
+            if (!ctx->gmin_dev) IC_CUDA(cudaMalloc(&ctx->gmin_dev, sizeof(uint32_t) * 4));
+            IC_CUDA(cudaMemsetAsync(ctx->gmin_dev, 0xFF, sizeof(uint32_t) * 4, ctx->stream));
+            a.gmin = ctx->gmin_dev;
+        }
         IC_CUDA(launch_mirror_lower(a, ctx->stream));
         ctx->stats.kernel_launches += 1;
         ctx->dm_lower_only = false;
+        ctx->gmin_valid = !real;
     }
     IC_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
     ctx->have_dm = true;
@@ -1359,6 +1375,30 @@ void fill_stats(ic_ctx* ctx) {
     s.n_iterations = s.loop_mode ? ctx->h_ctl[CTL_ITERS] : ctx->n_merges + ctx->h_ctl[CTL_BUBBLES];
 }
 
+// Start of a resident run.  With reference arithmetic and near lists on (one GPU, batched loop) the first launch of the loop
+// only ever reports the global minimum -- the first horizon is set from it, the band below it re-evaluated, and every row's
+// list re-selected from its near list.  So the first sweep (K2: 4 bytes per pair) is skipped: the mirror pass after K1 has
+// collected the minimum, the lists start empty and "dry", and the horizon is raised right away.  Anything else: K2.
+int fast_start(ic_ctx* ctx, int64_t n_target) {
+    const bool applies = ctx->fast_start && ctx->gmin_valid && ctx->exact_on && ctx->cen != nullptr && !ctx->dm_is_reference &&
+                         use_batch(ctx) && ctx->shard_world <= 1 && ctx->vranks <= 1 && ctx->near_meta != nullptr &&
+                         ctx->near_opt != 0 && ctx->n > n_target;
+    if (!applies) return nn_init(ctx);
+    uint32_t gmin = 0xFFFFFFFFu;
+    IC_CUDA(cudaMemcpyAsync(&gmin, ctx->gmin_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (gmin >= 0x7F7FFFFFu) return nn_init(ctx);  // (>= MaxFloat32) nothing selectable: the loop reports exhaustion the usual way
+    Nvtx range("ic start without the first sweep");
+    int rc = init_loop_state(ctx);
+    if (rc != IC_OK) return rc;
+    IC_CUDA(launch_init_lists_dry(ctx->nn, ctx->nn_more, static_cast<int32_t>(ctx->n), ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    IC_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->have_nn = true;
+    ctx->h_ctl[CTL_NEXT_DIST] = static_cast<int32_t>(gmin);
+    return raise_horizon(ctx);
+}
+
 int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offsets, int32_t* members,
                  int32_t* n_clusters, ic_stats* stats, double t_wall0) {
     if (!ctx->loaded) return fail(ctx, IC_ERR_STATE, "no matrix loaded");
@@ -1373,7 +1413,7 @@ int run_resident(ic_ctx* ctx, int64_t min_size, int64_t max_size, int32_t* offse
         ctx->prepped = ctx->prepped_i8 = false;  // K0 is part of the path: redo it on every run
         rc = initial_distances(ctx, ctx->gram_mode, max_size);
         if (rc != IC_OK) return rc;
-        rc = nn_init(ctx);
+        rc = fast_start(ctx, n_target);  // (K2 only if the start without it does not apply)
         if (rc != IC_OK) return rc;
         rc = run_loop(ctx, n_target, max_size, -1);
         if (rc != IC_OK) return rc;
@@ -1528,6 +1568,8 @@ int ic_set_option(ic_ctx* ctx, const char* name, double value) {
     } else if (k == "compact_ratio") {
         if (!(value >= 0.25 && value <= 0.9)) return fail(ctx, IC_ERR_BAD_ARG, "compact_ratio must be in [0.25, 0.9]");
         ctx->compact_ratio = value;
+    } else if (k == "fast_start") {
+        ctx->fast_start = value != 0.0;
     } else if (k == "mirror_init") {
         ctx->mirror_init = value != 0.0;
     } else if (k == "compact_tiles") {

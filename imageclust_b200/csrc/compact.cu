@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a, 
     const int32_t j_lo = bj * kMT, j_hi = j_lo + kMT;
     if (j_hi <= a.row0 || j_lo >= a.row1) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 float4 across, 16 rows per pass
+    uint32_t my_min = 0xFFFFFFFFu;
 #pragma unroll
     for (int r = ty; r < kMT; r += 16) {
         const int32_t i = bi * kMT + r, j0 = bj * kMT + tx * 4;
@@ -167,6 +168,16 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a, 
         tile[r][tx * 4 + 1] = v.y;
         tile[r][tx * 4 + 2] = v.z;
         tile[r][tx * 4 + 3] = v.w;
+        if (a.gmin != nullptr) {  // smallest selectable value of the lower triangle (what the first sweep's minimum head would be)
+            const float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j0 + e < i && i < a.n_new && __float_as_uint(vs[e]) < kMaxFloatBits) my_min = min(my_min, __float_as_uint(vs[e]));
+        }
+    }
+    if (a.gmin != nullptr) {
+        my_min = __reduce_min_sync(0xffffffffu, my_min);
+        if ((threadIdx.x & 31) == 0 && my_min != 0xFFFFFFFFu) atomicMin(a.gmin, my_min);
     }
     __syncthreads();
 #pragma unroll

@@ -316,6 +316,7 @@ struct CompactArgs {
     const int2* near_meta_old;              // near lists follow their rows (nullptr: not in use)
     int2* near_meta_new;
     int32_t* slot_of_key;                   // rewritten for the live clusters' new slots
+    uint32_t* gmin;                         // mirror pass: atomicMin of the selectable lower-triangle values' bits (or nullptr)
 };
 // newslot / oldslot from the live keys (ascending); *n_live_out = live clusters found
 cudaError_t launch_compact_map(const SlotKS* ks, int32_t n_old, int32_t* keymap, int32_t key_cap, int32_t* newslot,
@@ -345,6 +346,7 @@ struct NearArgs {
 cudaError_t launch_slot_of_key_init(int32_t* sok, int32_t n, int32_t cap, cudaStream_t s);  // sok[k] = k for items, -1 above
 cudaError_t launch_near_build(const NearArgs& a, cudaStream_t s);  // count sweep, scan, fill sweep
 cudaError_t launch_mark_rows_dry(const int32_t* gkey, int32_t* nn_more, int32_t r_lo, int32_t r_hi, cudaStream_t s);
+cudaError_t launch_init_lists_dry(SlotNN* nn, int32_t* nn_more, int32_t n, cudaStream_t s);  // no lists: every row rebuilt before use
 
 // device-side barrier of the P single-GPU processes (one lane per peer, flags in the rank mailboxes)
 cudaError_t launch_rank_barrier(void* const* rankbox, int n_ranks, int rank, uint64_t seq, cudaStream_t s);

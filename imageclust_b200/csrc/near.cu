@@ -105,7 +105,21 @@ __global__ void __launch_bounds__(256) mark_rows_dry_kernel(const int32_t* __res
     const int32_t r = r_lo + static_cast<int32_t>(blockIdx.x) * 256 + threadIdx.x;
     if (r < r_hi && gkey[r] >= 0) nn_more[r] |= 3;
 }
+// no partner lists yet: every row is rebuilt (from its near list) before it is used -- the start without a first sweep
+__global__ void __launch_bounds__(256) init_lists_dry_kernel(uint4* __restrict__ nn, int32_t* __restrict__ nn_more, int32_t n) {
+    const int32_t r = static_cast<int32_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (r >= n) return;
+#pragma unroll
+    for (int x = 0; x < kNNK; ++x) nn[static_cast<int64_t>(r) * kNNK + x] = make_uint4(kNoPartner, kNoPartner, kNoPartner, 0u);
+    nn_more[r] = 3;  // kMoreBit | kDryBit
+}
 }  // namespace
+
+cudaError_t launch_init_lists_dry(SlotNN* nn, int32_t* nn_more, int32_t n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    init_lists_dry_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4*>(nn), nn_more, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_slot_of_key_init(int32_t* sok, int32_t n, int32_t cap, cudaStream_t s) {
     if (cap <= 0) return cudaSuccess;

@@ -118,7 +118,8 @@ void ic_pinned_free(void *p);
  * "near_lists" (0/1), "abs_slack".
  * K4: "compact" (0/1), "compact_ratio" (0.25..0.9, default 0.7), "compact_min" (no compaction below this many slots,
  * default 4096), "compact_tiles" (1: one-pass tile kernel on an unsharded context; 0: the two-pass path sharded runs use),
- * "mirror_init" (mirror pass after K1). */
+ * "mirror_init" (mirror pass after K1), "fast_start" (1: ic_run_resident / ic_cluster_with_constraints skip the first
+ * nearest-neighbour sweep when the horizon and near lists are on -- the mirror pass collects the global minimum). */
 int ic_set_option(ic_ctx *ctx, const char *name, double value);
 
 /* ---- CalculateOptimalClusters, clustering.go:168-186 (host, exact) ---- */

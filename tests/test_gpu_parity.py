@@ -311,8 +311,8 @@ def knobs(eng):
         for k, v in kw.items():
             eng.set_option(k, v)
     yield set_
-    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode", "exact", "mirror_init", "compact", "near_lists"):
-        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode", "exact", "mirror_init", "compact", "near_lists") else 0)
+    for k in ("virtual_ranks", "loop_blocks", "no_replica", "loop_mode", "exact", "mirror_init", "compact", "near_lists", "fast_start"):
+        eng.set_option(k, 1 if k in ("virtual_ranks", "loop_mode", "exact", "mirror_init", "compact", "near_lists", "fast_start") else 0)
 
 
 @pytest.mark.parametrize("name", SMALL_GOLDENS)
@@ -653,6 +653,22 @@ def test_near_lists_do_not_change_the_trace(eng, knobs, n, d, mn, mx, ranks):
         digests.append(_trace_digest(eng.merge_trace()))
         _assert_reference_run(res.stats)
     assert digests[0] == digests[1]
+
+
+@pytest.mark.parametrize("n,d,mn,mx", [(6000, 2048, 10, 50), (5000, 32, 6, 8), (3000, 64, 1, 4), (9000, 96, 4, 12)])
+def test_start_without_the_first_sweep_does_not_change_the_trace(eng, knobs, n, d, mn, mx):
+    """With the horizon and near lists on, K2's only product that outlives the first horizon is the global minimum, which the
+    mirror pass after K1 collects: the run that skips K2 (default) and the one that does not give the same trace."""
+    x = synth.gaussian_mixture(n, d, mn, mx, seed=41 + n)
+    digests, launches = [], []
+    for fast in (0, 1):
+        knobs(fast_start=fast)
+        res = eng.cluster(x, mn, mx)
+        digests.append(_trace_digest(eng.merge_trace()))
+        launches.append(res.stats["kernel_launches"])
+        _assert_reference_run(res.stats)
+    assert digests[0] == digests[1]
+    assert launches[1] < launches[0]  # (no first sweep, no first loop launch that only reports the minimum)
 
 
 def test_barrier_timeout_is_reported_and_the_context_survives(eng, oracle):
