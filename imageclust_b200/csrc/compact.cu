@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a, 
     if (j_hi <= a.row0 || j_lo >= a.row1) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 float4 across, 16 rows per pass
     uint32_t my_min = 0xFFFFFFFFu;
+    __shared__ uint32_t s_wmin[8];
 #pragma unroll
     for (int r = ty; r < kMT; r += 16) {
         const int32_t i = bi * kMT + r, j0 = bj * kMT + tx * 4;
@@ -175,11 +176,17 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(const CompactArgs a, 
                 if (j0 + e < i && i < a.n_new && __float_as_uint(vs[e]) < kMaxFloatBits) my_min = min(my_min, __float_as_uint(vs[e]));
         }
     }
-    if (a.gmin != nullptr) {
+    if (a.gmin != nullptr) {  // (one word for 1.2 M blocks: the atomic only where the block beats the running minimum)
         my_min = __reduce_min_sync(0xffffffffu, my_min);
-        if ((threadIdx.x & 31) == 0 && my_min != 0xFFFFFFFFu) atomicMin(a.gmin, my_min);
+        if ((threadIdx.x & 31) == 0) s_wmin[threadIdx.x >> 5] = my_min;
     }
     __syncthreads();
+    if (a.gmin != nullptr && threadIdx.x == 0) {
+        uint32_t bmin = s_wmin[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) bmin = min(bmin, s_wmin[w]);
+        if (bmin < __ldcg(a.gmin)) atomicMin(a.gmin, bmin);
+    }
 #pragma unroll
     for (int r = ty; r < kMT; r += 16) {
         const int32_t j = bj * kMT + r, i0 = bi * kMT + tx * 4;  // write dm[j][i0..i0+3] = dm[i0..i0+3][j]

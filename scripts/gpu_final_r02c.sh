@@ -3,7 +3,7 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-T=f3
+T=f4
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_C.json 2> gpurun_out/${T}_bench_C.err; echo "bench C exit $?"
 for c in A B E; do timeout 600 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_$c.json 2> gpurun_out/${T}_bench_$c.err; echo "bench $c exit $?"; done
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
